@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- PD bond-updates/s of the fused NS + ARD step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libpdgpu.so on B200)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU/OpenMP path
+
+A "step" = one PD-NS loop body (inlet, outlet, wall, solid BCs + bond kernel + wall mirror of
+the new buffers, src/pd_ns.cpp:196-205) followed by one explicit PD-ARD loop body (inlet,
+outlet, wall-C BCs + bond kernel, src/coupling.cpp:232-238) on the 3D params_fine geometry
+(dx = 2 um, 157 x 157 x 707 nodes, BASELINE config 4).  bond-updates per step = CSR row
+lengths summed over FLUID rows (NS) + FLUID and SOLID_MG rows (ARD).
+For N > 1 the tube is lengthened N-fold (weak scaling: every GPU owns the same z-slab) and
+each rank drives one GPU; halos travel over NCCL.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from pd_mg_pin_corrosion_b200.config import Config  # noqa: E402
+
+METRIC = "pd_bond_updates_per_s_ns_plus_ard_step"
+UNIT = "bond-updates/s"
+
+
+def workload_cfg(n_gpus: int, sample: bool = False) -> tuple[Config, str]:
+    """3D params_fine (+ use_implicit = 0); tube x n_gpus for weak scaling; `sample` = the
+    same cross-section with a short tube (bounded CPU-baseline sample)."""
+    ov = {"use_implicit": 0}
+    base = Config.load(os.path.join(ROOT, "configs", "params_fine.cfg"), ov, quiet=True)
+    if sample:
+        ov.update({"L_wire": 24e-6, "L_upstream": 16e-6, "L_downstream": 16e-6})
+        name = "3D params_fine cross-section (dx=2um, 157x157), tube shortened to 35 axial planes"
+    else:
+        ov.update({"L_wire": base.L_wire * n_gpus, "L_upstream": base.L_upstream * n_gpus,
+                   "L_downstream": base.L_downstream * n_gpus})
+        name = "3D params_fine (dx=2um, 157x157x707, use_implicit=0)" + (
+            f", tube x{n_gpus} (one params_fine slab per GPU)" if n_gpus > 1 else "")
+    return Config.load(os.path.join(ROOT, "configs", "params_fine.cfg"), ov, quiet=True), name
+
+
+# ------------------------------------------------------------------ clocks ------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.05:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0]))
+                smax = float(p[1])
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:   # region shorter than the sampling period: take whatever was seen
+            for ts, line in self.rows[-3:]:
+                p = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(p[0])); smax = float(p[1])
+                except (ValueError, IndexError):
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------- CPU reference ---------
+class _StdoutToStderr:
+    """The reference printf()s progress to fd 1; keep stdout clean for the ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def cpu_reference(steps: int, warmup: int, threads: int | None = None) -> dict:
+    with _StdoutToStderr():
+        return _cpu_reference(steps, warmup, threads)
+
+
+def _cpu_reference(steps: int, warmup: int, threads: int | None = None) -> dict:
+    """The reference's own OpenMP path (oracle/_ref, else the plain-C port) on the host cores,
+    on the bounded sample of the workload. Test/baseline infrastructure only."""
+    from oracle import refapi
+    cfg, name = workload_cfg(1, sample=True)
+    cores = threads or os.cpu_count() or 1
+    ov = {"L_wire": cfg.L_wire, "L_upstream": cfg.L_upstream, "L_downstream": cfg.L_downstream}
+    t_build = time.time()
+    if refapi.have_ref(3):
+        sim = refapi.RefSim(3, "params_fine.cfg", ov, threads=cores)
+        kind = "reference"
+        nt = sim.get("node_type")
+        rowlen = np.diff(sim.get("nbr_offset").astype(np.int64))
+    else:
+        from oracle.portapi import PortSim
+        sim = PortSim(3, cfg, threads=cores)
+        sim.init_fields()
+        kind = "port"
+        nt = sim.node_type
+        rowlen = np.diff(sim.csr()[0])
+    t_build = time.time() - t_build
+    ns_bonds = int(rowlen[nt == 0].sum())
+    ard_bonds = int(rowlen[(nt == 0) | (nt == 1)].sum())
+    dt = sim.ns_compute_dt()
+    dtc = sim.ard_compute_dt()
+    for _ in range(warmup):
+        sim.ns_iterate(1, dt)
+        sim.ard_iterate(1, dtc)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.ns_iterate(1, dt)
+        sim.ard_iterate(1, dtc)
+    el = time.perf_counter() - t0
+    value = (ns_bonds + ard_bonds) * steps / el
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{name}: {ns_bonds + ard_bonds} bond-updates/step, {steps} steps in {el:.2f} s "
+                      f"(+{t_build:.1f} s grid/CSR build, untimed)",
+            "ms_per_step": 1e3 * el / steps}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    base = cpu_reference(steps, min(args.warmup, 1))
+    _, wname = workload_cfg(args.gpus)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic (deterministic geometry from the cfg; Poiseuille initial flow)",
+            "config": {"workload": wname, "measured_on": base["sample"]},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------- our arm ---------
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small", action="store_true", help="dx=5um params.cfg 3D (debug)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    from pd_mg_pin_corrosion_b200 import lib as L_, solver as S
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    L = L_.load()
+    cfg, wname = workload_cfg(world)
+    if args.small:
+        cfg = Config.load(os.path.join(ROOT, "configs", "params.cfg"), {"use_implicit": 0}, quiet=True)
+        wname = "3D params.cfg (dx=5um, 67x67x287) [debug]"
+    grid = S.Grid(3, device=local, rank=rank, nranks=world)
+    grid.build(cfg)
+    if world > 1:
+        nb = L.pdgpu_comm_uid_bytes()
+        uid = torch.zeros(nb, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * nb)()
+            L_.check(L.pdgpu_comm_get_uid(buf))
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        ub = bytes(uid.cpu().tolist())
+        L_.check(L.pdgpu_comm_init(grid.ctx, ub, rank, world))
+    fields = S.Fields()
+    fields.bind(grid)
+    L_.check(L.pdgpu_fields_init(grid.ctx, None, None))   # grains: none (flags only matter at the wire surface)
+    ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
+    ns.init(grid, cfg)
+    ard.init(grid, cfg)
+    dt = ns.compute_dt(fields, grid, cfg)
+    dtc = ard.compute_dt(fields, grid, cfg)
+    info = grid.info
+    bonds_local = info.ns_bonds + info.ard_bonds
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        L_.check(L.pdgpu_ns_iterate(grid.ctx, 1, dt))
+        L_.check(L.pdgpu_ard_iterate(grid.ctx, 1, dtc))
+
+    for _ in range(args.warmup):
+        one_step()
+    # ---- device-resident throughput (`value`) ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    L.pdgpu_launch_count(grid.ctx, None, 1)
+    barrier()
+    t0 = time.time()
+    L_.check(L.pdgpu_timer_start(grid.ctx))
+    for _ in range(args.steps):
+        one_step()
+    ms = C.c_float()
+    L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
+    barrier()
+    t1 = time.time()
+    launches = C.c_longlong()
+    L.pdgpu_launch_count(grid.ctx, C.byref(launches), 0)
+    clocks = sampler.stop(t0, t1)
+    t_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(bonds_local)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total = float(t_ms.item())
+    bonds_total = float(tot.item())
+    value = bonds_total * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the host-array API (`e2e`): pinned host state -> H2D -> step -> D2H ----
+    n_own = (info.a1 - info.a0) * info.plane
+    N = info.N_total
+    host = {}
+    for name, shape in (("rho", (N,)), ("vel", (N, 3)), ("C", (N,))):
+        t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        host[name] = t.numpy()
+        L_.check(L.pdgpu_fields_download(grid.ctx, S._FIELD_IDS[name], host[name].ctypes.data_as(C.c_void_p)))
+        host["_t_" + name] = t
+    n_up = (min(info.a1 + info.reach, cfg_planes(info)) - max(info.a0 - info.reach, 0)) * info.plane
+    h2d = n_up * 8 * 5
+    d2h = n_own * 8 * 5
+
+    def e2e_step():
+        for name in ("rho", "vel", "C"):
+            L_.check(L.pdgpu_fields_upload(grid.ctx, S._FIELD_IDS[name], host[name].ctypes.data_as(C.c_void_p)))
+        one_step()
+        for name in ("rho", "vel", "C"):
+            L_.check(L.pdgpu_fields_download(grid.ctx, S._FIELD_IDS[name], host[name].ctypes.data_as(C.c_void_p)))
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    L_.check(L.pdgpu_timer_start(grid.ctx))
+    for _ in range(e2e_steps):
+        e2e_step()
+    ms2 = C.c_float()
+    L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms2)))
+    barrier()
+    t2 = torch.tensor([ms2.value], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = bonds_total * e2e_steps / (float(t2.item()) * 1e-3)
+
+    # ---- roofline of the dominant kernel (PD-NS bond kernel), timed alone with CUDA events ----
+    kms = C.c_float()
+    L_.check(L.pdgpu_time_kernel(grid.ctx, 0, 10, C.byref(kms)))
+    kms_ard = C.c_float()
+    L_.check(L.pdgpu_time_kernel(grid.ctx, 1, 10, C.byref(kms_ard)))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    # algorithmic bytes (reference CSR formulation): 44 B per bond-update
+    # + 65 B per updated FLUID node (read rho,v,type; write rho_new,v_new)
+    alg_bytes = info.ns_bonds * 44 + int(info.counts[0]) * 65
+    achieved = alg_bytes / (kms.value * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ns_kernel_traffic.json"))).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "pd-ns bond kernel", "kernel_ms": kms.value,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "model": "reference CSR layout: 44 B/bond-update + 65 B/FLUID node (SURVEY.md 8d); the "
+                         "offset-table kernel does not stream a CSR, so frac can exceed 1 -- see DESIGN.md",
+                "ns_bond_updates_per_s": info.ns_bonds / (kms.value * 1e-3),
+                "ard_kernel_ms": kms_ard.value,
+                "ard_bond_updates_per_s": info.ard_bonds / (kms_ard.value * 1e-3)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        b = cpu_reference(4, 1)
+        cpu = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic (deterministic geometry from the cfg; Poiseuille initial flow)",
+                "config": {"workload": wname, "nodes": int(N), "bond_updates_per_step": int(bonds_total),
+                           "parallelism": f"z-slab x{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2",
+                           "ns_kernel": "tile" if grid.info.m == 3 else "generic"},
+                "clocks": clocks, "gpu_launches": int(launches.value),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                        "what": "pinned host rho/vel/C -> pdgpu_fields_upload -> NS body + ARD body -> "
+                                "pdgpu_fields_download, every step"},
+                "roofline": roofline}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cfg_planes(info) -> int:
+    return info.Nz
+
+
+if __name__ == "__main__":
+    main()

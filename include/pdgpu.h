@@ -1,0 +1,192 @@
+/* include/pdgpu.h -- C ABI of libpdgpu.so, the B200 (sm_100a) implementation of the
+ * per-timestep peridynamic bond-summation hot path of alhermann/pd-mg-pin-corrosion.
+ *
+ * The reference has no FFI/plugin layer: the seam is the C++ surface
+ * that src/main.cpp and src/coupling.cpp call.  Every entry point below names the
+ * reference interface (file:line under the reference's src/) it replaces.  Plain
+ * pointers and sizes only; the library owns all device memory; the caller is single
+ * threaded per context (like the reference's host thread).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; pdgpu_last_error()
+ *     returns a message for the calling thread's last failure.  There is NO CPU
+ *     fallback: without a CUDA device pdgpu_create* fails.
+ *   - host arrays use the reference's layouts: node index n = k*Nx*Ny + j*Nx + i
+ *     (src/grid.h:58-64), velocity interleaved [N][dim] (std::vector<Vec>,
+ *     src/utils.h:14), node types uint8 (src/grid.h:9-17).
+ *   - a context covers a z-slab [a0,a1) of the axial index (k in 3D, j in 2D) of the
+ *     global grid plus `reach` ghost planes per side; pdgpu_create makes the slab the
+ *     whole grid.  Host arrays passed to upload/download are GLOBAL-sized; a slab
+ *     context reads/writes only its own planes (and its ghosts on upload).
+ */
+#ifndef PDGPU_H
+#define PDGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDGPU_VERSION 100
+
+/* POD copy of the numeric members of the reference's Config AFTER compute_derived()
+ * (src/config.h:4-99, src/config.cpp:98-112): c0 already raised to 25*U_in, delta and
+ * U_in filled in. */
+typedef struct PdConfig {
+    double dx, R_wire, L_wire, R_tube, L_upstream, L_downstream;
+    double rho_f, mu_f, gamma_eos, c0, eta_density, Q_flow, rho_m;
+    double D_liquid, D_grain, D_gb, D_precip;
+    double C_solid_init, C_liquid_init, C_thresh, C_sat, alpha_art_diff, corrosion_decay_l;
+    double cfl_factor, cfl_factor_corr, flow_conv_tol, T_final;
+    double delta, U_in;
+    int m_ratio, flow_max_iters, corrosion_steps_per_check;
+    int output_every_flow, output_every_corr, channel_flow_corrections, use_implicit;
+    int reserved;
+} PdConfig;
+
+/* NodeType (src/grid.h:9-17). FICTITIOUS (6) is AMR-only and never produced. */
+enum { PDGPU_FLUID = 0, PDGPU_SOLID_MG = 1, PDGPU_WALL = 2, PDGPU_INLET = 3, PDGPU_OUTLET = 4,
+       PDGPU_OUTSIDE = 5 };
+
+/* Members of Fields (src/fields.h:7-26) + Grid::node_type addressable by upload/download. */
+enum { PDGPU_F_RHO = 0, PDGPU_F_VEL = 1, PDGPU_F_PRESSURE = 2, PDGPU_F_C = 3, PDGPU_F_RHO_NEW = 4,
+       PDGPU_F_VEL_NEW = 5, PDGPU_F_C_NEW = 6, PDGPU_F_PHASE = 7, PDGPU_F_IS_GB = 8,
+       PDGPU_F_IS_PRECIP = 9, PDGPU_F_NODE_TYPE = 10 };
+
+typedef struct pdgpu_ctx pdgpu_ctx;
+
+typedef struct PdGridInfo {
+    int dim, Nx, Ny, Nz;          /* Grid::Nx,Ny,Nz (src/grid.h:20) */
+    int m, n_off, reach;          /* m_ratio, stencil size (36 / 178 for m=3), ghost width */
+    int a0, a1;                   /* owned axial planes [a0,a1) */
+    long long N_total;            /* Nx*Ny*Nz */
+    long long plane;              /* nodes per axial plane: Nx (2D) or Nx*Ny (3D) */
+    long long counts[6];          /* owned nodes per NodeType */
+    long long ns_bonds;           /* sum of CSR row lengths over owned FLUID rows   */
+    long long ard_bonds;          /* ... over owned FLUID + SOLID_MG rows           */
+    long long nnz;                /* CSR entries of owned rows (all non-OUTSIDE)    */
+    double origin[3];             /* Grid::origin_x,y,z */
+} PdGridInfo;
+
+/* Convergence-block scalars of PD_NS_Solver::solve_steady (src/pd_ns.cpp:273-301). */
+typedef struct PdResidual {
+    double num, den;              /* sum |dv|^2, sum |v|^2 over FLUID */
+    double v_max, rho_min, rho_max;
+    int has_nan, pad;
+} PdResidual;
+
+/* Outcome of pdgpu_ns_solve_steady. status: 0 converged, 1 hit flow_max_iters,
+ * 2 diverged (NaN), 3 diverged (v_max > 100 U_in). iters = the reference's return value. */
+typedef struct PdSteadyResult {
+    int iters, status;
+    double eps, dt, v_max, rho_min, rho_max;
+    double poiseuille_l2;         /* 2D only (src/pd_ns.cpp:341-368), -1 if not evaluated */
+    int poiseuille_nodes, pad;
+} PdSteadyResult;
+
+/* Reductions of CoupledSolver::write_diagnostics (src/coupling.cpp:20-49). */
+typedef struct PdDiag {
+    long long solid_count;
+    double v_max, C_max_fluid;
+} PdDiag;
+
+const char* pdgpu_last_error(void);
+int pdgpu_version(void);
+int pdgpu_device_count(int* count);
+
+/* ---- host-only helpers (no device needed) -------------------------------------- */
+/* Grid extents of Grid::build (src/grid.cpp:38-67). */
+int pdgpu_grid_extents(const PdConfig* cfg, int dim, int* Nx, int* Ny, int* Nz, double origin[3]);
+/* Balanced z-slab [a0,a1) of `rank` among `nranks` over n_axial planes. */
+int pdgpu_partition(int n_axial, int nranks, int rank, int* a0, int* a1);
+/* Horizon-offset stencil of Grid::build_neighbors (src/grid.cpp:161-187,274-288) in CSR
+ * order: off_d [n][3], dist [n], evec [n][dim], vol [n]; returns count in *n_off
+ * (arrays may be NULL to query the count). */
+int pdgpu_stencil(const PdConfig* cfg, int dim, int* n_off, int* off_d, double* dist, double* evec,
+                  double* vol);
+
+/* ---- lifetime --------------------------------------------------------------------- */
+int pdgpu_create(const PdConfig* cfg, int dim, int device, pdgpu_ctx** out);
+int pdgpu_create_slab(const PdConfig* cfg, int dim, int device, int rank, int nranks,
+                      pdgpu_ctx** out);
+int pdgpu_destroy(pdgpu_ctx* ctx);
+int pdgpu_sync(pdgpu_ctx* ctx);
+
+/* ---- Grid (src/grid.h:52-53) -------------------------------------------------------- */
+/* Grid::build: node classification on device, stencil table, per-type node lists,
+ * wall-mirror table, outlet sweep schedule. */
+int pdgpu_grid_build(pdgpu_ctx* ctx);
+/* Replace the classification by a caller-made one (hand-built geometries as in the
+ * reference's tests/test_implicit.cpp:737-772); rebuilds the derived tables. */
+int pdgpu_grid_set_types(pdgpu_ctx* ctx, const uint8_t* node_type_global);
+int pdgpu_grid_info(pdgpu_ctx* ctx, PdGridInfo* out);
+/* Grid::build_neighbors: materialise the reference-layout CSR on device
+ * (count -> prefix scan -> fill). Optional: the solvers use the offset table. */
+int pdgpu_grid_build_neighbors(pdgpu_ctx* ctx, long long* nnz);
+/* nbr_offset is 64-bit here (int32 overflows at 3D dx=2um). Rows are the
+ * context's owned nodes in index order; indices are GLOBAL node indices. */
+int pdgpu_grid_download_csr(pdgpu_ctx* ctx, long long* nbr_offset, int* nbr_index,
+                            double* nbr_dist, double* nbr_evec, double* nbr_vol);
+int pdgpu_grid_free_neighbors(pdgpu_ctx* ctx);
+/* Mirror node (global index, -1 = none) of every owned node; -1 for non-WALL nodes
+ * (apply_wall_mirror_proper, src/boundary.cpp:143-264). [N_total], owned part written. */
+int pdgpu_grid_download_wall_mirror(pdgpu_ctx* ctx, int* mirror_global);
+
+/* ---- Fields (src/fields.h:28-58, src/main.cpp:9-127) ------------------------------- */
+int pdgpu_fields_upload(pdgpu_ctx* ctx, int field, const void* host_global);
+int pdgpu_fields_download(pdgpu_ctx* ctx, int field, void* host_global);
+/* initialize_fields on device (is_gb / is_precip from the host grain generator, NULL = 0). */
+int pdgpu_fields_init(pdgpu_ctx* ctx, const uint8_t* is_gb_global, const uint8_t* is_precip_global);
+int pdgpu_swap_flow(pdgpu_ctx* ctx);                 /* Fields::swap_buffers       */
+int pdgpu_swap_C(pdgpu_ctx* ctx);                    /* std::swap(C, C_new), coupling.cpp:238 */
+/* out[t] = field[idx[t]] for scalar double fields (ordered host sums, coupling.cpp:32-38) */
+int pdgpu_gather(pdgpu_ctx* ctx, int field, const int* idx_global, long long n, double* out);
+
+/* ---- boundary operators (src/boundary.h:6-13) ---------------------------------------- */
+int pdgpu_bc_inlet(pdgpu_ctx* ctx);                  /* apply_inlet_bc               */
+int pdgpu_bc_outlet(pdgpu_ctx* ctx);                 /* apply_outlet_bc (in-place GS)*/
+int pdgpu_bc_wall(pdgpu_ctx* ctx);                   /* apply_wall_bc                */
+int pdgpu_bc_wall_new(pdgpu_ctx* ctx);               /* apply_wall_bc_new            */
+int pdgpu_bc_wall_conc(pdgpu_ctx* ctx);              /* apply_wall_concentration_bc  */
+int pdgpu_bc_solid(pdgpu_ctx* ctx);                  /* apply_solid_surface_bc       */
+
+/* ---- PD_NS_Solver (src/pd_ns.h:9-17) --------------------------------------------------- */
+int pdgpu_ns_compute_dt(pdgpu_ctx* ctx, double* dt);
+int pdgpu_ns_step(pdgpu_ctx* ctx, double dt);        /* EOS + bond sums + Euler -> *_new */
+/* `iters` x { inlet, outlet, wall, solid, step, wall_new, swap } (src/pd_ns.cpp:196-205,325),
+ * device resident, no host round trip. */
+int pdgpu_ns_iterate(pdgpu_ctx* ctx, int iters, double dt);
+int pdgpu_ns_residual(pdgpu_ctx* ctx, PdResidual* out);
+int pdgpu_ns_solve_steady(pdgpu_ctx* ctx, PdSteadyResult* out, int verbose);
+
+/* ---- PD_ARD_Solver, explicit (src/pd_ard.h:9-20) ---------------------------------------- */
+int pdgpu_ard_set_volume_loss(pdgpu_ctx* ctx, double vl);
+int pdgpu_ard_compute_dt(pdgpu_ctx* ctx, double* dt);
+int pdgpu_ard_step(pdgpu_ctx* ctx, double dt);       /* salt pre-pass + bond sums -> C_new */
+/* `steps` x { inlet, outlet, wall_conc, step, swap C } (src/coupling.cpp:232-240). */
+int pdgpu_ard_iterate(pdgpu_ctx* ctx, int steps, double dt);
+/* apply_phase_change + update_node_types + table rebuild (src/coupling.cpp:256-271).
+ * dissolved_global (may be NULL) receives up to `cap` ascending global indices. */
+int pdgpu_phase_change(pdgpu_ctx* ctx, int* n_dissolved, int* dissolved_global, int cap);
+int pdgpu_diag(pdgpu_ctx* ctx, PdDiag* out);
+
+/* ---- multi-GPU: one process per GPU, z-slabs, NCCL halo exchange ------------------------ */
+int pdgpu_comm_uid_bytes(void);
+int pdgpu_comm_get_uid(void* uid_out);               /* rank 0; broadcast by the caller */
+int pdgpu_comm_init(pdgpu_ctx* ctx, const void* uid, int rank, int nranks);
+int pdgpu_halo_exchange(pdgpu_ctx* ctx, int which);  /* 0: rho,vel,p   1: C   2: all (incl. _new) */
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+int pdgpu_timer_start(pdgpu_ctx* ctx);               /* cudaEventRecord on the ctx stream */
+int pdgpu_timer_stop(pdgpu_ctx* ctx, float* ms);     /* record + synchronize + elapsed    */
+int pdgpu_launch_count(pdgpu_ctx* ctx, long long* launches, int reset);
+int pdgpu_set_option(pdgpu_ctx* ctx, const char* name, int value);
+int pdgpu_flush_l2(pdgpu_ctx* ctx);                  /* write a > L2-sized scratch buffer */
+/* kernel-only timing of the dominant kernel: average ms of `reps` launches of the NS
+ * (which=0) or ARD (which=1) bond kernel alone, CUDA events on the ctx stream. */
+int pdgpu_time_kernel(pdgpu_ctx* ctx, int which, int reps, float* ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

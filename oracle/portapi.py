@@ -10,6 +10,7 @@ import subprocess
 
 import numpy as np
 
+PDO_FLUID, PDO_SOLID, PDO_WALL, PDO_INLET, PDO_OUTLET, PDO_OUTSIDE = range(6)
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libpdoracle.so")
 
@@ -156,6 +157,13 @@ class PortSim:
                             _dp(evec), _dp(vol))
         return off, idx, dist, evec, vol
 
+    # RefSim-compatible accessors
+    def get(self, name):
+        return np.array(getattr(self, name), copy=True)
+
+    def set(self, name, value):
+        getattr(self, name)[...] = value
+
     def load_state(self, src):
         """Copy rho/vel/C/(_new)/phase/is_gb/is_precip from an object exposing .get(name)."""
         for n in ("rho", "vel", "pressure", "C", "rho_new", "vel_new", "C_new", "phase", "is_gb", "is_precip"):
@@ -200,8 +208,48 @@ class PortSim:
         return self.L.pdo_ard_iterate(self.g, self.c, n, dt, self.volume_loss, _dp(self.rho), _dp(self.vel),
                                       _dp(self.C), _dp(self.C_new), _u8(self.is_gb), _u8(self.is_precip))
 
-    def phase_change(self):
+    def phase_change(self) -> int:
         d = np.zeros(self.N, np.int32)
         n = self.L.pdo_phase_change(self.g, self.c, _u8(self.phase), _dp(self.rho), _dp(self.vel),
                                     _dp(self.C), _ip(d))
-        return d[:n].copy()
+        self.last_dissolved = d[:n].copy()
+        return n
+
+    def rebuild_neighbors(self):
+        pass  # stencil-implicit: nothing to rebuild (wall-mirror table is refreshed by pdo_phase_change)
+
+    def ard_set_volume_loss(self, v):
+        self.volume_loss = v
+
+    def init_fields(self, is_gb=None, is_precip=None):
+        """initialize_fields (src/main.cpp:9-127) restated with numpy."""
+        nt, dim, c = self.node_type, self.dim, self.cfg
+        N = self.N
+        idx = np.arange(N)
+        i = idx % self.Nx
+        # pos = origin + i*dx evaluated as one fma in the reference build; the difference is
+        # <= 1 ulp in a velocity profile value and only enters fields at the 1e-16 level.
+        px = self.origin[0] + i * c.dx
+        R2 = c.R_tube * c.R_tube
+        if dim == 2:
+            rr = np.minimum(px * px / R2, 1.0)
+            vax = 1.5 * c.U_in * (1.0 - rr)
+        else:
+            j = (idx % (self.Nx * self.Ny)) // self.Nx
+            py = self.origin[1] + j * c.dx
+            rr = np.minimum((px * px + py * py) / R2, 1.0)
+            vax = 2.0 * c.U_in * (1.0 - rr)
+        self.rho[:] = np.where(nt == PDO_OUTSIDE, 0.0, c.rho_f)
+        self.vel[:] = 0.0
+        prof = (nt == PDO_FLUID) | (nt == PDO_INLET)
+        self.vel[prof, dim - 1] = vax[prof]
+        self.C[:] = 0.0
+        self.C[nt == PDO_SOLID] = c.C_solid_init
+        self.C[(nt == PDO_FLUID) | (nt == PDO_INLET) | (nt == PDO_OUTLET)] = c.C_liquid_init
+        self.phase[:] = 1
+        self.phase[nt == PDO_SOLID] = 0
+        self.is_gb[:] = 0 if is_gb is None else is_gb
+        self.is_precip[:] = 0 if is_precip is None else is_precip
+        self.rho_new[:] = self.rho
+        self.vel_new[:] = self.vel
+        self.C_new[:] = self.C

@@ -1,0 +1,202 @@
+// api.cu -- context lifetime, error reporting, instrumentation of libpdgpu.so.
+#include <cstdarg>
+
+#include "common.cuh"
+#include "geom.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void pd_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* pdgpu_last_error(void) { return g_err; }
+extern "C" int pdgpu_version(void) { return PDGPU_VERSION; }
+
+extern "C" int pdgpu_device_count(int* count) {
+    if (!count) PD_FAIL("pdgpu_device_count: null output");
+    *count = 0;
+    CUDA_OK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+extern "C" int pdgpu_create_slab(const PdConfig* cfg, int dim, int device, int rank, int nranks,
+                                 pdgpu_ctx** out) {
+    if (!cfg || !out) PD_FAIL("pdgpu_create: null argument");
+    if (dim != 2 && dim != 3) PD_FAIL("pdgpu_create: dim must be 2 or 3 (PD_DIM, src/utils.h:8-12)");
+    if (cfg->use_implicit) PD_FAIL("pdgpu_create: use_implicit = 1 (Eigen/GMRES branch) is out of scope; set use_implicit = 0");
+    if (cfg->m_ratio < 1 || cfg->m_ratio > 5) PD_FAIL("pdgpu_create: m_ratio must be in [1,5]");
+    if (!(cfg->dx > 0.0) || !(cfg->delta > 0.0)) PD_FAIL("pdgpu_create: dx/delta must be positive (run compute_derived)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        PD_FAIL("pdgpu_create: no CUDA device available (%s); libpdgpu has no CPU fallback",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) PD_FAIL("pdgpu_create: device %d out of range [0,%d)", device, ndev);
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) PD_FAIL("pdgpu_create: built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+
+    pdgpu_ctx* c = new pdgpu_ctx();
+    c->cfg = *cfg;
+    c->dim = dim;
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    geom_extents(*cfg, dim, &c->Nx, &c->Ny, &c->Nz, c->origin);
+    c->Na = (dim == 2) ? c->Ny : c->Nz;
+    c->P = (dim == 2) ? c->Nx : (long long)c->Nx * c->Ny;
+    c->N_total = (long long)c->Nx * c->Ny * c->Nz;
+    c->R = cfg->m_ratio;
+    if (pdgpu_partition(c->Na, nranks, rank, &c->a0, &c->a1)) { delete c; return 1; }
+    if (nranks > 1 && (c->a1 - c->a0) < 2 * c->R + 2) {
+        int planes = c->a1 - c->a0;
+        delete c;
+        PD_FAIL("pdgpu_create_slab: slab of %d planes is thinner than 2*reach+2", planes);
+    }
+    c->nlp = (c->a1 - c->a0) + 2 * c->R;
+    c->NL = (long long)c->nlp * c->P;
+    c->own_lo = (long long)c->R * c->P;
+    c->own_hi = c->own_lo + (long long)(c->a1 - c->a0) * c->P;
+    if (c->NL >= (1LL << 31)) {
+        long long nl = c->NL;
+        delete c;
+        PD_FAIL("pdgpu_create: slab of %lld nodes exceeds int32 local indexing; use more ranks", nl);
+    }
+
+    // stencil (+ local linear offsets)
+    int n_off = 0;
+    pdgpu_stencil(cfg, dim, &n_off, nullptr, nullptr, nullptr, nullptr);
+    std::vector<int> od(3 * n_off);
+    std::vector<double> dist(n_off), evec((size_t)dim * n_off), vol(n_off);
+    pdgpu_stencil(cfg, dim, &n_off, od.data(), dist.data(), evec.data(), vol.data());
+    c->n_off = n_off;
+    c->h_off.resize(n_off);
+    for (int o = 0; o < n_off; ++o) {
+        OffEntry& en = c->h_off[o];
+        en.di = od[3 * o]; en.dj = od[3 * o + 1]; en.dk = od[3 * o + 2]; en.pad = 0;
+        en.lin = (dim == 2) ? (long long)en.dj * c->P + en.di
+                            : (long long)en.dk * c->P + (long long)en.dj * c->Nx + en.di;
+        en.dist = dist[o];
+        en.ex = evec[(size_t)dim * o]; en.ey = evec[(size_t)dim * o + 1];
+        en.ez = (dim == 3) ? evec[(size_t)dim * o + 2] : 0.0;
+        en.vol = vol[o];
+        double inv_xi = 1.0 / en.dist;
+        en.w1 = inv_xi * en.vol;
+        en.w2 = inv_xi * inv_xi * en.vol;
+    }
+    CUDA_OK(cudaMalloc(&c->d_off, sizeof(OffEntry) * n_off));
+    CUDA_OK(cudaMemcpy(c->d_off, c->h_off.data(), sizeof(OffEntry) * n_off, cudaMemcpyHostToDevice));
+
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreate(&c->ev_t0));
+    CUDA_OK(cudaEventCreate(&c->ev_t1));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    CUDA_OK(cudaMalloc(&c->d_red, sizeof(double) * 8192));
+    CUDA_OK(cudaMallocHost(&c->h_red, sizeof(double) * 64));
+    CUDA_OK(cudaMalloc(&c->d_u64, sizeof(unsigned long long) * 16));
+    CUDA_OK(cudaMalloc(&c->d_int, sizeof(int) * 16));
+    CUDA_OK(cudaMalloc(&c->d_dt, sizeof(double) * 8));
+    *out = c;
+    return 0;
+}
+
+extern "C" int pdgpu_create(const PdConfig* cfg, int dim, int device, pdgpu_ctx** out) {
+    return pdgpu_create_slab(cfg, dim, device, 0, 1, out);
+}
+
+void pd_invalidate_graphs(pdgpu_ctx* c) {
+    for (int a = 0; a < 2; ++a) {
+        if (c->g_ns[a]) { cudaGraphExecDestroy(c->g_ns[a]); c->g_ns[a] = nullptr; }
+        for (int b = 0; b < 2; ++b)
+            if (c->g_ard[a][b]) { cudaGraphExecDestroy(c->g_ard[a][b]); c->g_ard[a][b] = nullptr; }
+    }
+}
+
+int pd_comm_destroy(pdgpu_ctx* c);
+
+extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    pd_invalidate_graphs(c);
+    pd_comm_destroy(c);
+    void* ptrs[] = {c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->rho[0], c->rho[1],
+                    c->p[0], c->p[1], c->C[0], c->C[1], c->v[0][0], c->v[0][1], c->v[0][2], c->v[1][0],
+                    c->v[1][1], c->v[1][2], c->vmag, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,
+                    c->l_solid, c->inlet_vax, c->out_nodes, c->out_level_off, c->d_red, c->d_u64, c->d_int,
+                    c->d_dissolved, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol,
+                    c->l2_scratch, c->d_dt, c->stage};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_red) cudaFreeHost(c->h_red);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    delete c;
+    return 0;
+}
+
+extern "C" int pdgpu_sync(pdgpu_ctx* c) {
+    CHECK_CTX(c);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pdgpu_timer_start(pdgpu_ctx* c) {
+    CHECK_CTX(c);
+    CUDA_OK(cudaEventRecord(c->ev_t0, c->stream));
+    return 0;
+}
+
+extern "C" int pdgpu_timer_stop(pdgpu_ctx* c, float* ms) {
+    CHECK_CTX(c);
+    CUDA_OK(cudaEventRecord(c->ev_t1, c->stream));
+    CUDA_OK(cudaEventSynchronize(c->ev_t1));
+    if (ms) CUDA_OK(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return 0;
+}
+
+extern "C" int pdgpu_launch_count(pdgpu_ctx* c, long long* launches, int reset) {
+    if (!c) PD_FAIL("null context");
+    if (launches) *launches = c->launches;
+    if (reset) c->launches = 0;
+    return 0;
+}
+
+extern "C" int pdgpu_set_option(pdgpu_ctx* c, const char* name, int value) {
+    if (!c || !name) PD_FAIL("pdgpu_set_option: null argument");
+    std::string n(name);
+    if (n == "ns_kernel") c->opt_ns_kernel = value;
+    else if (n == "ard_kernel") c->opt_ard_kernel = value;
+    else if (n == "graph") c->opt_graph = value;
+    else PD_FAIL("pdgpu_set_option: unknown option '%s'", name);
+    pd_invalidate_graphs(c);
+    return 0;
+}
+
+__global__ void k_flush(double* buf, size_t n, double v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = v;
+}
+
+extern "C" int pdgpu_flush_l2(pdgpu_ctx* c) {
+    CHECK_CTX(c);
+    if (!c->l2_scratch) {
+        c->l2_scratch_bytes = (size_t)256 << 20;   // 256 MiB > 126 MB L2
+        CUDA_OK(cudaMalloc(&c->l2_scratch, c->l2_scratch_bytes));
+    }
+    k_flush<<<148 * 8, 256, 0, c->stream>>>((double*)c->l2_scratch, c->l2_scratch_bytes / 8, 1.0);
+    return 0;
+}

@@ -1,0 +1,336 @@
+// ard.cu -- explicit PD_ARD_Solver (reference src/pd_ard.cpp) on device: salt-layer
+// pre-pass, bond-classified diffusion + artificial diffusion + non-conservative advection
+// with the forward-Euler update in one kernel, CFL dt, phase change, diagnostics.
+#include <algorithm>
+
+#include "common.cuh"
+
+struct ArdParams {
+    double D_liquid, D_grain, D_gb, D_precip, decay;
+    double alpha_dx;        // alpha_art_diff * dx
+    double beta;            // 4/(pi delta^2) or 12/(pi delta^2)
+    double div_coeff;       // alpha_p / V_H
+    double C_sat;
+};
+
+static ArdParams ard_params(const pdgpu_ctx* c) {
+    PdConsts k = pd_consts(c->cfg, c->dim);
+    ArdParams p;
+    p.D_liquid = c->cfg.D_liquid; p.D_grain = c->cfg.D_grain; p.D_gb = c->cfg.D_gb; p.D_precip = c->cfg.D_precip;
+    p.decay = 1.0;                                                      // src/pd_ard.cpp:75-79
+    if (c->cfg.corrosion_decay_l > 0.0) p.decay = std::pow(10.0, -c->volume_loss / c->cfg.corrosion_decay_l);
+    p.alpha_dx = c->cfg.alpha_art_diff * c->cfg.dx;
+    p.beta = k.beta_lap;
+    p.div_coeff = k.alpha / k.V_H;
+    p.C_sat = c->cfg.C_sat;
+    return p;
+}
+
+// Pre-pass over every local node: |v| (for D_art) and, for owned SOLID_MG nodes, the
+// salt-layer flag of src/pd_ard.cpp:61-73 (any FLUID neighbour with C >= C_sat).
+template <int DIM>
+__global__ void k_ard_prepass(Lat L, long long NL, long long own_lo, long long own_hi,
+                              const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
+                              const double* __restrict__ C, const double* __restrict__ vx,
+                              const double* __restrict__ vy, const double* __restrict__ vz, double C_sat,
+                              double* __restrict__ vmag, uint8_t* __restrict__ salt) {
+    long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= NL) return;
+    double s = vx[l] * vx[l] + vy[l] * vy[l];
+    if (DIM == 3) s += vz[l] * vz[l];
+    vmag[l] = sqrt(s);
+    if (l < own_lo || l >= own_hi) return;
+    uint8_t blocked = 0;
+    if (type[l] == PDGPU_SOLID_MG) {
+        int q = (int)(l % L.P);
+        int jj = (DIM == 3) ? q / L.Nx : 0;
+        int ii = q - jj * L.Nx;
+        for (int o = 0; o < n_off; ++o) {
+            long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
+            if (nn >= 0 && type[nn] == PDGPU_FLUID && C[nn] >= C_sat) { blocked = 1; break; }
+        }
+    }
+    salt[l] = blocked;
+}
+
+// Generic kernel: one thread per owned node (PD_ARD_Solver::step, src/pd_ard.cpp:81-190).
+template <int DIM>
+__global__ void __launch_bounds__(128)
+k_ard_step_generic(Lat L, long long own_lo, long long own_n, const uint8_t* __restrict__ type,
+                   const OffEntry* __restrict__ off, int n_off, ArdParams P, const double* __restrict__ d_dt,
+                   const double* __restrict__ C, const double* __restrict__ vx, const double* __restrict__ vy,
+                   const double* __restrict__ vz, const double* __restrict__ vmag,
+                   const uint8_t* __restrict__ is_gb, const uint8_t* __restrict__ is_precip,
+                   const uint8_t* __restrict__ salt, double* __restrict__ C_n) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= own_n) return;
+    long long l = own_lo + t;
+    uint8_t ti = type[l];
+    double C_i = C[l];
+    if (ti != PDGPU_FLUID && ti != PDGPU_SOLID_MG) { C_n[l] = C_i; return; }   // :86-89
+    const double dt = *d_dt;
+    bool i_fluid = (ti == PDGPU_FLUID);
+    double vi0 = 0.0, vi1 = 0.0, vi2 = 0.0, vi_mag = 0.0;
+    if (i_fluid) { vi0 = vx[l]; vi1 = vy[l]; if (DIM == 3) vi2 = vz[l]; vi_mag = vmag[l]; }
+    int q = (int)(l % L.P);
+    int jj = (DIM == 3) ? q / L.Nx : 0;
+    int ii = q - jj * L.Nx;
+    double diff_sum = 0.0, adv_sum = 0.0;
+    for (int o = 0; o < n_off; ++o) {
+        const OffEntry e = off[o];
+        long long nn = nbr_local(L, e, DIM, ii, jj, l, type);
+        if (nn < 0) continue;
+        uint8_t tj = type[nn];
+        if (tj == PDGPU_WALL) continue;                                          // :120
+        bool j_fluid = (tj == PDGPU_FLUID || tj == PDGPU_INLET || tj == PDGPU_OUTLET);
+        if (!i_fluid && !j_fluid) continue;                                      // solid-solid :134
+        double dC = C[nn] - C_i;
+        double D;
+        if (i_fluid && j_fluid) {                                                // :137-139, :166-170
+            D = P.D_liquid + P.alpha_dx * fmax(vi_mag, vmag[nn]);
+            double vde = vi0 * e.ex + vi1 * e.ey;
+            if (DIM == 3) vde += vi2 * e.ez;
+            adv_sum += dC * vde * e.w1;                                          // :178-181
+        } else {                                                                 // interface :140-162
+            long long s = i_fluid ? nn : l;
+            if (salt[s]) D = 0.0;
+            else {
+                double D_s = is_gb[s] ? P.D_gb : (is_precip[s] ? P.D_precip : P.D_grain);
+                D_s *= P.decay;
+                D = 2.0 * P.D_liquid * D_s / (P.D_liquid + D_s + 1e-30);
+            }
+        }
+        diff_sum += P.beta * D * dC * e.w2;                                      // :173
+    }
+    adv_sum *= P.div_coeff;
+    double cn = C_i + dt * (diff_sum - adv_sum);
+    C_n[l] = cn < 0.0 ? 0.0 : cn;
+}
+
+int pd_enqueue_ard_step_fast(pdgpu_ctx* c, int buf, int srcC, const ArdParams& P, const double* d_dt);
+
+int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
+    Lat L = make_lat(c);
+    ArdParams P = ard_params(c);
+    long long own_n = c->own_hi - c->own_lo;
+    int dstC = 1 - srcC;
+    if (c->dim == 2)
+        LAUNCH(c, k_ard_prepass<2>, nblocks(c->NL, 256), 256, 0, L, c->NL, c->own_lo, c->own_hi, c->type, c->d_off,
+               c->n_off, c->C[srcC], VXYZ(c, buf), P.C_sat, c->vmag, c->salt);
+    else
+        LAUNCH(c, k_ard_prepass<3>, nblocks(c->NL, 256), 256, 0, L, c->NL, c->own_lo, c->own_hi, c->type, c->d_off,
+               c->n_off, c->C[srcC], VXYZ(c, buf), P.C_sat, c->vmag, c->salt);
+    if (c->nranks > 1 && c->comm && c->n_solid) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));   // salt flags
+    if (c->dim == 2)
+        LAUNCH(c, k_ard_step_generic<2>, nblocks(own_n, 128), 128, 0, L, c->own_lo, own_n, c->type, c->d_off,
+               c->n_off, P, d_dt, c->C[srcC], VXYZ(c, buf), c->vmag, c->is_gb, c->is_precip, c->salt, c->C[dstC]);
+    else
+        LAUNCH(c, k_ard_step_generic<3>, nblocks(own_n, 128), 128, 0, L, c->own_lo, own_n, c->type, c->d_off,
+               c->n_off, P, d_dt, c->C[srcC], VXYZ(c, buf), c->vmag, c->is_gb, c->is_precip, c->salt, c->C[dstC]);
+    return 0;
+}
+
+// ----------------------------------------------------------------- C ABI -------
+extern "C" int pdgpu_ard_set_volume_loss(pdgpu_ctx* c, double vl) {
+    if (!c) PD_FAIL("null context");
+    if (vl != c->volume_loss) pd_invalidate_graphs(c);   // decay factor is baked into the kernel params
+    c->volume_loss = vl;
+    return 0;
+}
+
+extern "C" int pdgpu_ard_compute_dt(pdgpu_ctx* c, double* dt) {   // src/pd_ard.cpp:34-53
+    NEED_GRID(c);
+    if (!dt) PD_FAIL("pdgpu_ard_compute_dt: null output");
+    const PdConfig& k = c->cfg;
+    double D_max = std::max(k.D_liquid, std::max(k.D_grain, k.D_gb));
+    double v_max = 0.0;
+    PD_TRY(pd_max_fluid_speed(c, &v_max));
+    double D_eff = D_max + k.alpha_art_diff * v_max * k.dx;
+    double dt_diff = 0.25 * k.dx * k.dx / (D_eff + 1e-30);
+    double dt_adv = k.dx / (v_max + 1e-30);
+    *dt = k.cfl_factor_corr * std::min(dt_diff, dt_adv);
+    return 0;
+}
+
+extern "C" int pdgpu_ard_step(pdgpu_ctx* c, double dt) {
+    NEED_FIELDS(c);
+    PD_TRY(pd_set_dt(c, 1, dt));
+    PD_TRY(pd_enqueue_ard_step(c, c->cur, c->curC, c->d_dt + 1));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// explicit coupling-loop body (src/coupling.cpp:232-238)
+static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
+    PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
+    PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
+    PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
+    PD_TRY(pd_enqueue_ard_step(c, buf, srcC, c->d_dt + 1));
+    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 1, buf, 1 - srcC));
+    return 0;
+}
+
+extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
+    NEED_FIELDS(c);
+    PD_TRY(pd_set_dt(c, 1, dt));
+    bool use_graph = c->opt_graph && !(c->nranks > 1 && c->comm);
+    for (int it = 0; it < steps; ++it) {
+        int buf = c->cur, srcC = c->curC;
+        if (!use_graph) {
+            PD_TRY(enqueue_ard_body(c, buf, srcC));
+        } else {
+            if (!c->g_ard[buf][srcC]) {
+                cudaGraph_t g = nullptr;
+                long long before = c->launches;
+                CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int r = enqueue_ard_body(c, buf, srcC);
+                cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+                c->launches = before;
+                if (r) return r;
+                if (e != cudaSuccess) PD_FAIL("graph capture failed: %s", cudaGetErrorString(e));
+                size_t nn = 0;
+                CUDA_OK(cudaGraphGetNodes(g, nullptr, &nn));
+                c->g_ard_nodes[buf][srcC] = (long long)nn;
+                CUDA_OK(cudaGraphInstantiate(&c->g_ard[buf][srcC], g, 0));
+                CUDA_OK(cudaGraphDestroy(g));
+            }
+            CUDA_OK(cudaGraphLaunch(c->g_ard[buf][srcC], c->stream));
+            c->launches += c->g_ard_nodes[buf][srcC];
+        }
+        c->curC = 1 - c->curC;   // std::swap(fields.C, fields.C_new)
+    }
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// PD_ARD_Solver::apply_phase_change (src/pd_ard.cpp:193-212)
+template <int DIM>
+__global__ void k_phase_change(const int* __restrict__ l_solid, long long n_solid, uint8_t* __restrict__ type,
+                               uint8_t* __restrict__ phase, double* __restrict__ C, double* __restrict__ rho,
+                               double* __restrict__ p, double* __restrict__ vx, double* __restrict__ vy,
+                               double* __restrict__ vz, double C_thresh, double rho_f, int* __restrict__ count,
+                               int* __restrict__ out, long long cap) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_solid) return;
+    int l = l_solid[t];
+    if (phase[l] == 0 && type[l] == PDGPU_SOLID_MG && C[l] < C_thresh) {
+        phase[l] = 1;
+        type[l] = PDGPU_FLUID;
+        rho[l] = rho_f;
+        p[l] = 0.0;
+        vx[l] = 0.0; vy[l] = 0.0;
+        if (DIM == 3) vz[l] = 0.0;
+        C[l] = C_thresh;
+        int pos = atomicAdd(count, 1);
+        if (pos < cap) out[pos] = l;
+    }
+}
+
+extern "C" int pdgpu_phase_change(pdgpu_ctx* c, int* n_dissolved, int* dissolved_global, int cap) {
+    NEED_FIELDS(c);
+    if (!n_dissolved) PD_FAIL("pdgpu_phase_change: null output");
+    *n_dissolved = 0;
+    int n = 0;
+    std::vector<int> h;
+    if (c->n_solid > 0) {
+        if (c->dissolved_cap < c->n_solid) {
+            if (c->d_dissolved) CUDA_OK(cudaFree(c->d_dissolved));
+            CUDA_OK(cudaMalloc(&c->d_dissolved, sizeof(int) * c->n_solid));
+            c->dissolved_cap = c->n_solid;
+        }
+        CUDA_OK(cudaMemsetAsync(c->d_int, 0, sizeof(int), c->stream));
+        int b = c->cur, bc = c->curC;
+        if (c->dim == 2)
+            LAUNCH(c, k_phase_change<2>, nblocks(c->n_solid, 256), 256, 0, c->l_solid, c->n_solid, c->type, c->phase,
+                   c->C[bc], c->rho[b], c->p[b], VXYZ(c, b), c->cfg.C_thresh, c->cfg.rho_f, c->d_int, c->d_dissolved,
+                   c->dissolved_cap);
+        else
+            LAUNCH(c, k_phase_change<3>, nblocks(c->n_solid, 256), 256, 0, c->l_solid, c->n_solid, c->type, c->phase,
+                   c->C[bc], c->rho[b], c->p[b], VXYZ(c, b), c->cfg.C_thresh, c->cfg.rho_f, c->d_int, c->d_dissolved,
+                   c->dissolved_cap);
+        CUDA_OK(cudaMemcpyAsync(&n, c->d_int, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        if (n > 0) {
+            h.resize(n);
+            CUDA_OK(cudaMemcpy(h.data(), c->d_dissolved, sizeof(int) * n, cudaMemcpyDeviceToHost));
+            std::sort(h.begin(), h.end());
+        }
+    }
+    // a rank must also learn about dissolved nodes inside its ghost planes
+    int n_any = n;
+    if (c->nranks > 1 && c->comm) {
+        c->h_red[0] = (double)n;
+        CUDA_OK(cudaMemcpyAsync(c->d_red, c->h_red, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        PD_TRY(pd_comm_allreduce(c, c->d_red, 1, 0));
+        CUDA_OK(cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        n_any = (int)c->h_red[0];
+        if (n_any > 0) PD_TRY(pd_enqueue_halo(c, 2, c->cur, c->curC));   // types, phase, rho, vel, p, C
+    }
+    if (n_any > 0) PD_TRY(pd_rebuild_tables(c));   // node lists, wall-mirror fallback, bond counts, graphs
+    *n_dissolved = n;
+    long long halo_shift = (long long)(c->a0 - c->R) * c->P;
+    if (dissolved_global)
+        for (int t = 0; t < n && t < cap; ++t) dissolved_global[t] = (int)(h[t] + halo_shift);
+    return 0;
+}
+
+// Reductions of write_diagnostics (src/coupling.cpp:20-49): solid count, max |v| and max C
+// over FLUID nodes. All order-free (integer count, max of non-negative doubles).
+template <int DIM>
+__global__ void k_diag(long long own_lo, long long own_n, const uint8_t* __restrict__ type,
+                       const double* __restrict__ C, const double* __restrict__ vx, const double* __restrict__ vy,
+                       const double* __restrict__ vz, unsigned long long* __restrict__ out) {
+    double vm = 0.0, cm = 0.0;
+    unsigned long long ns = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < own_n;
+         t += (long long)gridDim.x * blockDim.x) {
+        long long l = own_lo + t;
+        uint8_t ty = type[l];
+        if (ty == PDGPU_SOLID_MG) ++ns;
+        if (ty == PDGPU_FLUID) {
+            double s = vx[l] * vx[l] + vy[l] * vy[l];
+            if (DIM == 3) s += vz[l] * vz[l];
+            vm = fmax(vm, sqrt(s));
+            if (C[l] > cm) cm = C[l];
+        }
+    }
+    vm = warp_max(vm);
+    cm = warp_max(cm);
+    for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(0xffffffffu, ns, o);
+    if ((threadIdx.x & 31) == 0) {
+        if (ns) atomicAdd(&out[0], ns);
+        if (vm > 0.0) atomicMax(&out[1], (unsigned long long)__double_as_longlong(vm));
+        if (cm > 0.0) atomicMax(&out[2], (unsigned long long)__double_as_longlong(cm));
+    }
+}
+
+extern "C" int pdgpu_diag(pdgpu_ctx* c, PdDiag* out) {
+    NEED_FIELDS(c);
+    if (!out) PD_FAIL("pdgpu_diag: null output");
+    long long own_n = c->own_hi - c->own_lo;
+    CUDA_OK(cudaMemsetAsync(c->d_u64, 0, sizeof(unsigned long long) * 4, c->stream));
+    unsigned g = std::min<unsigned>(nblocks(own_n, 256), 148 * 8);
+    if (c->dim == 2)
+        LAUNCH(c, k_diag<2>, g, 256, 0, c->own_lo, own_n, c->type, c->C[c->curC], VXYZ(c, c->cur), c->d_u64);
+    else
+        LAUNCH(c, k_diag<3>, g, 256, 0, c->own_lo, own_n, c->type, c->C[c->curC], VXYZ(c, c->cur), c->d_u64);
+    unsigned long long h[4];
+    CUDA_OK(cudaMemcpyAsync(h, c->d_u64, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    out->solid_count = (long long)h[0];
+    memcpy(&out->v_max, &h[1], 8);
+    memcpy(&out->C_max_fluid, &h[2], 8);
+    if (c->nranks > 1 && c->comm) {
+        c->h_red[0] = (double)out->solid_count; c->h_red[1] = out->v_max; c->h_red[2] = out->C_max_fluid;
+        CUDA_OK(cudaMemcpyAsync(c->d_red, c->h_red, sizeof(double) * 3, cudaMemcpyHostToDevice, c->stream));
+        PD_TRY(pd_comm_allreduce(c, c->d_red, 1, 0));
+        PD_TRY(pd_comm_allreduce(c, c->d_red + 1, 2, 1));
+        CUDA_OK(cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double) * 3, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        out->solid_count = (long long)c->h_red[0]; out->v_max = c->h_red[1]; out->C_max_fluid = c->h_red[2];
+    }
+    return 0;
+}

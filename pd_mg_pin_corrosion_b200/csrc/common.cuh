@@ -1,0 +1,264 @@
+// common.cuh -- context, error handling and small device helpers shared by the
+// translation units of libpdgpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pdgpu.h"
+
+// ------------------------------------------------------------------ errors ----
+void pd_set_error(const char* fmt, ...);
+#define PD_FAIL(...)            \
+    do {                        \
+        pd_set_error(__VA_ARGS__); \
+        return 1;               \
+    } while (0)
+#define CUDA_OK(expr)                                                                     \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            pd_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)
+#define PD_TRY(expr)            \
+    do {                        \
+        int _r = (expr);        \
+        if (_r) return _r;      \
+    } while (0)
+#define CHECK_CTX(c)                                   \
+    do {                                               \
+        if (!(c)) PD_FAIL("null context");             \
+        CUDA_OK(cudaSetDevice((c)->device));           \
+    } while (0)
+#define NEED_GRID(c)                                                        \
+    do {                                                                    \
+        CHECK_CTX(c);                                                       \
+        if (!(c)->grid_built) PD_FAIL("pdgpu_grid_build has not been called"); \
+    } while (0)
+
+// ---------------------------------------------------------- stencil entry -----
+// One horizon offset.  dist/evec/vol are the reference's CSR values
+// (src/grid.cpp:176-183,275-288); w1 = vol/dist and w2 = vol/dist^2 are the hoisted
+// bond weights; lin = local linear offset d_axial*plane + in-plane part.
+struct OffEntry {
+    int di, dj, dk, pad;
+    long long lin;
+    double dist, ex, ey, ez, vol, w1, w2;
+};
+
+constexpr int kMaxLevels = 1 << 20;
+
+// ------------------------------------------------------------------ context ---
+struct pdgpu_ctx {
+    PdConfig cfg;
+    int dim = 0, device = 0, rank = 0, nranks = 1;
+    int Nx = 0, Ny = 0, Nz = 0;     // global grid
+    int Na = 0;                     // number of axial planes (Ny in 2D, Nz in 3D)
+    int R = 0;                      // stencil reach == ghost width (= m_ratio)
+    int a0 = 0, a1 = 0;             // owned axial planes
+    int nlp = 0;                    // local planes incl. ghosts
+    long long P = 0;                // nodes per plane
+    long long NL = 0;               // local nodes incl. ghosts
+    long long own_lo = 0, own_hi = 0;  // owned local index range
+    long long N_total = 0;
+    double origin[3] = {0, 0, 0};
+    bool grid_built = false, fields_ready = false;
+
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr;
+
+    // stencil
+    int n_off = 0;
+    std::vector<OffEntry> h_off;
+    OffEntry* d_off = nullptr;
+
+    // per-node device arrays (local indexing, ghosts included)
+    uint8_t *type = nullptr, *phase = nullptr, *is_gb = nullptr, *is_precip = nullptr, *salt = nullptr;
+    double *rho[2] = {nullptr, nullptr}, *p[2] = {nullptr, nullptr}, *C[2] = {nullptr, nullptr};
+    double* v[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    double* vmag = nullptr;         // |v| per node (ARD artificial diffusion)
+    int cur = 0, curC = 0;          // which buffer is "current"
+    int p_input = 0;                // buffer whose p is the reference's `pressure` member
+
+    // per-type node lists (owned nodes, local indices, ascending)
+    int *l_wall = nullptr, *l_wall_mirror = nullptr, *l_inlet = nullptr, *l_outlet = nullptr,
+        *l_solid = nullptr;
+    long long n_wall = 0, n_inlet = 0, n_outlet = 0, n_solid = 0;
+    double* inlet_vax = nullptr;    // prescribed axial inlet velocity per inlet-list entry
+    // outlet Gauss-Seidel wavefront schedule
+    int* out_nodes = nullptr;       // outlet nodes ordered by wavefront level
+    int* out_level_off = nullptr;   // [n_levels+1]
+    int n_levels = 0;
+    int max_level_width = 0;
+
+    // reductions
+    double* d_red = nullptr;        // device scratch
+    double* h_red = nullptr;        // pinned host mirror
+    unsigned long long* d_u64 = nullptr;
+    int* d_int = nullptr;
+    int* d_dissolved = nullptr;
+    long long dissolved_cap = 0;
+
+    // materialised CSR (optional)
+    long long* csr_off = nullptr;
+    int* csr_idx = nullptr;
+    double *csr_dist = nullptr, *csr_evec = nullptr, *csr_vol = nullptr;
+    long long nnz = -1;
+
+    long long counts[6] = {0, 0, 0, 0, 0, 0};
+    long long ns_bonds = 0, ard_bonds = 0, nnz_rows = 0;
+    bool full_rows = false;         // every owned FLUID/SOLID row has the full in-box stencil
+
+    double volume_loss = 0.0;
+    long long launches = 0;
+
+    // options
+    int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled fast path
+    int opt_ard_kernel = 1;
+    int opt_graph = 1;
+
+    // NCCL
+    void* comm = nullptr;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    void* l2_scratch = nullptr;
+    size_t l2_scratch_bytes = 0;
+
+    // CUDA graphs of one loop body per buffer parity
+    cudaGraphExec_t g_ns[2] = {nullptr, nullptr};
+    cudaGraphExec_t g_ard[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    double* d_dt = nullptr;         // device scalars: [0] ns dt, [1] ard dt, [2] decay factor
+    long long g_ns_nodes[2] = {0, 0}, g_ard_nodes[2][2] = {{0, 0}, {0, 0}};
+};
+
+// PD constants of PD_NS_Solver::init / PD_ARD_Solver::init (src/pd_ns.cpp:7-16).
+struct PdConsts {
+    double alpha, V_H, inv_VH, beta_lap, dens_diff_coeff, B_eos;
+};
+inline PdConsts pd_consts(const PdConfig& c, int dim) {
+    const double PI = 3.14159265358979323846;
+    PdConsts k;
+    k.alpha = (double)dim;
+    if (dim == 2) {
+        k.V_H = PI * c.delta * c.delta;
+        k.beta_lap = 4.0 / (PI * c.delta * c.delta);
+    } else {
+        k.V_H = (4.0 / 3.0) * PI * c.delta * c.delta * c.delta;
+        k.beta_lap = 12.0 / (PI * c.delta * c.delta);
+    }
+    k.inv_VH = 1.0 / k.V_H;
+    k.dens_diff_coeff = k.beta_lap * (c.eta_density * c.c0 * c.delta);
+    k.B_eos = c.rho_f * c.c0 * c.c0 / c.gamma_eos;
+    return k;
+}
+
+// ------------------------------------------------------------ launch helpers --
+inline unsigned nblocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+#define LAUNCH(ctx, kern, grid, block, smem, ...)                          \
+    do {                                                                   \
+        kern<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);     \
+        (ctx)->launches++;                                                 \
+    } while (0)
+
+// device-side geometry of a local index
+struct Lat {
+    int Nx, Ny;          // in-plane extents (Ny == 1 in 2D)
+    long long P;         // plane size
+    int a0, R;           // owned axial start, ghost width
+    int Na;              // global number of axial planes
+};
+inline Lat make_lat(const pdgpu_ctx* c) {
+    Lat L;
+    L.Nx = c->Nx;
+    L.Ny = (c->dim == 3) ? c->Ny : 1;
+    L.P = c->P;
+    L.a0 = c->a0;
+    L.R = c->R;
+    L.Na = c->Na;
+    return L;
+}
+
+#ifdef __CUDACC__
+// Tait EOS of PD_NS_Solver::compute_pressure (src/pd_ns.cpp:36-50)
+__device__ __forceinline__ double eos_pressure(double rho, double rho0, double gamma, double B) {
+    double ratio = rho / rho0;
+    if (ratio < 0.5) ratio = 0.5;
+    if (ratio > 2.0) ratio = 2.0;
+    return B * (pow(ratio, gamma) - 1.0);
+}
+// local index -> global lattice indices. In 2D the axial index is j.
+__device__ __forceinline__ void local_to_ijk(const Lat& L, long long l, int dim, int* i, int* j, int* k,
+                                             int* a_glob) {
+    int al = (int)(l / L.P);
+    int q = (int)(l - (long long)al * L.P);
+    int a = al - L.R + L.a0;
+    *a_glob = a;
+    if (dim == 2) { *i = q; *j = a; *k = 0; }
+    else { *j = q / L.Nx; *i = q - *j * L.Nx; *k = a; }
+}
+
+// neighbour through offset o of local node (in-plane ii,jj; local index l): local index or -1
+__device__ __forceinline__ long long nbr_local(const Lat& L, const OffEntry& e, int dim, int ii, int jj,
+                                               long long l, const uint8_t* __restrict__ type) {
+    int ni = ii + e.di;
+    if (ni < 0 || ni >= L.Nx) return -1;
+    if (dim == 3) {
+        int nj = jj + e.dj;
+        if (nj < 0 || nj >= L.Ny) return -1;
+    }
+    long long nn = l + e.lin;
+    return type[nn] == PDGPU_OUTSIDE ? -1 : nn;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif
+
+// ------------------------------------------------- cross-TU internal functions
+int pd_alloc_fields(pdgpu_ctx* c);
+int pd_rebuild_tables(pdgpu_ctx* c);                 // lists, mirror table, bond counts
+int pd_enqueue_bc_inlet(pdgpu_ctx* c, int buf, int bufC);
+int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
+int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf);
+int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC);
+int pd_enqueue_bc_solid(pdgpu_ctx* c, int buf);
+int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt);
+int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);
+int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC);
+int pd_max_fluid_speed(pdgpu_ctx* c, double* vmax);
+void pd_invalidate_graphs(pdgpu_ctx* c);
+int pd_refresh_eos(pdgpu_ctx* c, int buf);           // p[buf] = EOS(rho[buf]) on all local nodes
+int pd_refresh_vmag(pdgpu_ctx* c, int buf);
+int pd_set_dt(pdgpu_ctx* c, int slot, double value);
+int pd_comm_allreduce(pdgpu_ctx* c, double* d_buf, int n, int op);   // op 0 sum, 1 max
+#define NEED_FIELDS(c)                                                                       \
+    do {                                                                                     \
+        NEED_GRID(c);                                                                        \
+        if (!(c)->fields_ready) PD_FAIL("fields not initialised (pdgpu_fields_init/upload)"); \
+    } while (0)
+#define VXYZ(c, b) (c)->v[b][0], (c)->v[b][1], (c)->v[b][2]

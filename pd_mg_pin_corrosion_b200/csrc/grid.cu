@@ -1,0 +1,465 @@
+// grid.cu -- Grid::build / Grid::build_neighbors on device (reference src/grid.cpp:29-294)
+// plus the static tables the boundary operators need (wall-mirror table of
+// src/boundary.cpp:143-264, outlet Gauss-Seidel wavefront schedule).
+#include <algorithm>
+#include <numeric>
+
+#include "common.cuh"
+#include "geom.cuh"
+#include "scan.cuh"
+
+// ---------------------------------------------------------------- host-only ----
+static int build_stencil_host(const PdConfig& cfg, int dim, std::vector<OffEntry>& out) {
+    // src/grid.cpp:161-187 (offset enumeration, dk -> dj -> di so that neighbours are
+    // index-ascending) and :274-288 (partial-volume beta).
+    int m = cfg.m_ratio, mext = m + 1;
+    double dx = cfg.dx, delta = cfg.delta;
+    double dx_dim = 1.0;
+    for (int d = 0; d < dim; ++d) dx_dim *= dx;
+    out.clear();
+    int klo = dim == 3 ? -mext : 0, khi = dim == 3 ? mext : 0;
+    for (int dk = klo; dk <= khi; ++dk)
+        for (int dj = -mext; dj <= mext; ++dj)
+            for (int di = -mext; di <= mext; ++di) {
+                if (di == 0 && dj == 0 && dk == 0) continue;
+                double r = std::sqrt((double)(di * di + dj * dj + dk * dk)) * dx;
+                if (!(r <= delta + 0.5 * dx)) continue;
+                OffEntry e;
+                e.di = di; e.dj = dj; e.dk = dk; e.pad = 0; e.lin = 0;
+                e.dist = r;
+                e.ex = di * dx / r;
+                e.ey = dj * dx / r;
+                e.ez = dk * dx / r;
+                double beta;
+                if (r <= delta - 0.5 * dx) beta = 1.0;
+                else if (r <= delta + 0.5 * dx) beta = (delta + 0.5 * dx - r) / dx;
+                else beta = 0.0;
+                e.vol = beta * dx_dim;
+                double inv_xi = 1.0 / r;
+                e.w1 = inv_xi * e.vol;
+                e.w2 = inv_xi * inv_xi * e.vol;
+                out.push_back(e);
+            }
+    return 0;
+}
+
+extern "C" int pdgpu_grid_extents(const PdConfig* cfg, int dim, int* Nx, int* Ny, int* Nz, double origin[3]) {
+    if (!cfg || (dim != 2 && dim != 3)) PD_FAIL("pdgpu_grid_extents: bad arguments");
+    geom_extents(*cfg, dim, Nx, Ny, Nz, origin);
+    return 0;
+}
+
+extern "C" int pdgpu_partition(int n_axial, int nranks, int rank, int* a0, int* a1) {
+    if (nranks < 1 || rank < 0 || rank >= nranks || n_axial < nranks) PD_FAIL("pdgpu_partition: bad arguments");
+    long long q = n_axial / nranks, r = n_axial % nranks;
+    *a0 = (int)(rank * q + std::min<long long>(rank, r));
+    *a1 = (int)(*a0 + q + (rank < r ? 1 : 0));
+    return 0;
+}
+
+extern "C" int pdgpu_stencil(const PdConfig* cfg, int dim, int* n_off, int* off_d, double* dist, double* evec,
+                             double* vol) {
+    if (!cfg || (dim != 2 && dim != 3) || !n_off) PD_FAIL("pdgpu_stencil: bad arguments");
+    std::vector<OffEntry> st;
+    build_stencil_host(*cfg, dim, st);
+    *n_off = (int)st.size();
+    for (size_t o = 0; o < st.size(); ++o) {
+        if (off_d) { off_d[3 * o] = st[o].di; off_d[3 * o + 1] = st[o].dj; off_d[3 * o + 2] = st[o].dk; }
+        if (dist) dist[o] = st[o].dist;
+        if (evec) {
+            evec[dim * o] = st[o].ex; evec[dim * o + 1] = st[o].ey;
+            if (dim == 3) evec[dim * o + 2] = st[o].ez;
+        }
+        if (vol) vol[o] = st[o].vol;
+    }
+    return 0;
+}
+
+// --------------------------------------------------------------- kernels -------
+__global__ void k_classify(GeomParams g, Lat L, long long NL, uint8_t* __restrict__ type) {
+    long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= NL) return;
+    int i, j, k, a;
+    local_to_ijk(L, l, g.dim, &i, &j, &k, &a);
+    uint8_t t = PDGPU_OUTSIDE;                 // ghost planes beyond the domain act as padding
+    if (a >= 0 && a < L.Na) t = geom_classify(g, i, j, k);
+    type[l] = t;
+}
+
+// Row length of every owned node (CSR count pass, src/grid.cpp:194-227).
+__global__ void k_rowlen(Lat L, int dim, long long own_lo, long long own_n, const uint8_t* __restrict__ type,
+                         const OffEntry* __restrict__ off, int n_off, int* __restrict__ rowlen,
+                         unsigned long long* __restrict__ sums /* [0]=ns [1]=ard [2]=nnz [3]=short rows */) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long s_ns = 0, s_ard = 0, s_all = 0, s_short = 0;
+    if (t < own_n) {
+        long long l = own_lo + t;
+        uint8_t ty = type[l];
+        int cnt = 0;
+        if (ty != PDGPU_OUTSIDE) {
+            int q = (int)(l % L.P);
+            int jj = (dim == 3) ? q / L.Nx : 0;
+            int ii = q - jj * L.Nx;
+            for (int o = 0; o < n_off; ++o) cnt += nbr_local(L, off[o], dim, ii, jj, l, type) >= 0;
+        }
+        rowlen[t] = cnt;
+        s_all = cnt;
+        if (ty == PDGPU_FLUID) { s_ns = cnt; s_ard = cnt; s_short = (cnt != n_off); }
+        if (ty == PDGPU_SOLID_MG) { s_ard = cnt; s_short = (cnt != n_off); }
+    }
+    // warp-aggregate, then one atomic per warp (integers: order-free)
+    for (int o = 16; o > 0; o >>= 1) {
+        s_ns += __shfl_xor_sync(0xffffffffu, s_ns, o);
+        s_ard += __shfl_xor_sync(0xffffffffu, s_ard, o);
+        s_all += __shfl_xor_sync(0xffffffffu, s_all, o);
+        s_short += __shfl_xor_sync(0xffffffffu, s_short, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (s_ns) atomicAdd(&sums[0], s_ns);
+        if (s_ard) atomicAdd(&sums[1], s_ard);
+        if (s_all) atomicAdd(&sums[2], s_all);
+        if (s_short) atomicAdd(&sums[3], s_short);
+    }
+}
+
+__global__ void k_type_flags(const uint8_t* __restrict__ type, long long own_lo, long long own_n, int want,
+                             int* __restrict__ flag) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= own_n) return;
+    flag[t] = (type[own_lo + t] == want);
+}
+
+// histogram of owned node types (block-local shared counters, one global atomic per bin)
+__global__ void k_type_hist(const uint8_t* __restrict__ type, long long own_lo, long long own_n,
+                            unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int sh[8];
+    if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < own_n;
+         t += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&sh[type[own_lo + t] & 7], 1u);
+    __syncthreads();
+    if (threadIdx.x < 8 && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+
+__global__ void k_compact(const int* __restrict__ flag, const long long* __restrict__ pos, long long own_lo,
+                          long long own_n, int* __restrict__ list) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= own_n) return;
+    if (flag[t]) list[pos[t]] = (int)(own_lo + t);
+}
+
+// Static wall-mirror table (src/boundary.cpp:143-264).
+__global__ void k_wall_mirror(GeomParams g, Lat L, const int* __restrict__ l_wall, long long n_wall,
+                              const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
+                              int* __restrict__ mirror) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_wall) return;
+    long long l = l_wall[t];
+    int i, j, k, a;
+    local_to_ijk(L, l, g.dim, &i, &j, &k, &a);
+    long long m = -1;
+    int im, jm;
+    if (geom_wall_mirror(g, i, j, &im, &jm)) {
+        if (g.dim == 2) {
+            // same axial row j (always inside: j_mirror = j_grid)
+            if (im >= 0 && im < L.Nx) {
+                long long cand = l - i + im;
+                uint8_t mt = type[cand];
+                if (mt == PDGPU_FLUID || mt == PDGPU_INLET || mt == PDGPU_OUTLET || mt == PDGPU_SOLID_MG) m = cand;
+            }
+        } else {
+            if (im >= 0 && im < L.Nx && jm >= 0 && jm < L.Ny) {
+                long long cand = l + (long long)(jm - j) * L.Nx + (im - i);
+                uint8_t mt = type[cand];
+                if (mt == PDGPU_FLUID || mt == PDGPU_INLET || mt == PDGPU_OUTLET || mt == PDGPU_SOLID_MG) m = cand;
+            }
+        }
+    }
+    if (m < 0) {   // fallback :254-263, nearest FLUID neighbour, strict '<', CSR order
+        int q = (int)(l % L.P);
+        int jj = (g.dim == 3) ? q / L.Nx : 0;
+        int ii = q - jj * L.Nx;
+        double best = 1e30;
+        for (int o = 0; o < n_off; ++o) {
+            long long nn = nbr_local(L, off[o], g.dim, ii, jj, l, type);
+            if (nn >= 0 && type[nn] == PDGPU_FLUID && off[o].dist < best) {
+                best = off[o].dist;
+                m = nn;
+            }
+        }
+    }
+    mirror[t] = (int)m;
+}
+
+__global__ void k_inlet_velocity(GeomParams g, Lat L, double U_in, const int* __restrict__ l_inlet,
+                                 long long n_inlet, double* __restrict__ vax) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_inlet) return;
+    int i, j, k, a;
+    local_to_ijk(L, l_inlet[t], g.dim, &i, &j, &k, &a);
+    vax[t] = geom_inlet_velocity(g, U_in, i, j);
+}
+
+// CSR fill (src/grid.cpp:246-291): one warp per owned row, ballot-compacted writes.
+__global__ void k_csr_fill(Lat L, int dim, long long own_lo, long long own_n, long long halo_shift,
+                           const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
+                           const long long* __restrict__ row_off, int* __restrict__ idx,
+                           double* __restrict__ dist, double* __restrict__ evec, double* __restrict__ vol) {
+    long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= own_n) return;
+    long long l = own_lo + w;
+    if (type[l] == PDGPU_OUTSIDE) return;
+    int q = (int)(l % L.P);
+    int jj = (dim == 3) ? q / L.Nx : 0;
+    int ii = q - jj * L.Nx;
+    long long wr = row_off[w];
+    for (int base = 0; base < n_off; base += 32) {
+        int o = base + lane;
+        long long nn = -1;
+        if (o < n_off) nn = nbr_local(L, off[o], dim, ii, jj, l, type);
+        unsigned mask = __ballot_sync(0xffffffffu, nn >= 0);
+        if (nn >= 0) {
+            long long pos = wr + __popc(mask & ((1u << lane) - 1u));
+            idx[pos] = (int)(nn + halo_shift);          // local -> global node index
+            dist[pos] = off[o].dist;
+            evec[pos * dim] = off[o].ex;
+            evec[pos * dim + 1] = off[o].ey;
+            if (dim == 3) evec[pos * dim + 2] = off[o].ez;
+            vol[pos] = off[o].vol;
+        }
+        wr += __popc(mask);
+    }
+}
+
+__global__ void k_mirror_to_global(const int* __restrict__ l_wall, const int* __restrict__ mirror,
+                                   long long n_wall, long long own_lo, long long halo_shift,
+                                   int* __restrict__ out_own) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_wall) return;
+    int m = mirror[t];
+    out_own[l_wall[t] - own_lo] = m < 0 ? -1 : (int)(m + halo_shift);
+}
+
+// ---------------------------------------------------------------- host side ----
+static int build_list(pdgpu_ctx* c, int want, int* d_flag, long long* d_pos, int** list, long long* n) {
+    long long own_n = c->own_hi - c->own_lo;
+    LAUNCH(c, k_type_flags, nblocks(own_n, 256), 256, 0, c->type, c->own_lo, own_n, want, d_flag);
+    long long total = 0;
+    PD_TRY(pdscan::exclusive_scan(c, d_flag, own_n, d_pos, &total));
+    if (*list) { CUDA_OK(cudaFree(*list)); *list = nullptr; }
+    *n = total;
+    CUDA_OK(cudaMalloc(list, sizeof(int) * std::max<long long>(total, 1)));
+    if (total > 0) LAUNCH(c, k_compact, nblocks(own_n, 256), 256, 0, d_flag, d_pos, c->own_lo, own_n, *list);
+    return 0;
+}
+
+static int build_outlet_schedule(pdgpu_ctx* c) {
+    // Lexicographic Gauss-Seidel order of apply_outlet_bc (src/boundary.cpp:92-130) is
+    // preserved by the hyperplane schedule tau = i + (R+1) j + (R+1)^2 k: two outlet nodes
+    // of equal tau are never within each other's stencil, and every lexicographically
+    // earlier stencil neighbour has a smaller tau.
+    if (c->out_nodes) { cudaFree(c->out_nodes); c->out_nodes = nullptr; }
+    if (c->out_level_off) { cudaFree(c->out_level_off); c->out_level_off = nullptr; }
+    c->n_levels = 0;
+    c->max_level_width = 0;
+    if (c->n_outlet == 0) return 0;
+    std::vector<int> nodes(c->n_outlet);
+    CUDA_OK(cudaMemcpy(nodes.data(), c->l_outlet, sizeof(int) * c->n_outlet, cudaMemcpyDeviceToHost));
+    std::vector<long long> tau(c->n_outlet);
+    long long base = c->R + 1;
+    long long al_min = nodes.front() / c->P;
+    for (long long t = 0; t < c->n_outlet; ++t) {
+        long long l = nodes[t];
+        long long al = l / c->P, q = l % c->P;
+        if (c->dim == 2) tau[t] = q + base * (al - al_min);
+        else tau[t] = (q % c->Nx) + base * (q / c->Nx) + base * base * (al - al_min);
+    }
+    std::vector<int> order(c->n_outlet);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return tau[x] < tau[y]; });
+    std::vector<int> sorted(c->n_outlet), level_off;
+    long long prev = -1;
+    for (long long t = 0; t < c->n_outlet; ++t) {
+        sorted[t] = nodes[order[t]];
+        if (tau[order[t]] != prev) { level_off.push_back((int)t); prev = tau[order[t]]; }
+    }
+    level_off.push_back((int)c->n_outlet);
+    c->n_levels = (int)level_off.size() - 1;
+    for (int lv = 0; lv < c->n_levels; ++lv)
+        c->max_level_width = std::max(c->max_level_width, level_off[lv + 1] - level_off[lv]);
+    CUDA_OK(cudaMalloc(&c->out_nodes, sizeof(int) * c->n_outlet));
+    CUDA_OK(cudaMalloc(&c->out_level_off, sizeof(int) * level_off.size()));
+    CUDA_OK(cudaMemcpy(c->out_nodes, sorted.data(), sizeof(int) * c->n_outlet, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->out_level_off, level_off.data(), sizeof(int) * level_off.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int pd_rebuild_tables(pdgpu_ctx* c) {
+    pd_invalidate_graphs(c);
+    long long own_n = c->own_hi - c->own_lo;
+    Lat L = make_lat(c);
+    double org[3] = {c->origin[0], c->origin[1], c->origin[2]};
+    GeomParams g = geom_params(c->cfg, c->dim, org);
+
+    int* d_flag = nullptr;
+    long long* d_pos = nullptr;
+    unsigned long long* d_counts = nullptr;
+    CUDA_OK(cudaMalloc(&d_flag, sizeof(int) * own_n));
+    CUDA_OK(cudaMalloc(&d_pos, sizeof(long long) * (own_n + 1)));
+    CUDA_OK(cudaMalloc(&d_counts, sizeof(unsigned long long) * 16));
+    CUDA_OK(cudaMemsetAsync(d_counts, 0, sizeof(unsigned long long) * 16, c->stream));
+
+    LAUNCH(c, k_type_hist, std::min<unsigned>(nblocks(own_n, 256), 148 * 8), 256, 0, c->type, c->own_lo, own_n, d_counts);
+    PD_TRY(build_list(c, PDGPU_WALL, d_flag, d_pos, &c->l_wall, &c->n_wall));
+    PD_TRY(build_list(c, PDGPU_INLET, d_flag, d_pos, &c->l_inlet, &c->n_inlet));
+    PD_TRY(build_list(c, PDGPU_OUTLET, d_flag, d_pos, &c->l_outlet, &c->n_outlet));
+    PD_TRY(build_list(c, PDGPU_SOLID_MG, d_flag, d_pos, &c->l_solid, &c->n_solid));
+
+    // row lengths + bond counts (d_flag reused as rowlen scratch)
+    LAUNCH(c, k_rowlen, nblocks(own_n, 256), 256, 0, L, c->dim, c->own_lo, own_n, c->type, c->d_off, c->n_off,
+           d_flag, d_counts + 8);
+    unsigned long long h[16];
+    CUDA_OK(cudaMemcpyAsync(h, d_counts, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    for (int t = 0; t < 6; ++t) c->counts[t] = (long long)h[t];
+    c->ns_bonds = (long long)h[8];
+    c->ard_bonds = (long long)h[9];
+    c->nnz_rows = (long long)h[10];
+    c->full_rows = (h[11] == 0);
+
+    // wall mirror table
+    if (c->l_wall_mirror) { CUDA_OK(cudaFree(c->l_wall_mirror)); c->l_wall_mirror = nullptr; }
+    CUDA_OK(cudaMalloc(&c->l_wall_mirror, sizeof(int) * std::max<long long>(c->n_wall, 1)));
+    if (c->n_wall)
+        LAUNCH(c, k_wall_mirror, nblocks(c->n_wall, 128), 128, 0, g, L, c->l_wall, c->n_wall, c->type, c->d_off,
+               c->n_off, c->l_wall_mirror);
+    // inlet velocity table
+    if (c->inlet_vax) { CUDA_OK(cudaFree(c->inlet_vax)); c->inlet_vax = nullptr; }
+    CUDA_OK(cudaMalloc(&c->inlet_vax, sizeof(double) * std::max<long long>(c->n_inlet, 1)));
+    if (c->n_inlet)
+        LAUNCH(c, k_inlet_velocity, nblocks(c->n_inlet, 128), 128, 0, g, L, c->cfg.U_in, c->l_inlet, c->n_inlet,
+               c->inlet_vax);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d_flag));
+    CUDA_OK(cudaFree(d_pos));
+    CUDA_OK(cudaFree(d_counts));
+    PD_TRY(build_outlet_schedule(c));
+
+    // multi-GPU sanity: owned WALL mirrors must not live in ghost planes of another rank's
+    // slab unless those are plain copies ("halo invariants").
+    return 0;
+}
+
+extern "C" int pdgpu_grid_build(pdgpu_ctx* c) {
+    CHECK_CTX(c);
+    Lat L = make_lat(c);
+    double org[3] = {c->origin[0], c->origin[1], c->origin[2]};
+    GeomParams g = geom_params(c->cfg, c->dim, org);
+    if (!c->type) PD_TRY(pd_alloc_fields(c));
+    LAUNCH(c, k_classify, nblocks(c->NL, 256), 256, 0, g, L, c->NL, c->type);
+    c->grid_built = true;
+    PD_TRY(pd_rebuild_tables(c));
+    return 0;
+}
+
+extern "C" int pdgpu_grid_set_types(pdgpu_ctx* c, const uint8_t* node_type_global) {
+    CHECK_CTX(c);
+    if (!node_type_global) PD_FAIL("pdgpu_grid_set_types: null array");
+    if (!c->type) PD_TRY(pd_alloc_fields(c));
+    CUDA_OK(cudaMemsetAsync(c->type, PDGPU_OUTSIDE, c->NL, c->stream));
+    int ga = std::max(c->a0 - c->R, 0), gb = std::min(c->a1 + c->R, c->Na);
+    long long loff = (long long)(ga - (c->a0 - c->R)) * c->P;
+    CUDA_OK(cudaMemcpyAsync(c->type + loff, node_type_global + (long long)ga * c->P, (size_t)(gb - ga) * c->P,
+                            cudaMemcpyHostToDevice, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->grid_built = true;
+    PD_TRY(pd_rebuild_tables(c));
+    return 0;
+}
+
+extern "C" int pdgpu_grid_info(pdgpu_ctx* c, PdGridInfo* out) {
+    CHECK_CTX(c);
+    if (!out) PD_FAIL("pdgpu_grid_info: null output");
+    memset(out, 0, sizeof(*out));
+    out->dim = c->dim; out->Nx = c->Nx; out->Ny = c->Ny; out->Nz = c->Nz;
+    out->m = c->cfg.m_ratio; out->n_off = c->n_off; out->reach = c->R;
+    out->a0 = c->a0; out->a1 = c->a1;
+    out->N_total = c->N_total; out->plane = c->P;
+    for (int t = 0; t < 6; ++t) out->counts[t] = c->counts[t];
+    out->ns_bonds = c->ns_bonds; out->ard_bonds = c->ard_bonds; out->nnz = c->nnz_rows;
+    for (int d = 0; d < 3; ++d) out->origin[d] = c->origin[d];
+    return 0;
+}
+
+extern "C" int pdgpu_grid_free_neighbors(pdgpu_ctx* c) {
+    CHECK_CTX(c);
+    cudaFree(c->csr_off); cudaFree(c->csr_idx); cudaFree(c->csr_dist); cudaFree(c->csr_evec); cudaFree(c->csr_vol);
+    c->csr_off = nullptr; c->csr_idx = nullptr; c->csr_dist = c->csr_evec = c->csr_vol = nullptr;
+    c->nnz = -1;
+    return 0;
+}
+
+extern "C" int pdgpu_grid_build_neighbors(pdgpu_ctx* c, long long* nnz_out) {
+    NEED_GRID(c);
+    PD_TRY(pdgpu_grid_free_neighbors(c));
+    long long own_n = c->own_hi - c->own_lo;
+    Lat L = make_lat(c);
+    int* d_rowlen = nullptr;
+    unsigned long long* d_sums = nullptr;
+    CUDA_OK(cudaMalloc(&d_rowlen, sizeof(int) * own_n));
+    CUDA_OK(cudaMalloc(&d_sums, sizeof(unsigned long long) * 4));
+    CUDA_OK(cudaMemsetAsync(d_sums, 0, sizeof(unsigned long long) * 4, c->stream));
+    LAUNCH(c, k_rowlen, nblocks(own_n, 256), 256, 0, L, c->dim, c->own_lo, own_n, c->type, c->d_off, c->n_off,
+           d_rowlen, d_sums);
+    CUDA_OK(cudaMalloc(&c->csr_off, sizeof(long long) * (own_n + 1)));
+    long long total = 0;
+    PD_TRY(pdscan::exclusive_scan(c, d_rowlen, own_n, c->csr_off, &total));
+    c->nnz = total;
+    size_t n = (size_t)std::max<long long>(total, 1);
+    CUDA_OK(cudaMalloc(&c->csr_idx, sizeof(int) * n));
+    CUDA_OK(cudaMalloc(&c->csr_dist, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&c->csr_evec, sizeof(double) * n * c->dim));
+    CUDA_OK(cudaMalloc(&c->csr_vol, sizeof(double) * n));
+    long long halo_shift = (long long)(c->a0 - c->R) * c->P;     // local index + shift = global index
+    LAUNCH(c, k_csr_fill, nblocks(own_n * 32, 256), 256, 0, L, c->dim, c->own_lo, own_n, halo_shift, c->type,
+           c->d_off, c->n_off, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol);
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d_rowlen));
+    CUDA_OK(cudaFree(d_sums));
+    if (nnz_out) *nnz_out = total;
+    return 0;
+}
+
+extern "C" int pdgpu_grid_download_csr(pdgpu_ctx* c, long long* nbr_offset, int* nbr_index, double* nbr_dist,
+                                       double* nbr_evec, double* nbr_vol) {
+    NEED_GRID(c);
+    if (c->nnz < 0) PD_FAIL("pdgpu_grid_download_csr: call pdgpu_grid_build_neighbors first");
+    long long own_n = c->own_hi - c->own_lo;
+    size_t n = (size_t)c->nnz;
+    if (nbr_offset) CUDA_OK(cudaMemcpy(nbr_offset, c->csr_off, sizeof(long long) * (own_n + 1), cudaMemcpyDeviceToHost));
+    if (nbr_index && n) CUDA_OK(cudaMemcpy(nbr_index, c->csr_idx, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    if (nbr_dist && n) CUDA_OK(cudaMemcpy(nbr_dist, c->csr_dist, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    if (nbr_evec && n) CUDA_OK(cudaMemcpy(nbr_evec, c->csr_evec, sizeof(double) * n * c->dim, cudaMemcpyDeviceToHost));
+    if (nbr_vol && n) CUDA_OK(cudaMemcpy(nbr_vol, c->csr_vol, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int pdgpu_grid_download_wall_mirror(pdgpu_ctx* c, int* mirror_global) {
+    NEED_GRID(c);
+    if (!mirror_global) PD_FAIL("pdgpu_grid_download_wall_mirror: null output");
+    long long own_n = c->own_hi - c->own_lo;
+    int* d_out = nullptr;
+    CUDA_OK(cudaMalloc(&d_out, sizeof(int) * own_n));
+    CUDA_OK(cudaMemsetAsync(d_out, 0xff, sizeof(int) * own_n, c->stream));
+    long long halo_shift = (long long)(c->a0 - c->R) * c->P;
+    if (c->n_wall)
+        LAUNCH(c, k_mirror_to_global, nblocks(c->n_wall, 256), 256, 0, c->l_wall, c->l_wall_mirror, c->n_wall,
+               c->own_lo, halo_shift, d_out);
+    CUDA_OK(cudaMemcpyAsync(mirror_global + (long long)c->a0 * c->P, d_out, sizeof(int) * own_n,
+                            cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaFree(d_out));
+    return 0;
+}

@@ -1,0 +1,237 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path through the C ABI
+(libpdgpu.so via pd_mg_pin_corrosion_b200.solver) against the oracle -- oracle/_ref (the
+unmodified reference, compiled from its sources) when it was built, else the plain-C port.
+
+Bars (BASELINE.json north_star / SURVEY.md 7.3):
+  bit-exact : node classification, CSR neighbour list, wall-mirror table, dissolved sets
+  1e-12 rel : per-step fields (rho, u, C), max-abs error over max-abs value
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12   # north_star: per-step fields within 1e-12 relative max-error in FP64
+
+
+def gpu_side(case, extra=None, ref=None, upload=True):
+    from pd_mg_pin_corrosion_b200 import solver as S
+    dim, cfg, _ = H.load_cfg(case, extra)
+    grid = S.Grid(dim)
+    grid.build(cfg)
+    fields = S.Fields()
+    fields.allocate(grid.N_total, grid)
+
+    class G:   # grains as produced by the host generator (here: taken from the oracle)
+        is_grain_boundary = ref.get("is_gb") if ref is not None else np.zeros(grid.N_total, np.uint8)
+        is_precipitate = ref.get("is_precip") if ref is not None else np.zeros(grid.N_total, np.uint8)
+        grain_id = np.full(grid.N_total, -1, np.int32)
+
+    S.initialize_fields(fields, grid, G, cfg)
+    if ref is not None and upload:
+        for n in ("rho", "vel", "C", "rho_new", "vel_new", "C_new", "phase"):
+            fields.set(n, ref.get(n))
+    return S, cfg, grid, fields
+
+
+def assert_fields(fields, ref, names, tol=TOL, where=None):
+    for n in names:
+        a, b = fields.get(n), ref.get(n)
+        if where is not None:
+            a, b = a[where], b[where]
+        e = H.rel_err(a, b)
+        assert e <= tol, f"{n}: rel err {e:.3e} > {tol:.1e}"
+
+
+GEOM_CASES = ["2d_default", "2d_poiseuille", "2d_offgrid", "3d_small", "3d_offgrid", "3d_default"]
+
+
+@pytest.mark.parametrize("case", GEOM_CASES)
+def test_classification_and_tables_bit_exact(case):
+    ref = H.make_ref(case)
+    S, cfg, grid, fields = gpu_side(case, ref=None)
+    assert (grid.Nx, grid.Ny, grid.Nz, grid.N_total) == (ref.Nx, ref.Ny, ref.Nz, ref.N)
+    nt_ref = ref.get("node_type")
+    assert np.array_equal(grid.node_type, nt_ref)
+    assert [int(c) for c in grid.info.counts] == np.bincount(nt_ref, minlength=6).tolist()
+    # wall-mirror table: index trick on the reference, direct download here
+    N = ref.N
+    ref.set("rho", np.arange(N) + 0.25)
+    ref.wall_bc()
+    rr = ref.get("rho")
+    w = nt_ref == 2
+    mir_ref = np.where(np.modf(rr[w])[0] == 0.25, (rr[w] - 0.25).astype(np.int64), -1)
+    assert np.array_equal(grid.wall_mirror[w], mir_ref)
+    assert np.all(grid.wall_mirror[~w] == -1)
+
+
+@pytest.mark.parametrize("case", ["2d_default", "2d_offgrid", "3d_small", "3d_default"])
+def test_csr_bit_exact(case):
+    ref = H.make_ref(case)
+    S, cfg, grid, fields = gpu_side(case, ref=None)
+    nnz = grid.build_neighbors()
+    off, idx, dist, evec, vol = grid.csr()
+    if hasattr(ref, "csr"):
+        roff, ridx, rdist, revec, rvol = ref.csr()
+    else:
+        roff, ridx, rdist, revec, rvol = (ref.get(n) for n in ("nbr_offset", "nbr_index", "nbr_dist", "nbr_evec", "nbr_vol"))
+    assert nnz == int(roff[-1]) == grid.info.nnz
+    assert np.array_equal(off, roff.astype(np.int64))
+    assert np.array_equal(idx, ridx)
+    assert dist.tobytes() == rdist.tobytes()
+    assert evec.tobytes() == revec.tobytes()
+    assert vol.tobytes() == rvol.tobytes()
+    # bond-update counts of the metric
+    nt = ref.get("node_type")
+    rowlen = np.diff(roff.astype(np.int64))
+    assert grid.info.ns_bonds == int(rowlen[nt == 0].sum())
+    assert grid.info.ard_bonds == int(rowlen[(nt == 0) | (nt == 1)].sum())
+    grid.free_neighbors()
+
+
+@pytest.mark.parametrize("case", ["2d_default", "2d_poiseuille", "2d_offgrid", "3d_small", "3d_default"])
+def test_boundary_operators(case):
+    ref = H.make_ref(case)
+    H.perturbed_state(ref, seed=1)
+    S, cfg, grid, fields = gpu_side(case, ref=ref)
+    ops = [("inlet_bc", lambda: S.apply_inlet_bc(fields, grid, cfg)),
+           ("outlet_bc", lambda: S.apply_outlet_bc(fields, grid, cfg)),
+           ("wall_bc", lambda: S.apply_wall_bc(fields, grid, cfg)),
+           ("solid_bc", lambda: S.apply_solid_surface_bc(fields, grid)),
+           ("wall_conc_bc", lambda: S.apply_wall_concentration_bc(fields, grid, cfg)),
+           ("wall_bc_new", lambda: S.apply_wall_bc_new(fields, grid, cfg))]
+    for name, gpu_op in ops:
+        getattr(ref, name)()
+        gpu_op()
+        assert_fields(fields, ref, ("rho", "vel", "C", "rho_new", "vel_new"))
+
+
+@pytest.mark.parametrize("case", ["2d_default", "2d_poiseuille", "2d_offgrid", "3d_small", "3d_default"])
+def test_ns_step_and_dt(case):
+    ref = H.make_ref(case)
+    H.perturbed_state(ref, seed=2)
+    S, cfg, grid, fields = gpu_side(case, ref=ref)
+    ns = S.PD_NS_Solver()
+    ns.init(grid, cfg)
+    dt_ref = ref.ns_compute_dt()
+    dt = ns.compute_dt(fields, grid, cfg)
+    assert abs(dt - dt_ref) <= 1e-15 * dt_ref
+    ref.ns_step(dt_ref)
+    ns.step(fields, grid, cfg, dt_ref)
+    assert_fields(fields, ref, ("rho_new", "vel_new"))
+    nt = ref.get("node_type")
+    assert_fields(fields, ref, ("pressure",), where=nt != 5)
+
+
+@pytest.mark.parametrize("case,iters", [("2d_default", 200), ("2d_poiseuille", 200), ("3d_small", 40)])
+def test_ns_iterate(case, iters):
+    """K full loop bodies (BCs + step + wall_new + swap) from the initial state."""
+    ref = H.make_ref(case)
+    S, cfg, grid, fields = gpu_side(case, ref=ref)
+    ns = S.PD_NS_Solver()
+    ns.init(grid, cfg)
+    dt = ref.ns_compute_dt()
+    ref.ns_iterate(iters, dt)
+    ns.iterate(fields, grid, cfg, iters, dt)
+    assert_fields(fields, ref, ("rho", "vel", "C", "rho_new", "vel_new"))
+    # convergence-block scalars (src/pd_ns.cpp:273-301) of one more un-swapped step
+    for bc in ("inlet_bc", "outlet_bc", "wall_bc", "solid_bc"):
+        getattr(ref, bc)()
+    S.apply_inlet_bc(fields, grid, cfg); S.apply_outlet_bc(fields, grid, cfg)
+    S.apply_wall_bc(fields, grid, cfg); S.apply_solid_surface_bc(fields, grid)
+    ref.ns_step(dt); ref.wall_bc_new()
+    ns.step(fields, grid, cfg, dt); S.apply_wall_bc_new(fields, grid, cfg)
+    r = ns.residual(grid)
+    nt = ref.get("node_type")
+    fl = nt == 0
+    v, vn, rn = ref.get("vel")[fl], ref.get("vel_new")[fl], ref.get("rho_new")[fl]
+    num, den = float(((vn - v) ** 2).sum()), float((v ** 2).sum())
+    assert abs(r.num - num) <= 1e-9 * num and abs(r.den - den) <= 1e-12 * den
+    assert abs(r.v_max - np.sqrt((vn ** 2).sum(1)).max()) <= 1e-12 * r.v_max
+    assert abs(r.rho_min - rn.min()) <= 1e-12 * rn.min() and abs(r.rho_max - rn.max()) <= 1e-12 * rn.max()
+    assert r.has_nan == 0
+
+
+@pytest.mark.parametrize("case", ["2d_default", "2d_dissolve", "3d_small", "3d_default"])
+def test_ard_step_and_dt(case):
+    ref = H.make_ref(case)
+    H.perturbed_state(ref, seed=3)
+    # exercise the salt layer: saturate some fluid next to the wire
+    C = ref.get("C")
+    nt = ref.get("node_type")
+    rng = np.random.default_rng(5)
+    C[(nt == 0) & (rng.random(C.size) < 0.02)] = 0.95
+    ref.set("C", C)
+    S, cfg, grid, fields = gpu_side(case, ref=ref)
+    ard = S.PD_ARD_Solver()
+    ard.init(grid, cfg)
+    dt_ref = ref.ard_compute_dt()
+    dt = ard.compute_dt(fields, grid, cfg)
+    assert abs(dt - dt_ref) <= 1e-15 * dt_ref
+    ref.ard_step(dt_ref)
+    ard.step(fields, grid, cfg, dt_ref)
+    assert_fields(fields, ref, ("C_new",))
+
+
+@pytest.mark.parametrize("case,flow_iters,steps", [("2d_default", 300, 100), ("3d_small", 50, 20)])
+def test_ard_iterate(case, flow_iters, steps):
+    ref = H.make_ref(case)
+    S, cfg, grid, fields = gpu_side(case, ref=ref)
+    ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
+    ns.init(grid, cfg); ard.init(grid, cfg)
+    dt = ref.ns_compute_dt()
+    ref.ns_iterate(flow_iters, dt)
+    ns.iterate(fields, grid, cfg, flow_iters, dt)
+    dtc = ref.ard_compute_dt()
+    assert abs(ard.compute_dt(fields, grid, cfg) - dtc) <= 1e-12 * dtc
+    ref.ard_iterate(steps, dtc)
+    ard.iterate(fields, grid, cfg, steps, dtc)
+    assert_fields(fields, ref, ("rho", "vel", "C"))
+
+
+def test_phase_change_sets_bit_exact():
+    """Coupling cycles of the explicit branch with dissolution: the set of
+    dissolved nodes per check must be identical, fields within tolerance."""
+    case = "2d_dissolve"
+    ref = H.make_ref(case)
+    S, cfg, grid, fields = gpu_side(case, ref=ref)
+    ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
+    ns.init(grid, cfg); ard.init(grid, cfg)
+    dt = ref.ns_compute_dt()
+    total = 0
+    for cycle in range(3):
+        ref.ns_iterate(300, dt)
+        ns.iterate(fields, grid, cfg, 300, dt)
+        dtc = ref.ard_compute_dt()
+        ref.ard_iterate(50, dtc)
+        ard.iterate(fields, grid, cfg, 50, dtc)
+        assert_fields(fields, ref, ("C",), tol=1e-11)
+        before = ref.get("node_type")
+        n_ref = ref.phase_change()
+        after = ref.get("node_type")
+        dissolved_ref = np.nonzero(before != after)[0]
+        n_gpu = ard.apply_phase_change(fields, grid, cfg)
+        assert n_gpu == n_ref == dissolved_ref.size
+        assert np.array_equal(ard.last_dissolved, dissolved_ref)
+        assert np.array_equal(grid.node_type, after)
+        assert np.array_equal(fields.get("phase"), ref.get("phase"))
+        ref.rebuild_neighbors()
+        assert_fields(fields, ref, ("rho", "vel", "C"), tol=1e-11)
+        total += n_ref
+    assert total > 0, "synthetic config must dissolve nodes"
+    d = S.diagnostics(grid)
+    assert d.solid_count == int((ref.get("node_type") == 1).sum())
+
+
+def test_errors_are_loud():
+    from pd_mg_pin_corrosion_b200 import lib as L, solver as S
+    dim, cfg, _ = H.load_cfg("2d_default", {"use_implicit": 1})
+    with pytest.raises(ValueError):
+        S.Grid(2).build(cfg)
+    s = cfg.to_struct()
+    import ctypes as C
+    ctx = C.c_void_p()
+    assert L.load().pdgpu_create(C.byref(s), 2, 0, C.byref(ctx)) != 0
+    assert b"use_implicit" in L.load().pdgpu_last_error()
