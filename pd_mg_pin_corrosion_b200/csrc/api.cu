@@ -129,10 +129,11 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     pd_comm_destroy(c);
     void* ptrs[] = {c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->rho[0], c->rho[1],
                     c->p[0], c->p[1], c->C[0], c->C[1], c->v[0][0], c->v[0][1], c->v[0][2], c->v[1][0],
-                    c->v[1][1], c->v[1][2], c->vmag, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,
+                    c->v[1][1], c->v[1][2], c->vmag, c->dsol, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,
                     c->l_solid, c->inlet_vax, c->out_nodes, c->out_level_off, c->d_red, c->d_u64, c->d_int,
                     c->d_dissolved, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol,
-                    c->l2_scratch, c->d_dt, c->stage};
+                    c->l2_scratch, c->d_dt, c->stage, c->out_base_v, c->out_base_c, c->out_cnt,
+                    c->out_mask, c->out_early};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_red) cudaFreeHost(c->h_red);
@@ -180,6 +181,7 @@ extern "C" int pdgpu_set_option(pdgpu_ctx* c, const char* name, int value) {
     if (n == "ns_kernel") c->opt_ns_kernel = value;
     else if (n == "ard_kernel") c->opt_ard_kernel = value;
     else if (n == "graph") c->opt_graph = value;
+    else if (n == "outlet_kernel") c->opt_outlet_kernel = value;
     else PD_FAIL("pdgpu_set_option: unknown option '%s'", name);
     pd_invalidate_graphs(c);
     return 0;

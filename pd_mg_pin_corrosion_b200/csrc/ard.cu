@@ -26,31 +26,44 @@ static ArdParams ard_params(const pdgpu_ctx* c) {
     return p;
 }
 
-// Pre-pass over every local node: |v| (for D_art) and, for owned SOLID_MG nodes, the
-// salt-layer flag of src/pd_ard.cpp:61-73 (any FLUID neighbour with C >= C_sat).
+// Pre-pass over every local node: vmag = |v| for fluid-like nodes (FLUID/INLET/OUTLET), -1
+// otherwise (feeds D_art, src/pd_ard.cpp:166-170); for owned SOLID_MG nodes the salt-layer
+// flag of src/pd_ard.cpp:61-73 (any FLUID neighbour with C >= C_sat) and the interface
+// diffusivity dsol = 2 D_l D_s / (D_l + D_s + 1e-30) (0 when blocked), src/pd_ard.cpp:140-162.
 template <int DIM>
 __global__ void k_ard_prepass(Lat L, long long NL, long long own_lo, long long own_hi,
                               const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
                               const double* __restrict__ C, const double* __restrict__ vx,
-                              const double* __restrict__ vy, const double* __restrict__ vz, double C_sat,
-                              double* __restrict__ vmag, uint8_t* __restrict__ salt) {
+                              const double* __restrict__ vy, const double* __restrict__ vz,
+                              const uint8_t* __restrict__ is_gb, const uint8_t* __restrict__ is_precip,
+                              ArdParams P, double* __restrict__ vmag, uint8_t* __restrict__ salt,
+                              double* __restrict__ dsol) {
     long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= NL) return;
+    uint8_t ty = type[l];
     double s = vx[l] * vx[l] + vy[l] * vy[l];
     if (DIM == 3) s += vz[l] * vz[l];
-    vmag[l] = sqrt(s);
-    if (l < own_lo || l >= own_hi) return;
+    bool fluid_like = (ty == PDGPU_FLUID || ty == PDGPU_INLET || ty == PDGPU_OUTLET);
+    vmag[l] = fluid_like ? sqrt(s) : -1.0;
+    if (l < own_lo || l >= own_hi) return;   // ghost planes: salt/dsol arrive with the halo exchange
     uint8_t blocked = 0;
-    if (type[l] == PDGPU_SOLID_MG) {
+    double ds = 0.0;
+    if (ty == PDGPU_SOLID_MG) {
         int q = (int)(l % L.P);
         int jj = (DIM == 3) ? q / L.Nx : 0;
         int ii = q - jj * L.Nx;
         for (int o = 0; o < n_off; ++o) {
             long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
-            if (nn >= 0 && type[nn] == PDGPU_FLUID && C[nn] >= C_sat) { blocked = 1; break; }
+            if (nn >= 0 && type[nn] == PDGPU_FLUID && C[nn] >= P.C_sat) { blocked = 1; break; }
+        }
+        if (!blocked) {
+            double D_s = is_gb[l] ? P.D_gb : (is_precip[l] ? P.D_precip : P.D_grain);
+            D_s *= P.decay;
+            ds = 2.0 * P.D_liquid * D_s / (P.D_liquid + D_s + 1e-30);
         }
     }
     salt[l] = blocked;
+    dsol[l] = ds;
 }
 
 // Generic kernel: one thread per owned node (PD_ARD_Solver::step, src/pd_ard.cpp:81-190).
@@ -107,7 +120,7 @@ k_ard_step_generic(Lat L, long long own_lo, long long own_n, const uint8_t* __re
     C_n[l] = cn < 0.0 ? 0.0 : cn;
 }
 
-int pd_enqueue_ard_step_fast(pdgpu_ctx* c, int buf, int srcC, const ArdParams& P, const double* d_dt);
+int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);   // ard_tile.cu
 
 int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
     Lat L = make_lat(c);
@@ -116,11 +129,15 @@ int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
     int dstC = 1 - srcC;
     if (c->dim == 2)
         LAUNCH(c, k_ard_prepass<2>, nblocks(c->NL, 256), 256, 0, L, c->NL, c->own_lo, c->own_hi, c->type, c->d_off,
-               c->n_off, c->C[srcC], VXYZ(c, buf), P.C_sat, c->vmag, c->salt);
+               c->n_off, c->C[srcC], VXYZ(c, buf), c->is_gb, c->is_precip, P, c->vmag, c->salt, c->dsol);
     else
         LAUNCH(c, k_ard_prepass<3>, nblocks(c->NL, 256), 256, 0, L, c->NL, c->own_lo, c->own_hi, c->type, c->d_off,
-               c->n_off, c->C[srcC], VXYZ(c, buf), P.C_sat, c->vmag, c->salt);
-    if (c->nranks > 1 && c->comm && c->n_solid) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));   // salt flags
+               c->n_off, c->C[srcC], VXYZ(c, buf), c->is_gb, c->is_precip, P, c->vmag, c->salt, c->dsol);
+    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));   // salt flags + dsol of ghost solids
+    if (c->opt_ard_kernel >= 1) {
+        int r = pd_enqueue_ard_tile(c, buf, srcC, d_dt);
+        if (r >= 0) return r;
+    }
     if (c->dim == 2)
         LAUNCH(c, k_ard_step_generic<2>, nblocks(own_n, 128), 128, 0, L, c->own_lo, own_n, c->type, c->d_off,
                c->n_off, P, d_dt, c->C[srcC], VXYZ(c, buf), c->vmag, c->is_gb, c->is_precip, c->salt, c->C[dstC]);

@@ -169,6 +169,8 @@ int pd_enqueue_bc_inlet(pdgpu_ctx* c, int buf, int bufC) {
 
 int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC) {
     if (!c->n_outlet) return 0;
+    int r = pd_enqueue_bc_outlet_fast(c, buf, bufC);
+    if (r >= 0) return r;
     Lat L = make_lat(c);
     if (c->dim == 2)
         LAUNCH(c, k_bc_outlet<2>, 1, 1024, 0, L, c->out_nodes, c->out_level_off, c->n_levels, c->type, c->d_off,

@@ -122,7 +122,7 @@ int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC) {
         add_d(c->C[oc]);
         add_b(c->type); add_b(c->phase); add_b(c->is_gb); add_b(c->is_precip);
     }
-    if (which == 3) add_b(c->salt);
+    if (which == 3) { add_b(c->salt); add_d(c->dsol); }
     int lo = c->rank - 1, hi = c->rank + 1;
     NCCL_OK(g_nccl.GroupStart());
     for (const Arr& a : arrs) {

@@ -83,7 +83,8 @@ struct pdgpu_ctx {
     uint8_t *type = nullptr, *phase = nullptr, *is_gb = nullptr, *is_precip = nullptr, *salt = nullptr;
     double *rho[2] = {nullptr, nullptr}, *p[2] = {nullptr, nullptr}, *C[2] = {nullptr, nullptr};
     double* v[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-    double* vmag = nullptr;         // |v| per node (ARD artificial diffusion)
+    double* vmag = nullptr;         // |v| per fluid-like node, -1 otherwise (ARD artificial diffusion)
+    double* dsol = nullptr;         // interface diffusivity of SOLID_MG nodes (0 elsewhere / salt blocked)
     int cur = 0, curC = 0;          // which buffer is "current"
     int p_input = 0;                // buffer whose p is the reference's `pressure` member
 
@@ -97,6 +98,15 @@ struct pdgpu_ctx {
     int* out_level_off = nullptr;   // [n_levels+1]
     int n_levels = 0;
     int max_level_width = 0;
+    // fast outlet sweep (outlet.cu)
+    double *out_base_v = nullptr, *out_base_c = nullptr;
+    int* out_cnt = nullptr;
+    unsigned* out_mask = nullptr;
+    void* out_early = nullptr;
+    bool out_fast = false;
+    int out_KP = 0, out_Wj = 0, out_ring = 0, out_mask_words = 0, out_tau_max = 0;
+    size_t out_smem = 0;
+    long long out_l0 = 0;
 
     // reductions
     double* d_red = nullptr;        // device scratch
@@ -123,6 +133,7 @@ struct pdgpu_ctx {
     int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled fast path
     int opt_ard_kernel = 1;
     int opt_graph = 1;
+    int opt_outlet_kernel = 1;      // 0 = level-list kernel, 1 = ring sweep (outlet.cu)
 
     // NCCL
     void* comm = nullptr;
@@ -244,6 +255,8 @@ int pd_alloc_fields(pdgpu_ctx* c);
 int pd_rebuild_tables(pdgpu_ctx* c);                 // lists, mirror table, bond counts
 int pd_enqueue_bc_inlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
+int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, -1 = not applicable
+int pd_outlet_setup(pdgpu_ctx* c);
 int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf);
 int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC);
 int pd_enqueue_bc_solid(pdgpu_ctx* c, int buf);

@@ -32,6 +32,8 @@ int pd_alloc_fields(pdgpu_ctx* c) {
     }
     CUDA_OK(cudaMalloc(&c->vmag, nb));
     CUDA_OK(cudaMemset(c->vmag, 0, nb));
+    CUDA_OK(cudaMalloc(&c->dsol, nb));
+    CUDA_OK(cudaMemset(c->dsol, 0, nb));
     return 0;
 }
 

@@ -346,6 +346,7 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
     CUDA_OK(cudaFree(d_pos));
     CUDA_OK(cudaFree(d_counts));
     PD_TRY(build_outlet_schedule(c));
+    PD_TRY(pd_outlet_setup(c));
 
     // multi-GPU sanity: owned WALL mirrors must not live in ghost planes of another rank's
     // slab unless those are plain copies ("halo invariants").

@@ -1,0 +1,268 @@
+// outlet.cu -- fast exact implementation of apply_outlet_bc (reference src/boundary.cpp:88-131).
+//
+// The reference sweep is an in-place Gauss-Seidel pass in index order: OUTLET node n
+// becomes the mean of its FLUID and OUTLET neighbours, seeing NEW values of OUTLET
+// neighbours with a smaller index and OLD values of those with a larger index.  Split:
+//
+//   pre-pass (fully parallel, all SMs): per outlet node, count of FLUID|OUTLET neighbours
+//       and base = sum over FLUID neighbours + sum over lexicographically LATER outlet
+//       neighbours (old values); also writes rho = rho_f, p = 0, transverse velocity = 0.
+//   sweep (sequential part only): new[n] = (base[n] + sum over EARLIER outlet neighbours
+//       of new[.]) / count, processed by hyperplane levels tau = i + B j + B^2 k'
+//       (B = reach+1): nodes of one level are independent and every earlier neighbour has
+//       a smaller tau.  The last RING levels live in a shared-memory
+//       ring addressed arithmetically (no adjacency lists, no global loads on the
+//       dependent path); the axial-velocity sweep and the concentration sweep are
+//       independent systems and run as two CTAs on two SMs.
+//
+// Levels are enumerated over ALL in-box lattice nodes of the outlet planes; non-outlet
+// nodes store 0 in the ring, so the sweep needs no type test per neighbour.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+struct OutletGeom {
+    int Nx, Ny;        // in-plane extents (Ny = 1 in 2D)
+    int KP;            // number of outlet planes
+    int Wj;            // max nodes per (level, plane)
+    int B, B2;         // tau bases
+    int ring;          // ring depth (power of two > max tau distance)
+    int n_early;       // lexicographically earlier offsets = first half of the stencil
+    int tau_max;
+    long long P;       // nodes per plane
+    long long l0;      // local index of the first node of the first outlet plane
+};
+
+__device__ __forceinline__ int ceil_div_pos(int a, int b) { return a <= 0 ? 0 : (a + b - 1) / b; }
+
+// node p of level tau: returns false if there is none
+__device__ __forceinline__ bool level_node(const OutletGeom& g, int tau, int p, int* kp, int* j, int* i, int* jj) {
+    *kp = p / g.Wj;
+    *jj = p - *kp * g.Wj;
+    int c = tau - g.B2 * *kp;
+    if (c < 0) return false;
+    int jlo = ceil_div_pos(c - (g.Nx - 1), g.B);
+    *j = jlo + *jj;
+    *i = c - g.B * *j;
+    return *j < g.Ny && *i >= 0;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128)
+k_outlet_prepass(Lat L, OutletGeom g, const int* __restrict__ list, long long n, const uint8_t* __restrict__ type,
+                 const OffEntry* __restrict__ off, int n_off, double* __restrict__ rho, double* __restrict__ p,
+                 double* __restrict__ vx, double* __restrict__ vy, double* __restrict__ vz,
+                 const double* __restrict__ C, double rho_f, double* __restrict__ base_v,
+                 double* __restrict__ base_c, int* __restrict__ cnt) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    long long l = list[t];
+    const double* vax = (DIM == 2) ? vy : vz;
+    int q = (int)(l % L.P);
+    int jj = (DIM == 3) ? q / L.Nx : 0;
+    int ii = q - jj * L.Nx;
+    double sv = 0.0, sc = 0.0;
+    int c = 0;
+    for (int o = 0; o < n_off; ++o) {
+        long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
+        if (nn < 0) continue;
+        uint8_t tj = type[nn];
+        if (tj == PDGPU_FLUID || (tj == PDGPU_OUTLET && o >= g.n_early)) {
+            sv += vax[nn];
+            sc += C[nn];
+            ++c;
+        } else if (tj == PDGPU_OUTLET) {
+            ++c;   // earlier outlet neighbour: value added by the sweep
+        }
+    }
+    long long d = l - g.l0;
+    base_v[d] = sv;
+    base_c[d] = sc;
+    cnt[d] = c;
+    rho[l] = rho_f;
+    p[l] = 0.0;          // EOS(rho_f) = 0 exactly
+    vx[l] = 0.0;
+    if (DIM == 3) vy[l] = 0.0;
+}
+
+// blockIdx.x = 0: axial velocity, 1: concentration
+__global__ void __launch_bounds__(1024, 1)
+k_outlet_sweep(OutletGeom g, const int4* __restrict__ early, const unsigned* __restrict__ mask_g, int mask_words,
+               const double* __restrict__ base_v, const double* __restrict__ base_c, const int* __restrict__ cnt,
+               double* vax, double* C, double U_in) {
+    extern __shared__ double smem[];
+    double* ring = smem;
+    int4* s_early = (int4*)(ring + (size_t)g.ring * g.KP * g.Wj);
+    unsigned* s_mask = (unsigned*)(s_early + g.n_early);
+    const bool is_vel = (blockIdx.x == 0);
+    const double* base = is_vel ? base_v : base_c;
+    double* out = is_vel ? vax : C;
+    for (int e = threadIdx.x; e < g.n_early; e += blockDim.x) s_early[e] = early[e];
+    for (int w = threadIdx.x; w < mask_words; w += blockDim.x) s_mask[w] = mask_g[w];
+    __syncthreads();
+
+    constexpr int G = 8;
+    const int lane = threadIdx.x & (G - 1);
+    const int group = threadIdx.x / G;
+    const int NG = blockDim.x / G;
+    const int npairs = g.KP * g.Wj;
+    const int rmask = g.ring - 1;
+    constexpr int MAXP = 4;   // pairs per group per level (npairs <= MAXP * NG is checked on the host)
+
+    // software-pipelined loads of (base, cnt) for the next level
+    double nb[MAXP];
+    int nc[MAXP];
+#pragma unroll
+    for (int s = 0; s < MAXP; ++s) {
+        nb[s] = 0.0; nc[s] = 0;
+        int p = group + s * NG, kp, j, i, jj;
+        if (p < npairs && level_node(g, 0, p, &kp, &j, &i, &jj)) {
+            long long d = (long long)kp * g.P + (long long)j * g.Nx + i;
+            nb[s] = base[d]; nc[s] = cnt[d];
+        }
+    }
+    for (int tau = 0; tau <= g.tau_max; ++tau) {
+        double cb[MAXP];
+        int cc[MAXP];
+#pragma unroll
+        for (int s = 0; s < MAXP; ++s) { cb[s] = nb[s]; cc[s] = nc[s]; }
+        if (tau < g.tau_max) {
+#pragma unroll
+            for (int s = 0; s < MAXP; ++s) {
+                int p = group + s * NG, kp, j, i, jj;
+                nb[s] = 0.0; nc[s] = 0;
+                if (p < npairs && level_node(g, tau + 1, p, &kp, &j, &i, &jj)) {
+                    long long d = (long long)kp * g.P + (long long)j * g.Nx + i;
+                    nb[s] = base[d]; nc[s] = cnt[d];
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < MAXP; ++s) {
+            int p = group + s * NG, kp = 0, j = 0, i = 0, jj = 0;
+            bool valid = (p < npairs) && level_node(g, tau, p, &kp, &j, &i, &jj);
+            bool is_out = false;
+            long long d = 0;
+            if (valid) {
+                d = (long long)kp * g.P + (long long)j * g.Nx + i;
+                is_out = (s_mask[d >> 5] >> (d & 31)) & 1u;
+            }
+            double sum = 0.0;
+            if (is_out) {
+                for (int e = lane; e < g.n_early; e += G) {
+                    int4 o = s_early[e];                 // di, dj (in-plane), dplane, dtau
+                    int k2 = kp + o.z;
+                    if (k2 < 0) continue;                // FLUID plane: in the pre-pass
+                    int j2 = j + o.y, i2 = i + o.x;
+                    if (j2 < 0 || j2 >= g.Ny || i2 < 0 || i2 >= g.Nx) continue;
+                    int tau2 = tau + o.w;
+                    int c2 = tau2 - g.B2 * k2;
+                    int jlo2 = ceil_div_pos(c2 - (g.Nx - 1), g.B);
+                    sum += ring[((size_t)(tau2 & rmask) * g.KP + k2) * g.Wj + (j2 - jlo2)];
+                }
+            }
+            // reduce over the 8 lanes of the group (aligned 8-lane segments of a warp)
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            if (valid && lane == 0) {
+                double val = 0.0;
+                if (is_out) {
+                    double tot = cb[s] + sum;
+                    int n = cc[s];
+                    if (is_vel) val = n > 0 ? tot * (1.0 / n) : U_in;   // src/boundary.cpp:113-124
+                    else val = n > 0 ? tot / n : 0.0;                   // :129
+                    out[g.l0 + d] = val;
+                }
+                ring[((size_t)(tau & rmask) * g.KP + kp) * g.Wj + jj] = val;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_outlet_mask(const uint8_t* __restrict__ type, long long l0, long long n, unsigned* __restrict__ mask) {
+    long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 32 >= n) return;
+    unsigned m = 0;
+    for (int b = 0; b < 32; ++b) {
+        long long d = w * 32 + b;
+        if (d < n && type[l0 + d] == PDGPU_OUTLET) m |= (1u << b);
+    }
+    mask[w] = m;
+}
+
+}  // namespace
+
+// Build the static data of the fast sweep (called from pd_rebuild_tables).
+int pd_outlet_setup(pdgpu_ctx* c) {
+    cudaFree(c->out_base_v); cudaFree(c->out_base_c); cudaFree(c->out_cnt); cudaFree(c->out_mask);
+    cudaFree(c->out_early);
+    c->out_base_v = c->out_base_c = nullptr; c->out_cnt = nullptr; c->out_mask = nullptr; c->out_early = nullptr;
+    c->out_fast = false;
+    if (c->n_outlet == 0) return 0;
+    std::vector<int> nodes(c->n_outlet);
+    CUDA_OK(cudaMemcpy(nodes.data(), c->l_outlet, sizeof(int) * c->n_outlet, cudaMemcpyDeviceToHost));
+    long long al_min = nodes.front() / c->P, al_max = nodes.back() / c->P;
+    int KP = (int)(al_max - al_min + 1);
+    int Nx = c->Nx, Ny = (c->dim == 3) ? c->Ny : 1;
+    int B = c->R + 1, B2 = B * B;
+    int maxd = c->R * (1 + B + B2);
+    int ring = 1;
+    while (ring <= maxd) ring <<= 1;
+    int Wj = std::min(Ny, (Nx - 1) / B + 1);
+    int n_early = c->n_off / 2;
+    long long nslab = (long long)KP * c->P;
+    int mask_words = (int)((nslab + 31) / 32);
+    size_t smem = sizeof(double) * (size_t)ring * KP * Wj + sizeof(int4) * n_early + sizeof(unsigned) * mask_words;
+    if (KP * Wj > 4 * (1024 / 8) || smem > 220 * 1024) return 0;   // fall back to the level-list kernel
+    // the stencil is symmetric and lexicographically ordered: first half = earlier neighbours
+    std::vector<int4> early(n_early);
+    for (int o = 0; o < n_early; ++o) {
+        const OffEntry& e = c->h_off[o];
+        int di = e.di, dj = (c->dim == 3) ? e.dj : 0, dp = (c->dim == 3) ? e.dk : e.dj;
+        if (!(dp < 0 || (dp == 0 && dj < 0) || (dp == 0 && dj == 0 && di < 0))) return 0;   // unexpected order
+        early[o] = make_int4(di, dj, dp, di + B * dj + B2 * dp);
+    }
+    c->out_KP = KP; c->out_Wj = Wj; c->out_ring = ring; c->out_smem = smem; c->out_mask_words = mask_words;
+    c->out_l0 = al_min * c->P;
+    c->out_tau_max = (Nx - 1) + B * (Ny - 1) + B2 * (KP - 1);
+    CUDA_OK(cudaMalloc(&c->out_base_v, sizeof(double) * nslab));
+    CUDA_OK(cudaMalloc(&c->out_base_c, sizeof(double) * nslab));
+    CUDA_OK(cudaMalloc(&c->out_cnt, sizeof(int) * nslab));
+    CUDA_OK(cudaMalloc(&c->out_mask, sizeof(unsigned) * mask_words));
+    CUDA_OK(cudaMalloc(&c->out_early, sizeof(int4) * n_early));
+    CUDA_OK(cudaMemset(c->out_base_v, 0, sizeof(double) * nslab));
+    CUDA_OK(cudaMemset(c->out_base_c, 0, sizeof(double) * nslab));
+    CUDA_OK(cudaMemset(c->out_cnt, 0, sizeof(int) * nslab));
+    CUDA_OK(cudaMemcpy(c->out_early, early.data(), sizeof(int4) * n_early, cudaMemcpyHostToDevice));
+    k_outlet_mask<<<nblocks(mask_words, 256), 256, 0, c->stream>>>(c->type, c->out_l0, nslab, c->out_mask);
+    CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    c->out_fast = true;
+    return 0;
+}
+
+// returns -1 when the fast sweep is not applicable
+int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
+    if (!c->out_fast || c->opt_outlet_kernel == 0) return -1;
+    Lat L = make_lat(c);
+    OutletGeom g;
+    g.Nx = c->Nx; g.Ny = (c->dim == 3) ? c->Ny : 1; g.KP = c->out_KP; g.Wj = c->out_Wj;
+    g.B = c->R + 1; g.B2 = g.B * g.B; g.ring = c->out_ring; g.n_early = c->n_off / 2;
+    g.tau_max = c->out_tau_max; g.P = c->P; g.l0 = c->out_l0;
+    double* vax = c->v[buf][c->dim - 1];
+    if (c->dim == 2)
+        LAUNCH(c, k_outlet_prepass<2>, nblocks(c->n_outlet, 128), 128, 0, L, g, c->l_outlet, c->n_outlet, c->type,
+               c->d_off, c->n_off, c->rho[buf], c->p[buf], VXYZ(c, buf), c->C[bufC], c->cfg.rho_f, c->out_base_v,
+               c->out_base_c, c->out_cnt);
+    else
+        LAUNCH(c, k_outlet_prepass<3>, nblocks(c->n_outlet, 128), 128, 0, L, g, c->l_outlet, c->n_outlet, c->type,
+               c->d_off, c->n_off, c->rho[buf], c->p[buf], VXYZ(c, buf), c->C[bufC], c->cfg.rho_f, c->out_base_v,
+               c->out_base_c, c->out_cnt);
+    LAUNCH(c, k_outlet_sweep, 2, 1024, c->out_smem, g, (const int4*)c->out_early, c->out_mask, c->out_mask_words,
+           c->out_base_v, c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
+    return 0;
+}
