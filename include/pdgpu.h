@@ -99,6 +99,10 @@ int pdgpu_device_count(int* count);
 int pdgpu_grid_extents(const PdConfig* cfg, int dim, int* Nx, int* Ny, int* Nz, double origin[3]);
 /* Balanced z-slab [a0,a1) of `rank` among `nranks` over n_axial planes. */
 int pdgpu_partition(int n_axial, int nranks, int rank, int* a0, int* a1);
+/* Local layout of a z-slab (what the halo exchange uses): out[0..9] = a0, a1, local planes,
+ * local nodes, own_lo, own_hi, send_lo, recv_lo, send_hi, recv_hi (node offsets into a local
+ * array; a halo block is reach*plane nodes). New: the reference has no distributed layer. */
+int pdgpu_slab_layout(int n_axial, long long plane, int reach, int nranks, int rank, long long* out);
 /* Horizon-offset stencil of Grid::build_neighbors (src/grid.cpp:161-187,274-288) in CSR
  * order: off_d [n][3], dist [n], evec [n][dim], vol [n]; returns count in *n_off
  * (arrays may be NULL to query the count). */

@@ -58,10 +58,13 @@ extern "C" int pdgpu_create_slab(const PdConfig* cfg, int dim, int device, int r
         delete c;
         PD_FAIL("pdgpu_create_slab: slab of %d planes is thinner than 2*reach+2", planes);
     }
-    c->nlp = (c->a1 - c->a0) + 2 * c->R;
-    c->NL = (long long)c->nlp * c->P;
-    c->own_lo = (long long)c->R * c->P;
-    c->own_hi = c->own_lo + (long long)(c->a1 - c->a0) * c->P;
+    long long lay[10];
+    if (pdgpu_slab_layout(c->Na, c->P, c->R, nranks, rank, lay)) { delete c; return 1; }
+    c->nlp = (int)lay[2];
+    c->NL = lay[3];
+    c->own_lo = lay[4];
+    c->own_hi = lay[5];
+    for (int t = 0; t < 4; ++t) c->halo_off[t] = lay[6 + t];
     if (c->NL >= (1LL << 31)) {
         long long nl = c->NL;
         delete c;

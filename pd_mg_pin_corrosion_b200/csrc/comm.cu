@@ -128,13 +128,14 @@ int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC) {
     for (const Arr& a : arrs) {
         char* base = (char*)a.p;
         size_t nb = (size_t)hp * a.bytes;
+        // offsets from pdgpu_slab_layout: send_lo, recv_lo, send_hi, recv_hi
         if (lo >= 0) {
-            NCCL_OK(g_nccl.Send(base + (size_t)c->own_lo * a.bytes, nb, ncclUint8, lo, comm, c->stream));
-            NCCL_OK(g_nccl.Recv(base, nb, ncclUint8, lo, comm, c->stream));
+            NCCL_OK(g_nccl.Send(base + (size_t)c->halo_off[0] * a.bytes, nb, ncclUint8, lo, comm, c->stream));
+            NCCL_OK(g_nccl.Recv(base + (size_t)c->halo_off[1] * a.bytes, nb, ncclUint8, lo, comm, c->stream));
         }
         if (hi < c->nranks) {
-            NCCL_OK(g_nccl.Send(base + (size_t)(c->own_hi - hp) * a.bytes, nb, ncclUint8, hi, comm, c->stream));
-            NCCL_OK(g_nccl.Recv(base + (size_t)c->own_hi * a.bytes, nb, ncclUint8, hi, comm, c->stream));
+            NCCL_OK(g_nccl.Send(base + (size_t)c->halo_off[2] * a.bytes, nb, ncclUint8, hi, comm, c->stream));
+            NCCL_OK(g_nccl.Recv(base + (size_t)c->halo_off[3] * a.bytes, nb, ncclUint8, hi, comm, c->stream));
         }
     }
     NCCL_OK(g_nccl.GroupEnd());

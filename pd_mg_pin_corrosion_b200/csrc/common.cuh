@@ -67,6 +67,7 @@ struct pdgpu_ctx {
     long long P = 0;                // nodes per plane
     long long NL = 0;               // local nodes incl. ghosts
     long long own_lo = 0, own_hi = 0;  // owned local index range
+    long long halo_off[4] = {0, 0, 0, 0};  // send_lo, recv_lo, send_hi, recv_hi (pdgpu_slab_layout)
     long long N_total = 0;
     double origin[3] = {0, 0, 0};
     bool grid_built = false, fields_ready = false;

@@ -57,6 +57,25 @@ extern "C" int pdgpu_partition(int n_axial, int nranks, int rank, int* a0, int* 
     return 0;
 }
 
+// Local layout of a z-slab: everything the halo exchange needs, as plain integers.
+// out[0..9] = a0, a1, local planes, NL, own_lo, own_hi, send_lo, recv_lo, send_hi, recv_hi
+// (node offsets into a local array; a halo block is reach*plane nodes).
+extern "C" int pdgpu_slab_layout(int n_axial, long long plane, int reach, int nranks, int rank, long long* out) {
+    if (!out || plane <= 0 || reach < 0) PD_FAIL("pdgpu_slab_layout: bad arguments");
+    int a0 = 0, a1 = 0;
+    PD_TRY(pdgpu_partition(n_axial, nranks, rank, &a0, &a1));
+    long long nlp = (long long)(a1 - a0) + 2 * reach;
+    long long hp = (long long)reach * plane;
+    out[0] = a0; out[1] = a1; out[2] = nlp; out[3] = nlp * plane;
+    out[4] = hp;                                   // own_lo
+    out[5] = hp + (long long)(a1 - a0) * plane;    // own_hi
+    out[6] = out[4];                               // send to rank-1: first `reach` owned planes
+    out[7] = 0;                                    // recv from rank-1: low ghost planes
+    out[8] = out[5] - hp;                          // send to rank+1: last `reach` owned planes
+    out[9] = out[5];                               // recv from rank+1: high ghost planes
+    return 0;
+}
+
 extern "C" int pdgpu_stencil(const PdConfig* cfg, int dim, int* n_off, int* off_d, double* dist, double* evec,
                              double* vol) {
     if (!cfg || (dim != 2 && dim != 3) || !n_off) PD_FAIL("pdgpu_stencil: bad arguments");

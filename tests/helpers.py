@@ -103,3 +103,87 @@ def perturbed_state(ref, seed: int = 0):
     ref.set("vel_new", vel)
     ref.set("C_new", C)
     return rho, vel, C
+
+
+def coupled_run(sim, cfg, log=None):
+    """CoupledSolver::run, explicit branch (src/coupling.cpp:82-302), restated over any object
+    with the RefSim/PortSim operator surface. Returns the diagnostics.csv rows (already
+    rounded through the reference's `%.6e` formatting)."""
+    nt0 = sim.get("node_type")
+    solid0 = np.nonzero(nt0 == 1)[0]
+    n0 = len(solid0)
+    rows = []
+
+    def solid_sum():
+        s = 0.0
+        for v in sim.get("C")[solid0].tolist():   # ordered sum, src/coupling.cpp:32-38
+            s += v
+        return s
+
+    def diagnostics(t):
+        nt = sim.get("node_type")
+        loss = (1.0 - solid_sum() / (n0 + 1e-30)) * 100.0
+        loss = max(loss, 0.0)
+        fl = nt == 0
+        v = sim.get("vel")[fl]
+        vmax = float(np.sqrt((v * v).sum(1)).max()) if fl.any() else 0.0
+        cmax = float(max(sim.get("C")[fl].max(), 0.0)) if fl.any() else 0.0
+        vals = [t, t / 3600.0, loss, float((nt == 1).sum()), vmax, cmax]
+        rows.append([float(f"{x:.6e}") for x in vals])
+
+    def solve_steady():   # src/pd_ns.cpp:182-372
+        dt = sim.ns_compute_dt()
+        it = 1
+        while it <= cfg.flow_max_iters:
+            sim.inlet_bc(); sim.outlet_bc(); sim.wall_bc(); sim.solid_bc()
+            sim.ns_step(dt)
+            sim.wall_bc_new()
+            if it <= 10 or it % 100 == 0:
+                nt = sim.get("node_type")
+                fl = nt == 0
+                v, vn, rn = sim.get("vel")[fl], sim.get("vel_new")[fl], sim.get("rho_new")[fl]
+                if np.isnan(vn[:, 0]).any() or np.isnan(rn).any():
+                    break
+                num, den = float(((vn - v) ** 2).sum()), float((v ** 2).sum())
+                eps = np.sqrt(num / den) if den > 1e-30 else np.sqrt(num)
+                if np.sqrt((vn ** 2).sum(1)).max() > 100.0 * cfg.U_in:
+                    break
+                if eps < cfg.flow_conv_tol and it > 100:
+                    break
+            sim.swap_flow()
+            if it % 200 == 0:
+                dt = sim.ns_compute_dt()
+            it += 1
+        return it
+
+    t_corr, need_flow = 0.0, True
+    while t_corr < cfg.T_final:
+        if need_flow:
+            solve_steady()
+            need_flow = False
+        vl = max(1.0 - solid_sum() / (n0 + 1e-30), 0.0)
+        sim.ard_set_volume_loss(vl)
+        dtc = sim.ard_compute_dt()
+        for step in range(1, cfg.corrosion_steps_per_check + 1):
+            sim.inlet_bc(); sim.outlet_bc(); sim.wall_conc_bc()
+            sim.ard_step(dtc)
+            sim.swap_C()
+            t_corr += dtc
+            if step % cfg.output_every_corr == 0:
+                diagnostics(t_corr)
+            if t_corr >= cfg.T_final:
+                break
+        n = sim.phase_change()
+        if n > 0:
+            sim.rebuild_neighbors()
+            need_flow = True
+        if (sim.get("node_type") == 1).sum() == 0:
+            break
+    return rows
+
+
+def port_coupled_run(case: str, is_gb, is_precip):
+    dim, cfg, _ = load_cfg(case)
+    p = PortSim(dim, cfg, threads=4)
+    p.init_fields(is_gb, is_precip)
+    return coupled_run(p, cfg)
