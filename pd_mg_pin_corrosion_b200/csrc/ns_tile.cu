@@ -1,43 +1,32 @@
 // ns_tile.cu -- tiled fast path of the PD-NS bond kernel (3D, m_ratio = 3, full FLUID rows).
+// Tile geometry, column walk and weight algebra: tile.cuh.
 //
-// Uniform-grid formulation (north star: "fixed horizon-offset table ... shared-memory staged
-// 3D tiles with halo"): a CTA stages a (32+6) x (8+6) x (4+6) block of (rho, vx, vy, vz, p)
-// in shared memory; thread (tx, ty) owns the 4 nodes (x0+tx, y0+ty, z0..z0+3) and walks the
-// 37 (di,dj) columns of the horizon sphere with a sliding window along z, so every staged
-// neighbour value is read from shared memory once per column and reused for up to 4 bonds.
-// Lanes map to consecutive x: every shared-memory access is a contiguous 256 B row
-// segment (conflict free).  The whole bond loop is unrolled at compile time; the bond
-// weights are kernel parameters, i.e. constant-bank operands of the DFMAs.
-//
-// Arithmetic (per bond, 14 FP64 ops): the reference's difference form
+// Arithmetic per bond (12 FP64 ops + ~2.5 amortised): the reference's difference form
 //     sum_j (f_j - f_i) e w        (src/pd_ns.cpp:115-157)
 // is evaluated as  sum_j f_j e w  for the odd (gradient/divergence) sums -- the f_i part
 // multiplies sum_j e_j w_j, which is exactly zero for the full symmetric stencil -- and as
-// sum_j f_j w2 - f_i * sum_j w2 for the two Laplacians.  The step changes a state value
-// by <= ~1e-3 relative, so the reassociation moves results by O(1e-16) relative
+// sum_j f_j w2 - f_i * sum_j w2 for the two Laplacians.  One explicit step changes a state
+// value by <= ~1e-3 relative, so this reassociation moves results by O(1e-16) relative
 // (DESIGN.md "numerics"); parity against the reference is asserted at 1e-12.
+//   g      = rho_j (v_j . d) kappa            (mass flux through the bond)
+//   mc    += g                                 mass convection
+//   md    += rho_j kappa                       density Laplacian (x 1/dx at the end)
+//   a_d   += v_jd g + p_j d_d kappa            momentum convection + pressure gradient
+//   s_d   += v_jd kappa                        velocity Laplacian (x 1/dx at the end)
+// with d = (di,dj,dk): the di/dj parts of the pressure term are factored out per column.
 #include <algorithm>
-#include <utility>
 
-#include "common.cuh"
+#include "tile.cuh"
 
 namespace {
-
-constexpr int TR = 3;                        // reach
-constexpr int TX = 32, TY = 8, RZ = 4;       // threads x, threads y, z-nodes per thread
-constexpr int SX = TX + 2 * TR, SY = TY + 2 * TR, SZ = RZ + 2 * TR;
-constexpr int SPLANE = SX * SY, SN = SPLANE * SZ;
-constexpr int NTHREADS = TX * TY;
-
-struct NsWeights {
-    double w[7][7][7][4];   // [dk+3][dj+3][di+3] -> { e_x w1, e_y w1, e_z w1, w2 }
-};
+using namespace tile;
 
 struct NsTileParams {
-    int Nx, Ny, nlp, z_lo, z_hi;   // in-plane extents, local planes, owned local plane range
-    long long P;
+    TileGeom g;
     double rho_f, gamma, B;        // EOS
-    double c_div, dens_diff, visc, rho_lo, rho_hi, W2;
+    double c_div, dens_diff, visc, rho_lo, rho_hi;
+    double W2;                     // sum of w2 over the stencil (= sum kappa / dx)
+    double inv_dx;
     int gamma_is_7;
 };
 
@@ -63,58 +52,59 @@ struct NsAcc {
     double mc[RZ], md[RZ], ax[RZ], ay[RZ], az[RZ], sx[RZ], sy[RZ], sz[RZ];
 };
 
-template <int DI, int DJ>
+template <int H>
 __device__ __forceinline__ void ns_column(const double* __restrict__ s_rho, const double* __restrict__ s_vx,
                                           const double* __restrict__ s_vy, const double* __restrict__ s_vz,
-                                          const double* __restrict__ s_p, int base, const NsWeights& W,
-                                          NsAcc& a) {
-    constexpr int r2 = 12 - DI * DI - DJ * DJ;   // di^2+dj^2+dk^2 <= 12  <=>  r <= 3.5 dx
-    if constexpr (r2 >= 0) {
-        constexpr int H = (r2 >= 9) ? 3 : (r2 >= 4) ? 2 : (r2 >= 1) ? 1 : 0;
-        const int cb = base + DJ * SX + DI;
+                                          const double* __restrict__ s_p, int cb, double dI, double dJ,
+                                          const double (&kap)[4], NsAcc& a) {
+    double kz[4];
 #pragma unroll
-        for (int zz = -H; zz < RZ + H; ++zz) {
-            const int si = cb + (zz + TR) * SPLANE;
-            const double rj = s_rho[si], pj = s_p[si], ux = s_vx[si], uy = s_vy[si], uz = s_vz[si];
-            const double mx = rj * ux, my = rj * uy, mz = rj * uz;
+    for (int k = 0; k < 4; ++k) kz[k] = (double)k * kap[k];
+    double colp[RZ];
 #pragma unroll
-            for (int t = 0; t < RZ; ++t) {
-                const int dk = zz - t;
-                if (dk >= -H && dk <= H && !(DI == 0 && DJ == 0 && dk == 0)) {
-                    const double* w = W.w[dk + 3][DJ + 3][DI + 3];
-                    double g = mx * w[0];
-                    g = fma(my, w[1], g);
-                    g = fma(mz, w[2], g);                 // rho_j (v_j . e) w1
-                    a.mc[t] += g;                          // mass convection
-                    a.md[t] = fma(rj, w[3], a.md[t]);      // density Laplacian
-                    a.ax[t] = fma(ux, g, a.ax[t]);         // momentum convection + pressure gradient
-                    a.ay[t] = fma(uy, g, a.ay[t]);
-                    a.az[t] = fma(uz, g, a.az[t]);
-                    a.ax[t] = fma(pj, w[0], a.ax[t]);
-                    a.ay[t] = fma(pj, w[1], a.ay[t]);
-                    a.az[t] = fma(pj, w[2], a.az[t]);
-                    a.sx[t] = fma(ux, w[3], a.sx[t]);      // velocity Laplacian
-                    a.sy[t] = fma(uy, w[3], a.sy[t]);
-                    a.sz[t] = fma(uz, w[3], a.sz[t]);
-                }
+    for (int t = 0; t < RZ; ++t) colp[t] = 0.0;
+#pragma unroll
+    for (int zz = -H; zz < RZ + H; ++zz) {
+        const int si = cb + (zz + TR) * SPLANE;
+        const double rj = s_rho[si], pj = s_p[si], ux = s_vx[si], uy = s_vy[si], uz = s_vz[si];
+        const double mz = rj * uz;
+        const double axy = dI * (rj * ux) + dJ * (rj * uy);
+#pragma unroll
+        for (int t = 0; t < RZ; ++t) {
+            const int dk = zz - t;
+            if (dk >= -H && dk <= H) {
+                const int ak = dk < 0 ? -dk : dk;
+                const double k = kap[ak];
+                double g = axy * k;
+                if (dk > 0) g = fma(mz, kz[ak], g);
+                if (dk < 0) g = fma(-mz, kz[ak], g);
+                a.mc[t] += g;
+                a.md[t] = fma(rj, k, a.md[t]);
+                a.ax[t] = fma(ux, g, a.ax[t]);
+                a.ay[t] = fma(uy, g, a.ay[t]);
+                a.az[t] = fma(uz, g, a.az[t]);
+                colp[t] = fma(pj, k, colp[t]);
+                if (dk > 0) a.az[t] = fma(pj, kz[ak], a.az[t]);
+                if (dk < 0) a.az[t] = fma(-pj, kz[ak], a.az[t]);
+                a.sx[t] = fma(ux, k, a.sx[t]);
+                a.sy[t] = fma(uy, k, a.sy[t]);
+                a.sz[t] = fma(uz, k, a.sz[t]);
             }
         }
     }
-}
-
-template <int... Is>
-__device__ __forceinline__ void ns_all_columns(std::integer_sequence<int, Is...>, const double* s_rho,
-                                               const double* s_vx, const double* s_vy, const double* s_vz,
-                                               const double* s_p, int base, const NsWeights& W, NsAcc& a) {
-    (ns_column<(Is % 7) - 3, (Is / 7) - 3>(s_rho, s_vx, s_vy, s_vz, s_p, base, W, a), ...);
+#pragma unroll
+    for (int t = 0; t < RZ; ++t) {
+        a.ax[t] = fma(dI, colp[t], a.ax[t]);
+        a.ay[t] = fma(dJ, colp[t], a.ay[t]);
+    }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-k_ns_tile(const NsTileParams q, const __grid_constant__ NsWeights W, const double* __restrict__ d_dt,
-          const uint8_t* __restrict__ type, const double* __restrict__ rho, const double* __restrict__ pr,
-          const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
-          double* __restrict__ rho_n, double* __restrict__ pr_n, double* __restrict__ vx_n,
-          double* __restrict__ vy_n, double* __restrict__ vz_n) {
+k_ns_tile(const __grid_constant__ NsTileParams q, const __grid_constant__ ColTable T,
+          const double* __restrict__ d_dt, const uint8_t* __restrict__ type, const double* __restrict__ rho,
+          const double* __restrict__ pr, const double* __restrict__ vx, const double* __restrict__ vy,
+          const double* __restrict__ vz, double* __restrict__ rho_n, double* __restrict__ pr_n,
+          double* __restrict__ vx_n, double* __restrict__ vy_n, double* __restrict__ vz_n) {
     extern __shared__ double sm[];
     double* s_rho = sm;
     double* s_vx = sm + SN;
@@ -124,9 +114,9 @@ k_ns_tile(const NsTileParams q, const __grid_constant__ NsWeights W, const doubl
 
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * TX + tx;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = q.z_lo + blockIdx.z * RZ;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = q.g.z_lo + blockIdx.z * RZ;
     const int gx = x0 + tx, gy = y0 + ty;
-    const bool in_xy = gx < q.Nx && gy < q.Ny;
+    const bool in_xy = gx < q.g.Nx && gy < q.g.Ny;
 
     bool fl[RZ];
     bool any = false;
@@ -134,8 +124,8 @@ k_ns_tile(const NsTileParams q, const __grid_constant__ NsWeights W, const doubl
     for (int t = 0; t < RZ; ++t) {
         const int lz = z0 + t;
         fl[t] = false;
-        if (in_xy && lz < q.z_hi) {
-            const long long l = (long long)lz * q.P + (long long)gy * q.Nx + gx;
+        if (in_xy && lz < q.g.z_hi) {
+            const long long l = (long long)lz * q.g.P + (long long)gy * q.g.Nx + gx;
             if (type[l] == PDGPU_FLUID) {
                 fl[t] = true;
                 any = true;
@@ -146,47 +136,65 @@ k_ns_tile(const NsTileParams q, const __grid_constant__ NsWeights W, const doubl
     }
     if (!__syncthreads_or(any)) return;   // tile without FLUID nodes
 
-    // stage the haloed block; outside the box the values are never used (full rows) -> 0
-    for (int idx = tid; idx < SN; idx += NTHREADS) {
-        const int sz = idx / SPLANE;
-        const int rem = idx - sz * SPLANE;
-        const int sy = rem / SX;
-        const int sx = rem - sy * SX;
-        const int ax = x0 - TR + sx, ay = y0 - TR + sy, az = z0 - TR + sz;
-        double r = 0.0, pp = 0.0, a = 0.0, b = 0.0, c = 0.0;
-        if (ax >= 0 && ax < q.Nx && ay >= 0 && ay < q.Ny && az < q.nlp) {
-            const long long l = (long long)az * q.P + (long long)ay * q.Nx + ax;
-            r = __ldg(rho + l); pp = __ldg(pr + l); a = __ldg(vx + l); b = __ldg(vy + l); c = __ldg(vz + l);
+    // stage the haloed block (4 elements x 5 fields in flight per thread); outside the box the
+    // values are never used by a FLUID row (full rows) -> 0
+    for (int i0 = tid; i0 < SN; i0 += 4 * NTHREADS) {
+        long long l[4];
+        double r[4], pp[4], a[4], b[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = i0 + u * NTHREADS;
+            l[u] = idx < SN ? staged_index(q.g, idx, x0, y0, z0) : -1;
         }
-        s_rho[idx] = r; s_p[idx] = pp; s_vx[idx] = a; s_vy[idx] = b; s_vz[idx] = c;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            r[u] = pp[u] = a[u] = b[u] = c[u] = 0.0;
+            if (l[u] >= 0) {
+                r[u] = __ldg(rho + l[u]); pp[u] = __ldg(pr + l[u]);
+                a[u] = __ldg(vx + l[u]); b[u] = __ldg(vy + l[u]); c[u] = __ldg(vz + l[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = i0 + u * NTHREADS;
+            if (idx < SN) { s_rho[idx] = r[u]; s_p[idx] = pp[u]; s_vx[idx] = a[u]; s_vy[idx] = b[u]; s_vz[idx] = c[u]; }
+        }
     }
     __syncthreads();
     if (!__any_sync(0xffffffffu, any)) return;   // warp without FLUID nodes
 
     NsAcc a;
 #pragma unroll
-    for (int t = 0; t < RZ; ++t) {
+    for (int t = 0; t < RZ; ++t)
         a.mc[t] = a.md[t] = a.ax[t] = a.ay[t] = a.az[t] = a.sx[t] = a.sy[t] = a.sz[t] = 0.0;
-    }
     const int base = (ty + TR) * SX + (tx + TR);
-    ns_all_columns(std::make_integer_sequence<int, 49>{}, s_rho, s_vx, s_vy, s_vz, s_p, base, W, a);
+#pragma unroll 1
+    for (int c = 0; c < NCOL; ++c) {
+        const int cb = base + T.off[c];
+        const double dI = T.di[c], dJ = T.dj[c];
+        const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
+        const int H = T.h[c];
+        if (H == 3) ns_column<3>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, a);
+        else if (H == 2) ns_column<2>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, a);
+        else ns_column<1>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, a);
+    }
 
     const double dt = *d_dt;
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
         if (!fl[t]) continue;
         const int si = base + (t + TR) * SPLANE;
-        const long long l = (long long)(z0 + t) * q.P + (long long)gy * q.Nx + gx;
+        const long long l = (long long)(z0 + t) * q.g.P + (long long)gy * q.g.Nx + gx;
         const double rho_i = s_rho[si], vi0 = s_vx[si], vi1 = s_vy[si], vi2 = s_vz[si];
-        const double mass_diff = a.md[t] - rho_i * q.W2;
+        const double mass_diff = a.md[t] * q.inv_dx - rho_i * q.W2;
         double rn = rho_i + dt * (-q.c_div * a.mc[t] + q.dens_diff * mass_diff);   // src/pd_ns.cpp:160-168
         rn = fmin(fmax(rn, q.rho_lo), q.rho_hi);
         rho_n[l] = rn;
         pr_n[l] = eos_tile(rn, q);
         const double s = dt / rho_i;                                                // :171-178
-        vx_n[l] = vi0 + s * (-q.c_div * a.ax[t] + q.visc * (a.sx[t] - vi0 * q.W2));
-        vy_n[l] = vi1 + s * (-q.c_div * a.ay[t] + q.visc * (a.sy[t] - vi1 * q.W2));
-        vz_n[l] = vi2 + s * (-q.c_div * a.az[t] + q.visc * (a.sz[t] - vi2 * q.W2));
+        vx_n[l] = vi0 + s * (-q.c_div * a.ax[t] + q.visc * (a.sx[t] * q.inv_dx - vi0 * q.W2));
+        vy_n[l] = vi1 + s * (-q.c_div * a.ay[t] + q.visc * (a.sy[t] * q.inv_dx - vi1 * q.W2));
+        vz_n[l] = vi2 + s * (-q.c_div * a.az[t] + q.visc * (a.sz[t] * q.inv_dx - vi2 * q.W2));
     }
 }
 
@@ -194,23 +202,18 @@ k_ns_tile(const NsTileParams q, const __grid_constant__ NsWeights W, const doubl
 
 // returns -1 when the tiled kernel does not apply (caller uses the generic kernel)
 int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt) {
-    if (c->dim != 3 || c->cfg.m_ratio != 3 || c->n_off != 178 || !c->full_rows) return -1;
-    static NsWeights W;   // rebuilt per call: cheap (343 entries) and context independent
-    memset(&W, 0, sizeof(W));
-    double W2 = 0.0;
-    for (const OffEntry& e : c->h_off) {
-        if (e.di * e.di + e.dj * e.dj + e.dk * e.dk > 12) return -1;
-        double* w = W.w[e.dk + 3][e.dj + 3][e.di + 3];
-        w[0] = e.ex * e.w1; w[1] = e.ey * e.w1; w[2] = e.ez * e.w1; w[3] = e.w2;
-        W2 += e.w2;
-    }
+    if (!c->full_rows) return -1;
+    static ColTable T;   // rebuilt per call: 37 columns, context independent
+    double sum_kappa = 0.0;
+    if (!build_columns(c, &T, &sum_kappa)) return -1;
     PdConsts k = pd_consts(c->cfg, c->dim);
     NsTileParams q;
-    q.Nx = c->Nx; q.Ny = c->Ny; q.nlp = c->nlp; q.z_lo = c->R; q.z_hi = c->R + (c->a1 - c->a0);
-    q.P = c->P;
+    q.g = make_geom(c);
     q.rho_f = c->cfg.rho_f; q.gamma = c->cfg.gamma_eos; q.B = k.B_eos;
     q.c_div = k.alpha * k.inv_VH; q.dens_diff = k.dens_diff_coeff; q.visc = c->cfg.mu_f * k.beta_lap;
-    q.rho_lo = 0.5 * c->cfg.rho_f; q.rho_hi = 2.0 * c->cfg.rho_f; q.W2 = W2;
+    q.rho_lo = 0.5 * c->cfg.rho_f; q.rho_hi = 2.0 * c->cfg.rho_f;
+    q.inv_dx = 1.0 / c->cfg.dx;
+    q.W2 = sum_kappa * q.inv_dx;
     q.gamma_is_7 = (c->cfg.gamma_eos == 7.0);
     const size_t smem = sizeof(double) * 5 * SN;
     static bool attr_done = false;
@@ -221,7 +224,7 @@ int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt) {
     int dst = 1 - src;
     dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((c->a1 - c->a0) + RZ - 1) / RZ);
     dim3 block(TX, TY, 1);
-    k_ns_tile<<<grid, block, smem, c->stream>>>(q, W, d_dt, c->type, c->rho[src], c->p[src], c->v[src][0],
+    k_ns_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->rho[src], c->p[src], c->v[src][0],
                                                  c->v[src][1], c->v[src][2], c->rho[dst], c->p[dst], c->v[dst][0],
                                                  c->v[dst][1], c->v[dst][2]);
     c->launches++;
