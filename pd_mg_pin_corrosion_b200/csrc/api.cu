@@ -101,6 +101,7 @@ extern "C" int pdgpu_create_slab(const PdConfig* cfg, int dim, int device, int r
     CUDA_OK(cudaEventCreate(&c->ev_t1));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming));
     CUDA_OK(cudaMalloc(&c->d_red, sizeof(double) * 8192));
     CUDA_OK(cudaMallocHost(&c->h_red, sizeof(double) * 64));
     CUDA_OK(cudaMalloc(&c->d_u64, sizeof(unsigned long long) * 16));
@@ -136,7 +137,7 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
                     c->l_solid, c->inlet_vax, c->out_nodes, c->out_level_off, c->d_red, c->d_u64, c->d_int,
                     c->d_dissolved, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol,
                     c->l2_scratch, c->d_dt, c->stage, c->out_base_v, c->out_base_c, c->out_cnt,
-                    c->out_mask, c->out_early};
+                    c->out_mask, c->out_early, c->out_rows};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_red) cudaFreeHost(c->h_red);
@@ -144,6 +145,7 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->ev_c) cudaEventDestroy(c->ev_c);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     delete c;
@@ -185,6 +187,7 @@ extern "C" int pdgpu_set_option(pdgpu_ctx* c, const char* name, int value) {
     else if (n == "ard_kernel") c->opt_ard_kernel = value;
     else if (n == "graph") c->opt_graph = value;
     else if (n == "outlet_kernel") c->opt_outlet_kernel = value;
+    else if (n == "overlap") c->opt_overlap = value;
     else PD_FAIL("pdgpu_set_option: unknown option '%s'", name);
     pd_invalidate_graphs(c);
     return 0;

@@ -31,15 +31,15 @@ static ArdParams ard_params(const pdgpu_ctx* c) {
 // flag of src/pd_ard.cpp:61-73 (any FLUID neighbour with C >= C_sat) and the interface
 // diffusivity dsol = 2 D_l D_s / (D_l + D_s + 1e-30) (0 when blocked), src/pd_ard.cpp:140-162.
 template <int DIM>
-__global__ void k_ard_prepass(Lat L, long long NL, long long own_lo, long long own_hi,
+__global__ void k_ard_prepass(Lat L, long long lo, long long hi, long long own_lo, long long own_hi,
                               const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
                               const double* __restrict__ C, const double* __restrict__ vx,
                               const double* __restrict__ vy, const double* __restrict__ vz,
                               const uint8_t* __restrict__ is_gb, const uint8_t* __restrict__ is_precip,
                               ArdParams P, double* __restrict__ vmag, uint8_t* __restrict__ salt,
                               double* __restrict__ dsol) {
-    long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= NL) return;
+    long long l = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= hi) return;
     uint8_t ty = type[l];
     double s = vx[l] * vx[l] + vy[l] * vy[l];
     if (DIM == 3) s += vz[l] * vz[l];
@@ -120,31 +120,48 @@ k_ard_step_generic(Lat L, long long own_lo, long long own_n, const uint8_t* __re
     C_n[l] = cn < 0.0 ? 0.0 : cn;
 }
 
-int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);   // ard_tile.cu
+int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid);   // ard_tile.cu
 
-int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
+// pre-pass over the local index range [lo, hi)
+int pd_enqueue_ard_prepass(pdgpu_ctx* c, int buf, int srcC, long long lo, long long hi) {
+    if (hi <= lo) return 0;
     Lat L = make_lat(c);
     ArdParams P = ard_params(c);
-    long long own_n = c->own_hi - c->own_lo;
-    int dstC = 1 - srcC;
+    long long n = hi - lo;
     if (c->dim == 2)
-        LAUNCH(c, k_ard_prepass<2>, nblocks(c->NL, 256), 256, 0, L, c->NL, c->own_lo, c->own_hi, c->type, c->d_off,
+        LAUNCH(c, k_ard_prepass<2>, nblocks(n, 256), 256, 0, L, lo, hi, c->own_lo, c->own_hi, c->type, c->d_off,
                c->n_off, c->C[srcC], VXYZ(c, buf), c->is_gb, c->is_precip, P, c->vmag, c->salt, c->dsol);
     else
-        LAUNCH(c, k_ard_prepass<3>, nblocks(c->NL, 256), 256, 0, L, c->NL, c->own_lo, c->own_hi, c->type, c->d_off,
+        LAUNCH(c, k_ard_prepass<3>, nblocks(n, 256), 256, 0, L, lo, hi, c->own_lo, c->own_hi, c->type, c->d_off,
                c->n_off, c->C[srcC], VXYZ(c, buf), c->is_gb, c->is_precip, P, c->vmag, c->salt, c->dsol);
-    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));   // salt flags + dsol of ghost solids
+    return 0;
+}
+
+// bond kernel over the local plane range [zb, ze) (negative = all owned planes)
+int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid) {
     if (c->opt_ard_kernel >= 1) {
-        int r = pd_enqueue_ard_tile(c, buf, srcC, d_dt);
+        int r = pd_enqueue_ard_tile(c, buf, srcC, d_dt, zb, ze, do_solid);
         if (r >= 0) return r;
     }
+    Lat L = make_lat(c);
+    ArdParams P = ard_params(c);
+    long long own_lo = c->own_lo, own_n = c->own_hi - c->own_lo;
+    if (zb >= 0) { own_lo = (long long)zb * c->P; own_n = (long long)(ze - zb) * c->P; }
+    if (own_n <= 0) return 0;
+    int dstC = 1 - srcC;
     if (c->dim == 2)
-        LAUNCH(c, k_ard_step_generic<2>, nblocks(own_n, 128), 128, 0, L, c->own_lo, own_n, c->type, c->d_off,
+        LAUNCH(c, k_ard_step_generic<2>, nblocks(own_n, 128), 128, 0, L, own_lo, own_n, c->type, c->d_off,
                c->n_off, P, d_dt, c->C[srcC], VXYZ(c, buf), c->vmag, c->is_gb, c->is_precip, c->salt, c->C[dstC]);
     else
-        LAUNCH(c, k_ard_step_generic<3>, nblocks(own_n, 128), 128, 0, L, c->own_lo, own_n, c->type, c->d_off,
+        LAUNCH(c, k_ard_step_generic<3>, nblocks(own_n, 128), 128, 0, L, own_lo, own_n, c->type, c->d_off,
                c->n_off, P, d_dt, c->C[srcC], VXYZ(c, buf), c->vmag, c->is_gb, c->is_precip, c->salt, c->C[dstC]);
     return 0;
+}
+
+int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
+    PD_TRY(pd_enqueue_ard_prepass(c, buf, srcC, 0, c->NL));
+    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));   // salt flags + dsol of ghost solids
+    return pd_enqueue_ard_main(c, buf, srcC, d_dt, -1, -1, true);
 }
 
 // ----------------------------------------------------------------- C ABI -------
@@ -180,6 +197,35 @@ extern "C" int pdgpu_ard_step(pdgpu_ctx* c, double dt) {
 
 // explicit coupling-loop body (src/coupling.cpp:232-238)
 static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
+    if (pd_can_overlap(c)) {
+        // fork/join as in the NS body: the outlet sweep and the few z-tiles that see outlet
+        // planes run on the side stream next to the bulk tiles (src/coupling.cpp:232-238 order
+        // is preserved for every data dependence).
+        cudaStream_t main_s = c->stream, side = c->stream2;
+        const int z_hi = c->R + (c->a1 - c->a0);
+        CUDA_OK(cudaEventRecord(c->ev_a, main_s));
+        CUDA_OK(cudaStreamWaitEvent(side, c->ev_a, 0));
+        {
+            StreamSwap sw(c, side);
+            PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
+            PD_TRY(pd_enqueue_ard_prepass(c, buf, srcC, c->out_l0, c->NL));
+        }
+        PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
+        PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
+        PD_TRY(pd_enqueue_ard_prepass(c, buf, srcC, 0, c->out_l0));
+        if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));
+        CUDA_OK(cudaEventRecord(c->ev_b, main_s));
+        PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, c->R, c->z_cut, c->solids_below_cut));
+        CUDA_OK(cudaStreamWaitEvent(side, c->ev_b, 0));
+        {
+            StreamSwap sw(c, side);
+            PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, c->z_cut, z_hi, !c->solids_below_cut));
+        }
+        CUDA_OK(cudaEventRecord(c->ev_c, side));
+        CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_c, 0));
+        if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 1, buf, 1 - srcC));
+        return 0;
+    }
     PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
     PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
     PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));

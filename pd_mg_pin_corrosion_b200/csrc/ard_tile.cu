@@ -185,7 +185,7 @@ k_ard_solid_rows(Lat L, const int* __restrict__ l_solid, long long n_solid, cons
 }  // namespace
 
 // returns -1 when the tiled kernel does not apply. Expects vmag (= vmf) and dsol to be current.
-int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
+int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid) {
     if (!c->full_rows) return -1;
     static ColTable T;
     double sum_kappa = 0.0;
@@ -193,6 +193,7 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
     PdConsts k = pd_consts(c->cfg, c->dim);
     ArdTileParams q;
     q.g = make_geom(c);
+    if (zb >= 0) { q.g.z_lo = zb; q.g.z_hi = ze; }
     q.D_liquid = c->cfg.D_liquid; q.alpha_dx = c->cfg.alpha_art_diff * c->cfg.dx;
     q.beta = k.beta_lap; q.div_coeff = k.alpha / k.V_H; q.inv_dx = 1.0 / c->cfg.dx;
     const size_t smem = sizeof(double) * 3 * SN;
@@ -202,12 +203,14 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
         attr_done = true;
     }
     int dstC = 1 - srcC;
-    dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((c->a1 - c->a0) + RZ - 1) / RZ);
-    dim3 block(TX, TY, 1);
-    k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->C[srcC], c->vmag, c->dsol, c->v[buf][0],
-                                                  c->v[buf][1], c->v[buf][2], c->C[dstC]);
-    c->launches++;
-    if (c->n_solid) {
+    if (q.g.z_hi > q.g.z_lo) {
+        dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + RZ - 1) / RZ);
+        dim3 block(TX, TY, 1);
+        k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->C[srcC], c->vmag, c->dsol, c->v[buf][0],
+                                                      c->v[buf][1], c->v[buf][2], c->C[dstC]);
+        c->launches++;
+    }
+    if (c->n_solid && do_solid) {
         Lat L = make_lat(c);
         LAUNCH(c, k_ard_solid_rows, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type, c->d_off,
                c->n_off, d_dt, k.beta_lap, c->C[srcC], c->dsol, c->C[dstC]);

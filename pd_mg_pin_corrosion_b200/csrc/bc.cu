@@ -181,13 +181,15 @@ int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC) {
     return 0;
 }
 
-int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf) {
-    if (!c->n_wall) return 0;
+int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part) {
+    long long first = (part == 2) ? c->n_wall_lo : 0;
+    long long n = (part == 1) ? c->n_wall_lo : c->n_wall - first;
+    if (n <= 0) return 0;
     if (c->dim == 2)
-        LAUNCH(c, k_bc_wall<2>, nblocks(c->n_wall, 256), 256, 0, c->l_wall, c->l_wall_mirror, c->n_wall, c->rho[buf],
+        LAUNCH(c, k_bc_wall<2>, nblocks(n, 256), 256, 0, c->l_wall + first, c->l_wall_mirror + first, n, c->rho[buf],
                c->p[buf], VXYZ(c, buf), c->cfg.rho_f);
     else
-        LAUNCH(c, k_bc_wall<3>, nblocks(c->n_wall, 256), 256, 0, c->l_wall, c->l_wall_mirror, c->n_wall, c->rho[buf],
+        LAUNCH(c, k_bc_wall<3>, nblocks(n, 256), 256, 0, c->l_wall + first, c->l_wall_mirror + first, n, c->rho[buf],
                c->p[buf], VXYZ(c, buf), c->cfg.rho_f);
     return 0;
 }

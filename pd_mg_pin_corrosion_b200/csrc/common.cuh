@@ -73,7 +73,7 @@ struct pdgpu_ctx {
     bool grid_built = false, fields_ready = false;
 
     cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
 
     // stencil
     int n_off = 0;
@@ -104,10 +104,19 @@ struct pdgpu_ctx {
     int* out_cnt = nullptr;
     unsigned* out_mask = nullptr;
     void* out_early = nullptr;
+    void* out_rows = nullptr;
+    bool out_mod = false;
+    int out_RJ = 1, out_n_rows = 0;
+    size_t out_smem_mod = 0;
     bool out_fast = false;
     int out_KP = 0, out_Wj = 0, out_ring = 0, out_mask_words = 0, out_tau_max = 0;
     size_t out_smem = 0;
     long long out_l0 = 0;
+    // overlap of the outlet sweep with the bulk bond kernel: walls below the first outlet plane,
+    // first local plane whose stencil touches an outlet plane (tile aligned), -1 = no overlap
+    long long n_wall_lo = 0;
+    int z_cut = -1;
+    bool solids_below_cut = true;
 
     // reductions
     double* d_red = nullptr;        // device scratch
@@ -134,7 +143,8 @@ struct pdgpu_ctx {
     int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled fast path
     int opt_ard_kernel = 1;
     int opt_graph = 1;
-    int opt_outlet_kernel = 1;      // 0 = level-list kernel, 1 = ring sweep (outlet.cu)
+    int opt_overlap = 1;            // run the outlet sweep on a side stream next to the bulk kernel
+    int opt_outlet_kernel = 2;      // 0 = level-list kernel, 1 = level-addressed ring, 2 = lattice-addressed ring
 
     // NCCL
     void* comm = nullptr;
@@ -258,11 +268,13 @@ int pd_enqueue_bc_inlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, -1 = not applicable
 int pd_outlet_setup(pdgpu_ctx* c);
-int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf);
+int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part = 0);   // part 0 all, 1 below the outlet planes, 2 in them
 int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC);
 int pd_enqueue_bc_solid(pdgpu_ctx* c, int buf);
-int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt);
+int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt, int zb = -1, int ze = -1);   // local plane range
 int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);
+int pd_enqueue_ard_prepass(pdgpu_ctx* c, int buf, int srcC, long long lo, long long hi);
+int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid);
 int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC);
 int pd_max_fluid_speed(pdgpu_ctx* c, double* vmax);
 void pd_invalidate_graphs(pdgpu_ctx* c);
@@ -276,3 +288,14 @@ int pd_comm_allreduce(pdgpu_ctx* c, double* d_buf, int n, int op);   // op 0 sum
         if (!(c)->fields_ready) PD_FAIL("fields not initialised (pdgpu_fields_init/upload)"); \
     } while (0)
 #define VXYZ(c, b) (c)->v[b][0], (c)->v[b][1], (c)->v[b][2]
+
+// enqueue on another stream for the lifetime of the object (the LAUNCH macro uses c->stream)
+struct StreamSwap {
+    pdgpu_ctx* c;
+    cudaStream_t saved;
+    StreamSwap(pdgpu_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { ctx->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+};
+inline bool pd_can_overlap(const pdgpu_ctx* c) {
+    return c->opt_overlap && c->z_cut > 0 && c->n_outlet > 0 && c->out_fast && c->opt_outlet_kernel > 0;
+}

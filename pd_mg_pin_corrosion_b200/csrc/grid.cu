@@ -366,6 +366,27 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
     CUDA_OK(cudaFree(d_counts));
     PD_TRY(build_outlet_schedule(c));
     PD_TRY(pd_outlet_setup(c));
+    // split point for overlapping the outlet sweep with the bulk bond kernels
+    c->z_cut = -1;
+    c->n_wall_lo = c->n_wall;
+    c->solids_below_cut = true;
+    if (c->n_outlet > 0 && c->out_fast) {
+        const int RZ = 4;                                  // tile::RZ
+        int zo = (int)(c->out_l0 / c->P);                  // first outlet plane (local)
+        int z_lo = c->R;
+        int zc = z_lo + ((zo - c->R - z_lo) / RZ) * RZ;
+        if (zo - c->R - z_lo > 0 && zc - z_lo >= 2 * c->R + RZ) {
+            c->z_cut = zc;
+            std::vector<int> w(c->n_wall);
+            if (c->n_wall) CUDA_OK(cudaMemcpy(w.data(), c->l_wall, sizeof(int) * c->n_wall, cudaMemcpyDeviceToHost));
+            c->n_wall_lo = std::lower_bound(w.begin(), w.end(), (int)c->out_l0) - w.begin();
+            if (c->n_solid) {
+                int last = 0;
+                CUDA_OK(cudaMemcpy(&last, c->l_solid + (c->n_solid - 1), sizeof(int), cudaMemcpyDeviceToHost));
+                c->solids_below_cut = (last / c->P) < (zc - c->R);
+            }
+        }
+    }
 
     // multi-GPU sanity: owned WALL mirrors must not live in ghost planes of another rank's
     // slab unless those are plain copies ("halo invariants").

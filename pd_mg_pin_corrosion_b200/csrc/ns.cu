@@ -95,22 +95,24 @@ k_ns_step_generic(Lat L, long long own_lo, long long own_n, const uint8_t* __res
     if (DIM == 3) vz_n[l] = vi2 + s * (-P.c_div * mc2 - P.c_div * mp2 + P.visc * mv2);
 }
 
-int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt);   // ns_tile.cu
+int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze);   // ns_tile.cu
 
-int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt) {
+int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze) {
     if (c->opt_ns_kernel >= 1 && c->full_rows && c->cfg.m_ratio == 3) {
-        int r = pd_enqueue_ns_step_fast(c, src, d_dt);
+        int r = pd_enqueue_ns_step_fast(c, src, d_dt, zb, ze);
         if (r >= 0) return r;   // <0: fast path not applicable -> generic
     }
     int dst = 1 - src;
-    long long own_n = c->own_hi - c->own_lo;
+    long long own_lo = c->own_lo, own_n = c->own_hi - c->own_lo;
+    if (zb >= 0) { own_lo = (long long)zb * c->P; own_n = (long long)(ze - zb) * c->P; }
+    if (own_n <= 0) return 0;
     Lat L = make_lat(c);
     NsParams P = ns_params(c);
     if (c->dim == 2)
-        LAUNCH(c, k_ns_step_generic<2>, nblocks(own_n, 128), 128, 0, L, c->own_lo, own_n, c->type, c->d_off, c->n_off,
+        LAUNCH(c, k_ns_step_generic<2>, nblocks(own_n, 128), 128, 0, L, own_lo, own_n, c->type, c->d_off, c->n_off,
                P, d_dt, c->rho[src], c->p[src], VXYZ(c, src), c->rho[dst], c->p[dst], VXYZ(c, dst));
     else
-        LAUNCH(c, k_ns_step_generic<3>, nblocks(own_n, 128), 128, 0, L, c->own_lo, own_n, c->type, c->d_off, c->n_off,
+        LAUNCH(c, k_ns_step_generic<3>, nblocks(own_n, 128), 128, 0, L, own_lo, own_n, c->type, c->d_off, c->n_off,
                P, d_dt, c->rho[src], c->p[src], VXYZ(c, src), c->rho[dst], c->p[dst], VXYZ(c, dst));
     return 0;
 }
@@ -268,6 +270,36 @@ extern "C" int pdgpu_ns_step(pdgpu_ctx* c, double dt) {
 // one iteration of solve_steady without the convergence block (src/pd_ns.cpp:196-205):
 // reads buffer `src`, leaves the new state (with wall mirror applied) in 1-src.
 static int enqueue_ns_body(pdgpu_ctx* c, int src) {
+    if (pd_can_overlap(c)) {
+        // The in-place outlet sweep is a long dependent chain on two SMs; only the top few
+        // planes depend on it.  Fork: side stream = outlet sweep, outlet-plane walls, top z-tiles;
+        // main stream = inlet, lower walls, solid, bulk z-tiles.  Join before the wall mirror of
+        // the new buffers.  Same arithmetic as the sequential order of src/pd_ns.cpp:196-205.
+        cudaStream_t main_s = c->stream, side = c->stream2;
+        const int z_hi = c->R + (c->a1 - c->a0);
+        CUDA_OK(cudaEventRecord(c->ev_a, main_s));
+        CUDA_OK(cudaStreamWaitEvent(side, c->ev_a, 0));
+        {
+            StreamSwap sw(c, side);
+            PD_TRY(pd_enqueue_bc_outlet(c, src, c->curC));
+            PD_TRY(pd_enqueue_bc_wall(c, src, 2));
+        }
+        PD_TRY(pd_enqueue_bc_inlet(c, src, c->curC));
+        PD_TRY(pd_enqueue_bc_wall(c, src, 1));
+        PD_TRY(pd_enqueue_bc_solid(c, src));
+        CUDA_OK(cudaEventRecord(c->ev_b, main_s));
+        PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt, c->R, c->z_cut));
+        CUDA_OK(cudaStreamWaitEvent(side, c->ev_b, 0));
+        {
+            StreamSwap sw(c, side);
+            PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt, c->z_cut, z_hi));
+        }
+        CUDA_OK(cudaEventRecord(c->ev_c, side));
+        CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_c, 0));
+        PD_TRY(pd_enqueue_bc_wall(c, 1 - src));
+        if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 0, 1 - src, c->curC));
+        return 0;
+    }
     PD_TRY(pd_enqueue_bc_inlet(c, src, c->curC));
     PD_TRY(pd_enqueue_bc_outlet(c, src, c->curC));
     PD_TRY(pd_enqueue_bc_wall(c, src));

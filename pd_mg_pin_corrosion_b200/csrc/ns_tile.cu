@@ -201,7 +201,7 @@ k_ns_tile(const __grid_constant__ NsTileParams q, const __grid_constant__ ColTab
 }  // namespace
 
 // returns -1 when the tiled kernel does not apply (caller uses the generic kernel)
-int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt) {
+int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze) {
     if (!c->full_rows) return -1;
     static ColTable T;   // rebuilt per call: 37 columns, context independent
     double sum_kappa = 0.0;
@@ -209,6 +209,8 @@ int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt) {
     PdConsts k = pd_consts(c->cfg, c->dim);
     NsTileParams q;
     q.g = make_geom(c);
+    if (zb >= 0) { q.g.z_lo = zb; q.g.z_hi = ze; }
+    if (q.g.z_hi <= q.g.z_lo) return 0;
     q.rho_f = c->cfg.rho_f; q.gamma = c->cfg.gamma_eos; q.B = k.B_eos;
     q.c_div = k.alpha * k.inv_VH; q.dens_diff = k.dens_diff_coeff; q.visc = c->cfg.mu_f * k.beta_lap;
     q.rho_lo = 0.5 * c->cfg.rho_f; q.rho_hi = 2.0 * c->cfg.rho_f;
@@ -222,7 +224,7 @@ int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt) {
         attr_done = true;
     }
     int dst = 1 - src;
-    dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((c->a1 - c->a0) + RZ - 1) / RZ);
+    dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + RZ - 1) / RZ);
     dim3 block(TX, TY, 1);
     k_ns_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->rho[src], c->p[src], c->v[src][0],
                                                  c->v[src][1], c->v[src][2], c->rho[dst], c->p[dst], c->v[dst][0],

@@ -183,6 +183,105 @@ k_outlet_sweep(OutletGeom g, const int4* __restrict__ early, const unsigned* __r
     }
 }
 
+// Variant with a lattice-addressed ring: slot(i,j,k') = (k'*RJ + (j mod RJ))*RI + (i mod RI).
+// Inside the active window of RI = 64 levels a plane row holds at most 64 consecutive i and
+// the window covers at most RJ = 64 rows (needs (maxd + Nx - 1)/B + 1 <= 64), so the mapping is
+// collision free and a neighbour's slot is affine in (di,dj,dk): the earlier half of the
+// stencil is walked as (dj,dk) rows with contiguous di ranges, ~6 instructions per bond.
+__global__ void __launch_bounds__(1024, 1)
+k_outlet_sweep_mod(OutletGeom g, int RJ, const int4* __restrict__ rows, int n_rows,
+                   const unsigned* __restrict__ mask_g, int mask_words, const double* __restrict__ base_v,
+                   const double* __restrict__ base_c, const int* __restrict__ cnt, double* vax, double* C,
+                   double U_in) {
+    extern __shared__ double smem[];
+    double* ring = smem;
+    const int RI = g.ring;
+    int4* s_rows = (int4*)(ring + (size_t)g.KP * RJ * RI);
+    unsigned* s_mask = (unsigned*)(s_rows + n_rows);
+    const bool is_vel = (blockIdx.x == 0);
+    const double* base = is_vel ? base_v : base_c;
+    double* out = is_vel ? vax : C;
+    for (int e = threadIdx.x; e < n_rows; e += blockDim.x) s_rows[e] = rows[e];
+    for (int w = threadIdx.x; w < mask_words; w += blockDim.x) s_mask[w] = mask_g[w];
+    __syncthreads();
+
+    constexpr int G = 4;
+    const int lane = threadIdx.x & (G - 1);
+    const int group = threadIdx.x / G;
+    const int NG = blockDim.x / G;
+    const int npairs = g.KP * g.Wj;
+    const int imask = RI - 1, jmask = RJ - 1;
+    constexpr int MAXP = 2;
+
+    double nb[MAXP];
+    int nc[MAXP];
+#pragma unroll
+    for (int s = 0; s < MAXP; ++s) {
+        nb[s] = 0.0; nc[s] = 0;
+        int p = group + s * NG, kp, j, i, jj;
+        if (p < npairs && level_node(g, 0, p, &kp, &j, &i, &jj)) {
+            long long d = (long long)kp * g.P + (long long)j * g.Nx + i;
+            nb[s] = base[d]; nc[s] = cnt[d];
+        }
+    }
+    for (int tau = 0; tau <= g.tau_max; ++tau) {
+        double cb[MAXP];
+        int cc[MAXP];
+#pragma unroll
+        for (int s = 0; s < MAXP; ++s) { cb[s] = nb[s]; cc[s] = nc[s]; }
+        if (tau < g.tau_max) {
+#pragma unroll
+            for (int s = 0; s < MAXP; ++s) {
+                int p = group + s * NG, kp, j, i, jj;
+                nb[s] = 0.0; nc[s] = 0;
+                if (p < npairs && level_node(g, tau + 1, p, &kp, &j, &i, &jj)) {
+                    long long d = (long long)kp * g.P + (long long)j * g.Nx + i;
+                    nb[s] = base[d]; nc[s] = cnt[d];
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < MAXP; ++s) {
+            int p = group + s * NG, kp = 0, j = 0, i = 0, jj = 0;
+            if (s > 0 && s * NG >= npairs) break;          // uniform: no second pass needed
+            bool valid = (p < npairs) && level_node(g, tau, p, &kp, &j, &i, &jj);
+            bool is_out = false;
+            long long d = 0;
+            if (valid) {
+                d = (long long)kp * g.P + (long long)j * g.Nx + i;
+                is_out = (s_mask[d >> 5] >> (d & 31)) & 1u;
+            }
+            double sum = 0.0;
+            if (is_out) {
+                for (int r = lane; r < n_rows; r += G) {
+                    const int4 row = s_rows[r];              // dj, dplane, di_lo, di_hi
+                    const int k2 = kp + row.y;
+                    if (k2 < 0) continue;                    // FLUID plane: in the pre-pass
+                    const int j2 = j + row.x;
+                    if ((unsigned)j2 >= (unsigned)g.Ny) continue;
+                    const int rb = (k2 * RJ + (j2 & jmask)) * RI;
+                    const int lo = max(i + row.z, 0), hi = min(i + row.w, g.Nx - 1);
+                    for (int i2 = lo; i2 <= hi; ++i2) sum += ring[rb + (i2 & imask)];
+                }
+            }
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            if (valid && lane == 0) {
+                double val = 0.0;
+                if (is_out) {
+                    double tot = cb[s] + sum;
+                    int n = cc[s];
+                    if (is_vel) val = n > 0 ? tot * (1.0 / n) : U_in;   // src/boundary.cpp:113-124
+                    else val = n > 0 ? tot / n : 0.0;                   // :129
+                    out[g.l0 + d] = val;
+                }
+                ring[(kp * RJ + (j & jmask)) * RI + (i & imask)] = val;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_outlet_mask(const uint8_t* __restrict__ type, long long l0, long long n, unsigned* __restrict__ mask) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w * 32 >= n) return;
@@ -199,7 +298,8 @@ __global__ void k_outlet_mask(const uint8_t* __restrict__ type, long long l0, lo
 // Build the static data of the fast sweep (called from pd_rebuild_tables).
 int pd_outlet_setup(pdgpu_ctx* c) {
     cudaFree(c->out_base_v); cudaFree(c->out_base_c); cudaFree(c->out_cnt); cudaFree(c->out_mask);
-    cudaFree(c->out_early);
+    cudaFree(c->out_early); cudaFree(c->out_rows);
+    c->out_rows = nullptr;
     c->out_base_v = c->out_base_c = nullptr; c->out_cnt = nullptr; c->out_mask = nullptr; c->out_early = nullptr;
     c->out_fast = false;
     if (c->n_outlet == 0) return 0;
@@ -226,6 +326,17 @@ int pd_outlet_setup(pdgpu_ctx* c) {
         if (!(dp < 0 || (dp == 0 && dj < 0) || (dp == 0 && dj == 0 && di < 0))) return 0;   // unexpected order
         early[o] = make_int4(di, dj, dp, di + B * dj + B2 * dp);
     }
+    // (dj,dplane) rows of the earlier half with their contiguous di range (k_outlet_sweep_mod)
+    std::vector<int4> rows;
+    for (int o = 0; o < n_early; ++o) {
+        const int4& e = early[o];
+        if (!rows.empty() && rows.back().x == e.y && rows.back().y == e.z && rows.back().w + 1 == e.x) rows.back().w = e.x;
+        else rows.push_back(make_int4(e.y, e.z, e.x, e.x));
+    }
+    int RJ = (Ny == 1) ? 1 : 64;
+    size_t smem_mod = sizeof(double) * (size_t)KP * RJ * ring + sizeof(int4) * rows.size() + sizeof(unsigned) * mask_words;
+    c->out_mod = (Ny == 1 || (maxd + Nx - 1) / B + 1 <= 64) && smem_mod <= 220 * 1024 && KP * Wj <= 2 * (1024 / 4);
+    c->out_RJ = RJ; c->out_n_rows = (int)rows.size(); c->out_smem_mod = smem_mod;
     c->out_KP = KP; c->out_Wj = Wj; c->out_ring = ring; c->out_smem = smem; c->out_mask_words = mask_words;
     c->out_l0 = al_min * c->P;
     c->out_tau_max = (Nx - 1) + B * (Ny - 1) + B2 * (KP - 1);
@@ -238,6 +349,10 @@ int pd_outlet_setup(pdgpu_ctx* c) {
     CUDA_OK(cudaMemset(c->out_base_c, 0, sizeof(double) * nslab));
     CUDA_OK(cudaMemset(c->out_cnt, 0, sizeof(int) * nslab));
     CUDA_OK(cudaMemcpy(c->out_early, early.data(), sizeof(int4) * n_early, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->out_rows, sizeof(int4) * rows.size()));
+    CUDA_OK(cudaMemcpy(c->out_rows, rows.data(), sizeof(int4) * rows.size(), cudaMemcpyHostToDevice));
+    if (c->out_mod)
+        CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep_mod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mod));
     k_outlet_mask<<<nblocks(mask_words, 256), 256, 0, c->stream>>>(c->type, c->out_l0, nslab, c->out_mask);
     CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -262,6 +377,10 @@ int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
         LAUNCH(c, k_outlet_prepass<3>, nblocks(c->n_outlet, 128), 128, 0, L, g, c->l_outlet, c->n_outlet, c->type,
                c->d_off, c->n_off, c->rho[buf], c->p[buf], VXYZ(c, buf), c->C[bufC], c->cfg.rho_f, c->out_base_v,
                c->out_base_c, c->out_cnt);
+    if (c->out_mod && c->opt_outlet_kernel >= 2)
+        LAUNCH(c, k_outlet_sweep_mod, 2, 1024, c->out_smem_mod, g, c->out_RJ, (const int4*)c->out_rows, c->out_n_rows,
+               c->out_mask, c->out_mask_words, c->out_base_v, c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
+    else
     LAUNCH(c, k_outlet_sweep, 2, 1024, c->out_smem, g, (const int4*)c->out_early, c->out_mask, c->out_mask_words,
            c->out_base_v, c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
     return 0;

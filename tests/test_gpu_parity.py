@@ -235,3 +235,38 @@ def test_errors_are_loud():
     ctx = C.c_void_p()
     assert L.load().pdgpu_create(C.byref(s), 2, 0, C.byref(ctx)) != 0
     assert b"use_implicit" in L.load().pdgpu_last_error()
+
+
+@pytest.mark.parametrize("case", ["3d_small", "3d_default"])
+def test_kernel_variants_agree(case):
+    """Every fast path (tiled bond kernels, ring-buffer outlet sweeps, side-stream overlap, CUDA
+    graphs) against the generic one-thread-per-node kernels and against the oracle."""
+    ref = H.make_ref(case)
+    iters, steps = (30, 10) if case == "3d_small" else (6, 3)
+    variants = [
+        dict(ns_kernel=0, ard_kernel=0, outlet_kernel=0, overlap=0, graph=0),   # all generic
+        dict(ns_kernel=1, ard_kernel=1, outlet_kernel=1, overlap=0, graph=0),
+        dict(ns_kernel=1, ard_kernel=1, outlet_kernel=2, overlap=0, graph=1),
+        dict(ns_kernel=1, ard_kernel=1, outlet_kernel=2, overlap=1, graph=0),
+        dict(ns_kernel=1, ard_kernel=1, outlet_kernel=2, overlap=1, graph=1),   # default
+        dict(ns_kernel=0, ard_kernel=0, outlet_kernel=2, overlap=1, graph=1),
+    ]
+    dt = ref.ns_compute_dt()
+    results = []
+    for opts in variants:
+        S, cfg, grid, fields = gpu_side(case, ref=ref, upload=False)
+        for k, v in opts.items():
+            grid.set_option(k, v)
+        ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
+        ns.init(grid, cfg); ard.init(grid, cfg)
+        ns.iterate(fields, grid, cfg, iters, dt)
+        dtc = ard.compute_dt(fields, grid, cfg)
+        ard.iterate(fields, grid, cfg, steps, dtc)
+        results.append({n: fields.get(n) for n in ("rho", "vel", "C")})
+        grid.close()
+    ref.ns_iterate(iters, dt)
+    ref.ard_iterate(steps, ref.ard_compute_dt())
+    for opts, res in zip(variants, results):
+        for n in ("rho", "vel", "C"):
+            assert H.rel_err(res[n], results[0][n]) <= 1e-13, (opts, n, "vs generic")
+            assert H.rel_err(res[n], ref.get(n)) <= TOL, (opts, n, "vs oracle")
