@@ -79,17 +79,17 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
     double* s_vmf = sm + SN;
     double* s_ds = sm + 2 * SN;
 
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * TX + tx;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = q.g.z_lo + blockIdx.z * RZ;
-    const int gx = x0 + tx, gy = y0 + ty;
+    const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+    const int tid = (tz * TY + ty) * TX + tx;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = q.g.z_lo + blockIdx.z * TZ;
+    const int gx = x0 + tx, gy = y0 + ty, zt = z0 + tz * RZ;   // first z-node of this thread
     const bool in_xy = gx < q.g.Nx && gy < q.g.Ny;
 
     bool fl[RZ];
     bool any = false;
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
-        const int lz = z0 + t;
+        const int lz = zt + t;
         fl[t] = false;
         if (in_xy && lz < q.g.z_hi) {
             const long long l = (long long)lz * q.g.P + (long long)gy * q.g.Nx + gx;
@@ -126,7 +126,7 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
     __syncthreads();
     if (!__any_sync(0xffffffffu, any)) return;
 
-    const int base = (ty + TR) * SX + (tx + TR);
+    const int base = (tz * RZ * SY + ty + TR) * SX + (tx + TR);   // node t at base + (t+TR)*SPLANE
     double Ci[RZ], vmi[RZ];
     ArdAcc a;
 #pragma unroll
@@ -151,7 +151,7 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
         if (!fl[t]) continue;
-        const long long l = (long long)(z0 + t) * q.g.P + (long long)gy * q.g.Nx + gx;
+        const long long l = (long long)(zt + t) * q.g.P + (long long)gy * q.g.Nx + gx;
         // diff and G were accumulated with kappa = dx*w2: e w1 = d kappa, w2 = kappa/dx
         const double adv = q.div_coeff * (vx[l] * a.gx[t] + vy[l] * a.gy[t] + vz[l] * a.gz[t]);
         const double cn = Ci[t] + dt * (q.beta * (a.diff[t] * q.inv_dx) - adv);   // src/pd_ard.cpp:184-189
@@ -204,8 +204,8 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
     }
     int dstC = 1 - srcC;
     if (q.g.z_hi > q.g.z_lo) {
-        dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + RZ - 1) / RZ);
-        dim3 block(TX, TY, 1);
+        dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + TZ - 1) / TZ);
+        dim3 block(TX, TY, NZT);
         k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->C[srcC], c->vmag, c->dsol, c->v[buf][0],
                                                       c->v[buf][1], c->v[buf][2], c->C[dstC]);
         c->launches++;

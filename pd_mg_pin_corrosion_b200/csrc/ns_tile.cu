@@ -1,19 +1,20 @@
 // ns_tile.cu -- tiled fast path of the PD-NS bond kernel (3D, m_ratio = 3, full FLUID rows).
 // Tile geometry, column walk and weight algebra: tile.cuh.
 //
-// Arithmetic per bond (12 FP64 ops + ~2.5 amortised): the reference's difference form
+// Arithmetic per bond (10 FP64 ops + ~2.5 amortised): the reference's difference form
 //     sum_j (f_j - f_i) e w        (src/pd_ns.cpp:115-157)
 // is evaluated as  sum_j f_j e w  for the odd (gradient/divergence) sums -- the f_i part
 // multiplies sum_j e_j w_j, which is exactly zero for the full symmetric stencil -- and as
 // sum_j f_j w2 - f_i * sum_j w2 for the two Laplacians.  One explicit step changes a state
 // value by <= ~1e-3 relative, so this reassociation moves results by O(1e-16) relative
 // (DESIGN.md "numerics"); parity against the reference is asserted at 1e-12.
-//   g      = rho_j (v_j . d) kappa            (mass flux through the bond)
-//   mc    += g                                 mass convection
-//   md    += rho_j kappa                       density Laplacian (x 1/dx at the end)
-//   a_d   += v_jd g + p_j d_d kappa            momentum convection + pressure gradient
-//   s_d   += v_jd kappa                        velocity Laplacian (x 1/dx at the end)
-// with d = (di,dj,dk): the di/dj parts of the pressure term are factored out per column.
+//   g      = rho_j (v_j . d) kappa             mass flux through the bond
+//   mc    += g                                  mass convection
+//   md    += rho_j kappa                        density Laplacian (x 1/dx at the end)
+//   h      = (mu beta/dx) kappa - (alpha/V_H) g momentum convection and viscous Laplacian share
+//   a_d   += v_jd h                             one weight per bond
+//   P_d   += p_j d_d kappa                      pressure gradient (di/dj parts factored out per column)
+// with d = (di,dj,dk).
 #include <algorithm>
 
 #include "tile.cuh"
@@ -49,17 +50,20 @@ __device__ __forceinline__ double eos_tile(double rho, const NsTileParams& q) {
 }
 
 struct NsAcc {
-    double mc[RZ], md[RZ], ax[RZ], ay[RZ], az[RZ], sx[RZ], sy[RZ], sz[RZ];
+    double mc[RZ], md[RZ], ax[RZ], ay[RZ], az[RZ], px[RZ], py[RZ], pz[RZ];
 };
 
 template <int H>
 __device__ __forceinline__ void ns_column(const double* __restrict__ s_rho, const double* __restrict__ s_vx,
                                           const double* __restrict__ s_vy, const double* __restrict__ s_vz,
                                           const double* __restrict__ s_p, int cb, double dI, double dJ,
-                                          const double (&kap)[4], NsAcc& a) {
-    double kz[4];
+                                          const double (&kap)[4], double c_div, double visc_dx, NsAcc& a) {
+    double kz[4], nk[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) kz[k] = (double)k * kap[k];
+    for (int k = 0; k < 4; ++k) {
+        kz[k] = (double)k * kap[k];
+        nk[k] = visc_dx * kap[k];
+    }
     double colp[RZ];
 #pragma unroll
     for (int t = 0; t < RZ; ++t) colp[t] = 0.0;
@@ -80,22 +84,20 @@ __device__ __forceinline__ void ns_column(const double* __restrict__ s_rho, cons
                 if (dk < 0) g = fma(-mz, kz[ak], g);
                 a.mc[t] += g;
                 a.md[t] = fma(rj, k, a.md[t]);
-                a.ax[t] = fma(ux, g, a.ax[t]);
-                a.ay[t] = fma(uy, g, a.ay[t]);
-                a.az[t] = fma(uz, g, a.az[t]);
+                const double h = fma(-c_div, g, nk[ak]);
+                a.ax[t] = fma(ux, h, a.ax[t]);
+                a.ay[t] = fma(uy, h, a.ay[t]);
+                a.az[t] = fma(uz, h, a.az[t]);
                 colp[t] = fma(pj, k, colp[t]);
-                if (dk > 0) a.az[t] = fma(pj, kz[ak], a.az[t]);
-                if (dk < 0) a.az[t] = fma(-pj, kz[ak], a.az[t]);
-                a.sx[t] = fma(ux, k, a.sx[t]);
-                a.sy[t] = fma(uy, k, a.sy[t]);
-                a.sz[t] = fma(uz, k, a.sz[t]);
+                if (dk > 0) a.pz[t] = fma(pj, kz[ak], a.pz[t]);
+                if (dk < 0) a.pz[t] = fma(-pj, kz[ak], a.pz[t]);
             }
         }
     }
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
-        a.ax[t] = fma(dI, colp[t], a.ax[t]);
-        a.ay[t] = fma(dJ, colp[t], a.ay[t]);
+        a.px[t] = fma(dI, colp[t], a.px[t]);
+        a.py[t] = fma(dJ, colp[t], a.py[t]);
     }
 }
 
@@ -112,17 +114,17 @@ k_ns_tile(const __grid_constant__ NsTileParams q, const __grid_constant__ ColTab
     double* s_vz = sm + 3 * SN;
     double* s_p = sm + 4 * SN;
 
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int tid = ty * TX + tx;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = q.g.z_lo + blockIdx.z * RZ;
-    const int gx = x0 + tx, gy = y0 + ty;
+    const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+    const int tid = (tz * TY + ty) * TX + tx;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = q.g.z_lo + blockIdx.z * TZ;
+    const int gx = x0 + tx, gy = y0 + ty, zt = z0 + tz * RZ;   // first z-node of this thread
     const bool in_xy = gx < q.g.Nx && gy < q.g.Ny;
 
     bool fl[RZ];
     bool any = false;
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
-        const int lz = z0 + t;
+        const int lz = zt + t;
         fl[t] = false;
         if (in_xy && lz < q.g.z_hi) {
             const long long l = (long long)lz * q.g.P + (long long)gy * q.g.Nx + gx;
@@ -166,25 +168,27 @@ k_ns_tile(const __grid_constant__ NsTileParams q, const __grid_constant__ ColTab
     NsAcc a;
 #pragma unroll
     for (int t = 0; t < RZ; ++t)
-        a.mc[t] = a.md[t] = a.ax[t] = a.ay[t] = a.az[t] = a.sx[t] = a.sy[t] = a.sz[t] = 0.0;
-    const int base = (ty + TR) * SX + (tx + TR);
+        a.mc[t] = a.md[t] = a.ax[t] = a.ay[t] = a.az[t] = a.px[t] = a.py[t] = a.pz[t] = 0.0;
+    const int base = (tz * RZ * SY + ty + TR) * SX + (tx + TR);   // node t at base + (t+TR)*SPLANE
+    const double visc_dx = q.visc * q.inv_dx;
 #pragma unroll 1
     for (int c = 0; c < NCOL; ++c) {
         const int cb = base + T.off[c];
         const double dI = T.di[c], dJ = T.dj[c];
         const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
         const int H = T.h[c];
-        if (H == 3) ns_column<3>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, a);
-        else if (H == 2) ns_column<2>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, a);
-        else ns_column<1>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, a);
+        if (H == 3) ns_column<3>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, q.c_div, visc_dx, a);
+        else if (H == 2) ns_column<2>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, q.c_div, visc_dx, a);
+        else ns_column<1>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, q.c_div, visc_dx, a);
     }
 
     const double dt = *d_dt;
+    const double vW = q.visc * q.W2;
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
         if (!fl[t]) continue;
         const int si = base + (t + TR) * SPLANE;
-        const long long l = (long long)(z0 + t) * q.g.P + (long long)gy * q.g.Nx + gx;
+        const long long l = (long long)(zt + t) * q.g.P + (long long)gy * q.g.Nx + gx;
         const double rho_i = s_rho[si], vi0 = s_vx[si], vi1 = s_vy[si], vi2 = s_vz[si];
         const double mass_diff = a.md[t] * q.inv_dx - rho_i * q.W2;
         double rn = rho_i + dt * (-q.c_div * a.mc[t] + q.dens_diff * mass_diff);   // src/pd_ns.cpp:160-168
@@ -192,9 +196,9 @@ k_ns_tile(const __grid_constant__ NsTileParams q, const __grid_constant__ ColTab
         rho_n[l] = rn;
         pr_n[l] = eos_tile(rn, q);
         const double s = dt / rho_i;                                                // :171-178
-        vx_n[l] = vi0 + s * (-q.c_div * a.ax[t] + q.visc * (a.sx[t] * q.inv_dx - vi0 * q.W2));
-        vy_n[l] = vi1 + s * (-q.c_div * a.ay[t] + q.visc * (a.sy[t] * q.inv_dx - vi1 * q.W2));
-        vz_n[l] = vi2 + s * (-q.c_div * a.az[t] + q.visc * (a.sz[t] * q.inv_dx - vi2 * q.W2));
+        vx_n[l] = vi0 + s * (a.ax[t] - q.c_div * a.px[t] - vW * vi0);
+        vy_n[l] = vi1 + s * (a.ay[t] - q.c_div * a.py[t] - vW * vi1);
+        vz_n[l] = vi2 + s * (a.az[t] - q.c_div * a.pz[t] - vW * vi2);
     }
 }
 
@@ -224,8 +228,8 @@ int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt, int zb, i
         attr_done = true;
     }
     int dst = 1 - src;
-    dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + RZ - 1) / RZ);
-    dim3 block(TX, TY, 1);
+    dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + TZ - 1) / TZ);
+    dim3 block(TX, TY, NZT);
     k_ns_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->rho[src], c->p[src], c->v[src][0],
                                                  c->v[src][1], c->v[src][2], c->rho[dst], c->p[dst], c->v[dst][0],
                                                  c->v[dst][1], c->v[dst][2]);

@@ -1,12 +1,14 @@
 // tile.cuh -- shared geometry of the tiled bond kernels (ns_tile.cu, ard_tile.cu):
 // 3D, m_ratio = 3 (reach 3), full FLUID rows.
 //
-// A CTA stages a haloed (32+6) x (8+6) x (4+6) block in shared memory; thread (tx,ty) owns
-// the 4 nodes (x0+tx, y0+ty, z0..z0+3).  The horizon sphere (di^2+dj^2+dk^2 <= 12, 178
+// A CTA (32 x 8 x 2 threads) stages a haloed (32+6) x (8+6) x (4+6) block in shared memory;
+// thread (tx,ty,tz) owns the 2 nodes (x0+tx, y0+ty, z0+2tz..z0+2tz+1): 16 warps per SM hide the
+// FP64 and shared-memory latencies (8 warps with 4 nodes per thread reached 48 % FP64-pipe
+// utilisation, profiles/r1_notes.md).  The horizon sphere (di^2+dj^2+dk^2 <= 12, 178
 // offsets) is walked as 37 (di,dj) COLUMNS in a runtime loop; inside a column the window
 // slides along z, so a staged neighbour value is read from shared memory once and used for
-// up to 4 bonds.  Only the half-height H of the column (1, 2 or 3) is a compile-time
-// parameter: three unrolled bodies of 12/20/28 bonds keep the instruction footprint at
+// up to 2 bonds.  Only the half-height H of the column (1, 2 or 3) is a compile-time
+// parameter: three unrolled bodies of 6/10/14 bonds keep the instruction footprint at
 // ~20 KB (a fully unrolled 712-bond body is 230 KB and stalls on instruction fetch: ncu
 // "no_instruction" 3.2 per issue, profiles/r1_notes.md).
 //
@@ -19,10 +21,13 @@
 namespace tile {
 
 constexpr int TR = 3;
-constexpr int TX = 32, TY = 8, RZ = 4;
-constexpr int SX = TX + 2 * TR, SY = TY + 2 * TR, SZ = RZ + 2 * TR;
+constexpr int TX = 32, TY = 8;             // threads in x, y
+constexpr int RZ = 2;                      // z-nodes per thread (sliding window length)
+constexpr int NZT = 2;                     // thread layers in z
+constexpr int TZ = RZ * NZT;               // z-nodes per tile
+constexpr int SX = TX + 2 * TR, SY = TY + 2 * TR, SZ = TZ + 2 * TR;
 constexpr int SPLANE = SX * SY, SN = SPLANE * SZ;
-constexpr int NTHREADS = TX * TY;
+constexpr int NTHREADS = TX * TY * NZT;
 constexpr int NCOL = 37;
 
 struct ColTable {
