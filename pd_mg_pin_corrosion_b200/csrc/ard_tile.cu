@@ -85,45 +85,35 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
     const int gx = x0 + tx, gy = y0 + ty, zt = z0 + tz * RZ;   // first z-node of this thread
     const bool in_xy = gx < q.g.Nx && gy < q.g.Ny;
 
+    uint8_t nty[RZ];
+#pragma unroll
+    for (int t = 0; t < RZ; ++t) {
+        const int lz = zt + t;
+        nty[t] = 255;
+        if (in_xy && lz < q.g.z_hi) nty[t] = type[(long long)lz * q.g.P + (long long)gy * q.g.Nx + gx];
+    }
+    // asynchronous staging (see ns_tile.cu); outside the box: C = 0, vmf = 0 (never used), dsol = 0
+    for (int idx = tid; idx < SN; idx += NTHREADS) {
+        const long long l = staged_index(q.g, idx, x0, y0, z0);
+        const bool ok = l >= 0;
+        const long long ls = ok ? l : 0;
+        cp_async8(s_C + idx, C + ls, ok);
+        cp_async8(s_vmf + idx, vmf_g + ls, ok);
+        cp_async8(s_ds + idx, dsol_g + ls, ok);
+    }
     bool fl[RZ];
     bool any = false;
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
-        const int lz = zt + t;
-        fl[t] = false;
-        if (in_xy && lz < q.g.z_hi) {
-            const long long l = (long long)lz * q.g.P + (long long)gy * q.g.Nx + gx;
-            const uint8_t ty_ = type[l];
-            if (ty_ == PDGPU_FLUID) {
-                fl[t] = true;
-                any = true;
-            } else if (ty_ != PDGPU_SOLID_MG) {
-                C_n[l] = C[l];   // src/pd_ard.cpp:86-89 (SOLID_MG rows: k_ard_solid_rows)
-            }
+        fl[t] = (nty[t] == PDGPU_FLUID);
+        any = any || fl[t];
+        if (nty[t] != 255 && !fl[t] && nty[t] != PDGPU_SOLID_MG) {
+            const long long l = (long long)(zt + t) * q.g.P + (long long)gy * q.g.Nx + gx;
+            C_n[l] = C[l];   // src/pd_ard.cpp:86-89 (SOLID_MG rows: k_ard_solid_rows)
         }
     }
+    cp_async_wait_all();
     if (!__syncthreads_or(any)) return;
-
-    for (int i0 = tid; i0 < SN; i0 += 4 * NTHREADS) {
-        long long l[4];
-        double cc[4], vm[4], ds[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = i0 + u * NTHREADS;
-            l[u] = idx < SN ? staged_index(q.g, idx, x0, y0, z0) : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            cc[u] = 0.0; vm[u] = -1.0; ds[u] = 0.0;
-            if (l[u] >= 0) { cc[u] = __ldg(C + l[u]); vm[u] = __ldg(vmf_g + l[u]); ds[u] = __ldg(dsol_g + l[u]); }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = i0 + u * NTHREADS;
-            if (idx < SN) { s_C[idx] = cc[u]; s_vmf[idx] = vm[u]; s_ds[idx] = ds[u]; }
-        }
-    }
-    __syncthreads();
     if (!__any_sync(0xffffffffu, any)) return;
 
     const int base = (tz * RZ * SY + ty + TR) * SX + (tx + TR);   // node t at base + (t+TR)*SPLANE

@@ -120,49 +120,39 @@ k_ns_tile(const __grid_constant__ NsTileParams q, const __grid_constant__ ColTab
     const int gx = x0 + tx, gy = y0 + ty, zt = z0 + tz * RZ;   // first z-node of this thread
     const bool in_xy = gx < q.g.Nx && gy < q.g.Ny;
 
+    // node types of this thread's nodes (loads issued first, consumed after the staging copies)
+    uint8_t nty[RZ];
+#pragma unroll
+    for (int t = 0; t < RZ; ++t) {
+        const int lz = zt + t;
+        nty[t] = 255;
+        if (in_xy && lz < q.g.z_hi) nty[t] = type[(long long)lz * q.g.P + (long long)gy * q.g.Nx + gx];
+    }
+    // stage the haloed block with asynchronous copies; outside the box the values are never
+    // used by a FLUID row (full rows) -> zero fill
+    for (int idx = tid; idx < SN; idx += NTHREADS) {
+        const long long l = staged_index(q.g, idx, x0, y0, z0);
+        const bool ok = l >= 0;
+        const long long ls = ok ? l : 0;
+        cp_async8(s_rho + idx, rho + ls, ok);
+        cp_async8(s_p + idx, pr + ls, ok);
+        cp_async8(s_vx + idx, vx + ls, ok);
+        cp_async8(s_vy + idx, vy + ls, ok);
+        cp_async8(s_vz + idx, vz + ls, ok);
+    }
     bool fl[RZ];
     bool any = false;
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
-        const int lz = zt + t;
-        fl[t] = false;
-        if (in_xy && lz < q.g.z_hi) {
-            const long long l = (long long)lz * q.g.P + (long long)gy * q.g.Nx + gx;
-            if (type[l] == PDGPU_FLUID) {
-                fl[t] = true;
-                any = true;
-            } else {   // copy-through (src/pd_ns.cpp:93-97)
-                rho_n[l] = rho[l]; pr_n[l] = pr[l]; vx_n[l] = vx[l]; vy_n[l] = vy[l]; vz_n[l] = vz[l];
-            }
+        fl[t] = (nty[t] == PDGPU_FLUID);
+        any = any || fl[t];
+        if (nty[t] != 255 && !fl[t]) {   // copy-through (src/pd_ns.cpp:93-97)
+            const long long l = (long long)(zt + t) * q.g.P + (long long)gy * q.g.Nx + gx;
+            rho_n[l] = rho[l]; pr_n[l] = pr[l]; vx_n[l] = vx[l]; vy_n[l] = vy[l]; vz_n[l] = vz[l];
         }
     }
-    if (!__syncthreads_or(any)) return;   // tile without FLUID nodes
-
-    // stage the haloed block (4 elements x 5 fields in flight per thread); outside the box the
-    // values are never used by a FLUID row (full rows) -> 0
-    for (int i0 = tid; i0 < SN; i0 += 4 * NTHREADS) {
-        long long l[4];
-        double r[4], pp[4], a[4], b[4], c[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = i0 + u * NTHREADS;
-            l[u] = idx < SN ? staged_index(q.g, idx, x0, y0, z0) : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            r[u] = pp[u] = a[u] = b[u] = c[u] = 0.0;
-            if (l[u] >= 0) {
-                r[u] = __ldg(rho + l[u]); pp[u] = __ldg(pr + l[u]);
-                a[u] = __ldg(vx + l[u]); b[u] = __ldg(vy + l[u]); c[u] = __ldg(vz + l[u]);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = i0 + u * NTHREADS;
-            if (idx < SN) { s_rho[idx] = r[u]; s_p[idx] = pp[u]; s_vx[idx] = a[u]; s_vy[idx] = b[u]; s_vz[idx] = c[u]; }
-        }
-    }
-    __syncthreads();
+    cp_async_wait_all();
+    if (!__syncthreads_or(any)) return;          // tile without FLUID nodes
     if (!__any_sync(0xffffffffu, any)) return;   // warp without FLUID nodes
 
     NsAcc a;

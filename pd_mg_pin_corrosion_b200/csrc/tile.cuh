@@ -87,6 +87,19 @@ inline TileGeom make_geom(const pdgpu_ctx* c) {
 }
 
 #ifdef __CUDACC__
+// Asynchronous global -> shared copy of one double (LDGSTS); src_bytes = 0 zero-fills the
+// destination (elements outside the box). No registers are held while the copy is in flight,
+// so a thread keeps all of its ~52 staging copies outstanding at once.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int src_bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
 // local index of staged element idx of the block at (x0,y0,z0), or -1 outside the box
 __device__ __forceinline__ long long staged_index(const TileGeom& g, int idx, int x0, int y0, int z0) {
     const int sz = idx / SPLANE;
