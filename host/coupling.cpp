@@ -1,0 +1,128 @@
+// host/coupling.cpp -- see coupling.h. Control flow follows src/coupling.cpp:82-302 (explicit
+// branch); every solver call is one C-ABI call into libpdgpu.so, and the corrosion steps
+// between two output points run device resident (pdgpu_ard_iterate) instead of one host call
+// per step. VTI/PVD output (src/vtk_writer.cpp) is host IO and out of scope.
+#include "coupling.h"
+
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+
+#define PD(call)                                                                  \
+    do {                                                                          \
+        if ((call) != 0) {                                                        \
+            std::fprintf(stderr, "libpdgpu: %s failed: %s\n", #call, pdgpu_last_error()); \
+            std::exit(2);                                                         \
+        }                                                                         \
+    } while (0)
+
+// ordered host sum over the initially solid nodes: (1 - sum/n) cancels catastrophically
+// (SURVEY.md 7.2-4), so the values are gathered and added in index order like
+// src/coupling.cpp:32-38.
+double CoupledSolver::solid_C_sum(pdgpu_ctx* ctx) {
+    std::vector<double> vals(initial_solid_indices_.size());
+    PD(pdgpu_gather(ctx, PDGPU_F_C, initial_solid_indices_.data(), (long long)vals.size(), vals.data()));
+    double s = 0.0;
+    for (double v : vals) s += v;
+    return s;
+}
+
+void CoupledSolver::write_diagnostics(pdgpu_ctx* ctx, double t_corr, const HostConfig& cfg) {   // :20-68
+    PdDiag d;
+    PD(pdgpu_diag(ctx, &d));
+    double n0 = (double)initial_solid_indices_.size();
+    double loss = (1.0 - solid_C_sum(ctx) / (n0 + 1e-30)) * 100.0;
+    if (loss < 0.0) loss = 0.0;
+    std::printf("  t=%.1f s (%.2f h)  pin_mass_loss=%.2f%%  solid=%lld  v_max=%.3e  C_max_fluid=%.4f\n", t_corr,
+                t_corr / 3600.0, loss, d.solid_count, d.v_max, d.C_max_fluid);
+    std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::app);
+    csv << std::scientific << std::setprecision(6) << t_corr << "," << t_corr / 3600.0 << "," << loss << ","
+        << d.solid_count << "," << d.v_max << "," << d.C_max_fluid << "\n";
+    std::ofstream ml(cfg.output_dir + "/mass_loss.csv", std::ios::app);
+    ml << std::fixed << std::setprecision(6) << t_corr / 3600.0 << "," << loss << "\n";
+}
+
+double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, bool verbose) {
+    mkdir(cfg.output_dir.c_str(), 0755);
+    {
+        std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::trunc);
+        csv << "time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n";
+        std::ofstream ml(cfg.output_dir + "/mass_loss.csv", std::ios::trunc);
+        ml << "time_h,pin_mass_loss_pct\n";
+    }
+    initial_solid_indices_.clear();
+    for (long long i = 0; i < st.N; ++i)
+        if (st.node_type[i] == PDGPU_SOLID_MG) initial_solid_indices_.push_back((int)i);
+    const double n0 = (double)initial_solid_indices_.size();
+    std::printf("Initial solid nodes: %zu\nUsing EXPLICIT ARD solver\n", initial_solid_indices_.size());
+
+    double t_corr = 0.0;
+    int cycle = 0;
+    bool need_flow_solve = true;
+    dissolved_since_flow_ = 0;
+    std::vector<int> dissolved(std::max<size_t>(initial_solid_indices_.size(), 1));
+    while (t_corr < cfg.T_final) {
+        ++cycle;
+        std::printf("\n=== Coupling cycle %d, t=%.1f s (%.2f h) ===\n", cycle, t_corr, t_corr / 3600.0);
+        if (need_flow_solve) {   // phase 1 :136-151
+            std::printf("  Flow re-solve triggered (%d nodes dissolved since last flow solve)\n", dissolved_since_flow_);
+            PdSteadyResult r;
+            PD(pdgpu_ns_solve_steady(ctx, &r, verbose ? 1 : 0));
+            dissolved_since_flow_ = 0;
+            need_flow_solve = false;
+        } else {
+            std::printf("  Skipping flow solve (no dissolution since last flow solve)\n");
+        }
+        // phase 2, explicit :217-253
+        double vol_loss = 1.0 - solid_C_sum(ctx) / (n0 + 1e-30);
+        if (vol_loss < 0.0) vol_loss = 0.0;
+        PD(pdgpu_ard_set_volume_loss(ctx, vol_loss));
+        double dt_corr = 0.0;
+        PD(pdgpu_ard_compute_dt(ctx, &dt_corr));
+        std::printf("  Corrosion dt = %.4e s\n", dt_corr);
+        int step = 0;
+        const int n_steps = cfg.corrosion_steps_per_check, every = cfg.output_every_corr;
+        while (step < n_steps) {
+            // device-resident run up to the next output point; the reference leaves the cycle
+            // as soon as t_corr >= T_final (:251), so count the steps on the host first
+            int chunk = std::min(n_steps - step, every - step % every), done = 0;
+            double t_probe = t_corr;
+            while (done < chunk) {
+                t_probe += dt_corr;
+                ++done;
+                if (t_probe >= cfg.T_final) break;
+            }
+            PD(pdgpu_ard_iterate(ctx, done, dt_corr));
+            for (int s = 0; s < done; ++s) t_corr += dt_corr;   // same additions as the reference
+            step += done;
+            if (step % every == 0) write_diagnostics(ctx, t_corr, cfg);
+            if (t_corr >= cfg.T_final) break;
+        }
+        // phase 3 :255-290
+        int n_dissolved = 0;
+        PD(pdgpu_phase_change(ctx, &n_dissolved, dissolved.data(), (int)dissolved.size()));
+        total_dissolved_ += n_dissolved;
+        dissolved_since_flow_ += n_dissolved;
+        if (n_dissolved > 0) {
+            std::printf("  Phase change: %d nodes dissolved (total: %d, since flow: %d)\n", n_dissolved,
+                        total_dissolved_, dissolved_since_flow_);
+            for (int t = 0; t < n_dissolved; ++t) {   // host mirrors used for output only
+                st.node_type[dissolved[t]] = PDGPU_FLUID;
+                st.D_map[dissolved[t]] = cfg.D_liquid;
+            }
+            need_flow_solve = true;   // neighbour tables were rebuilt inside pdgpu_phase_change
+        } else {
+            std::printf("  No phase changes this cycle\n");
+        }
+        PdDiag d;
+        PD(pdgpu_diag(ctx, &d));
+        if (d.solid_count == 0) {
+            std::printf("\n=== All solid nodes dissolved at t=%.1f s (%.2f h) ===\n", t_corr, t_corr / 3600.0);
+            break;
+        }
+    }
+    std::printf("\n=== Simulation complete ===\n  Final time: %.1f s (%.2f h)\n", t_corr, t_corr / 3600.0);
+    return t_corr;
+}

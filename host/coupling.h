@@ -1,0 +1,33 @@
+// host/coupling.h -- host driver of the explicit coupling loop over libpdgpu.so: same phases,
+// triggers and CSV output as the reference's CoupledSolver::run (src/coupling.cpp:82-302,
+// explicit branch :217-253), with the solvers living on the device.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "config.h"
+#include "grains.h"
+
+struct pdgpu_ctx;
+
+// Host-side Grid/Fields of the driver: what the reference keeps in std::vectors and the GPU
+// path still needs on the host (types for the solid list, D_map / grain_id for output).
+struct HostState {
+    int dim = 2, Nx = 0, Ny = 0, Nz = 0;
+    long long N = 0;
+    std::vector<uint8_t> node_type;
+    std::vector<double> D_map;
+    std::vector<int> grain_id;
+};
+
+class CoupledSolver {
+public:
+    // returns the final corrosion time
+    double run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, bool verbose = true);
+
+private:
+    std::vector<int> initial_solid_indices_;
+    int total_dissolved_ = 0, dissolved_since_flow_ = 0;
+    double solid_C_sum(pdgpu_ctx* ctx);
+    void write_diagnostics(pdgpu_ctx* ctx, double t_corr, const HostConfig& cfg);
+};

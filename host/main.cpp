@@ -1,0 +1,100 @@
+// host/main.cpp -- pd_corrosion_gpu: the reference's main() (src/main.cpp:129-177) over
+// libpdgpu.so. The dimension is a run-time argument instead of the PD_DIM compile-time switch.
+//
+//   pd_corrosion_gpu [config/params.cfg] [--dim 2|3] [--device N] [--dump fields.bin]
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <string>
+
+#include "config.h"
+#include "coupling.h"
+#include "grains.h"
+
+#define PD(call)                                                                  \
+    do {                                                                          \
+        if ((call) != 0) {                                                        \
+            std::fprintf(stderr, "libpdgpu: %s failed: %s\n", #call, pdgpu_last_error()); \
+            return 2;                                                             \
+        }                                                                         \
+    } while (0)
+
+int main(int argc, char** argv) {
+    std::setvbuf(stdout, nullptr, _IONBF, 0);
+    std::string cfg_path = "configs/params.cfg", dump;
+    int dim = 2, device = 0;
+    for (int a = 1; a < argc; ++a) {
+        if (!std::strcmp(argv[a], "--dim") && a + 1 < argc) dim = std::atoi(argv[++a]);
+        else if (!std::strcmp(argv[a], "--device") && a + 1 < argc) device = std::atoi(argv[++a]);
+        else if (!std::strcmp(argv[a], "--dump") && a + 1 < argc) dump = argv[++a];
+        else cfg_path = argv[a];
+    }
+    std::printf("=== Peridynamic Mg-Pin Corrosion Simulation (B200 path) ===\n  Dimension: %dD\n\n", dim);
+    auto t0 = std::chrono::steady_clock::now();
+    HostConfig cfg;
+    cfg.load(cfg_path);
+    cfg.print(dim);
+    if (cfg.use_implicit || cfg.use_amr) {
+        std::fprintf(stderr, "use_implicit = 1 / use_amr = 1 are out of scope of the GPU path (set use_implicit = 0)\n");
+        return 1;
+    }
+    PdConfig pod = cfg.to_pod();
+    pdgpu_ctx* ctx = nullptr;
+    PD(pdgpu_create(&pod, dim, device, &ctx));
+    std::printf("Building grid...\n");
+    PD(pdgpu_grid_build(ctx));
+    PdGridInfo gi;
+    PD(pdgpu_grid_info(ctx, &gi));
+    std::printf("Grid: Nx=%d Ny=%d Nz=%d  N_total=%lld\n", gi.Nx, gi.Ny, gi.Nz, gi.N_total);
+    std::printf("Node types: FLUID=%lld SOLID_MG=%lld WALL=%lld INLET=%lld OUTLET=%lld OUTSIDE=%lld\n", gi.counts[0],
+                gi.counts[1], gi.counts[2], gi.counts[3], gi.counts[4], gi.counts[5]);
+    std::printf("Neighbor stencil size: %d   bond-updates per NS / ARD step: %lld / %lld\n", gi.n_off, gi.ns_bonds,
+                gi.ard_bonds);
+    HostState st;
+    st.dim = dim; st.Nx = gi.Nx; st.Ny = gi.Ny; st.Nz = gi.Nz; st.N = gi.N_total;
+    st.node_type.resize(st.N);
+    PD(pdgpu_fields_download(ctx, PDGPU_F_NODE_TYPE, st.node_type.data()));
+
+    std::printf("Generating grain structure...\n");
+    GrainParams gp;
+    gp.grain_size_mean = cfg.grain_size_mean; gp.precip_fraction = cfg.precip_fraction;
+    gp.gb_width_cells = cfg.gb_width_cells; gp.precip_cluster_cells = cfg.precip_cluster_cells;
+    GrainStructure grains;
+    grains.generate(pod, gp, dim, st.node_type.data());
+    std::printf("Grain generation: %d grains\n", grains.n_grains);
+    st.grain_id = grains.grain_id;
+
+    std::printf("Initializing fields...\n");
+    PD(pdgpu_fields_init(ctx, grains.is_grain_boundary.data(), grains.is_precipitate.data()));
+    st.D_map.assign(st.N, 0.0);   // host-only output field (src/main.cpp:19-112)
+    for (long long i = 0; i < st.N; ++i) {
+        uint8_t t = st.node_type[i];
+        if (t == PDGPU_FLUID || t == PDGPU_INLET || t == PDGPU_OUTLET) st.D_map[i] = cfg.D_liquid;
+        else if (t == PDGPU_SOLID_MG)
+            st.D_map[i] = grains.is_grain_boundary[i] ? cfg.D_gb : (grains.is_precipitate[i] ? cfg.D_precip : cfg.D_grain);
+    }
+    std::printf("  [Timer] initialization: %.3f s\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+
+    CoupledSolver solver;
+    auto t1 = std::chrono::steady_clock::now();
+    solver.run(ctx, st, cfg);
+    std::printf("  [Timer] total_simulation: %.3f s\n",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count());
+
+    if (!dump.empty()) {   // raw binary state: N, dim, then rho, vel[N][dim], C (FP64)
+        std::vector<double> rho(st.N), vel((size_t)st.N * dim), C(st.N);
+        PD(pdgpu_fields_download(ctx, PDGPU_F_RHO, rho.data()));
+        PD(pdgpu_fields_download(ctx, PDGPU_F_VEL, vel.data()));
+        PD(pdgpu_fields_download(ctx, PDGPU_F_C, C.data()));
+        std::ofstream f(dump, std::ios::binary);
+        long long hdr[2] = {st.N, dim};
+        f.write((const char*)hdr, sizeof(hdr));
+        f.write((const char*)rho.data(), sizeof(double) * rho.size());
+        f.write((const char*)vel.data(), sizeof(double) * vel.size());
+        f.write((const char*)C.data(), sizeof(double) * C.size());
+    }
+    PD(pdgpu_destroy(ctx));
+    return 0;
+}
