@@ -197,6 +197,9 @@ def main() -> None:
         run_reference(args)
         return
     args.warmup = max(args.warmup, 3)
+    # NCCL / the libraries may print to fd 1: keep stdout for the ONE JSON line
+    guard = _StdoutToStderr()
+    guard.__enter__()
 
     import torch
     from pd_mg_pin_corrosion_b200 import lib as L_, solver as S
@@ -346,7 +349,7 @@ def main() -> None:
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        b = cpu_reference(4, 1)
+        b = _cpu_reference(4, 1, None)
         cpu = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -365,7 +368,9 @@ def main() -> None:
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+    guard.__exit__()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -137,7 +137,7 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
                     c->l_solid, c->inlet_vax, c->out_nodes, c->out_level_off, c->d_red, c->d_u64, c->d_int,
                     c->d_dissolved, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol,
                     c->l2_scratch, c->d_dt, c->stage, c->out_base_v, c->out_base_c, c->out_cnt,
-                    c->out_mask, c->out_early, c->out_rows};
+                    c->out_mask, c->out_early, c->out_rows, c->l_gwall, c->l_gwall_mirror, c->moff};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->h_red) cudaFreeHost(c->h_red);

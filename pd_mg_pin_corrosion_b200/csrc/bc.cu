@@ -182,6 +182,16 @@ int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC) {
 }
 
 int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part) {
+    if (part == 3) {   // ghost-plane walls of a slab (refreshed locally like their owner does)
+        if (!c->n_gwall) return 0;
+        if (c->dim == 2)
+            LAUNCH(c, k_bc_wall<2>, nblocks(c->n_gwall, 256), 256, 0, c->l_gwall, c->l_gwall_mirror, c->n_gwall,
+                   c->rho[buf], c->p[buf], VXYZ(c, buf), c->cfg.rho_f);
+        else
+            LAUNCH(c, k_bc_wall<3>, nblocks(c->n_gwall, 256), 256, 0, c->l_gwall, c->l_gwall_mirror, c->n_gwall,
+                   c->rho[buf], c->p[buf], VXYZ(c, buf), c->cfg.rho_f);
+        return 0;
+    }
     long long first = (part == 2) ? c->n_wall_lo : 0;
     long long n = (part == 1) ? c->n_wall_lo : c->n_wall - first;
     if (n <= 0) return 0;
@@ -232,6 +242,7 @@ extern "C" int pdgpu_bc_outlet(pdgpu_ctx* c) {
 extern "C" int pdgpu_bc_wall(pdgpu_ctx* c) {
     NEED_FIELDS(c);
     PD_TRY(pd_enqueue_bc_wall(c, c->cur));
+    PD_TRY(pd_enqueue_bc_wall(c, c->cur, 3));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }

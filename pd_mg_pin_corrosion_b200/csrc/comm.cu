@@ -81,6 +81,7 @@ extern "C" int pdgpu_comm_init(pdgpu_ctx* c, const void* uid, int rank, int nran
     NCCL_OK(g_nccl.CommInitRank(&comm, nranks, id, rank));
     c->comm = comm;
     pd_invalidate_graphs(c);
+    if (c->grid_built) PD_TRY(pd_rebuild_tables(c));   // ghost-wall mirrors need the communicator (collective)
     return 0;
 }
 
@@ -123,6 +124,7 @@ int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC) {
         add_b(c->type); add_b(c->phase); add_b(c->is_gb); add_b(c->is_precip);
     }
     if (which == 3) { add_b(c->salt); add_d(c->dsol); }
+    if (which == 4 && c->moff) arrs.push_back({c->moff, 4});
     int lo = c->rank - 1, hi = c->rank + 1;
     NCCL_OK(g_nccl.GroupStart());
     for (const Arr& a : arrs) {

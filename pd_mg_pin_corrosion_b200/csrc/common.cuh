@@ -93,6 +93,9 @@ struct pdgpu_ctx {
     int *l_wall = nullptr, *l_wall_mirror = nullptr, *l_inlet = nullptr, *l_outlet = nullptr,
         *l_solid = nullptr;
     long long n_wall = 0, n_inlet = 0, n_outlet = 0, n_solid = 0;
+    // multi-GPU: WALL nodes in ghost planes + their mirrors, relative mirror offsets per node
+    int *l_gwall = nullptr, *l_gwall_mirror = nullptr, *moff = nullptr;
+    long long n_gwall = 0;
     double* inlet_vax = nullptr;    // prescribed axial inlet velocity per inlet-list entry
     // outlet Gauss-Seidel wavefront schedule
     int* out_nodes = nullptr;       // outlet nodes ordered by wavefront level
@@ -268,7 +271,7 @@ int pd_enqueue_bc_inlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, -1 = not applicable
 int pd_outlet_setup(pdgpu_ctx* c);
-int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part = 0);   // part 0 all, 1 below the outlet planes, 2 in them
+int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part = 0);   // part 0 all owned, 1 below the outlet planes, 2 in them, 3 ghost planes
 int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC);
 int pd_enqueue_bc_solid(pdgpu_ctx* c, int buf);
 int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt, int zb = -1, int ze = -1);   // local plane range

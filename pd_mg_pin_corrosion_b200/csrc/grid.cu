@@ -211,6 +211,41 @@ __global__ void k_wall_mirror(GeomParams g, Lat L, const int* __restrict__ l_wal
     mirror[t] = (int)m;
 }
 
+// ---- ghost-plane walls of a slab (multi-GPU) ----------------------------------------------
+// The owner of a WALL node knows its exact mirror; the relative offset (mirror - node) is
+// position independent, so it is exchanged with the halo and ghost-plane walls can be
+// refreshed locally by the pre-step wall BC exactly as their owner does.
+constexpr int kNoMirror = -2147483647 - 1;
+__global__ void k_moff_write(const int* __restrict__ l_wall, const int* __restrict__ mirror, long long n,
+                             int* __restrict__ moff) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int l = l_wall[t], m = mirror[t];
+    moff[l] = m < 0 ? kNoMirror : m - l;
+}
+__global__ void k_ghost_wall_flags(const uint8_t* __restrict__ type, long long NL, long long own_lo,
+                                   long long own_hi, int* __restrict__ flag) {
+    long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= NL) return;
+    flag[l] = (type[l] == PDGPU_WALL) && (l < own_lo || l >= own_hi);
+}
+__global__ void k_ghost_mirror(const int* __restrict__ list, long long n, const int* __restrict__ moff,
+                               const uint8_t* __restrict__ type, long long NL, int* __restrict__ mirror,
+                               int* __restrict__ bad) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int l = list[t], off = moff[l];
+    long long m = (off == kNoMirror) ? -1 : (long long)l + off;
+    if (m >= NL || (off != kNoMirror && m < 0)) { atomicAdd(bad, 1); m = -1; }
+    mirror[t] = (int)m;
+}
+__global__ void k_count_ghost_inout(const uint8_t* __restrict__ type, long long NL, long long own_lo,
+                                    long long own_hi, int* __restrict__ bad) {
+    long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= NL || (l >= own_lo && l < own_hi)) return;
+    if (type[l] == PDGPU_INLET || type[l] == PDGPU_OUTLET) atomicAdd(bad, 1);
+}
+
 __global__ void k_inlet_velocity(GeomParams g, Lat L, double U_in, const int* __restrict__ l_inlet,
                                  long long n_inlet, double* __restrict__ vax) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -354,6 +389,43 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
     if (c->n_wall)
         LAUNCH(c, k_wall_mirror, nblocks(c->n_wall, 128), 128, 0, g, L, c->l_wall, c->n_wall, c->type, c->d_off,
                c->n_off, c->l_wall_mirror);
+    // multi-GPU: mirrors of the ghost-plane walls from the owners' relative offsets
+    if (c->l_gwall) { CUDA_OK(cudaFree(c->l_gwall)); c->l_gwall = nullptr; }
+    if (c->l_gwall_mirror) { CUDA_OK(cudaFree(c->l_gwall_mirror)); c->l_gwall_mirror = nullptr; }
+    c->n_gwall = 0;
+    if (c->nranks > 1 && c->comm) {
+        if (!c->moff) CUDA_OK(cudaMalloc(&c->moff, sizeof(int) * c->NL));
+        CUDA_OK(cudaMemsetAsync(c->moff, 0, sizeof(int) * c->NL, c->stream));
+        if (c->n_wall)
+            LAUNCH(c, k_moff_write, nblocks(c->n_wall, 256), 256, 0, c->l_wall, c->l_wall_mirror, c->n_wall, c->moff);
+        PD_TRY(pd_enqueue_halo(c, 4, 0, 0));
+        int* gflag = nullptr;
+        long long* gpos = nullptr;
+        CUDA_OK(cudaMalloc(&gflag, sizeof(int) * c->NL));
+        CUDA_OK(cudaMalloc(&gpos, sizeof(long long) * (c->NL + 1)));
+        LAUNCH(c, k_ghost_wall_flags, nblocks(c->NL, 256), 256, 0, c->type, c->NL, c->own_lo, c->own_hi, gflag);
+        long long ng = 0;
+        PD_TRY(pdscan::exclusive_scan(c, gflag, c->NL, gpos, &ng));
+        c->n_gwall = ng;
+        CUDA_OK(cudaMalloc(&c->l_gwall, sizeof(int) * std::max<long long>(ng, 1)));
+        CUDA_OK(cudaMalloc(&c->l_gwall_mirror, sizeof(int) * std::max<long long>(ng, 1)));
+        CUDA_OK(cudaMemsetAsync(c->d_int, 0, sizeof(int) * 2, c->stream));
+        if (ng) {
+            LAUNCH(c, k_compact, nblocks(c->NL, 256), 256, 0, gflag, gpos, 0LL, c->NL, c->l_gwall);
+            LAUNCH(c, k_ghost_mirror, nblocks(ng, 256), 256, 0, c->l_gwall, ng, c->moff, c->type, c->NL,
+                   c->l_gwall_mirror, c->d_int);
+        }
+        LAUNCH(c, k_count_ghost_inout, nblocks(c->NL, 256), 256, 0, c->type, c->NL, c->own_lo, c->own_hi, c->d_int + 1);
+        int bad[2] = {0, 0};
+        CUDA_OK(cudaMemcpyAsync(bad, c->d_int, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        CUDA_OK(cudaFree(gflag));
+        CUDA_OK(cudaFree(gpos));
+        if (bad[0] || bad[1])
+            PD_FAIL("slab boundary of rank %d is within %d planes of the inlet/outlet ghost planes (%d wall mirrors, "
+                    "%d inlet/outlet nodes fall into ghost planes): use fewer ranks or a longer tube",
+                    c->rank, c->R, bad[0], bad[1]);
+    }
     // inlet velocity table
     if (c->inlet_vax) { CUDA_OK(cudaFree(c->inlet_vax)); c->inlet_vax = nullptr; }
     CUDA_OK(cudaMalloc(&c->inlet_vax, sizeof(double) * std::max<long long>(c->n_inlet, 1)));

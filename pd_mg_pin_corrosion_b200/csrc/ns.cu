@@ -286,6 +286,7 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
         }
         PD_TRY(pd_enqueue_bc_inlet(c, src, c->curC));
         PD_TRY(pd_enqueue_bc_wall(c, src, 1));
+        PD_TRY(pd_enqueue_bc_wall(c, src, 3));
         PD_TRY(pd_enqueue_bc_solid(c, src));
         CUDA_OK(cudaEventRecord(c->ev_b, main_s));
         PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt, c->R, c->z_cut));
@@ -303,6 +304,7 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
     PD_TRY(pd_enqueue_bc_inlet(c, src, c->curC));
     PD_TRY(pd_enqueue_bc_outlet(c, src, c->curC));
     PD_TRY(pd_enqueue_bc_wall(c, src));
+    PD_TRY(pd_enqueue_bc_wall(c, src, 3));
     PD_TRY(pd_enqueue_bc_solid(c, src));
     PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt));
     PD_TRY(pd_enqueue_bc_wall(c, 1 - src));
