@@ -235,6 +235,10 @@ def main() -> None:
         dist.broadcast(uid, 0)
         ub = bytes(uid.cpu().tolist())
         L_.check(L.pdgpu_comm_init(grid.ctx, ub, rank, world))
+    for opt in os.environ.get("PDGPU_OPTIONS", "").split(","):   # e.g. PDGPU_OPTIONS=debug_no_halo=1,graph=0
+        if "=" in opt:
+            k, v = opt.split("=")
+            grid.set_option(k.strip(), int(v))
     fields = S.Fields()
     fields.bind(grid)
     L_.check(L.pdgpu_fields_init(grid.ctx, None, None))   # grains: none (flags only matter at the wire surface)

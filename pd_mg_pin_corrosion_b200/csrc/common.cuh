@@ -146,6 +146,7 @@ struct pdgpu_ctx {
     int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled fast path
     int opt_ard_kernel = 1;
     int opt_graph = 1;
+    int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)
     int opt_overlap = 1;            // run the outlet sweep on a side stream next to the bulk kernel
     int opt_outlet_kernel = 2;      // 0 = level-list kernel, 1 = level-addressed ring, 2 = lattice-addressed ring
 

@@ -270,3 +270,52 @@ def test_kernel_variants_agree(case):
         for n in ("rho", "vel", "C"):
             assert H.rel_err(res[n], results[0][n]) <= 1e-13, (opts, n, "vs generic")
             assert H.rel_err(res[n], ref.get(n)) <= TOL, (opts, n, "vs oracle")
+
+
+def test_host_driver_whole_run_diagnostics(tmp_path):
+    """host/pd_corrosion_gpu (C++17 driver over the C ABI) on the dissolving synthetic config:
+    every numeric column of diagnostics.csv within 1e-6 relative of the reference's own main()
+    (tests/golden/diagnostics_2d_dissolve.csv); solid-node counts exact."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "pd_corrosion_gpu")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "host")])
+    dim, base, ov = H.CASES["2d_dissolve"]
+    ov = dict(ov, use_implicit=0, output_dir=str(tmp_path / "out"))
+    from oracle import refapi
+    cfg_path = refapi.write_cfg(base, ov, str(tmp_path / "run.cfg"))
+    r = subprocess.run([exe, cfg_path, "--dim", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = np.loadtxt(str(tmp_path / "out" / "diagnostics.csv"), delimiter=",", skiprows=1)
+    gold = np.loadtxt(os.path.join(root, "tests", "golden", "diagnostics_2d_dissolve.csv"), delimiter=",", skiprows=1)
+    assert got.shape == gold.shape
+    assert np.array_equal(got[:, 3], gold[:, 3])
+    for col in (0, 1, 2, 4, 5):
+        rel = np.abs(got[:, col] - gold[:, col]) / np.maximum(np.abs(gold[:, col]), 1e-300)
+        assert rel.max() <= 1e-6, (col, float(rel.max()))
+
+
+def test_python_coupled_solver_whole_run(tmp_path):
+    """solver.CoupledSolver.run (Python mirror of the coupling loop) against the same golden CSV."""
+    import os
+    from pd_mg_pin_corrosion_b200 import solver as S
+    from pd_mg_pin_corrosion_b200.grains import GrainStructure
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dim, cfg, _ = H.load_cfg("2d_dissolve", {"output_dir": str(tmp_path / "out")})
+    grid = S.Grid(dim)
+    grid.build(cfg)
+    grains = GrainStructure().generate(grid.node_type, cfg, dim)
+    fields = S.Fields()
+    fields.allocate(grid.N_total, grid)
+    S.initialize_fields(fields, grid, grains, cfg)
+    cs = S.CoupledSolver()
+    cs.log = lambda *a, **k: None
+    cs.run(grid, fields, cfg)
+    got = np.loadtxt(str(tmp_path / "out" / "diagnostics.csv"), delimiter=",", skiprows=1)
+    gold = np.loadtxt(os.path.join(root, "tests", "golden", "diagnostics_2d_dissolve.csv"), delimiter=",", skiprows=1)
+    assert got.shape == gold.shape and np.array_equal(got[:, 3], gold[:, 3])
+    for col in (0, 1, 2, 4, 5):
+        rel = np.abs(got[:, col] - gold[:, col]) / np.maximum(np.abs(gold[:, col]), 1e-300)
+        assert rel.max() <= 1e-6, (col, float(rel.max()))

@@ -29,7 +29,14 @@ def run(grid, cfg, iters, steps, dissolve_cycles):
     fields = S.Fields()
     fields.bind(grid)
     L = L_.load()
-    L_.check(L.pdgpu_fields_init(grid.ctx, None, None))
+    from pd_mg_pin_corrosion_b200.grains import GrainStructure
+    nt = np.zeros(grid.N_total, np.uint8)
+    full = S.Grid(grid.dim, device=grid.device)   # whole-domain types for the host grain generator
+    full.build(cfg)
+    gs = GrainStructure().generate(full.node_type, cfg, grid.dim)
+    full.close()
+    L_.check(L.pdgpu_fields_init(grid.ctx, gs.is_grain_boundary.ctypes.data_as(C.c_void_p),
+                                 gs.is_precipitate.ctypes.data_as(C.c_void_p)))
     ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
     ns.init(grid, cfg)
     ard.init(grid, cfg)
