@@ -267,6 +267,62 @@ extern "C" int pdgpu_ns_step(pdgpu_ctx* c, double dt) {
     return 0;
 }
 
+// Channel-flow corrections of solve_steady (src/pd_ns.cpp:209-270, Poiseuille validation only):
+// v_transverse = 0 on FLUID nodes of the new buffer and rho_new := mean over the FLUID nodes of
+// each axial plane. One CTA per owned plane, deterministic reduction; p follows rho.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_channel_corrections(Lat L, long long own_lo, NsParams P, const uint8_t* __restrict__ type,
+                      double* __restrict__ rho, double* __restrict__ pr, double* __restrict__ vx,
+                      double* __restrict__ vy) {
+    __shared__ double sh_s[8];
+    __shared__ int sh_c[8];
+    __shared__ double sh_avg;
+    __shared__ int sh_cnt;
+    const long long base = own_lo + (long long)blockIdx.x * L.P;
+    double s = 0.0;
+    int cnt = 0;
+    for (long long q = threadIdx.x; q < L.P; q += blockDim.x)
+        if (type[base + q] == PDGPU_FLUID) { s += rho[base + q]; ++cnt; }
+    s = warp_sum(s);
+    cnt = warp_sum_i(cnt);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh_s[wid] = s; sh_c[wid] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        int c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t += sh_s[w]; c += sh_c[w]; }
+        sh_cnt = c;
+        sh_avg = c > 0 ? t / c : 0.0;
+    }
+    __syncthreads();
+    const double avg = sh_avg;
+    const bool have = sh_cnt > 0;
+    const double pavg = have ? eos_pressure(avg, P.rho_f, P.gamma, P.B) : 0.0;
+    for (long long q = threadIdx.x; q < L.P; q += blockDim.x) {
+        const long long l = base + q;
+        if (type[l] != PDGPU_FLUID) continue;
+        vx[l] = 0.0;                       // d != ax: x (and y in 3D) are transverse
+        if (DIM == 3) vy[l] = 0.0;
+        if (have) { rho[l] = avg; pr[l] = pavg; }
+    }
+}
+
+static int enqueue_channel_corrections(pdgpu_ctx* c, int buf) {
+    if (!c->cfg.channel_flow_corrections) return 0;
+    Lat L = make_lat(c);
+    NsParams P = ns_params(c);
+    unsigned planes = (unsigned)(c->a1 - c->a0);
+    if (c->dim == 2)
+        LAUNCH(c, k_channel_corrections<2>, planes, 256, 0, L, c->own_lo, P, c->type, c->rho[buf], c->p[buf],
+               c->v[buf][0], c->v[buf][1]);
+    else
+        LAUNCH(c, k_channel_corrections<3>, planes, 256, 0, L, c->own_lo, P, c->type, c->rho[buf], c->p[buf],
+               c->v[buf][0], c->v[buf][1]);
+    return 0;
+}
+
 // one iteration of solve_steady without the convergence block (src/pd_ns.cpp:196-205):
 // reads buffer `src`, leaves the new state (with wall mirror applied) in 1-src.
 static int enqueue_ns_body(pdgpu_ctx* c, int src) {
@@ -298,6 +354,7 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
         CUDA_OK(cudaEventRecord(c->ev_c, side));
         CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_c, 0));
         PD_TRY(pd_enqueue_bc_wall(c, 1 - src));
+        PD_TRY(enqueue_channel_corrections(c, 1 - src));
         if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 0, 1 - src, c->curC));
         return 0;
     }
@@ -308,6 +365,7 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
     PD_TRY(pd_enqueue_bc_solid(c, src));
     PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt));
     PD_TRY(pd_enqueue_bc_wall(c, 1 - src));
+    PD_TRY(enqueue_channel_corrections(c, 1 - src));
     if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 0, 1 - src, c->curC));
     return 0;
 }
@@ -383,8 +441,6 @@ __global__ void k_poiseuille_l2(GeomParams g, Lat L, long long own_lo, long long
 extern "C" int pdgpu_ns_solve_steady(pdgpu_ctx* c, PdSteadyResult* out, int verbose) {
     NEED_FIELDS(c);
     if (!out) PD_FAIL("pdgpu_ns_solve_steady: null output");
-    if (c->cfg.channel_flow_corrections)
-        PD_FAIL("channel_flow_corrections = 1 (src/pd_ns.cpp:209-270) is not implemented on device");
     if (verbose) printf("\n--- Flow solver: solving to steady state ---\n");
     double dt = 0.0;
     PD_TRY(pdgpu_ns_compute_dt(c, &dt));
