@@ -319,3 +319,23 @@ def test_python_coupled_solver_whole_run(tmp_path):
     for col in (0, 1, 2, 4, 5):
         rel = np.abs(got[:, col] - gold[:, col]) / np.maximum(np.abs(gold[:, col]), 1e-300)
         assert rel.max() <= 1e-6, (col, float(rel.max()))
+
+
+@pytest.mark.parametrize("extra,expect_iters", [({"flow_conv_tol": 7e-5, "flow_max_iters": 3000}, 700),
+                                                ({"flow_max_iters": 250, "channel_flow_corrections": 1}, 251)])
+def test_solve_steady_matches_reference(extra, expect_iters):
+    """PD_NS_Solver::solve_steady (src/pd_ns.cpp:182-372): same iteration count, eps and final
+    state (on convergence the un-swapped pre-step state); second case exercises the channel-flow
+    corrections (:209-270)."""
+    case = "2d_poiseuille"
+    ref = H.make_ref(case, extra)
+    S, cfg, grid, fields = gpu_side(case, extra, ref=ref)
+    ns = S.PD_NS_Solver()
+    ns.init(grid, cfg)
+    it_ref = ref.ns_solve_steady()
+    it = ns.solve_steady(fields, grid, cfg, verbose=False)
+    assert it == it_ref == expect_iters
+    assert_fields(fields, ref, ("rho", "vel", "rho_new", "vel_new"))
+    if expect_iters == 700:
+        assert ns.last.status == 0 and abs(ns.last.eps - 6.438e-5) < 5e-8
+        assert 0 < ns.last.poiseuille_l2 < 0.1 and ns.last.poiseuille_nodes > 0
