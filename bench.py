@@ -278,6 +278,13 @@ def main() -> None:
     launches = C.c_longlong()
     L.pdgpu_launch_count(grid.ctx, C.byref(launches), 0)
     clocks = sampler.stop(t0, t1)
+    if world > 1:   # per-rank view on stderr (diagnostics only)
+        kk = C.c_float(); ka = C.c_float()
+        L_.check(L.pdgpu_time_kernel(grid.ctx, 0, 5, C.byref(kk)))
+        L_.check(L.pdgpu_time_kernel(grid.ctx, 1, 5, C.byref(ka)))
+        print(f"[bench rank {rank}] planes [{info.a0},{info.a1}) ms/step={ms.value / args.steps:.3f} "
+              f"ns_kernel={kk.value:.3f} ard_kernel={ka.value:.3f} outlet_nodes={int(info.counts[4])} "
+              f"solid={int(info.counts[1])} fluid={int(info.counts[0])}", file=sys.stderr, flush=True)
     t_ms = torch.tensor([ms.value], dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(bonds_local)], dtype=torch.float64, device="cuda")
     if dist is not None:

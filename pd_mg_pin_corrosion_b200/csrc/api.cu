@@ -96,7 +96,11 @@ extern "C" int pdgpu_create_slab(const PdConfig* cfg, int dim, int device, int r
     CUDA_OK(cudaMemcpy(c->d_off, c->h_off.data(), sizeof(OffEntry) * n_off, cudaMemcpyHostToDevice));
 
     CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CUDA_OK(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    // side stream (outlet sweep, halo exchange): highest priority, so that its few CTAs are placed
+    // as soon as an SM frees up even when the bulk bond kernel was launched first
+    int prio_least = 0, prio_greatest = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CUDA_OK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_greatest));
     CUDA_OK(cudaEventCreate(&c->ev_t0));
     CUDA_OK(cudaEventCreate(&c->ev_t1));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
