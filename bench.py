@@ -349,6 +349,15 @@ def main() -> None:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ns_kernel_traffic.json"))).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
+    fp64_peak = C.c_double()
+    L_.check(L.pdgpu_fp64_peak(grid.ctx, C.byref(fp64_peak)))
+    # FP64 work of the tiled NS kernel: 10 DFMA-class ops per bond + 5 per staged neighbour read
+    # (1.68 bonds per read on average) = 13 ops per bond, counted as 2 flop each
+    ns_flops = info.ns_bonds * 13.0 * 2.0
+    fp64_view = {"achieved_tflops": ns_flops / (kms.value * 1e-3) / 1e12, "peak_tflops": fp64_peak.value,
+                 "frac": ns_flops / (kms.value * 1e-3) / 1e12 / fp64_peak.value,
+                 "peak_source": "pdgpu_fp64_peak: DFMA micro-benchmark on this device",
+                 "model": "13 executed FP64 ops per bond-update (tiled kernel), 2 flop per op"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "pd-ns bond kernel", "kernel_ms": kms.value,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
@@ -356,7 +365,8 @@ def main() -> None:
                          "offset-table kernel does not stream a CSR, so frac can exceed 1 -- see DESIGN.md",
                 "ns_bond_updates_per_s": info.ns_bonds / (kms.value * 1e-3),
                 "ard_kernel_ms": kms_ard.value,
-                "ard_bond_updates_per_s": info.ard_bonds / (kms_ard.value * 1e-3)}
+                "ard_bond_updates_per_s": info.ard_bonds / (kms_ard.value * 1e-3),
+                "fp64": fp64_view}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

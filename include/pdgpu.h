@@ -189,6 +189,8 @@ int pdgpu_flush_l2(pdgpu_ctx* ctx);                  /* write a > L2-sized scrat
 /* kernel-only timing of the dominant kernel: average ms of `reps` launches of the NS
  * (which=0) or ARD (which=1) bond kernel alone, CUDA events on the ctx stream. */
 int pdgpu_time_kernel(pdgpu_ctx* ctx, int which, int reps, float* ms_avg);
+/* measured FP64 FMA peak of the device (TFLOP/s, DFMA micro-benchmark) */
+int pdgpu_fp64_peak(pdgpu_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

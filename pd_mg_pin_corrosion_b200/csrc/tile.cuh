@@ -31,7 +31,8 @@ constexpr int NTHREADS = TX * TY * NZT;
 constexpr int NCOL = 37;
 
 struct ColTable {
-    int off[NCOL];        // dj*SX + di
+    int off[NCOL];        // dj*SX + di (ns_tile / ard_tile block pitch)
+    int di_i[NCOL], dj_i[NCOL];
     int h[NCOL];          // half height of the column: |dk| <= h
     double di[NCOL], dj[NCOL];
     double kap[NCOL][4];  // kappa(|dk|), 0 where the offset does not exist (incl. the node itself)
@@ -57,6 +58,8 @@ inline bool build_columns(const pdgpu_ctx* c, ColTable* T, double* sum_kappa) {
                 if (H != pass) continue;
                 if (n >= NCOL) return false;
                 T->off[n] = dj * SX + di;
+                T->di_i[n] = di;
+                T->dj_i[n] = dj;
                 T->h[n] = H;
                 T->di[n] = di;
                 T->dj[n] = dj;
