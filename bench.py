@@ -350,13 +350,17 @@ def main() -> None:
     except (OSError, ValueError):
         pass
     fp64_peak = C.c_double()
+    fp64_peak3 = C.c_double()
     L_.check(L.pdgpu_fp64_peak(grid.ctx, C.byref(fp64_peak)))
+    L_.check(L.pdgpu_fp64_peak3(grid.ctx, C.byref(fp64_peak3)))
     # FP64 work of the tiled NS kernel: 10 DFMA-class ops per bond + 5 per staged neighbour read
     # (1.68 bonds per read on average) = 13 ops per bond, counted as 2 flop each
     ns_flops = info.ns_bonds * 13.0 * 2.0
     fp64_view = {"achieved_tflops": ns_flops / (kms.value * 1e-3) / 1e12, "peak_tflops": fp64_peak.value,
                  "frac": ns_flops / (kms.value * 1e-3) / 1e12 / fp64_peak.value,
-                 "peak_source": "pdgpu_fp64_peak: DFMA micro-benchmark on this device",
+                 "peak_tflops_3_register_sources": fp64_peak3.value,
+                 "peak_source": "pdgpu_fp64_peak / pdgpu_fp64_peak3: DFMA micro-benchmarks on this device "
+                                "(one register source + constants; three distinct register sources)",
                  "model": "13 executed FP64 ops per bond-update (tiled kernel), 2 flop per op"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "pd-ns bond kernel", "kernel_ms": kms.value,

@@ -191,6 +191,8 @@ int pdgpu_flush_l2(pdgpu_ctx* ctx);                  /* write a > L2-sized scrat
 int pdgpu_time_kernel(pdgpu_ctx* ctx, int which, int reps, float* ms_avg);
 /* measured FP64 FMA peak of the device (TFLOP/s, DFMA micro-benchmark) */
 int pdgpu_fp64_peak(pdgpu_ctx* ctx, double* tflops);
+/* same with three distinct register sources per DFMA (register-file operand bandwidth bound) */
+int pdgpu_fp64_peak3(pdgpu_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -56,3 +56,44 @@ extern "C" int pdgpu_fp64_peak(pdgpu_ctx* c, double* tflops) {
     *tflops = flops / (best * 1e-3) / 1e12;
     return 0;
 }
+
+// Same measurement with three distinct register-pair sources per DFMA (x = fma(x, y, z) with
+// per-chain y, z): the register-file operand bandwidth, not the FP64 pipe, bounds this form.
+__global__ void __launch_bounds__(256)
+k_dfma_peak3(double* out, int iters) {
+    double x[8], y[8], z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        x[i] = threadIdx.x + i;
+        y[i] = 1.0 - 1e-9 * (threadIdx.x + i);
+        z[i] = 1e-9 * (blockIdx.x + i);
+    }
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fma(x[i], y[i], z[i]);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" int pdgpu_fp64_peak3(pdgpu_ctx* c, double* tflops) {
+    CHECK_CTX(c);
+    if (!tflops) PD_FAIL("pdgpu_fp64_peak3: null output");
+    const int iters = 1 << 14, blocks = 148 * 8, threads = 256;
+    k_dfma_peak3<<<blocks, threads, 0, c->stream>>>(c->d_red, 64);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_OK(cudaEventRecord(c->ev_t0, c->stream));
+        k_dfma_peak3<<<blocks, threads, 0, c->stream>>>(c->d_red, iters);
+        CUDA_OK(cudaEventRecord(c->ev_t1, c->stream));
+        CUDA_OK(cudaEventSynchronize(c->ev_t1));
+        float ms = 0.f;
+        CUDA_OK(cudaEventElapsedTime(&ms, c->ev_t0, c->ev_t1));
+        if (ms < best) best = ms;
+    }
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return 0;
+}

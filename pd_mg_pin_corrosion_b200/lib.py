@@ -96,7 +96,7 @@ def load() -> C.CDLL:
         "pdgpu_launch_count": [vp, C.POINTER(C.c_longlong), C.c_int],
         "pdgpu_set_option": [vp, C.c_char_p, C.c_int], "pdgpu_flush_l2": [vp],
         "pdgpu_time_kernel": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
-        "pdgpu_fp64_peak": [vp, dp],
+        "pdgpu_fp64_peak": [vp, dp], "pdgpu_fp64_peak3": [vp, dp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
