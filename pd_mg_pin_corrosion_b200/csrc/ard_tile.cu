@@ -32,11 +32,8 @@ struct ArdAcc {
 template <int H>
 __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const double* __restrict__ s_vmf,
                                            const double* __restrict__ s_ds, int cb, double dI, double dJ,
-                                           const double (&kap)[4], const ArdTileParams& q,
+                                           const double (&kap)[4], const double (&kz)[4], const ArdTileParams& q,
                                            const double (&Ci)[RZ], const double (&vmi)[RZ], ArdAcc& a) {
-    double kz[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) kz[k] = (double)k * kap[k];
     double colg[RZ];
 #pragma unroll
     for (int t = 0; t < RZ; ++t) colg[t] = 0.0;
@@ -131,10 +128,11 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
         const int cb = base + T.off[c];
         const double dI = T.di[c], dJ = T.dj[c];
         const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
+        const double kz[4] = {T.kz[c][0], T.kz[c][1], T.kz[c][2], T.kz[c][3]};
         const int H = T.h[c];
-        if (H == 3) ard_column<3>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, q, Ci, vmi, a);
-        else if (H == 2) ard_column<2>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, q, Ci, vmi, a);
-        else ard_column<1>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, q, Ci, vmi, a);
+        if (H == 3) ard_column<3>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
+        else if (H == 2) ard_column<2>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
+        else ard_column<1>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
     }
 
     const double dt = *d_dt;

@@ -57,13 +57,8 @@ template <int H>
 __device__ __forceinline__ void ns_column(const double* __restrict__ s_rho, const double* __restrict__ s_vx,
                                           const double* __restrict__ s_vy, const double* __restrict__ s_vz,
                                           const double* __restrict__ s_p, int cb, double dI, double dJ,
-                                          const double (&kap)[4], double c_div, double visc_dx, NsAcc& a) {
-    double kz[4], nk[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        kz[k] = (double)k * kap[k];
-        nk[k] = visc_dx * kap[k];
-    }
+                                          const double (&kap)[4], const double (&kz)[4], const double (&nk)[4],
+                                          double c_div, NsAcc& a) {
     double colp[RZ];
 #pragma unroll
     for (int t = 0; t < RZ; ++t) colp[t] = 0.0;
@@ -160,16 +155,17 @@ k_ns_tile(const __grid_constant__ NsTileParams q, const __grid_constant__ ColTab
     for (int t = 0; t < RZ; ++t)
         a.mc[t] = a.md[t] = a.ax[t] = a.ay[t] = a.az[t] = a.px[t] = a.py[t] = a.pz[t] = 0.0;
     const int base = (tz * RZ * SY + ty + TR) * SX + (tx + TR);   // node t at base + (t+TR)*SPLANE
-    const double visc_dx = q.visc * q.inv_dx;
 #pragma unroll 1
     for (int c = 0; c < NCOL; ++c) {
         const int cb = base + T.off[c];
         const double dI = T.di[c], dJ = T.dj[c];
         const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
+        const double kz[4] = {T.kz[c][0], T.kz[c][1], T.kz[c][2], T.kz[c][3]};
+        const double nk[4] = {T.aux[c][0], T.aux[c][1], T.aux[c][2], T.aux[c][3]};
         const int H = T.h[c];
-        if (H == 3) ns_column<3>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, q.c_div, visc_dx, a);
-        else if (H == 2) ns_column<2>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, q.c_div, visc_dx, a);
-        else ns_column<1>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, q.c_div, visc_dx, a);
+        if (H == 3) ns_column<3>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, kz, nk, q.c_div, a);
+        else if (H == 2) ns_column<2>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, kz, nk, q.c_div, a);
+        else ns_column<1>(s_rho, s_vx, s_vy, s_vz, s_p, cb, dI, dJ, kap, kz, nk, q.c_div, a);
     }
 
     const double dt = *d_dt;
@@ -211,6 +207,8 @@ int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt, int zb, i
     q.inv_dx = 1.0 / c->cfg.dx;
     q.W2 = sum_kappa * q.inv_dx;
     q.gamma_is_7 = (c->cfg.gamma_eos == 7.0);
+    for (int col = 0; col < tile::NCOL; ++col)
+        for (int kk = 0; kk < 4; ++kk) T.aux[col][kk] = q.visc * q.inv_dx * T.kap[col][kk];
     const size_t smem = sizeof(double) * 5 * SN;
     static bool attr_done = false;
     if (!attr_done) {

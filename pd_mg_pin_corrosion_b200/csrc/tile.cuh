@@ -36,6 +36,10 @@ struct ColTable {
     int h[NCOL];          // half height of the column: |dk| <= h
     double di[NCOL], dj[NCOL];
     double kap[NCOL][4];  // kappa(|dk|), 0 where the offset does not exist (incl. the node itself)
+    double kz[NCOL][4];   // |dk| * kappa(|dk|)
+    double aux[NCOL][4];  // kernel specific (NS: mu*beta/dx * kappa); kept in the table so that the
+                          // weights reach the DFMAs as uniform-register operands (two register
+                          // sources per DFMA instead of three, profiles/r1_notes.md)
 };
 
 struct TileGeom {
@@ -63,7 +67,7 @@ inline bool build_columns(const pdgpu_ctx* c, ColTable* T, double* sum_kappa) {
                 T->h[n] = H;
                 T->di[n] = di;
                 T->dj[n] = dj;
-                for (int k = 0; k < 4; ++k) T->kap[n][k] = 0.0;
+                for (int k = 0; k < 4; ++k) T->kap[n][k] = T->kz[n][k] = T->aux[n][k] = 0.0;
                 ++n;
             }
     if (n != NCOL) return false;
@@ -76,6 +80,7 @@ inline bool build_columns(const pdgpu_ctx* c, ColTable* T, double* sum_kappa) {
         if (col < 0 || ak > T->h[col]) return false;
         double kappa = c->cfg.dx * e.w2;
         T->kap[col][ak] = kappa;
+        T->kz[col][ak] = ak * kappa;
         sk += kappa;
     }
     *sum_kappa = sk;
