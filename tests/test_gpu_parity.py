@@ -341,3 +341,33 @@ def test_solve_steady_matches_reference(extra, expect_iters):
     if expect_iters == 700:
         assert ns.last.status == 0 and abs(ns.last.eps - 6.438e-5) < 5e-8
         assert 0 < ns.last.poiseuille_l2 < 0.1 and ns.last.poiseuille_nodes > 0
+
+
+@pytest.mark.parametrize("case,iters,eps,l2", [("2d_poiseuille", 19000, 8.612e-07, 6.427e-04),
+                                               ("2d_default", 25300, 4.945e-06, 1.132e-02)])
+def test_steady_state_known_answers(case, iters, eps, l2):
+    """Full flow solves of BASELINE configs 1 and 2 to convergence: iteration count, epsilon and the
+    Poiseuille L2 the reference prints, and the converged velocity field
+    against tests/golden/steady.json (generated from oracle/_ref)."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gold = json.load(open(os.path.join(root, "tests", "golden", "steady.json")))[case]
+    from pd_mg_pin_corrosion_b200 import solver as S
+    from pd_mg_pin_corrosion_b200.grains import GrainStructure
+    dim, cfg, _ = H.load_cfg(case)
+    grid = S.Grid(dim)
+    grid.build(cfg)
+    grains = GrainStructure().generate(grid.node_type, cfg, dim)
+    fields = S.Fields()
+    fields.allocate(grid.N_total, grid)
+    S.initialize_fields(fields, grid, grains, cfg)
+    ns = S.PD_NS_Solver()
+    ns.init(grid, cfg)
+    it = ns.solve_steady(fields, grid, cfg, verbose=False)
+    assert it == iters == gold["iters"]
+    assert abs(ns.last.eps - eps) <= 1e-3 * eps          # the reference prints 4 significant digits
+    assert abs(ns.last.poiseuille_l2 - l2) <= 1e-3 * l2
+    v = fields.get("vel")
+    assert H.rel_err(v[::97], np.array(gold["vel_sample"])) <= 1e-10   # ~2e4 iterations of rounding drift
+    assert H.rel_err(fields.get("rho")[::97], np.array(gold["rho_sample"])) <= 1e-12
