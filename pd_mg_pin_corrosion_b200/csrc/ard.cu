@@ -139,6 +139,7 @@ int pd_enqueue_ard_prepass(pdgpu_ctx* c, int buf, int srcC, long long lo, long l
 
 // bond kernel over the local plane range [zb, ze) (negative = all owned planes)
 int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid) {
+    if (c->opt_ard_kernel == 3) return pd_enqueue_ard_step_csr(c, buf, srcC, d_dt);
     if (c->opt_ard_kernel >= 1) {
         int r = pd_enqueue_ard_tile(c, buf, srcC, d_dt, zb, ze, do_solid);
         if (r >= 0) return r;

@@ -143,7 +143,7 @@ struct pdgpu_ctx {
     long long launches = 0;
 
     // options
-    int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled fast path
+    int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled, 2 = z-marching tiles, 3 = materialised CSR
     int opt_ard_kernel = 1;
     int opt_graph = 1;
     int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)
@@ -284,6 +284,8 @@ int pd_max_fluid_speed(pdgpu_ctx* c, double* vmax);
 void pd_invalidate_graphs(pdgpu_ctx* c);
 int pd_refresh_eos(pdgpu_ctx* c, int buf);           // p[buf] = EOS(rho[buf]) on all local nodes
 int pd_refresh_vmag(pdgpu_ctx* c, int buf);
+int pd_enqueue_ns_step_csr(pdgpu_ctx* c, int src, const double* d_dt);                 // csr_path.cu
+int pd_enqueue_ard_step_csr(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);       // csr_path.cu
 int pd_set_dt(pdgpu_ctx* c, int slot, double value);
 int pd_comm_allreduce(pdgpu_ctx* c, double* d_buf, int n, int op);   // op 0 sum, 1 max
 #define NEED_FIELDS(c)                                                                       \
@@ -301,5 +303,6 @@ struct StreamSwap {
     ~StreamSwap() { c->stream = saved; }
 };
 inline bool pd_can_overlap(const pdgpu_ctx* c) {
-    return c->opt_overlap && c->z_cut > 0 && c->n_outlet > 0 && c->out_fast && c->opt_outlet_kernel > 0;
+    return c->opt_overlap && c->z_cut > 0 && c->n_outlet > 0 && c->out_fast && c->opt_outlet_kernel > 0 &&
+           c->opt_ns_kernel != 3 && c->opt_ard_kernel != 3;   // the CSR kernels take no plane range
 }

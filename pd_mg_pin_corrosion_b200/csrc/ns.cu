@@ -99,6 +99,7 @@ int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt, int zb, i
 int pd_enqueue_ns_march(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze);       // ns_march.cu
 
 int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze) {
+    if (c->opt_ns_kernel == 3) return pd_enqueue_ns_step_csr(c, src, d_dt);
     if (c->opt_ns_kernel >= 1 && c->full_rows && c->cfg.m_ratio == 3) {
         int r = (c->opt_ns_kernel >= 2) ? pd_enqueue_ns_march(c, src, d_dt, zb, ze)
                                         : pd_enqueue_ns_step_fast(c, src, d_dt, zb, ze);
