@@ -192,6 +192,8 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="dx=5um params.cfg 3D (debug)")
+    ap.add_argument("--csr", action="store_true",
+                    help="also time the materialised-CSR (reference layout, HBM-bound) bond kernels")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -372,6 +374,23 @@ def main() -> None:
                 "ard_bond_updates_per_s": info.ard_bonds / (kms_ard.value * 1e-3),
                 "fp64": fp64_view}
 
+    csr_view = None
+    if args.csr and world == 1:
+        # reference-layout CSR on device: 44 B per entry (105 GB for 3D params_fine)
+        nnz = grid.build_neighbors()
+        grid.set_option("ns_kernel", 3)
+        grid.set_option("ard_kernel", 3)
+        kc = C.c_float(); ka = C.c_float()
+        L_.check(L.pdgpu_time_kernel(grid.ctx, 0, 5, C.byref(kc)))
+        L_.check(L.pdgpu_time_kernel(grid.ctx, 1, 5, C.byref(ka)))
+        csr_bytes = info.ns_bonds * 44 + int(info.counts[0]) * 65
+        csr_view = {"nnz": int(nnz), "csr_gbytes": nnz * 44 / 1e9, "ns_kernel_ms": kc.value, "ard_kernel_ms": ka.value,
+                    "ns_bond_updates_per_s": info.ns_bonds / (kc.value * 1e-3),
+                    "achieved_gbs": csr_bytes / (kc.value * 1e-3) / 1e9, "frac_of_hbm_peak": csr_bytes / (kc.value * 1e-3) / 1e9 / peak,
+                    "what": "k_ns_step_csr: one warp per row streaming the reference CSR layout"}
+        grid.set_option("ns_kernel", 1)
+        grid.set_option("ard_kernel", 1)
+        grid.free_neighbors()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         b = _cpu_reference(4, 1, None)
@@ -393,6 +412,8 @@ def main() -> None:
                 "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if csr_view is not None:
+            line["csr_path"] = csr_view
     guard.__exit__()
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -252,6 +252,7 @@ def test_kernel_variants_agree(case):
         dict(ns_kernel=0, ard_kernel=0, outlet_kernel=2, overlap=1, graph=1),
         dict(ns_kernel=2, ard_kernel=1, outlet_kernel=2, overlap=1, graph=1),   # z-marching NS kernel
         dict(ns_kernel=2, ard_kernel=2, outlet_kernel=2, overlap=0, graph=0),
+        dict(ns_kernel=3, ard_kernel=3, outlet_kernel=2, overlap=1, graph=1),   # materialised-CSR path
     ]
     dt = ref.ns_compute_dt()
     results = []
@@ -259,6 +260,8 @@ def test_kernel_variants_agree(case):
         S, cfg, grid, fields = gpu_side(case, ref=ref, upload=False)
         for k, v in opts.items():
             grid.set_option(k, v)
+        if opts["ns_kernel"] == 3:
+            grid.build_neighbors()
         ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
         ns.init(grid, cfg); ard.init(grid, cfg)
         ns.iterate(fields, grid, cfg, iters, dt)
