@@ -18,7 +18,7 @@ struct CsrNsParams {
 };
 
 template <int DIM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_ns_step_csr(long long own_lo, long long own_n, long long halo_shift, const uint8_t* __restrict__ type,
               const long long* __restrict__ row_off, const int* __restrict__ nbr_idx,
               const double* __restrict__ nbr_dist, const double* __restrict__ nbr_evec,
@@ -40,7 +40,9 @@ k_ns_step_csr(long long own_lo, long long own_n, long long halo_shift, const uin
         }
         return;
     }
-    double mc = 0.0, md = 0.0, c0 = 0.0, c1 = 0.0, c2 = 0.0, q0 = 0.0, q1 = 0.0, q2 = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    // (rho_j v_j v_j - rho_i v_i v_i) . e = v_j q_j - v_i q_i with q = rho (v . e): same sum as
+    // src/pd_ns.cpp:136-143, fewer live values (occupancy matters: the kernel is latency bound)
+    double mc = 0.0, md = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0;
     const long long beg = row_off[row], end = row_off[row + 1];
     for (long long jj = beg + lane; jj < end; jj += 32) {
         const long long j = (long long)nbr_idx[jj] - halo_shift;
@@ -48,29 +50,20 @@ k_ns_step_csr(long long own_lo, long long own_n, long long halo_shift, const uin
         const double e0 = nbr_evec[jj * DIM], e1 = nbr_evec[jj * DIM + 1], e2 = (DIM == 3) ? nbr_evec[jj * DIM + 2] : 0.0;
         if (V < 1e-30) continue;
         const double inv_xi = 1.0 / xi, w1 = inv_xi * V, w2 = inv_xi * inv_xi * V;
-        const double rho_j = rho[j], p_j = pr[j];
+        const double rho_j = rho[j], dp = pr[j] - p_i;
         const double vj0 = vx[j], vj1 = vy[j], vj2 = (DIM == 3) ? vz[j] : 0.0;
-        double dd = (rho_j * vj0 - rho_i * vi0) * e0 + (rho_j * vj1 - rho_i * vi1) * e1;
-        if (DIM == 3) dd += (rho_j * vj2 - rho_i * vi2) * e2;
-        mc += dd * w1;
+        const double q_j = rho_j * (vj0 * e0 + vj1 * e1 + vj2 * e2);
+        const double q_i = rho_i * (vi0 * e0 + vi1 * e1 + vi2 * e2);
+        mc += (q_j - q_i) * w1;
         md += (rho_j - rho_i) * w2;
-        double a0 = (rho_j * vj0 * vj0 - rho_i * vi0 * vi0) * e0 + (rho_j * vj0 * vj1 - rho_i * vi0 * vi1) * e1;
-        double a1 = (rho_j * vj1 * vj0 - rho_i * vi1 * vi0) * e0 + (rho_j * vj1 * vj1 - rho_i * vi1 * vi1) * e1;
-        double a2 = 0.0;
-        if (DIM == 3) {
-            a0 += (rho_j * vj0 * vj2 - rho_i * vi0 * vi2) * e2;
-            a1 += (rho_j * vj1 * vj2 - rho_i * vi1 * vi2) * e2;
-            a2 = (rho_j * vj2 * vj0 - rho_i * vi2 * vi0) * e0 + (rho_j * vj2 * vj1 - rho_i * vi2 * vi1) * e1 +
-                 (rho_j * vj2 * vj2 - rho_i * vi2 * vi2) * e2;
-        }
-        c0 += a0 * w1; c1 += a1 * w1; c2 += a2 * w1;
-        const double dp = (p_j - p_i) * w1;
-        q0 += dp * e0; q1 += dp * e1; q2 += dp * e2;
+        a0 += (vj0 * q_j - vi0 * q_i + dp * e0) * w1;      // convection + pressure (both x -alpha/V_H)
+        a1 += (vj1 * q_j - vi1 * q_i + dp * e1) * w1;
+        a2 += (vj2 * q_j - vi2 * q_i + dp * e2) * w1;
         s0 += (vj0 - vi0) * w2; s1 += (vj1 - vi1) * w2; s2 += (vj2 - vi2) * w2;
     }
     mc = warp_sum(mc); md = warp_sum(md);
-    c0 = warp_sum(c0); c1 = warp_sum(c1); q0 = warp_sum(q0); q1 = warp_sum(q1); s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if (DIM == 3) { c2 = warp_sum(c2); q2 = warp_sum(q2); s2 = warp_sum(s2); }
+    a0 = warp_sum(a0); a1 = warp_sum(a1); s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if (DIM == 3) { a2 = warp_sum(a2); s2 = warp_sum(s2); }
     if (lane != 0) return;
     const double dt = *d_dt;
     double rn = rho_i + dt * (-P.c_div * mc + P.dens_diff * md);
@@ -78,9 +71,9 @@ k_ns_step_csr(long long own_lo, long long own_n, long long halo_shift, const uin
     rho_n[l] = rn;
     pr_n[l] = eos_pressure(rn, P.rho_f, P.gamma, P.B);
     const double s = dt / rho_i;
-    vx_n[l] = vi0 + s * (-P.c_div * c0 - P.c_div * q0 + P.visc * s0);
-    vy_n[l] = vi1 + s * (-P.c_div * c1 - P.c_div * q1 + P.visc * s1);
-    if (DIM == 3) vz_n[l] = vi2 + s * (-P.c_div * c2 - P.c_div * q2 + P.visc * s2);
+    vx_n[l] = vi0 + s * (-P.c_div * a0 + P.visc * s0);
+    vy_n[l] = vi1 + s * (-P.c_div * a1 + P.visc * s1);
+    if (DIM == 3) vz_n[l] = vi2 + s * (-P.c_div * a2 + P.visc * s2);
 }
 
 struct CsrArdParams {
