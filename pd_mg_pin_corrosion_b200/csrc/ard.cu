@@ -26,18 +26,13 @@ static ArdParams ard_params(const pdgpu_ctx* c) {
     return p;
 }
 
-// Pre-pass over every local node: vmag = |v| for fluid-like nodes (FLUID/INLET/OUTLET), -1
-// otherwise (feeds D_art, src/pd_ard.cpp:166-170); for owned SOLID_MG nodes the salt-layer
-// flag of src/pd_ard.cpp:61-73 (any FLUID neighbour with C >= C_sat) and the interface
-// diffusivity dsol = 2 D_l D_s / (D_l + D_s + 1e-30) (0 when blocked), src/pd_ard.cpp:140-162.
+// vmag = |v| for fluid-like nodes (FLUID/INLET/OUTLET), -1 otherwise (feeds D_art,
+// src/pd_ard.cpp:166-170). Velocities of FLUID nodes are frozen during the ARD phase, so the full
+// pass runs once per flow state (pd_ensure_vmag); only the outlet planes are refreshed per step.
 template <int DIM>
-__global__ void k_ard_prepass(Lat L, long long lo, long long hi, long long own_lo, long long own_hi,
-                              const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
-                              const double* __restrict__ C, const double* __restrict__ vx,
-                              const double* __restrict__ vy, const double* __restrict__ vz,
-                              const uint8_t* __restrict__ is_gb, const uint8_t* __restrict__ is_precip,
-                              ArdParams P, double* __restrict__ vmag, uint8_t* __restrict__ salt,
-                              double* __restrict__ dsol) {
+__global__ void k_ard_vmag(long long lo, long long hi, const uint8_t* __restrict__ type,
+                           const double* __restrict__ vx, const double* __restrict__ vy,
+                           const double* __restrict__ vz, double* __restrict__ vmag) {
     long long l = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= hi) return;
     uint8_t ty = type[l];
@@ -45,22 +40,33 @@ __global__ void k_ard_prepass(Lat L, long long lo, long long hi, long long own_l
     if (DIM == 3) s += vz[l] * vz[l];
     bool fluid_like = (ty == PDGPU_FLUID || ty == PDGPU_INLET || ty == PDGPU_OUTLET);
     vmag[l] = fluid_like ? sqrt(s) : -1.0;
-    if (l < own_lo || l >= own_hi) return;   // ghost planes: salt/dsol arrive with the halo exchange
+}
+
+// Per step, owned SOLID_MG nodes only: the salt-layer flag of src/pd_ard.cpp:61-73 (any FLUID
+// neighbour with C >= C_sat) and the interface diffusivity dsol = 2 D_l D_s / (D_l + D_s + 1e-30)
+// (0 when blocked), src/pd_ard.cpp:140-162.
+template <int DIM>
+__global__ void k_ard_prepass_solids(Lat L, const int* __restrict__ l_solid, long long n_solid,
+                                     const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
+                                     const double* __restrict__ C, const uint8_t* __restrict__ is_gb,
+                                     const uint8_t* __restrict__ is_precip, ArdParams P,
+                                     uint8_t* __restrict__ salt, double* __restrict__ dsol) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_solid) return;
+    long long l = l_solid[t];
+    int q = (int)(l % L.P);
+    int jj = (DIM == 3) ? q / L.Nx : 0;
+    int ii = q - jj * L.Nx;
     uint8_t blocked = 0;
+    for (int o = 0; o < n_off; ++o) {
+        long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
+        if (nn >= 0 && type[nn] == PDGPU_FLUID && C[nn] >= P.C_sat) { blocked = 1; break; }
+    }
     double ds = 0.0;
-    if (ty == PDGPU_SOLID_MG) {
-        int q = (int)(l % L.P);
-        int jj = (DIM == 3) ? q / L.Nx : 0;
-        int ii = q - jj * L.Nx;
-        for (int o = 0; o < n_off; ++o) {
-            long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
-            if (nn >= 0 && type[nn] == PDGPU_FLUID && C[nn] >= P.C_sat) { blocked = 1; break; }
-        }
-        if (!blocked) {
-            double D_s = is_gb[l] ? P.D_gb : (is_precip[l] ? P.D_precip : P.D_grain);
-            D_s *= P.decay;
-            ds = 2.0 * P.D_liquid * D_s / (P.D_liquid + D_s + 1e-30);
-        }
+    if (!blocked) {
+        double D_s = is_gb[l] ? P.D_gb : (is_precip[l] ? P.D_precip : P.D_grain);
+        D_s *= P.decay;
+        ds = 2.0 * P.D_liquid * D_s / (P.D_liquid + D_s + 1e-30);
     }
     salt[l] = blocked;
     dsol[l] = ds;
@@ -120,28 +126,48 @@ k_ard_step_generic(Lat L, long long own_lo, long long own_n, const uint8_t* __re
     C_n[l] = cn < 0.0 ? 0.0 : cn;
 }
 
-int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid);   // ard_tile.cu
+int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid,
+                        bool skip_wall_copy);   // ard_tile.cu
 
-// pre-pass over the local index range [lo, hi)
-int pd_enqueue_ard_prepass(pdgpu_ctx* c, int buf, int srcC, long long lo, long long hi) {
+int pd_enqueue_ard_vmag_range(pdgpu_ctx* c, int buf, long long lo, long long hi) {
     if (hi <= lo) return 0;
-    Lat L = make_lat(c);
-    ArdParams P = ard_params(c);
     long long n = hi - lo;
     if (c->dim == 2)
-        LAUNCH(c, k_ard_prepass<2>, nblocks(n, 256), 256, 0, L, lo, hi, c->own_lo, c->own_hi, c->type, c->d_off,
-               c->n_off, c->C[srcC], VXYZ(c, buf), c->is_gb, c->is_precip, P, c->vmag, c->salt, c->dsol);
+        LAUNCH(c, k_ard_vmag<2>, nblocks(n, 256), 256, 0, lo, hi, c->type, VXYZ(c, buf), c->vmag);
     else
-        LAUNCH(c, k_ard_prepass<3>, nblocks(n, 256), 256, 0, L, lo, hi, c->own_lo, c->own_hi, c->type, c->d_off,
-               c->n_off, c->C[srcC], VXYZ(c, buf), c->is_gb, c->is_precip, P, c->vmag, c->salt, c->dsol);
+        LAUNCH(c, k_ard_vmag<3>, nblocks(n, 256), 256, 0, lo, hi, c->type, VXYZ(c, buf), c->vmag);
+    return 0;
+}
+
+// full |v| pass when the cached array does not belong to the current flow state (never inside a
+// graph capture: called by the public entry points before the loop bodies are enqueued)
+int pd_ensure_vmag(pdgpu_ctx* c, int buf) {
+    if (c->vmag_epoch == c->flow_epoch && c->vmag_buf == buf) return 0;
+    PD_TRY(pd_enqueue_ard_vmag_range(c, buf, 0, c->NL));
+    c->vmag_epoch = c->flow_epoch;
+    c->vmag_buf = buf;
+    return 0;
+}
+
+int pd_enqueue_ard_prepass_solids(pdgpu_ctx* c, int srcC) {
+    if (!c->n_solid) return 0;
+    Lat L = make_lat(c);
+    ArdParams P = ard_params(c);
+    if (c->dim == 2)
+        LAUNCH(c, k_ard_prepass_solids<2>, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type,
+               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol);
+    else
+        LAUNCH(c, k_ard_prepass_solids<3>, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type,
+               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol);
     return 0;
 }
 
 // bond kernel over the local plane range [zb, ze) (negative = all owned planes)
-int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid) {
+int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid,
+                        bool skip_wall_copy) {
     if (c->opt_ard_kernel == 3) return pd_enqueue_ard_step_csr(c, buf, srcC, d_dt);
     if (c->opt_ard_kernel >= 1) {
-        int r = pd_enqueue_ard_tile(c, buf, srcC, d_dt, zb, ze, do_solid);
+        int r = pd_enqueue_ard_tile(c, buf, srcC, d_dt, zb, ze, do_solid, skip_wall_copy);
         if (r >= 0) return r;
     }
     Lat L = make_lat(c);
@@ -160,7 +186,8 @@ int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
 }
 
 int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt) {
-    PD_TRY(pd_enqueue_ard_prepass(c, buf, srcC, 0, c->NL));
+    PD_TRY(pd_ensure_vmag(c, buf));
+    PD_TRY(pd_enqueue_ard_prepass_solids(c, srcC));
     if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));   // salt flags + dsol of ghost solids
     return pd_enqueue_ard_main(c, buf, srcC, d_dt, -1, -1, true);
 }
@@ -206,21 +233,24 @@ static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
         const int z_hi = c->R + (c->a1 - c->a0);
         CUDA_OK(cudaEventRecord(c->ev_a, main_s));
         CUDA_OK(cudaStreamWaitEvent(side, c->ev_a, 0));
+        const bool tiles = (c->opt_ard_kernel == 1 || c->opt_ard_kernel == 2);   // kernels that can skip the wall copy
         {
             StreamSwap sw(c, side);
             PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
-            PD_TRY(pd_enqueue_ard_prepass(c, buf, srcC, c->out_l0, c->NL));
+            PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0, c->NL));
+            // WALL concentrations are never read by a bond (src/pd_ard.cpp:120): off the critical path
+            if (tiles) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC, true));
         }
         PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
-        PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
-        PD_TRY(pd_enqueue_ard_prepass(c, buf, srcC, 0, c->out_l0));
+        if (!tiles) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
+        PD_TRY(pd_enqueue_ard_prepass_solids(c, srcC));
         if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));
         CUDA_OK(cudaEventRecord(c->ev_b, main_s));
-        PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, c->R, c->z_cut, c->solids_below_cut));
+        PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, c->R, c->z_cut, false, tiles));
         CUDA_OK(cudaStreamWaitEvent(side, c->ev_b, 0));
         {
             StreamSwap sw(c, side);
-            PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, c->z_cut, z_hi, !c->solids_below_cut));
+            PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, c->z_cut, z_hi, true, tiles));
         }
         CUDA_OK(cudaEventRecord(c->ev_c, side));
         CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_c, 0));
@@ -230,7 +260,10 @@ static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
     PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
     PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
     PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
-    PD_TRY(pd_enqueue_ard_step(c, buf, srcC, c->d_dt + 1));
+    if (c->n_outlet) PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0_any, c->NL));   // outlet velocities just changed
+    PD_TRY(pd_enqueue_ard_prepass_solids(c, srcC));
+    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));
+    PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, -1, -1, true));
     if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 1, buf, 1 - srcC));
     return 0;
 }
@@ -238,6 +271,7 @@ static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
 extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
     NEED_FIELDS(c);
     PD_TRY(pd_set_dt(c, 1, dt));
+    PD_TRY(pd_ensure_vmag(c, c->cur));
     bool use_graph = c->opt_graph && !(c->nranks > 1 && c->comm);
     for (int it = 0; it < steps; ++it) {
         int buf = c->cur, srcC = c->curC;
@@ -274,8 +308,9 @@ template <int DIM>
 __global__ void k_phase_change(const int* __restrict__ l_solid, long long n_solid, uint8_t* __restrict__ type,
                                uint8_t* __restrict__ phase, double* __restrict__ C, double* __restrict__ rho,
                                double* __restrict__ p, double* __restrict__ vx, double* __restrict__ vy,
-                               double* __restrict__ vz, double C_thresh, double rho_f, int* __restrict__ count,
-                               int* __restrict__ out, long long cap) {
+                               double* __restrict__ vz, double C_thresh, double rho_f, uint8_t* __restrict__ salt,
+                               double* __restrict__ dsol, int* __restrict__ count, int* __restrict__ out,
+                               long long cap) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_solid) return;
     int l = l_solid[t];
@@ -287,6 +322,8 @@ __global__ void k_phase_change(const int* __restrict__ l_solid, long long n_soli
         vx[l] = 0.0; vy[l] = 0.0;
         if (DIM == 3) vz[l] = 0.0;
         C[l] = C_thresh;
+        salt[l] = 0;
+        dsol[l] = 0.0;
         int pos = atomicAdd(count, 1);
         if (pos < cap) out[pos] = l;
     }
@@ -308,11 +345,11 @@ extern "C" int pdgpu_phase_change(pdgpu_ctx* c, int* n_dissolved, int* dissolved
         int b = c->cur, bc = c->curC;
         if (c->dim == 2)
             LAUNCH(c, k_phase_change<2>, nblocks(c->n_solid, 256), 256, 0, c->l_solid, c->n_solid, c->type, c->phase,
-                   c->C[bc], c->rho[b], c->p[b], VXYZ(c, b), c->cfg.C_thresh, c->cfg.rho_f, c->d_int, c->d_dissolved,
+                   c->C[bc], c->rho[b], c->p[b], VXYZ(c, b), c->cfg.C_thresh, c->cfg.rho_f, c->salt, c->dsol, c->d_int, c->d_dissolved,
                    c->dissolved_cap);
         else
             LAUNCH(c, k_phase_change<3>, nblocks(c->n_solid, 256), 256, 0, c->l_solid, c->n_solid, c->type, c->phase,
-                   c->C[bc], c->rho[b], c->p[b], VXYZ(c, b), c->cfg.C_thresh, c->cfg.rho_f, c->d_int, c->d_dissolved,
+                   c->C[bc], c->rho[b], c->p[b], VXYZ(c, b), c->cfg.C_thresh, c->cfg.rho_f, c->salt, c->dsol, c->d_int, c->d_dissolved,
                    c->dissolved_cap);
         CUDA_OK(cudaMemcpyAsync(&n, c->d_int, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -333,7 +370,7 @@ extern "C" int pdgpu_phase_change(pdgpu_ctx* c, int* n_dissolved, int* dissolved
         n_any = (int)c->h_red[0];
         if (n_any > 0) PD_TRY(pd_enqueue_halo(c, 2, c->cur, c->curC));   // types, phase, rho, vel, p, C
     }
-    if (n_any > 0) PD_TRY(pd_rebuild_tables(c));   // node lists, wall-mirror fallback, bond counts, graphs
+    if (n_any > 0) { pd_touch_flow(c); PD_TRY(pd_rebuild_tables(c)); }   // node lists, wall-mirror fallback, bond counts, graphs
     *n_dissolved = n;
     long long halo_shift = (long long)(c->a0 - c->R) * c->P;
     if (dissolved_global)

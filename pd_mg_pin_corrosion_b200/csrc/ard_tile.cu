@@ -21,6 +21,7 @@ using namespace tile;
 
 struct ArdTileParams {
     TileGeom g;
+    int skip_wall_copy;   // WALL values of the new buffer are written by the wall-concentration BC kernel
     double D_liquid, alpha_dx, beta, div_coeff, inv_dx;
 };
 
@@ -104,7 +105,7 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
     for (int t = 0; t < RZ; ++t) {
         fl[t] = (nty[t] == PDGPU_FLUID);
         any = any || fl[t];
-        if (nty[t] != 255 && !fl[t] && nty[t] != PDGPU_SOLID_MG) {
+        if (nty[t] != 255 && !fl[t] && nty[t] != PDGPU_SOLID_MG && !(q.skip_wall_copy && nty[t] == PDGPU_WALL)) {
             const long long l = (long long)(zt + t) * q.g.P + (long long)gy * q.g.Nx + gx;
             C_n[l] = C[l];   // src/pd_ard.cpp:86-89 (SOLID_MG rows: k_ard_solid_rows)
         }
@@ -173,7 +174,8 @@ k_ard_solid_rows(Lat L, const int* __restrict__ l_solid, long long n_solid, cons
 }  // namespace
 
 // returns -1 when the tiled kernel does not apply. Expects vmag (= vmf) and dsol to be current.
-int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid) {
+int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid,
+                        bool skip_wall_copy) {
     if (!c->full_rows) return -1;
     static ColTable T;
     double sum_kappa = 0.0;
@@ -181,6 +183,7 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
     PdConsts k = pd_consts(c->cfg, c->dim);
     ArdTileParams q;
     q.g = make_geom(c);
+    q.skip_wall_copy = skip_wall_copy ? 1 : 0;
     if (zb >= 0) { q.g.z_lo = zb; q.g.z_hi = ze; }
     q.D_liquid = c->cfg.D_liquid; q.alpha_dx = c->cfg.alpha_art_diff * c->cfg.dx;
     q.beta = k.beta_lap; q.div_coeff = k.alpha / k.V_H; q.inv_dx = 1.0 / c->cfg.dx;

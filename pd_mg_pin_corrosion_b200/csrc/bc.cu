@@ -122,7 +122,8 @@ __global__ void k_bc_wall(const int* __restrict__ list, const int* __restrict__ 
 // apply_wall_concentration_bc (src/boundary.cpp:302-321)
 template <int DIM>
 __global__ void k_bc_wall_conc(Lat L, const int* __restrict__ list, long long n, const uint8_t* __restrict__ type,
-                               const OffEntry* __restrict__ off, int n_off, double* __restrict__ C) {
+                               const OffEntry* __restrict__ off, int n_off, double* __restrict__ C,
+                               double* __restrict__ C_other) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     long long l = list[t];
@@ -135,7 +136,9 @@ __global__ void k_bc_wall_conc(Lat L, const int* __restrict__ list, long long n,
         long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
         if (nn >= 0 && type[nn] == PDGPU_FLUID) { s += C[nn]; ++cnt; }
     }
-    C[l] = cnt > 0 ? s / cnt : 0.0;
+    const double cw = cnt > 0 ? s / cnt : 0.0;
+    C[l] = cw;
+    if (C_other) C_other[l] = cw;   // the ARD step would copy it there (src/pd_ard.cpp:86-89)
 }
 
 // apply_solid_surface_bc (src/boundary.cpp:381-390)
@@ -204,15 +207,16 @@ int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part) {
     return 0;
 }
 
-int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC) {
+int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC, bool both_buffers) {
     if (!c->n_wall) return 0;
     Lat L = make_lat(c);
+    double* other = both_buffers ? c->C[1 - bufC] : nullptr;
     if (c->dim == 2)
         LAUNCH(c, k_bc_wall_conc<2>, nblocks(c->n_wall, 128), 128, 0, L, c->l_wall, c->n_wall, c->type, c->d_off,
-               c->n_off, c->C[bufC]);
+               c->n_off, c->C[bufC], other);
     else
         LAUNCH(c, k_bc_wall_conc<3>, nblocks(c->n_wall, 128), 128, 0, L, c->l_wall, c->n_wall, c->type, c->d_off,
-               c->n_off, c->C[bufC]);
+               c->n_off, c->C[bufC], other);
     return 0;
 }
 
@@ -229,18 +233,21 @@ int pd_enqueue_bc_solid(pdgpu_ctx* c, int buf) {
 
 extern "C" int pdgpu_bc_inlet(pdgpu_ctx* c) {
     NEED_FIELDS(c);
+    pd_touch_flow(c);
     PD_TRY(pd_enqueue_bc_inlet(c, c->cur, c->curC));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 extern "C" int pdgpu_bc_outlet(pdgpu_ctx* c) {
     NEED_FIELDS(c);
+    pd_touch_flow(c);
     PD_TRY(pd_enqueue_bc_outlet(c, c->cur, c->curC));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 extern "C" int pdgpu_bc_wall(pdgpu_ctx* c) {
     NEED_FIELDS(c);
+    pd_touch_flow(c);
     PD_TRY(pd_enqueue_bc_wall(c, c->cur));
     PD_TRY(pd_enqueue_bc_wall(c, c->cur, 3));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -248,6 +255,7 @@ extern "C" int pdgpu_bc_wall(pdgpu_ctx* c) {
 }
 extern "C" int pdgpu_bc_wall_new(pdgpu_ctx* c) {
     NEED_FIELDS(c);
+    pd_touch_flow(c);
     PD_TRY(pd_enqueue_bc_wall(c, 1 - c->cur));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
@@ -260,6 +268,7 @@ extern "C" int pdgpu_bc_wall_conc(pdgpu_ctx* c) {
 }
 extern "C" int pdgpu_bc_solid(pdgpu_ctx* c) {
     NEED_FIELDS(c);
+    pd_touch_flow(c);
     PD_TRY(pd_enqueue_bc_solid(c, c->cur));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;

@@ -115,6 +115,7 @@ struct pdgpu_ctx {
     int out_KP = 0, out_Wj = 0, out_ring = 0, out_mask_words = 0, out_tau_max = 0;
     size_t out_smem = 0;
     long long out_l0 = 0;
+    long long out_l0_any = 0;       // local index of the first node of the first outlet plane (any sweep variant)
     // overlap of the outlet sweep with the bulk bond kernel: walls below the first outlet plane,
     // first local plane whose stencil touches an outlet plane (tile aligned), -1 = no overlap
     long long n_wall_lo = 0;
@@ -140,6 +141,10 @@ struct pdgpu_ctx {
     bool full_rows = false;         // every owned FLUID/SOLID row has the full in-box stencil
 
     double volume_loss = 0.0;
+    // vmag cache: valid when computed from v[vmag_buf] at flow_epoch (velocities of FLUID nodes are
+    // frozen during the ARD phase; only the outlet planes are refreshed per step)
+    long long flow_epoch = 1, vmag_epoch = 0;
+    int vmag_buf = -1;
     long long launches = 0;
 
     // options
@@ -273,12 +278,16 @@ int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, -1 = not applicable
 int pd_outlet_setup(pdgpu_ctx* c);
 int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part = 0);   // part 0 all owned, 1 below the outlet planes, 2 in them, 3 ghost planes
-int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC);
+int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC, bool both_buffers = false);
 int pd_enqueue_bc_solid(pdgpu_ctx* c, int buf);
 int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt, int zb = -1, int ze = -1);   // local plane range
 int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);
-int pd_enqueue_ard_prepass(pdgpu_ctx* c, int buf, int srcC, long long lo, long long hi);
-int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid);
+int pd_enqueue_ard_prepass_solids(pdgpu_ctx* c, int srcC);
+int pd_enqueue_ard_vmag_range(pdgpu_ctx* c, int buf, long long lo, long long hi);
+int pd_ensure_vmag(pdgpu_ctx* c, int buf);
+inline void pd_touch_flow(pdgpu_ctx* c) { c->flow_epoch++; }
+int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid,
+                        bool skip_wall_copy = false);
 int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC);
 int pd_max_fluid_speed(pdgpu_ctx* c, double* vmax);
 void pd_invalidate_graphs(pdgpu_ctx* c);

@@ -202,6 +202,7 @@ extern "C" int pdgpu_fields_upload(pdgpu_ctx* c, int field, const void* host) {
                    (double*)r.ptr[1] + loff, (double*)r.ptr[2] + loff);
     }
     if (r.flow_buf >= 0) PD_TRY(pd_refresh_eos(c, r.flow_buf));
+    pd_touch_flow(c);
     CUDA_OK(cudaStreamSynchronize(c->stream));
     c->fields_ready = true;
     return 0;
@@ -259,13 +260,14 @@ extern "C" int pdgpu_fields_init(pdgpu_ctx* c, const uint8_t* is_gb, const uint8
         LAUNCH(c, k_init_fields<3>, nblocks(c->NL, 256), 256, 0, g, L, c->NL, c->cfg, k.B_eos, c->type, c->phase,
                c->rho[0], c->rho[1], c->p[0], c->p[1], c->C[0], c->C[1], c->v[0][0], c->v[0][1], c->v[0][2],
                c->v[1][0], c->v[1][1], c->v[1][2]);
-    PD_TRY(pd_refresh_vmag(c, 0));
+    pd_touch_flow(c);
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 extern "C" int pdgpu_swap_flow(pdgpu_ctx* c) {
     CHECK_CTX(c);
+    pd_touch_flow(c);
     c->cur = 1 - c->cur;
     return 0;
 }

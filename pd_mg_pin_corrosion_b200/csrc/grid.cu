@@ -324,6 +324,7 @@ static int build_outlet_schedule(pdgpu_ctx* c) {
     std::vector<long long> tau(c->n_outlet);
     long long base = c->R + 1;
     long long al_min = nodes.front() / c->P;
+    c->out_l0_any = al_min * c->P;
     for (long long t = 0; t < c->n_outlet; ++t) {
         long long l = nodes[t];
         long long al = l / c->P, q = l % c->P;
@@ -352,6 +353,7 @@ static int build_outlet_schedule(pdgpu_ctx* c) {
 
 int pd_rebuild_tables(pdgpu_ctx* c) {
     pd_invalidate_graphs(c);
+    pd_touch_flow(c);   // node types may have changed: cached |v| is stale
     long long own_n = c->own_hi - c->own_lo;
     Lat L = make_lat(c);
     double org[3] = {c->origin[0], c->origin[1], c->origin[2]};

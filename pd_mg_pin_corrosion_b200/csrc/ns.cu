@@ -262,6 +262,7 @@ int pd_set_dt(pdgpu_ctx* c, int slot, double dt) {
 
 extern "C" int pdgpu_ns_step(pdgpu_ctx* c, double dt) {
     NEED_FIELDS(c);
+    pd_touch_flow(c);
     PD_TRY(pd_set_dt(c, 0, dt));
     PD_TRY(pd_enqueue_ns_step(c, c->cur, c->d_dt));
     c->p_input = c->cur;
@@ -375,6 +376,7 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
 
 static int run_ns_body(pdgpu_ctx* c) {
     int src = c->cur;
+    pd_touch_flow(c);
     bool use_graph = c->opt_graph && !(c->nranks > 1 && c->comm);
     if (!use_graph) return enqueue_ns_body(c, src);
     if (!c->g_ns[src]) {
