@@ -216,6 +216,7 @@ extern "C" int pdgpu_ard_compute_dt(pdgpu_ctx* c, double* dt) {   // src/pd_ard.
 
 extern "C" int pdgpu_ard_step(pdgpu_ctx* c, double dt) {
     NEED_FIELDS(c);
+    PD_TRY(pd_flush_wall_c(c));
     PD_TRY(pd_set_dt(c, 1, dt));
     PD_TRY(pd_enqueue_ard_step(c, c->cur, c->curC, c->d_dt + 1));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -239,10 +240,10 @@ static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
             PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
             PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0, c->NL));
             // WALL concentrations are never read by a bond (src/pd_ard.cpp:120): off the critical path
-            if (tiles) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC, true));
+            if (tiles && !c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC, true));
         }
         PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
-        if (!tiles) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
+        if (!tiles && !c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
         PD_TRY(pd_enqueue_ard_prepass_solids(c, srcC));
         if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));
         CUDA_OK(cudaEventRecord(c->ev_b, main_s));
@@ -259,7 +260,7 @@ static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
     }
     PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
     PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
-    PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
+    if (!c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
     if (c->n_outlet) PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0_any, c->NL));   // outlet velocities just changed
     PD_TRY(pd_enqueue_ard_prepass_solids(c, srcC));
     if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));
@@ -270,6 +271,9 @@ static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
 
 extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
     NEED_FIELDS(c);
+    if (steps <= 0) return 0;
+    // an owed wall-C evaluation is superseded by the one of the first step of this call (both write
+    // every WALL node from FLUID values only), unless nobody evaluates it again: keep it pending
     PD_TRY(pd_set_dt(c, 1, dt));
     PD_TRY(pd_ensure_vmag(c, c->cur));
     bool use_graph = c->opt_graph && !(c->nranks > 1 && c->comm);
@@ -297,6 +301,7 @@ extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
             c->launches += c->g_ard_nodes[buf][srcC];
         }
         c->curC = 1 - c->curC;   // std::swap(fields.C, fields.C_new)
+        if (c->opt_lazy_wallc) { c->wallC_pending = true; c->wallC_src = 1 - c->curC; }
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaGetLastError());
@@ -331,6 +336,7 @@ __global__ void k_phase_change(const int* __restrict__ l_solid, long long n_soli
 
 extern "C" int pdgpu_phase_change(pdgpu_ctx* c, int* n_dissolved, int* dissolved_global, int cap) {
     NEED_FIELDS(c);
+    PD_TRY(pd_flush_wall_c(c));   // node types are about to change
     if (!n_dissolved) PD_FAIL("pdgpu_phase_change: null output");
     *n_dissolved = 0;
     int n = 0;

@@ -122,8 +122,8 @@ __global__ void k_bc_wall(const int* __restrict__ list, const int* __restrict__ 
 // apply_wall_concentration_bc (src/boundary.cpp:302-321)
 template <int DIM>
 __global__ void k_bc_wall_conc(Lat L, const int* __restrict__ list, long long n, const uint8_t* __restrict__ type,
-                               const OffEntry* __restrict__ off, int n_off, double* __restrict__ C,
-                               double* __restrict__ C_other) {
+                               const OffEntry* __restrict__ off, int n_off, const double* Csrc, double* C,
+                               double* C_other) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     long long l = list[t];
@@ -134,7 +134,7 @@ __global__ void k_bc_wall_conc(Lat L, const int* __restrict__ list, long long n,
     int cnt = 0;
     for (int o = 0; o < n_off; ++o) {
         long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
-        if (nn >= 0 && type[nn] == PDGPU_FLUID) { s += C[nn]; ++cnt; }
+        if (nn >= 0 && type[nn] == PDGPU_FLUID) { s += Csrc[nn]; ++cnt; }
     }
     const double cw = cnt > 0 ? s / cnt : 0.0;
     C[l] = cw;
@@ -207,16 +207,17 @@ int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part) {
     return 0;
 }
 
-int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC, bool both_buffers) {
+int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC, bool both_buffers, int srcC) {
     if (!c->n_wall) return 0;
     Lat L = make_lat(c);
     double* other = both_buffers ? c->C[1 - bufC] : nullptr;
+    const double* src = c->C[srcC >= 0 ? srcC : bufC];   // FLUID values that are averaged
     if (c->dim == 2)
         LAUNCH(c, k_bc_wall_conc<2>, nblocks(c->n_wall, 128), 128, 0, L, c->l_wall, c->n_wall, c->type, c->d_off,
-               c->n_off, c->C[bufC], other);
+               c->n_off, src, c->C[bufC], other);
     else
         LAUNCH(c, k_bc_wall_conc<3>, nblocks(c->n_wall, 128), 128, 0, L, c->l_wall, c->n_wall, c->type, c->d_off,
-               c->n_off, c->C[bufC], other);
+               c->n_off, src, c->C[bufC], other);
     return 0;
 }
 
@@ -260,8 +261,19 @@ extern "C" int pdgpu_bc_wall_new(pdgpu_ctx* c) {
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;
 }
+// The reference applies apply_wall_concentration_bc before every explicit step and the step copies
+// the WALL values into C_new (src/coupling.cpp:235-238, src/pd_ard.cpp:86-89). Device-resident
+// steps skip it (no bond reads WALL C) and leave it owed; it is evaluated here from the pre-step
+// buffer as soon as anything could observe WALL concentrations.
+int pd_flush_wall_c(pdgpu_ctx* c) {
+    if (!c->wallC_pending) return 0;
+    c->wallC_pending = false;
+    return pd_enqueue_bc_wall_conc(c, 1 - c->wallC_src, true, c->wallC_src);
+}
+
 extern "C" int pdgpu_bc_wall_conc(pdgpu_ctx* c) {
     NEED_FIELDS(c);
+    PD_TRY(pd_flush_wall_c(c));
     PD_TRY(pd_enqueue_bc_wall_conc(c, c->curC));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     return 0;

@@ -143,6 +143,10 @@ struct pdgpu_ctx {
     double volume_loss = 0.0;
     // vmag cache: valid when computed from v[vmag_buf] at flow_epoch (velocities of FLUID nodes are
     // frozen during the ARD phase; only the outlet planes are refreshed per step)
+    // lazy wall-concentration BC: WALL C is never read by a bond; after a device-resident ARD step the
+    // BC of that step is still owed: C[wallC_src] holds the pre-step FLUID values it averages
+    bool wallC_pending = false;
+    int wallC_src = 0;
     long long flow_epoch = 1, vmag_epoch = 0;
     int vmag_buf = -1;
     long long launches = 0;
@@ -152,6 +156,7 @@ struct pdgpu_ctx {
     int opt_ard_kernel = 1;
     int opt_graph = 1;
     int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)
+    int opt_lazy_wallc = 1;         // evaluate the wall-concentration BC only when somebody reads WALL C
     int opt_overlap = 1;            // run the outlet sweep on a side stream next to the bulk kernel
     int opt_outlet_kernel = 2;      // 0 = level-list kernel, 1 = level-addressed ring, 2 = lattice-addressed ring
 
@@ -278,7 +283,8 @@ int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, -1 = not applicable
 int pd_outlet_setup(pdgpu_ctx* c);
 int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part = 0);   // part 0 all owned, 1 below the outlet planes, 2 in them, 3 ghost planes
-int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC, bool both_buffers = false);
+int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC, bool both_buffers = false, int srcC = -1);
+int pd_flush_wall_c(pdgpu_ctx* c);   // run an owed wall-concentration BC (no-op otherwise)
 int pd_enqueue_bc_solid(pdgpu_ctx* c, int buf);
 int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt, int zb = -1, int ze = -1);   // local plane range
 int pd_enqueue_ard_step(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);

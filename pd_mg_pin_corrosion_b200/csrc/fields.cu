@@ -176,6 +176,7 @@ static int field_ref(pdgpu_ctx* c, int field, FieldRef* r) {
 
 extern "C" int pdgpu_fields_upload(pdgpu_ctx* c, int field, const void* host) {
     NEED_GRID(c);
+    if (field == PDGPU_F_C || field == PDGPU_F_C_NEW) PD_TRY(pd_flush_wall_c(c));
     if (!host) PD_FAIL("pdgpu_fields_upload: null host array");
     if (field == PDGPU_F_NODE_TYPE) return pdgpu_grid_set_types(c, (const uint8_t*)host);
     if (field == PDGPU_F_PRESSURE) return 0;   // derived: p == EOS(rho) is maintained on device
@@ -210,6 +211,7 @@ extern "C" int pdgpu_fields_upload(pdgpu_ctx* c, int field, const void* host) {
 
 extern "C" int pdgpu_fields_download(pdgpu_ctx* c, int field, void* host) {
     NEED_GRID(c);
+    if (field == PDGPU_F_C || field == PDGPU_F_C_NEW) PD_TRY(pd_flush_wall_c(c));
     if (!host) PD_FAIL("pdgpu_fields_download: null host array");
     FieldRef r;
     PD_TRY(field_ref(c, field, &r));
@@ -273,12 +275,14 @@ extern "C" int pdgpu_swap_flow(pdgpu_ctx* c) {
 }
 extern "C" int pdgpu_swap_C(pdgpu_ctx* c) {
     CHECK_CTX(c);
+    PD_TRY(pd_flush_wall_c(c));
     c->curC = 1 - c->curC;
     return 0;
 }
 
 extern "C" int pdgpu_gather(pdgpu_ctx* c, int field, const int* idx, long long n, double* out) {
     NEED_GRID(c);
+    if (field == PDGPU_F_C || field == PDGPU_F_C_NEW) PD_TRY(pd_flush_wall_c(c));
     if (n <= 0) return 0;
     FieldRef r;
     PD_TRY(field_ref(c, field, &r));
