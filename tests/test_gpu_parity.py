@@ -374,3 +374,50 @@ def test_steady_state_known_answers(case, iters, eps, l2):
     v = fields.get("vel")
     assert H.rel_err(v[::97], np.array(gold["vel_sample"])) <= 1e-10   # ~2e4 iterations of rounding drift
     assert H.rel_err(fields.get("rho")[::97], np.array(gold["rho_sample"])) <= 1e-12
+
+
+def test_full_size_params_fine_vs_port_oracle():
+    """BASELINE config 4 at full size (3D params_fine, dx = 2 um, 157 x 157 x 707 = 17.4 M nodes,
+    2.39 G CSR-equivalent bonds -- beyond the reference's int32 CSR): classification,
+    wall-mirror table and one full NS + ARD loop body against the stencil-implicit plain-C oracle."""
+    import os
+    from oracle.portapi import PortSim
+    from pd_mg_pin_corrosion_b200 import solver as S
+    from pd_mg_pin_corrosion_b200.config import Config
+    from pd_mg_pin_corrosion_b200.grains import GrainStructure
+    cfg = Config.load(os.path.join(H.CONFIG_DIR, "params_fine.cfg"), {"use_implicit": 0}, quiet=True)
+    port = PortSim(3, cfg, threads=os.cpu_count() or 4)
+    grid = S.Grid(3)
+    grid.build(cfg)
+    assert (grid.Nx, grid.Ny, grid.Nz) == (157, 157, 707) == (port.Nx, port.Ny, port.Nz)
+    nt = grid.node_type
+    assert np.array_equal(nt, port.node_type)
+    assert np.array_equal(grid.wall_mirror, port.wall_mirror)
+    assert grid.info.ns_bonds == 178 * int((nt == 0).sum())          # every FLUID row is full (appendix A)
+    grains = GrainStructure().generate(nt, cfg, 3)
+    port.init_fields(grains.is_grain_boundary, grains.is_precipitate)
+    # non-trivial state: perturb, then let both sides start from the identical arrays
+    rng = np.random.default_rng(11)
+    fl = nt != 5
+    port.rho *= 1.0 + 1e-4 * rng.standard_normal(port.N) * fl
+    port.vel += 1e-3 * rng.standard_normal(port.vel.shape) * (nt == 0)[:, None]
+    port.C[:] = np.abs(port.C + 0.02 * rng.standard_normal(port.N)) * fl
+    port.rho_new[:] = port.rho; port.vel_new[:] = port.vel; port.C_new[:] = port.C
+    fields = S.Fields()
+    fields.allocate(grid.N_total, grid)
+    S.initialize_fields(fields, grid, grains, cfg)
+    for n in ("rho", "vel", "C", "rho_new", "vel_new", "C_new"):
+        fields.set(n, getattr(port, n))
+    ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
+    ns.init(grid, cfg); ard.init(grid, cfg)
+    dt = port.ns_compute_dt()
+    assert abs(ns.compute_dt(fields, grid, cfg) - dt) <= 1e-15 * dt
+    port.ns_iterate(1, dt)
+    ns.iterate(fields, grid, cfg, 1, dt)
+    for n in ("rho", "vel"):
+        assert H.rel_err(fields.get(n), getattr(port, n)) <= TOL, n
+    dtc = port.ard_compute_dt()
+    port.ard_iterate(1, dtc)
+    ard.iterate(fields, grid, cfg, 1, dtc)
+    for n in ("rho", "vel", "C"):
+        assert H.rel_err(fields.get(n), getattr(port, n)) <= TOL, n
