@@ -215,6 +215,10 @@ class PortSim:
         self.last_dissolved = d[:n].copy()
         return n
 
+    def rebuild_tables(self):
+        """after editing node_type in place (hand-built geometries)"""
+        self.L.pdo_wall_mirror_build(self.g, self.c)
+
     def rebuild_neighbors(self):
         pass  # stencil-implicit: nothing to rebuild (wall-mirror table is refreshed by pdo_phase_change)
 

@@ -202,6 +202,9 @@ class RefSim:
     def rebuild_neighbors(self):
         self.lib.ref_update_node_types(self.h)
         self.lib.ref_build_neighbors(self.h)
+    def rebuild_tables(self):
+        """after editing node_type in place: Grid::build_neighbors filters OUTSIDE only -> nothing to do"""
+
     def time_ns(self, n, dt) -> float: return self.lib.ref_time_ns_iterate(self.h, n, dt)
     def time_ard(self, n, dt) -> float: return self.lib.ref_time_ard_iterate(self.h, n, dt)
 

@@ -36,7 +36,7 @@ def load_cfg(case: str, extra: dict | None = None) -> tuple[int, Config, dict]:
     ov = dict(ov)
     ov["use_implicit"] = 0
     ov.update(extra or {})
-    cfg = Config.load(os.path.join(CONFIG_DIR, base), ov, quiet=True)
+    cfg = Config.load(os.path.join(CONFIG_DIR, base) if base else None, ov, quiet=True)
     return dim, cfg, ov
 
 
