@@ -21,6 +21,7 @@
  */
 #ifndef PDGPU_H
 #define PDGPU_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -169,6 +170,22 @@ int pdgpu_ard_compute_dt(pdgpu_ctx* ctx, double* dt);
 int pdgpu_ard_step(pdgpu_ctx* ctx, double dt);       /* salt pre-pass + bond sums -> C_new */
 /* `steps` x { inlet, outlet, wall_conc, step, swap C } (src/coupling.cpp:232-240). */
 int pdgpu_ard_iterate(pdgpu_ctx* ctx, int steps, double dt);
+
+/* ---- One coupling-loop pass on HOST-resident Fields -------------------------------------
+ * What a caller that keeps the reference's Fields vectors (src/fields.h:28-58) in host memory
+ * runs per pass: rho/vel/C in, { NS loop body (src/pd_ns.cpp:196-205,325) ; ARD loop body
+ * (src/coupling.cpp:232-240) } on the device, rho/vel/C out, in place. `vel` is the reference's
+ * AoS std::vector<Vec> ([N][dim]); all arrays are global [N_total]. The axial planes are cut
+ * into `n_chunks` chunks (0/1 = whole domain at once) whose uploads, kernels and downloads
+ * overlap; results are bit-identical to upload + pdgpu_ns_iterate(1) + pdgpu_ard_iterate(1) +
+ * download. Pin the arrays (pdgpu_host_register) or the copies serialise. */
+int pdgpu_step_host(pdgpu_ctx* ctx, double dt_ns, double dt_ard, double* rho, double* vel, double* C,
+                    int n_chunks);
+/* Chunks pdgpu_step_host would use for `n_chunks` on this geometry, and why it fell back to 1. */
+int pdgpu_step_host_chunks(pdgpu_ctx* ctx, int n_chunks, int* n_used, char* why, int why_len);
+/* cudaHostRegister / cudaHostUnregister of caller-owned memory (e.g. std::vector storage). */
+int pdgpu_host_register(void* ptr, size_t bytes);
+int pdgpu_host_unregister(void* ptr);
 /* apply_phase_change + update_node_types + table rebuild (src/coupling.cpp:256-271).
  * dissolved_global (may be NULL) receives up to `cap` ascending global indices. */
 int pdgpu_phase_change(pdgpu_ctx* ctx, int* n_dissolved, int* dissolved_global, int cap);

@@ -120,10 +120,12 @@ extern "C" int pdgpu_create(const PdConfig* cfg, int dim, int device, pdgpu_ctx*
 }
 
 void pd_invalidate_graphs(pdgpu_ctx* c) {
+    c->tables_epoch++;   // also drops the chunk plan of pdgpu_step_host
     for (int a = 0; a < 2; ++a) {
-        if (c->g_ns[a]) { cudaGraphExecDestroy(c->g_ns[a]); c->g_ns[a] = nullptr; }
-        for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < 2; ++b) {
+            if (c->g_ns[a][b]) { cudaGraphExecDestroy(c->g_ns[a][b]); c->g_ns[a][b] = nullptr; }
             if (c->g_ard[a][b]) { cudaGraphExecDestroy(c->g_ard[a][b]); c->g_ard[a][b] = nullptr; }
+        }
     }
 }
 
@@ -134,6 +136,7 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     pd_invalidate_graphs(c);
+    pd_host_step_free(c);
     pd_comm_destroy(c);
     void* ptrs[] = {c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->rho[0], c->rho[1],
                     c->p[0], c->p[1], c->C[0], c->C[1], c->v[0][0], c->v[0][1], c->v[0][2], c->v[1][0],

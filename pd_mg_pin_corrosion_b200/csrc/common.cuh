@@ -168,10 +168,14 @@ struct pdgpu_ctx {
     size_t l2_scratch_bytes = 0;
 
     // CUDA graphs of one loop body per buffer parity
-    cudaGraphExec_t g_ns[2] = {nullptr, nullptr};
+    cudaGraphExec_t g_ns[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [flow buffer][C buffer the BCs write]
     cudaGraphExec_t g_ard[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     double* d_dt = nullptr;         // device scalars: [0] ns dt, [1] ard dt, [2] decay factor
-    long long g_ns_nodes[2] = {0, 0}, g_ard_nodes[2][2] = {{0, 0}, {0, 0}};
+    long long g_ns_nodes[2][2] = {{0, 0}, {0, 0}}, g_ard_nodes[2][2] = {{0, 0}, {0, 0}};
+
+    // host-array step (host_step.cu): chunk plan, copy streams, AoS staging
+    long long tables_epoch = 0;     // bumped by pd_rebuild_tables
+    struct HostStep* hs = nullptr;
 };
 
 // PD constants of PD_NS_Solver::init / PD_ARD_Solver::init (src/pd_ns.cpp:7-16).
@@ -299,6 +303,11 @@ int pd_max_fluid_speed(pdgpu_ctx* c, double* vmax);
 void pd_invalidate_graphs(pdgpu_ctx* c);
 int pd_refresh_eos(pdgpu_ctx* c, int buf);           // p[buf] = EOS(rho[buf]) on all local nodes
 int pd_refresh_vmag(pdgpu_ctx* c, int buf);
+int pd_enqueue_eos_range(pdgpu_ctx* c, int buf, long long lo, long long n);             // fields.cu
+int pd_enqueue_deinterleave(pdgpu_ctx* c, const double* aos, long long lo, long long n, int buf);
+int pd_enqueue_interleave(pdgpu_ctx* c, double* aos, long long lo, long long n, int buf);
+int pd_enqueue_channel_corrections(pdgpu_ctx* c, int buf);                              // ns.cu
+void pd_host_step_free(pdgpu_ctx* c);                                                   // host_step.cu
 int pd_enqueue_ns_step_csr(pdgpu_ctx* c, int src, const double* d_dt);                 // csr_path.cu
 int pd_enqueue_ard_step_csr(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);       // csr_path.cu
 int pd_set_dt(pdgpu_ctx* c, int slot, double value);

@@ -124,6 +124,34 @@ int pd_refresh_eos(pdgpu_ctx* c, int buf) {
     return 0;
 }
 
+int pd_enqueue_eos_range(pdgpu_ctx* c, int buf, long long lo, long long n) {
+    if (n <= 0) return 0;
+    PdConsts k = pd_consts(c->cfg, c->dim);
+    LAUNCH(c, k_eos, nblocks(n, 256), 256, 0, c->rho[buf] + lo, c->p[buf] + lo, n, c->cfg.rho_f, c->cfg.gamma_eos,
+           k.B_eos);
+    return 0;
+}
+
+// AoS (reference std::vector<Vec>) <-> SoA for n nodes starting at local index lo of flow buffer buf
+int pd_enqueue_deinterleave(pdgpu_ctx* c, const double* aos, long long lo, long long n, int buf) {
+    if (n <= 0) return 0;
+    if (c->dim == 2)
+        LAUNCH(c, k_deinterleave<2>, nblocks(n, 256), 256, 0, aos, n, c->v[buf][0] + lo, c->v[buf][1] + lo, nullptr);
+    else
+        LAUNCH(c, k_deinterleave<3>, nblocks(n, 256), 256, 0, aos, n, c->v[buf][0] + lo, c->v[buf][1] + lo,
+               c->v[buf][2] + lo);
+    return 0;
+}
+int pd_enqueue_interleave(pdgpu_ctx* c, double* aos, long long lo, long long n, int buf) {
+    if (n <= 0) return 0;
+    if (c->dim == 2)
+        LAUNCH(c, k_interleave<2>, nblocks(n, 256), 256, 0, aos, n, c->v[buf][0] + lo, c->v[buf][1] + lo, nullptr);
+    else
+        LAUNCH(c, k_interleave<3>, nblocks(n, 256), 256, 0, aos, n, c->v[buf][0] + lo, c->v[buf][1] + lo,
+               c->v[buf][2] + lo);
+    return 0;
+}
+
 int pd_refresh_vmag(pdgpu_ctx* c, int buf) {
     if (c->dim == 2)
         LAUNCH(c, k_vmag<2>, nblocks(c->NL, 256), 256, 0, c->v[buf][0], c->v[buf][1], nullptr, c->vmag, c->NL);

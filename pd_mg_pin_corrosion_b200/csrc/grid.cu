@@ -353,6 +353,7 @@ static int build_outlet_schedule(pdgpu_ctx* c) {
 
 int pd_rebuild_tables(pdgpu_ctx* c) {
     pd_invalidate_graphs(c);
+    c->tables_epoch++;
     pd_touch_flow(c);   // node types may have changed: cached |v| is stale
     long long own_n = c->own_hi - c->own_lo;
     Lat L = make_lat(c);

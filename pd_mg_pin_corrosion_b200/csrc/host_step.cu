@@ -1,0 +1,298 @@
+// host_step.cu -- one coupling-loop pass (NS loop body + ARD loop body) on HOST-resident state.
+//
+// The reference keeps Fields in host memory (src/fields.h:28-58) and its loop bodies
+// (src/pd_ns.cpp:196-205, src/coupling.cpp:232-240) read and write those vectors.  A drop-in call
+// with host arrays therefore moves rho, vel and C over PCIe in both directions every step, and
+// those copies -- not the bond kernels -- bound the step (5 doubles per node each way).
+//
+// pdgpu_step_host hides the compute and one of the two copy directions: the axial planes are cut
+// into chunks that are processed from the outlet end downwards,
+//
+//     upload(k)        copy engine 1   rho, vel (AoS), C of chunk k
+//     A(k)             compute         EOS, inlet/outlet/wall/solid BCs on chunk k
+//     N(k+1), W(k+1)   compute         NS bond kernel and wall mirror of the new buffers
+//     B(k+1)           compute         ARD-body BCs, |v|, wall concentration, salt pre-pass
+//     D(k+2)           compute         ARD bond kernel
+//     download(k+2)    copy engine 2   new rho, vel, C of chunk k+2
+//
+// so that every bond kernel sees its +-reach planes in the state the sequential order gives
+// them.  The arithmetic per node is that of pdgpu_ns_iterate(1) + pdgpu_ard_iterate(1); results
+// are bit-identical (tests/test_gpu_parity.py::test_step_host_*).  Geometries that do not meet
+// the chunk invariants (checked when the plan is built) run the same operators unchunked.
+#include <algorithm>
+
+#include "common.cuh"
+
+struct HostStep {
+    long long epoch = -1;
+    int n_req = 0;
+    int n = 1;                          // chunks (1 = unchunked)
+    std::vector<int> zb;                // local plane boundaries [n+1]
+    std::vector<long long> wall_lo, solid_lo;   // list offsets per chunk [n+1]
+    cudaStream_t s_up = nullptr, s_down = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_cmp;
+    cudaEvent_t ev_start = nullptr, ev_end = nullptr;
+    double *stage_up = nullptr, *stage_down = nullptr;
+    size_t stage_elems = 0;
+    char why[160] = {0};                // why the plan fell back to one chunk
+};
+
+void pd_host_step_free(pdgpu_ctx* c) {
+    HostStep* h = c->hs;
+    if (!h) return;
+    for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_cmp) cudaEventDestroy(e);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_end) cudaEventDestroy(h->ev_end);
+    if (h->s_up) cudaStreamDestroy(h->s_up);
+    if (h->s_down) cudaStreamDestroy(h->s_down);
+    if (h->stage_up) cudaFree(h->stage_up);
+    if (h->stage_down) cudaFree(h->stage_down);
+    delete h;
+    c->hs = nullptr;
+}
+
+namespace {
+
+// narrows the WALL and SOLID lists of the context to the entries of one chunk
+struct ListWindow {
+    pdgpu_ctx* c;
+    int *w, *wm, *s;
+    long long nw, ns;
+    ListWindow(pdgpu_ctx* ctx, const HostStep& h, int k)
+        : c(ctx), w(ctx->l_wall), wm(ctx->l_wall_mirror), s(ctx->l_solid), nw(ctx->n_wall), ns(ctx->n_solid) {
+        c->l_wall = w + h.wall_lo[k];
+        c->l_wall_mirror = wm + h.wall_lo[k];
+        c->n_wall = h.wall_lo[k + 1] - h.wall_lo[k];
+        c->l_solid = s + h.solid_lo[k];
+        c->n_solid = h.solid_lo[k + 1] - h.solid_lo[k];
+    }
+    ~ListWindow() {
+        c->l_wall = w; c->l_wall_mirror = wm; c->n_wall = nw;
+        c->l_solid = s; c->n_solid = ns;
+    }
+};
+
+int fallback(HostStep* h, const char* why) {
+    h->n = 1;
+    snprintf(h->why, sizeof(h->why), "%s", why);
+    return 0;
+}
+
+int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
+    h->epoch = c->tables_epoch;
+    h->n_req = n_req;
+    h->why[0] = 0;
+    const int lo = c->R, nz = c->a1 - c->a0, hi = lo + nz;
+    const int TZ = 4;   // tile::TZ: chunk boundaries stay tile aligned
+    h->zb.assign(2, lo);
+    h->zb[1] = hi;
+    h->n = 1;
+    if (n_req < 2) return fallback(h, "one chunk requested");
+    if (c->nranks > 1) return fallback(h, "slab contexts exchange halos: unchunked");
+    if (c->opt_ns_kernel == 3 || c->opt_ard_kernel == 3) return fallback(h, "CSR kernels take no plane range");
+    if (c->cfg.channel_flow_corrections) return fallback(h, "channel_flow_corrections");
+    if (c->n_outlet > 0 && !(c->out_fast && c->opt_outlet_kernel > 0)) {
+        // the level-list sweep is fine too, it only needs the outlet planes; nothing to check
+    }
+    // top chunk: every OUTLET node and its reach must lie inside it
+    int thick = ((nz + n_req - 1) / n_req + TZ - 1) / TZ * TZ;
+    thick = std::max(thick, 2 * c->R + TZ);
+    int zt = hi - thick;
+    int zo_first = hi, zi_last = -1;
+    if (c->n_outlet) {
+        int first = 0;
+        CUDA_OK(cudaMemcpy(&first, c->l_outlet, sizeof(int), cudaMemcpyDeviceToHost));
+        zo_first = (int)(first / c->P);
+        zt = std::min(zt, zo_first - c->R);
+    }
+    if (c->n_inlet) {
+        int last = 0;
+        CUDA_OK(cudaMemcpy(&last, c->l_inlet + (c->n_inlet - 1), sizeof(int), cudaMemcpyDeviceToHost));
+        zi_last = (int)(last / c->P);
+    }
+    zt = lo + (zt - lo) / TZ * TZ;
+    if (zt - lo < 2 * c->R + TZ) return fallback(h, "domain too short for two chunks");
+    // lower chunks: equal thickness, tile aligned
+    int n_low = std::max(1, std::min(n_req - 1, (zt - lo) / std::max(2 * c->R + TZ, TZ)));
+    std::vector<int> zb;
+    zb.push_back(lo);
+    for (int k = 1; k < n_low; ++k) {
+        int z = lo + (int)((long long)(zt - lo) * k / n_low) / TZ * TZ;
+        if (z - zb.back() >= 2 * c->R + TZ && zt - z >= 2 * c->R + TZ) zb.push_back(z);
+    }
+    zb.push_back(zt);
+    zb.push_back(hi);
+    const int n = (int)zb.size() - 1;
+    if (zi_last >= zb[1]) return fallback(h, "INLET nodes above the first chunk");
+
+    std::vector<int> w(c->n_wall), wm(c->n_wall), s(c->n_solid);
+    if (c->n_wall) {
+        CUDA_OK(cudaMemcpy(w.data(), c->l_wall, sizeof(int) * c->n_wall, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(wm.data(), c->l_wall_mirror, sizeof(int) * c->n_wall, cudaMemcpyDeviceToHost));
+    }
+    if (c->n_solid) CUDA_OK(cudaMemcpy(s.data(), c->l_solid, sizeof(int) * c->n_solid, cudaMemcpyDeviceToHost));
+    std::vector<long long> wl(n + 1), sl(n + 1);
+    for (int k = 0; k <= n; ++k) {
+        long long first = (long long)zb[k] * c->P;
+        wl[k] = std::lower_bound(w.begin(), w.end(), first, [](int a, long long b) { return (long long)a < b; }) - w.begin();
+        sl[k] = std::lower_bound(s.begin(), s.end(), first, [](int a, long long b) { return (long long)a < b; }) - s.begin();
+    }
+    wl[0] = 0; sl[0] = 0; wl[n] = c->n_wall; sl[n] = c->n_solid;
+    // a WALL node must find its mirror node inside its own chunk (same BC state as unchunked)
+    for (int k = 0; k < n; ++k)
+        for (long long t = wl[k]; t < wl[k + 1]; ++t) {
+            if (wm[t] < 0) continue;
+            int zm = (int)(wm[t] / c->P);
+            if (zm < zb[k] || zm >= zb[k + 1]) return fallback(h, "a wall mirror crosses a chunk boundary");
+        }
+    h->n = n;
+    h->zb = zb;
+    h->wall_lo = wl;
+    h->solid_lo = sl;
+    return 0;
+}
+
+int ensure(pdgpu_ctx* c, int n_req) {
+    if (!c->hs) c->hs = new HostStep();
+    HostStep* h = c->hs;
+    if (!h->s_up) {
+        CUDA_OK(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&h->ev_end, cudaEventDisableTiming));
+    }
+    if (h->epoch != c->tables_epoch || h->n_req != n_req) PD_TRY(build_plan(c, h, n_req));
+    while ((int)h->ev_up.size() < h->n) {
+        cudaEvent_t a, b;
+        CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_up.push_back(a);
+        h->ev_cmp.push_back(b);
+    }
+    size_t need = (size_t)(c->own_hi - c->own_lo) * c->dim;
+    if (h->n > 1 && h->stage_elems < need) {
+        if (h->stage_up) CUDA_OK(cudaFree(h->stage_up));
+        if (h->stage_down) CUDA_OK(cudaFree(h->stage_down));
+        h->stage_up = h->stage_down = nullptr;
+        CUDA_OK(cudaMalloc(&h->stage_up, sizeof(double) * need));
+        CUDA_OK(cudaMalloc(&h->stage_down, sizeof(double) * need));
+        h->stage_elems = need;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pdgpu_step_host_chunks(pdgpu_ctx* c, int n_chunks, int* n_used, char* why, int why_len) {
+    NEED_GRID(c);
+    PD_TRY(ensure(c, n_chunks));
+    if (n_used) *n_used = c->hs->n;
+    if (why && why_len > 0) snprintf(why, (size_t)why_len, "%s", c->hs->why);
+    return 0;
+}
+
+extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double* rho, double* vel, double* C,
+                               int n_chunks) {
+    NEED_GRID(c);
+    if (!rho || !vel || !C) PD_FAIL("pdgpu_step_host: null host array");
+    PD_TRY(ensure(c, n_chunks));
+    HostStep* h = c->hs;
+    if (h->n <= 1) {   // same operators, whole domain at once
+        PD_TRY(pdgpu_fields_upload(c, PDGPU_F_RHO, rho));
+        PD_TRY(pdgpu_fields_upload(c, PDGPU_F_VEL, vel));
+        PD_TRY(pdgpu_fields_upload(c, PDGPU_F_C, C));
+        PD_TRY(pdgpu_ns_iterate(c, 1, dt_ns));
+        PD_TRY(pdgpu_ard_iterate(c, 1, dt_ard));
+        PD_TRY(pdgpu_fields_download(c, PDGPU_F_RHO, rho));
+        PD_TRY(pdgpu_fields_download(c, PDGPU_F_VEL, vel));
+        PD_TRY(pdgpu_fields_download(c, PDGPU_F_C, C));
+        return 0;
+    }
+    c->wallC_pending = false;   // every WALL concentration is rewritten below
+    c->fields_ready = true;
+    const int n = h->n, dim = c->dim;
+    const int cur = c->cur, nw = 1 - c->cur, sC = c->curC, dC = 1 - c->curC;
+    const long long P = c->P;
+    const long long gshift = (long long)(c->a0 - c->R) * P;   // global index = local + gshift
+    cudaStream_t cs = c->stream;
+    PD_TRY(pd_set_dt(c, 0, dt_ns));
+    PD_TRY(pd_set_dt(c, 1, dt_ard));
+    CUDA_OK(cudaEventRecord(h->ev_start, cs));
+    CUDA_OK(cudaStreamWaitEvent(h->s_up, h->ev_start, 0));
+    CUDA_OK(cudaStreamWaitEvent(h->s_down, h->ev_start, 0));
+
+    // uploads, outlet end first
+    for (int k = n - 1; k >= 0; --k) {
+        const long long l0 = (long long)h->zb[k] * P, cnt = (long long)(h->zb[k + 1] - h->zb[k]) * P;
+        const long long g0 = l0 + gshift, s0 = (l0 - c->own_lo) * dim;
+        CUDA_OK(cudaMemcpyAsync(c->rho[cur] + l0, rho + g0, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->s_up));
+        CUDA_OK(cudaMemcpyAsync(h->stage_up + s0, vel + g0 * dim, sizeof(double) * cnt * dim, cudaMemcpyHostToDevice,
+                                h->s_up));
+        CUDA_OK(cudaMemcpyAsync(c->C[sC] + l0, C + g0, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->s_up));
+        CUDA_OK(cudaEventRecord(h->ev_up[k], h->s_up));
+    }
+
+    for (int k = n - 1; k >= -2; --k) {
+        if (k >= 0) {   // A(k): src/pd_ns.cpp:197-200 restricted to chunk k
+            const long long l0 = (long long)h->zb[k] * P, cnt = (long long)(h->zb[k + 1] - h->zb[k]) * P;
+            CUDA_OK(cudaStreamWaitEvent(cs, h->ev_up[k], 0));
+            PD_TRY(pd_enqueue_eos_range(c, cur, l0, cnt));
+            PD_TRY(pd_enqueue_deinterleave(c, h->stage_up + (l0 - c->own_lo) * dim, l0, cnt, cur));
+            ListWindow win(c, *h, k);
+            if (k == 0) PD_TRY(pd_enqueue_bc_inlet(c, cur, sC));
+            if (k == n - 1) PD_TRY(pd_enqueue_bc_outlet(c, cur, sC));
+            PD_TRY(pd_enqueue_bc_wall(c, cur));
+            PD_TRY(pd_enqueue_bc_solid(c, cur));
+        }
+        const int kn = k + 1;
+        if (kn >= 0 && kn < n) {   // N, W: src/pd_ns.cpp:201-204; B: src/coupling.cpp:232-235 + ARD pre-passes
+            PD_TRY(pd_enqueue_ns_step(c, cur, c->d_dt, h->zb[kn], h->zb[kn + 1]));
+            ListWindow win(c, *h, kn);
+            PD_TRY(pd_enqueue_bc_wall(c, nw));
+            if (kn == 0) PD_TRY(pd_enqueue_bc_inlet(c, nw, sC));
+            if (kn == n - 1) PD_TRY(pd_enqueue_bc_outlet(c, nw, sC));
+            PD_TRY(pd_enqueue_ard_vmag_range(c, nw, (long long)h->zb[kn] * P, (long long)h->zb[kn + 1] * P));
+            PD_TRY(pd_enqueue_bc_wall_conc(c, sC, true));
+            PD_TRY(pd_enqueue_ard_prepass_solids(c, sC));
+        }
+        const int kd = k + 2;
+        if (kd >= 0 && kd < n) {   // D: src/coupling.cpp:236-238, then the download of the finished chunk
+            {
+                ListWindow win(c, *h, kd);
+                const bool tiles = (c->opt_ard_kernel == 1 || c->opt_ard_kernel == 2);
+                PD_TRY(pd_enqueue_ard_main(c, nw, sC, c->d_dt + 1, h->zb[kd], h->zb[kd + 1], true, tiles));
+            }
+            const long long l0 = (long long)h->zb[kd] * P, cnt = (long long)(h->zb[kd + 1] - h->zb[kd]) * P;
+            const long long g0 = l0 + gshift, s0 = (l0 - c->own_lo) * dim;
+            PD_TRY(pd_enqueue_interleave(c, h->stage_down + s0, l0, cnt, nw));
+            CUDA_OK(cudaEventRecord(h->ev_cmp[kd], cs));
+            CUDA_OK(cudaStreamWaitEvent(h->s_down, h->ev_cmp[kd], 0));
+            CUDA_OK(cudaMemcpyAsync(rho + g0, c->rho[nw] + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->s_down));
+            CUDA_OK(cudaMemcpyAsync(vel + g0 * dim, h->stage_down + s0, sizeof(double) * cnt * dim,
+                                    cudaMemcpyDeviceToHost, h->s_down));
+            CUDA_OK(cudaMemcpyAsync(C + g0, c->C[dC] + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->s_down));
+        }
+    }
+    CUDA_OK(cudaEventRecord(h->ev_end, h->s_down));
+    CUDA_OK(cudaStreamWaitEvent(cs, h->ev_end, 0));
+    // std::swap(rho, rho_new) ... (src/pd_ns.cpp:325) and std::swap(C, C_new) (src/coupling.cpp:239)
+    c->p_input = cur;
+    c->cur = nw;
+    c->curC = dC;
+    pd_touch_flow(c);
+    CUDA_OK(cudaStreamSynchronize(cs));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int pdgpu_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) PD_FAIL("pdgpu_host_register: null argument");
+    CUDA_OK(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return 0;
+}
+extern "C" int pdgpu_host_unregister(void* ptr) {
+    if (!ptr) PD_FAIL("pdgpu_host_unregister: null argument");
+    CUDA_OK(cudaHostUnregister(ptr));
+    return 0;
+}

@@ -313,7 +313,7 @@ k_channel_corrections(Lat L, long long own_lo, NsParams P, const uint8_t* __rest
     }
 }
 
-static int enqueue_channel_corrections(pdgpu_ctx* c, int buf) {
+int pd_enqueue_channel_corrections(pdgpu_ctx* c, int buf) {
     if (!c->cfg.channel_flow_corrections) return 0;
     Lat L = make_lat(c);
     NsParams P = ns_params(c);
@@ -358,7 +358,7 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
         CUDA_OK(cudaEventRecord(c->ev_c, side));
         CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_c, 0));
         PD_TRY(pd_enqueue_bc_wall(c, 1 - src));
-        PD_TRY(enqueue_channel_corrections(c, 1 - src));
+        PD_TRY(pd_enqueue_channel_corrections(c, 1 - src));
         if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 0, 1 - src, c->curC));
         return 0;
     }
@@ -369,7 +369,7 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
     PD_TRY(pd_enqueue_bc_solid(c, src));
     PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt));
     PD_TRY(pd_enqueue_bc_wall(c, 1 - src));
-    PD_TRY(enqueue_channel_corrections(c, 1 - src));
+    PD_TRY(pd_enqueue_channel_corrections(c, 1 - src));
     if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 0, 1 - src, c->curC));
     return 0;
 }
@@ -379,7 +379,10 @@ static int run_ns_body(pdgpu_ctx* c) {
     pd_touch_flow(c);
     bool use_graph = c->opt_graph && !(c->nranks > 1 && c->comm);
     if (!use_graph) return enqueue_ns_body(c, src);
-    if (!c->g_ns[src]) {
+    // the inlet/outlet BCs of the body also write C of the current concentration buffer
+    // (src/boundary.cpp:31-131): one graph per (flow buffer, C buffer)
+    const int bC = c->curC;
+    if (!c->g_ns[src][bC]) {
         cudaGraph_t g = nullptr;
         long long before = c->launches;
         CUDA_OK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -390,12 +393,12 @@ static int run_ns_body(pdgpu_ctx* c) {
         if (e != cudaSuccess) PD_FAIL("graph capture failed: %s", cudaGetErrorString(e));
         size_t nn = 0;
         CUDA_OK(cudaGraphGetNodes(g, nullptr, &nn));
-        c->g_ns_nodes[src] = (long long)nn;
-        CUDA_OK(cudaGraphInstantiate(&c->g_ns[src], g, 0));
+        c->g_ns_nodes[src][bC] = (long long)nn;
+        CUDA_OK(cudaGraphInstantiate(&c->g_ns[src][bC], g, 0));
         CUDA_OK(cudaGraphDestroy(g));
     }
-    CUDA_OK(cudaGraphLaunch(c->g_ns[src], c->stream));
-    c->launches += c->g_ns_nodes[src];
+    CUDA_OK(cudaGraphLaunch(c->g_ns[src][bC], c->stream));
+    c->launches += c->g_ns_nodes[src][bC];
     return 0;
 }
 

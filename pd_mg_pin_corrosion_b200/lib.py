@@ -97,6 +97,9 @@ def load() -> C.CDLL:
         "pdgpu_set_option": [vp, C.c_char_p, C.c_int], "pdgpu_flush_l2": [vp],
         "pdgpu_time_kernel": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
         "pdgpu_fp64_peak": [vp, dp], "pdgpu_fp64_peak3": [vp, dp],
+        "pdgpu_step_host": [vp, C.c_double, C.c_double, vp, vp, vp, C.c_int],
+        "pdgpu_step_host_chunks": [vp, C.c_int, ip, C.c_char_p, C.c_int],
+        "pdgpu_host_register": [vp, C.c_size_t], "pdgpu_host_unregister": [vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -240,6 +240,28 @@ def update_node_types_after_dissolution(g: Grid, f: Fields) -> None:
     """Already a no-op in the reference (src/boundary.cpp:395-402): apply_phase_change set the types."""
 
 
+def step_host(grid: Grid, dt_ns: float, dt_ard: float, rho: np.ndarray, vel: np.ndarray, Cc: np.ndarray,
+              n_chunks: int = 16) -> None:
+    """One coupling-loop pass (NS loop body, src/pd_ns.cpp:196-205,325; ARD loop body,
+    src/coupling.cpp:232-240) on HOST arrays, in place: the call a driver that keeps the
+    reference's Fields vectors in host memory makes. rho [N], vel [N,dim], Cc [N], float64,
+    C-contiguous; pinned memory lets uploads, kernels and downloads overlap."""
+    for a in (rho, vel, Cc):
+        if a.dtype != np.float64 or not a.flags.c_contiguous:
+            raise ValueError("step_host: float64 C-contiguous arrays required")
+    if rho.shape != (grid.N_total,) or Cc.shape != (grid.N_total,) or vel.shape != (grid.N_total, grid.dim):
+        raise ValueError("step_host: arrays must be global [N_total] / [N_total, dim]")
+    _l.check(_l.load().pdgpu_step_host(grid.ctx, dt_ns, dt_ard, _ptr(rho), _ptr(vel), _ptr(Cc), n_chunks))
+
+
+def step_host_chunks(grid: Grid, n_chunks: int) -> tuple[int, str]:
+    """(chunks pdgpu_step_host uses on this geometry, reason when it fell back to one)"""
+    n = C.c_int()
+    why = C.create_string_buffer(160)
+    _l.check(_l.load().pdgpu_step_host_chunks(grid.ctx, n_chunks, C.byref(n), why, 160))
+    return n.value, why.value.decode()
+
+
 class PD_NS_Solver:
     """PD_NS_Solver (src/pd_ns.h:9-17)."""
 

@@ -277,6 +277,53 @@ def test_kernel_variants_agree(case):
             assert H.rel_err(res[n], ref.get(n)) <= TOL, (opts, n, "vs oracle")
 
 
+@pytest.mark.parametrize("case,extra,n_chunks,expect", [
+    ("3d_small", None, 3, 2), ("3d_default", None, 8, 8), ("3d_default", None, 16, 12),
+    ("2d_default", None, 6, 4), ("2d_dissolve", None, 4, 3),
+    ("2d_poiseuille", {"channel_flow_corrections": 1}, 4, 1)])   # falls back to one chunk
+def test_step_host_chunked_is_bit_identical(case, extra, n_chunks, expect):
+    """pdgpu_step_host (host arrays in/out, chunked upload/compute/download pipeline) against
+    upload + ns_iterate(1) + ard_iterate(1) + download, bit for bit, and against the oracle."""
+    ref = H.make_ref(case, extra)
+    S, cfg, grid, fields = gpu_side(case, extra, ref=ref, upload=False)
+    ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
+    ns.init(grid, cfg); ard.init(grid, cfg)
+    dt = ref.ns_compute_dt()
+    ns.iterate(fields, grid, cfg, 12, dt)            # some flow so that every term is exercised
+    dtc = ard.compute_dt(fields, grid, cfg)
+    ard.iterate(fields, grid, cfg, 3, dtc)
+    state0 = {n: fields.get(n) for n in ("rho", "vel", "C")}
+    used, why = S.step_host_chunks(grid, n_chunks)
+    assert (used == 1 if expect == 1 else used >= expect), (used, why)
+    outs = []
+    for nc in (1, n_chunks):
+        st = {n: state0[n].copy() for n in state0}
+        for _ in range(3):                           # buffer parity flips between calls
+            S.step_host(grid, dt, dtc, st["rho"], st["vel"], st["C"], nc)
+        outs.append(st)
+        # the device state after the call is the downloaded one
+        for n in ("rho", "vel", "C"):
+            assert np.array_equal(fields.get(n), st[n]), (nc, n)
+    for n in ("rho", "vel", "C"):
+        assert np.array_equal(outs[0][n], outs[1][n]), n
+    grid.close()
+    if extra:      # (the shim's ns_iterate has no channel corrections: solve_steady-only in the reference)
+        return
+    # and the unchunked call is the reference's sequence
+    for n in ("rho", "vel", "C"):
+        ref.set(n, state0[n])
+    for _ in range(3):
+        ref.ns_iterate(1, dt)
+        ref.ard_iterate(1, dtc)
+    for n in ("rho", "vel", "C"):
+        assert H.rel_err(outs[1][n], ref.get(n)) <= TOL, n
+    # OUTLET concentrations are many orders below C_solid: compare them on their own scale (they see
+    # the outlet sweeps of BOTH loop bodies, which must hit the current C buffer whatever its parity)
+    outlet = ref.get("node_type") == 4
+    for st in outs:
+        assert H.rel_err(st["C"][outlet], ref.get("C")[outlet]) <= 1e-11
+
+
 def test_host_driver_whole_run_diagnostics(tmp_path):
     """host/pd_corrosion_gpu (C++17 driver over the C ABI) on the dissolving synthetic config:
     every numeric column of diagnostics.csv within 1e-6 relative of the reference's own main()
