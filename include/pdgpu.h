@@ -183,6 +183,9 @@ int pdgpu_step_host(pdgpu_ctx* ctx, double dt_ns, double dt_ard, double* rho, do
                     int n_chunks);
 /* Chunks pdgpu_step_host would use for `n_chunks` on this geometry, and why it fell back to 1. */
 int pdgpu_step_host_chunks(pdgpu_ctx* ctx, int n_chunks, int* n_used, char* why, int why_len);
+/* Timeline of the last chunked pdgpu_step_host call: per chunk (axial order) milliseconds from the
+ * start of the call to { upload done, kernels done, download done }; out[3 * n_chunks]. */
+int pdgpu_step_host_trace(pdgpu_ctx* ctx, double* out, int cap, int* n_chunks);
 /* cudaHostRegister / cudaHostUnregister of caller-owned memory (e.g. std::vector storage). */
 int pdgpu_host_register(void* ptr, size_t bytes);
 int pdgpu_host_unregister(void* ptr);

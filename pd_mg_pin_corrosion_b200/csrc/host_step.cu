@@ -16,7 +16,9 @@
 //     download(k+2)    copy engine 2   new rho, vel, C of chunk k+2
 //
 // so that every bond kernel sees its +-reach planes in the state the sequential order gives
-// them.  The arithmetic per node is that of pdgpu_ns_iterate(1) + pdgpu_ard_iterate(1); results
+// them.  The top chunk T is the thin outlet region: its chain (outlet sweep -> N(T) -> outlet sweep
+// -> D(T), D(T-1)) is 4-5 ms of dependent single-CTA work and runs on the high-priority side
+// stream with its own download stream, while the main stream streams the chunks below it.  The arithmetic per node is that of pdgpu_ns_iterate(1) + pdgpu_ard_iterate(1); results
 // are bit-identical (tests/test_gpu_parity.py::test_step_host_*).  Geometries that do not meet
 // the chunk invariants (checked when the plan is built) run the same operators unchunked.
 #include <algorithm>
@@ -29,8 +31,11 @@ struct HostStep {
     int n = 1;                          // chunks (1 = unchunked)
     std::vector<int> zb;                // local plane boundaries [n+1]
     std::vector<long long> wall_lo, solid_lo;   // list offsets per chunk [n+1]
-    cudaStream_t s_up = nullptr, s_down = nullptr;
-    std::vector<cudaEvent_t> ev_up, ev_cmp;
+    long long wall_split = 0;           // first WALL entry in an outlet plane (entries of the top chunk
+                                        // before it do not depend on the outlet sweep)
+    cudaStream_t s_up = nullptr, s_down = nullptr, s_down2 = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_a = nullptr, ev_x = nullptr, ev_end2 = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_cmp, ev_down;   // per chunk: upload done, kernels done, download done
     cudaEvent_t ev_start = nullptr, ev_end = nullptr;
     double *stage_up = nullptr, *stage_down = nullptr;
     size_t stage_elems = 0;
@@ -42,10 +47,14 @@ void pd_host_step_free(pdgpu_ctx* c) {
     if (!h) return;
     for (cudaEvent_t e : h->ev_up) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_cmp) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_down) cudaEventDestroy(e);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_end) cudaEventDestroy(h->ev_end);
     if (h->s_up) cudaStreamDestroy(h->s_up);
     if (h->s_down) cudaStreamDestroy(h->s_down);
+    if (h->s_down2) cudaStreamDestroy(h->s_down2);
+    for (cudaEvent_t e : {h->ev_t0, h->ev_a, h->ev_x, h->ev_end2})
+        if (e) cudaEventDestroy(e);
     if (h->stage_up) cudaFree(h->stage_up);
     if (h->stage_down) cudaFree(h->stage_down);
     delete h;
@@ -59,14 +68,16 @@ struct ListWindow {
     pdgpu_ctx* c;
     int *w, *wm, *s;
     long long nw, ns;
-    ListWindow(pdgpu_ctx* ctx, const HostStep& h, int k)
+    ListWindow(pdgpu_ctx* ctx, long long w0, long long w1, long long s0, long long s1)
         : c(ctx), w(ctx->l_wall), wm(ctx->l_wall_mirror), s(ctx->l_solid), nw(ctx->n_wall), ns(ctx->n_solid) {
-        c->l_wall = w + h.wall_lo[k];
-        c->l_wall_mirror = wm + h.wall_lo[k];
-        c->n_wall = h.wall_lo[k + 1] - h.wall_lo[k];
-        c->l_solid = s + h.solid_lo[k];
-        c->n_solid = h.solid_lo[k + 1] - h.solid_lo[k];
+        c->l_wall = w + w0;
+        c->l_wall_mirror = wm + w0;
+        c->n_wall = w1 - w0;
+        c->l_solid = s + s0;
+        c->n_solid = s1 - s0;
     }
+    ListWindow(pdgpu_ctx* ctx, const HostStep& h, int k)
+        : ListWindow(ctx, h.wall_lo[k], h.wall_lo[k + 1], h.solid_lo[k], h.solid_lo[k + 1]) {}
     ~ListWindow() {
         c->l_wall = w; c->l_wall_mirror = wm; c->n_wall = nw;
         c->l_solid = s; c->n_solid = ns;
@@ -95,7 +106,8 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
     if (c->n_outlet > 0 && !(c->out_fast && c->opt_outlet_kernel > 0)) {
         // the level-list sweep is fine too, it only needs the outlet planes; nothing to check
     }
-    // top chunk: every OUTLET node and its reach must lie inside it
+    // top chunk: every OUTLET node and its reach must lie inside it; with an outlet it is just that
+    // region (its kernels wait for the sequential outlet sweeps)
     int thick = ((nz + n_req - 1) / n_req + TZ - 1) / TZ * TZ;
     thick = std::max(thick, 2 * c->R + TZ);
     int zt = hi - thick;
@@ -104,7 +116,7 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
         int first = 0;
         CUDA_OK(cudaMemcpy(&first, c->l_outlet, sizeof(int), cudaMemcpyDeviceToHost));
         zo_first = (int)(first / c->P);
-        zt = std::min(zt, zo_first - c->R);
+        zt = zo_first - c->R;
     }
     if (c->n_inlet) {
         int last = 0;
@@ -112,7 +124,7 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
         zi_last = (int)(last / c->P);
     }
     zt = lo + (zt - lo) / TZ * TZ;
-    if (zt - lo < 2 * c->R + TZ) return fallback(h, "domain too short for two chunks");
+    if (zt - lo < 2 * c->R + TZ || hi - zt <= c->R) return fallback(h, "domain too short for two chunks");
     // lower chunks: equal thickness, tile aligned
     int n_low = std::max(1, std::min(n_req - 1, (zt - lo) / std::max(2 * c->R + TZ, TZ)));
     std::vector<int> zb;
@@ -146,10 +158,28 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
             int zm = (int)(wm[t] / c->P);
             if (zm < zb[k] || zm >= zb[k + 1]) return fallback(h, "a wall mirror crosses a chunk boundary");
         }
+    // WALL entries of the top chunk below the first outlet plane are mirrored before the outlet sweep
+    // has run: they must not mirror an OUTLET node
+    long long split = std::lower_bound(w.begin(), w.end(), (long long)zo_first * c->P,
+                                       [](int a, long long b) { return (long long)a < b; }) - w.begin();
+    split = std::max(split, wl[n - 1]);
+    if (c->n_outlet) {
+        const long long t0 = (long long)zb[n - 1] * c->P, tn = (long long)(hi - zb[n - 1]) * c->P;
+        std::vector<uint8_t> ty(tn);
+        CUDA_OK(cudaMemcpy(ty.data(), c->type + t0, (size_t)tn, cudaMemcpyDeviceToHost));
+        for (long long t = wl[n - 1]; t < split; ++t)
+            if (wm[t] >= 0 && ty[wm[t] - t0] == PDGPU_OUTLET)
+                return fallback(h, "a wall below the outlet planes mirrors an OUTLET node");
+        // ... and the walls of the outlet planes are mirrored next to the solid no-slip BC of the chunk
+        for (long long t = split; t < wl[n]; ++t)
+            if (wm[t] >= 0 && ty[wm[t] - t0] == PDGPU_SOLID_MG)
+                return fallback(h, "a wall of the outlet planes mirrors a SOLID_MG node");
+    }
     h->n = n;
     h->zb = zb;
     h->wall_lo = wl;
     h->solid_lo = sl;
+    h->wall_split = split;
     return 0;
 }
 
@@ -159,16 +189,21 @@ int ensure(pdgpu_ctx* c, int n_req) {
     if (!h->s_up) {
         CUDA_OK(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
-        CUDA_OK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&h->ev_end, cudaEventDisableTiming));
+        CUDA_OK(cudaStreamCreateWithFlags(&h->s_down2, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&h->ev_t0, &h->ev_a, &h->ev_x, &h->ev_end2})
+            CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreate(&h->ev_start));
+        CUDA_OK(cudaEventCreate(&h->ev_end));
     }
     if (h->epoch != c->tables_epoch || h->n_req != n_req) PD_TRY(build_plan(c, h, n_req));
     while ((int)h->ev_up.size() < h->n) {
-        cudaEvent_t a, b;
-        CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        cudaEvent_t a, b, d;   // timing enabled: pdgpu_step_host_trace reads them
+        CUDA_OK(cudaEventCreate(&a));
+        CUDA_OK(cudaEventCreate(&b));
+        CUDA_OK(cudaEventCreate(&d));
         h->ev_up.push_back(a);
         h->ev_cmp.push_back(b);
+        h->ev_down.push_back(d);
     }
     size_t need = (size_t)(c->own_hi - c->own_lo) * c->dim;
     if (h->n > 1 && h->stage_elems < need) {
@@ -233,47 +268,96 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
         CUDA_OK(cudaEventRecord(h->ev_up[k], h->s_up));
     }
 
+    const int T = n - 1;
+    cudaStream_t side = c->stream2;
+    CUDA_OK(cudaStreamWaitEvent(h->s_down2, h->ev_start, 0));
+    const bool tiles = (c->opt_ard_kernel == 1 || c->opt_ard_kernel == 2);
+    auto span = [&](int k, long long* l0, long long* cnt) {
+        *l0 = (long long)h->zb[k] * P;
+        *cnt = (long long)(h->zb[k + 1] - h->zb[k]) * P;
+    };
+    // D(kd) + download of the finished chunk on (stream, download stream)
+    auto finish_chunk = [&](int kd, cudaStream_t st, cudaStream_t sd) -> int {
+        StreamSwap sw(c, st);
+        {
+            ListWindow win(c, *h, kd);   // src/coupling.cpp:236-238
+            PD_TRY(pd_enqueue_ard_main(c, nw, sC, c->d_dt + 1, h->zb[kd], h->zb[kd + 1], true, tiles));
+        }
+        long long l0, cnt;
+        span(kd, &l0, &cnt);
+        const long long g0 = l0 + gshift, s0 = (l0 - c->own_lo) * dim;
+        PD_TRY(pd_enqueue_interleave(c, h->stage_down + s0, l0, cnt, nw));
+        CUDA_OK(cudaEventRecord(h->ev_cmp[kd], st));
+        CUDA_OK(cudaStreamWaitEvent(sd, h->ev_cmp[kd], 0));
+        CUDA_OK(cudaMemcpyAsync(rho + g0, c->rho[nw] + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, sd));
+        CUDA_OK(cudaMemcpyAsync(vel + g0 * dim, h->stage_down + s0, sizeof(double) * cnt * dim,
+                                cudaMemcpyDeviceToHost, sd));
+        CUDA_OK(cudaMemcpyAsync(C + g0, c->C[dC] + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, sd));
+        CUDA_OK(cudaEventRecord(h->ev_down[kd], sd));
+        return 0;
+    };
+
     for (int k = n - 1; k >= -2; --k) {
         if (k >= 0) {   // A(k): src/pd_ns.cpp:197-200 restricted to chunk k
-            const long long l0 = (long long)h->zb[k] * P, cnt = (long long)(h->zb[k + 1] - h->zb[k]) * P;
+            long long l0, cnt;
+            span(k, &l0, &cnt);
             CUDA_OK(cudaStreamWaitEvent(cs, h->ev_up[k], 0));
             PD_TRY(pd_enqueue_eos_range(c, cur, l0, cnt));
             PD_TRY(pd_enqueue_deinterleave(c, h->stage_up + (l0 - c->own_lo) * dim, l0, cnt, cur));
-            ListWindow win(c, *h, k);
-            if (k == 0) PD_TRY(pd_enqueue_bc_inlet(c, cur, sC));
-            if (k == n - 1) PD_TRY(pd_enqueue_bc_outlet(c, cur, sC));
-            PD_TRY(pd_enqueue_bc_wall(c, cur));
-            PD_TRY(pd_enqueue_bc_solid(c, cur));
+            if (k == T) {
+                // outlet sweep and the walls of the outlet planes: side stream; the walls below them
+                // (all that the chunk underneath reads) and the solids: main stream
+                CUDA_OK(cudaEventRecord(h->ev_t0, cs));
+                CUDA_OK(cudaStreamWaitEvent(side, h->ev_t0, 0));
+                {
+                    StreamSwap sw(c, side);
+                    ListWindow win(c, h->wall_split, h->wall_lo[T + 1], h->solid_lo[T], h->solid_lo[T]);
+                    PD_TRY(pd_enqueue_bc_outlet(c, cur, sC));
+                    PD_TRY(pd_enqueue_bc_wall(c, cur));
+                }
+                ListWindow win(c, h->wall_lo[T], h->wall_split, h->solid_lo[T], h->solid_lo[T + 1]);
+                if (k == 0) PD_TRY(pd_enqueue_bc_inlet(c, cur, sC));
+                PD_TRY(pd_enqueue_bc_wall(c, cur));
+                PD_TRY(pd_enqueue_bc_solid(c, cur));
+            } else {
+                ListWindow win(c, *h, k);
+                if (k == 0) PD_TRY(pd_enqueue_bc_inlet(c, cur, sC));
+                PD_TRY(pd_enqueue_bc_wall(c, cur));
+                PD_TRY(pd_enqueue_bc_solid(c, cur));
+            }
         }
         const int kn = k + 1;
         if (kn >= 0 && kn < n) {   // N, W: src/pd_ns.cpp:201-204; B: src/coupling.cpp:232-235 + ARD pre-passes
+            cudaStream_t st = cs;
+            if (kn == T) {         // after A(T-1) on the main stream, behind the sweep on the side stream
+                CUDA_OK(cudaEventRecord(h->ev_a, cs));
+                CUDA_OK(cudaStreamWaitEvent(side, h->ev_a, 0));
+                st = side;
+            }
+            StreamSwap sw(c, st);
             PD_TRY(pd_enqueue_ns_step(c, cur, c->d_dt, h->zb[kn], h->zb[kn + 1]));
             ListWindow win(c, *h, kn);
             PD_TRY(pd_enqueue_bc_wall(c, nw));
             if (kn == 0) PD_TRY(pd_enqueue_bc_inlet(c, nw, sC));
-            if (kn == n - 1) PD_TRY(pd_enqueue_bc_outlet(c, nw, sC));
+            if (kn == T) PD_TRY(pd_enqueue_bc_outlet(c, nw, sC));
             PD_TRY(pd_enqueue_ard_vmag_range(c, nw, (long long)h->zb[kn] * P, (long long)h->zb[kn + 1] * P));
             PD_TRY(pd_enqueue_bc_wall_conc(c, sC, true));
             PD_TRY(pd_enqueue_ard_prepass_solids(c, sC));
         }
         const int kd = k + 2;
-        if (kd >= 0 && kd < n) {   // D: src/coupling.cpp:236-238, then the download of the finished chunk
-            {
-                ListWindow win(c, *h, kd);
-                const bool tiles = (c->opt_ard_kernel == 1 || c->opt_ard_kernel == 2);
-                PD_TRY(pd_enqueue_ard_main(c, nw, sC, c->d_dt + 1, h->zb[kd], h->zb[kd + 1], true, tiles));
+        if (kd >= 0 && kd < n) {
+            if (kd >= T - 1) {     // reads |v| of the top chunk: side stream, behind everything the main
+                                   // stream has enqueued up to here (B of the chunks around it)
+                CUDA_OK(cudaEventRecord(h->ev_x, cs));
+                CUDA_OK(cudaStreamWaitEvent(side, h->ev_x, 0));
+                PD_TRY(finish_chunk(kd, side, h->s_down2));
+            } else {
+                PD_TRY(finish_chunk(kd, cs, h->s_down));
             }
-            const long long l0 = (long long)h->zb[kd] * P, cnt = (long long)(h->zb[kd + 1] - h->zb[kd]) * P;
-            const long long g0 = l0 + gshift, s0 = (l0 - c->own_lo) * dim;
-            PD_TRY(pd_enqueue_interleave(c, h->stage_down + s0, l0, cnt, nw));
-            CUDA_OK(cudaEventRecord(h->ev_cmp[kd], cs));
-            CUDA_OK(cudaStreamWaitEvent(h->s_down, h->ev_cmp[kd], 0));
-            CUDA_OK(cudaMemcpyAsync(rho + g0, c->rho[nw] + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->s_down));
-            CUDA_OK(cudaMemcpyAsync(vel + g0 * dim, h->stage_down + s0, sizeof(double) * cnt * dim,
-                                    cudaMemcpyDeviceToHost, h->s_down));
-            CUDA_OK(cudaMemcpyAsync(C + g0, c->C[dC] + l0, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->s_down));
         }
     }
+    CUDA_OK(cudaEventRecord(h->ev_end2, h->s_down2));
+    CUDA_OK(cudaStreamWaitEvent(cs, h->ev_end2, 0));
     CUDA_OK(cudaEventRecord(h->ev_end, h->s_down));
     CUDA_OK(cudaStreamWaitEvent(cs, h->ev_end, 0));
     // std::swap(rho, rho_new) ... (src/pd_ns.cpp:325) and std::swap(C, C_new) (src/coupling.cpp:239)
@@ -283,6 +367,23 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
     pd_touch_flow(c);
     CUDA_OK(cudaStreamSynchronize(cs));
     CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Timeline of the last chunked pdgpu_step_host call: per chunk (axial order) the milliseconds from
+// the start of the call to { upload done, kernels done, download done }. out[3*n_chunks].
+extern "C" int pdgpu_step_host_trace(pdgpu_ctx* c, double* out, int cap, int* n_chunks) {
+    NEED_GRID(c);
+    HostStep* h = c->hs;
+    if (!h || h->n <= 1) { if (n_chunks) *n_chunks = h ? h->n : 0; return 0; }
+    if (n_chunks) *n_chunks = h->n;
+    for (int k = 0; k < h->n && 3 * k + 2 < cap; ++k) {
+        float a = 0, b = 0, d = 0;
+        CUDA_OK(cudaEventElapsedTime(&a, h->ev_start, h->ev_up[k]));
+        CUDA_OK(cudaEventElapsedTime(&b, h->ev_start, h->ev_cmp[k]));
+        CUDA_OK(cudaEventElapsedTime(&d, h->ev_start, h->ev_down[k]));
+        out[3 * k] = a; out[3 * k + 1] = b; out[3 * k + 2] = d;
+    }
     return 0;
 }
 

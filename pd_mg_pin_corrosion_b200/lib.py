@@ -99,6 +99,7 @@ def load() -> C.CDLL:
         "pdgpu_fp64_peak": [vp, dp], "pdgpu_fp64_peak3": [vp, dp],
         "pdgpu_step_host": [vp, C.c_double, C.c_double, vp, vp, vp, C.c_int],
         "pdgpu_step_host_chunks": [vp, C.c_int, ip, C.c_char_p, C.c_int],
+        "pdgpu_step_host_trace": [vp, dp, C.c_int, ip],
         "pdgpu_host_register": [vp, C.c_size_t], "pdgpu_host_unregister": [vp],
     }
     for name, args in sig.items():

@@ -241,7 +241,7 @@ def update_node_types_after_dissolution(g: Grid, f: Fields) -> None:
 
 
 def step_host(grid: Grid, dt_ns: float, dt_ard: float, rho: np.ndarray, vel: np.ndarray, Cc: np.ndarray,
-              n_chunks: int = 16) -> None:
+              n_chunks: int = 32) -> None:
     """One coupling-loop pass (NS loop body, src/pd_ns.cpp:196-205,325; ARD loop body,
     src/coupling.cpp:232-240) on HOST arrays, in place: the call a driver that keeps the
     reference's Fields vectors in host memory makes. rho [N], vel [N,dim], Cc [N], float64,
