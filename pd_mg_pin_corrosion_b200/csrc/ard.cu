@@ -26,9 +26,11 @@ static ArdParams ard_params(const pdgpu_ctx* c) {
     return p;
 }
 
-// vmag = |v| for fluid-like nodes (FLUID/INLET/OUTLET), -1 otherwise (feeds D_art,
-// src/pd_ard.cpp:166-170). Velocities of FLUID nodes are frozen during the ARD phase, so the full
-// pass runs once per flow state (pd_ensure_vmag); only the outlet planes are refreshed per step.
+// vmag is the packed per-node weight the bond kernels read: |v| >= +0 for fluid-like nodes
+// (FLUID/INLET/OUTLET; feeds D_art, src/pd_ard.cpp:166-170), -dsol <= -0 for SOLID_MG nodes
+// (written by the salt pre-pass below, never here) and -0.0 for WALL/OUTSIDE: the SIGN BIT
+// says "not fluid-like". Velocities of FLUID nodes are frozen during the ARD phase, so the
+// full pass runs once per flow state (pd_ensure_vmag); only the outlet planes are refreshed per step.
 template <int DIM>
 __global__ void k_ard_vmag(long long lo, long long hi, const uint8_t* __restrict__ type,
                            const double* __restrict__ vx, const double* __restrict__ vy,
@@ -36,10 +38,11 @@ __global__ void k_ard_vmag(long long lo, long long hi, const uint8_t* __restrict
     long long l = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= hi) return;
     uint8_t ty = type[l];
+    if (ty == PDGPU_SOLID_MG) return;   // owned by k_ard_prepass_solids
     double s = vx[l] * vx[l] + vy[l] * vy[l];
     if (DIM == 3) s += vz[l] * vz[l];
     bool fluid_like = (ty == PDGPU_FLUID || ty == PDGPU_INLET || ty == PDGPU_OUTLET);
-    vmag[l] = fluid_like ? sqrt(s) : -1.0;
+    vmag[l] = fluid_like ? sqrt(s) : -0.0;
 }
 
 // Per step, owned SOLID_MG nodes only: the salt-layer flag of src/pd_ard.cpp:61-73 (any FLUID
@@ -50,7 +53,8 @@ __global__ void k_ard_prepass_solids(Lat L, const int* __restrict__ l_solid, lon
                                      const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
                                      const double* __restrict__ C, const uint8_t* __restrict__ is_gb,
                                      const uint8_t* __restrict__ is_precip, ArdParams P,
-                                     uint8_t* __restrict__ salt, double* __restrict__ dsol) {
+                                     uint8_t* __restrict__ salt, double* __restrict__ dsol,
+                                     double* __restrict__ vmag) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_solid) return;
     long long l = l_solid[t];
@@ -70,6 +74,7 @@ __global__ void k_ard_prepass_solids(Lat L, const int* __restrict__ l_solid, lon
     }
     salt[l] = blocked;
     dsol[l] = ds;
+    vmag[l] = -ds;   // packed weight: sign bit set (-0.0 when blocked)
 }
 
 // Generic kernel: one thread per owned node (PD_ARD_Solver::step, src/pd_ard.cpp:81-190).
@@ -155,10 +160,10 @@ int pd_enqueue_ard_prepass_solids(pdgpu_ctx* c, int srcC) {
     ArdParams P = ard_params(c);
     if (c->dim == 2)
         LAUNCH(c, k_ard_prepass_solids<2>, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type,
-               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol);
+               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol, c->vmag);
     else
         LAUNCH(c, k_ard_prepass_solids<3>, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type,
-               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol);
+               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol, c->vmag);
     return 0;
 }
 

@@ -3,10 +3,12 @@
 // Same staging scheme as ns_tile.cu (38 x 14 x 10 haloed block, 4 z-nodes per thread, sliding
 // z-window, runtime column loop: tile.cuh).  Staged per node:
 //     C      concentration
-//     vmf    |v| for fluid-like nodes (FLUID / INLET / OUTLET), -1 otherwise
-//     dsol   interface diffusivity 2 D_l D_s / (D_l + D_s) of a SOLID_MG node (0 when salt
-//            blocked; grain-boundary / precipitate / grain class and the volume-loss decay
-//            folded in), 0 for every other type                      (src/pd_ard.cpp:136-162)
+//     w      packed weight (ard.cu): |v| >= +0 for fluid-like nodes (FLUID / INLET / OUTLET);
+//            -dsol <= -0 for a SOLID_MG node, dsol = interface diffusivity 2 D_l D_s / (D_l + D_s)
+//            (0 when salt blocked; grain-boundary / precipitate / grain class and the
+//            volume-loss decay folded in); -0 for WALL/OUTSIDE      (src/pd_ard.cpp:136-162)
+// Two staged fields = 77 KB per CTA: two CTAs per SM, so one CTA's staging overlaps the other's
+// bond loop.  With vmf = w, f = [sign bit clear], dsol = f ? 0 : -w
 // so the bond classification of src/pd_ard.cpp:120-181 becomes branch free for a FLUID row:
 //     D_ij = f_j (D_l + alpha dx max(|v_i|, |v_j|)) + dsol_j ,   f_j = [vmf_j >= 0]
 //     diff += D_ij (C_j - C_i) w2 ;   G += f_j (C_j - C_i) e w1 ;   adv = (alpha/V_H) v_i . G
@@ -31,8 +33,8 @@ struct ArdAcc {
 
 // per bond (9 FP64 ops): dC, max, D_ff, D, D*dC, diff, f*dC, colg, gz
 template <int H>
-__device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const double* __restrict__ s_vmf,
-                                           const double* __restrict__ s_ds, int cb, double dI, double dJ,
+__device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const double* __restrict__ s_w, int cb,
+                                           double dI, double dJ,
                                            const double (&kap)[4], const double (&kz)[4], const ArdTileParams& q,
                                            const double (&Ci)[RZ], const double (&vmi)[RZ], ArdAcc& a) {
     double colg[RZ];
@@ -41,8 +43,10 @@ __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const
 #pragma unroll
     for (int zz = -H; zz < RZ + H; ++zz) {
         const int si = cb + (zz + TR) * SPLANE;
-        const double Cj = s_C[si], vmf = s_vmf[si], dsj = s_ds[si];
-        const double f = vmf >= 0.0 ? 1.0 : 0.0;
+        const double Cj = s_C[si], vmf = s_w[si];
+        const bool fluid_like = __double2hiint(vmf) >= 0;   // sign bit clear
+        const double f = fluid_like ? 1.0 : 0.0;
+        const double dsj = fluid_like ? 0.0 : -vmf;
 #pragma unroll
         for (int t = 0; t < RZ; ++t) {
             const int dk = zz - t;
@@ -67,15 +71,14 @@ __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColTable T,
            const double* __restrict__ d_dt, const uint8_t* __restrict__ type, const double* __restrict__ C,
-           const double* __restrict__ vmf_g, const double* __restrict__ dsol_g, const double* __restrict__ vx,
+           const double* __restrict__ w_g, const double* __restrict__ vx,
            const double* __restrict__ vy, const double* __restrict__ vz, double* __restrict__ C_n) {
     extern __shared__ double sm[];
     double* s_C = sm;
-    double* s_vmf = sm + SN;
-    double* s_ds = sm + 2 * SN;
+    double* s_w = sm + SN;
 
     const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
     const int tid = (tz * TY + ty) * TX + tx;
@@ -90,14 +93,13 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
         nty[t] = 255;
         if (in_xy && lz < q.g.z_hi) nty[t] = type[(long long)lz * q.g.P + (long long)gy * q.g.Nx + gx];
     }
-    // asynchronous staging (see ns_tile.cu); outside the box: C = 0, vmf = 0 (never used), dsol = 0
+    // asynchronous staging (see ns_tile.cu); outside the box: C = 0, w = +0 (never used by a full row)
     for (int idx = tid; idx < SN; idx += NTHREADS) {
         const long long l = staged_index(q.g, idx, x0, y0, z0);
         const bool ok = l >= 0;
         const long long ls = ok ? l : 0;
         cp_async8(s_C + idx, C + ls, ok);
-        cp_async8(s_vmf + idx, vmf_g + ls, ok);
-        cp_async8(s_ds + idx, dsol_g + ls, ok);
+        cp_async8(s_w + idx, w_g + ls, ok);
     }
     bool fl[RZ];
     bool any = false;
@@ -121,7 +123,7 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
     for (int t = 0; t < RZ; ++t) {
         const int si = base + (t + TR) * SPLANE;
         Ci[t] = s_C[si];
-        vmi[t] = fmax(s_vmf[si], 0.0);
+        vmi[t] = fmax(s_w[si], 0.0);
         a.diff[t] = a.gx[t] = a.gy[t] = a.gz[t] = 0.0;
     }
 #pragma unroll 1
@@ -131,9 +133,9 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
         const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
         const double kz[4] = {T.kz[c][0], T.kz[c][1], T.kz[c][2], T.kz[c][3]};
         const int H = T.h[c];
-        if (H == 3) ard_column<3>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
-        else if (H == 2) ard_column<2>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
-        else ard_column<1>(s_C, s_vmf, s_ds, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
+        if (H == 3) ard_column<3>(s_C, s_w, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
+        else if (H == 2) ard_column<2>(s_C, s_w, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
+        else ard_column<1>(s_C, s_w, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
     }
 
     const double dt = *d_dt;
@@ -187,7 +189,7 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
     if (zb >= 0) { q.g.z_lo = zb; q.g.z_hi = ze; }
     q.D_liquid = c->cfg.D_liquid; q.alpha_dx = c->cfg.alpha_art_diff * c->cfg.dx;
     q.beta = k.beta_lap; q.div_coeff = k.alpha / k.V_H; q.inv_dx = 1.0 / c->cfg.dx;
-    const size_t smem = sizeof(double) * 3 * SN;
+    const size_t smem = sizeof(double) * 2 * SN;
     static bool attr_done = false;
     if (!attr_done) {
         CUDA_OK(cudaFuncSetAttribute(k_ard_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -197,7 +199,7 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
     if (q.g.z_hi > q.g.z_lo) {
         dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + TZ - 1) / TZ);
         dim3 block(TX, TY, NZT);
-        k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->C[srcC], c->vmag, c->dsol, c->v[buf][0],
+        k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->C[srcC], c->vmag, c->v[buf][0],
                                                       c->v[buf][1], c->v[buf][2], c->C[dstC]);
         c->launches++;
     }

@@ -21,7 +21,7 @@
 namespace tile {
 
 constexpr int TR = 3;
-constexpr int TX = 32, TY = 8;             // threads in x, y
+constexpr int TX = 16, TY = 16;            // threads in x, y
 constexpr int RZ = 2;                      // z-nodes per thread (sliding window length)
 constexpr int NZT = 2;                     // thread layers in z
 constexpr int TZ = RZ * NZT;               // z-nodes per tile
