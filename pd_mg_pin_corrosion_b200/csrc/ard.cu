@@ -26,23 +26,28 @@ static ArdParams ard_params(const pdgpu_ctx* c) {
     return p;
 }
 
-// vmag is the packed per-node weight the bond kernels read: |v| >= +0 for fluid-like nodes
-// (FLUID/INLET/OUTLET; feeds D_art, src/pd_ard.cpp:166-170), -dsol <= -0 for SOLID_MG nodes
-// (written by the salt pre-pass below, never here) and -0.0 for WALL/OUTSIDE: the SIGN BIT
-// says "not fluid-like". Velocities of FLUID nodes are frozen during the ARD phase, so the
-// full pass runs once per flow state (pd_ensure_vmag); only the outlet planes are refreshed per step.
+// vmag = |v| for fluid-like nodes (FLUID/INLET/OUTLET), -1 otherwise (feeds D_art,
+// src/pd_ard.cpp:166-170).  wpack is what the tiled kernel stages instead of (vmag, dsol): the
+// node's own fluid-fluid diffusivity  D_l + alpha dx |v|  >= +0 for fluid-like nodes -- the bond
+// value D_l + alpha dx max(|v_i|, |v_j|) is the max of the two end values, bit for bit, because
+// the rounded fma is monotone in |v| --, -dsol <= -0 for SOLID_MG nodes (written by the salt
+// pre-pass below, never here) and -0.0 for WALL/OUTSIDE: the SIGN BIT says "not fluid-like".
+// Velocities of FLUID nodes are frozen during the ARD phase, so the full pass runs once per flow
+// state (pd_ensure_vmag); only the outlet planes are refreshed per step.
 template <int DIM>
 __global__ void k_ard_vmag(long long lo, long long hi, const uint8_t* __restrict__ type,
                            const double* __restrict__ vx, const double* __restrict__ vy,
-                           const double* __restrict__ vz, double* __restrict__ vmag) {
+                           const double* __restrict__ vz, double D_liquid, double alpha_dx,
+                           double* __restrict__ vmag, double* __restrict__ wpack) {
     long long l = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= hi) return;
     uint8_t ty = type[l];
-    if (ty == PDGPU_SOLID_MG) return;   // owned by k_ard_prepass_solids
     double s = vx[l] * vx[l] + vy[l] * vy[l];
     if (DIM == 3) s += vz[l] * vz[l];
     bool fluid_like = (ty == PDGPU_FLUID || ty == PDGPU_INLET || ty == PDGPU_OUTLET);
-    vmag[l] = fluid_like ? sqrt(s) : -0.0;
+    const double vm = sqrt(s);
+    vmag[l] = fluid_like ? vm : -1.0;
+    if (ty != PDGPU_SOLID_MG) wpack[l] = fluid_like ? fma(alpha_dx, vm, D_liquid) : -0.0;
 }
 
 // Per step, owned SOLID_MG nodes only: the salt-layer flag of src/pd_ard.cpp:61-73 (any FLUID
@@ -54,7 +59,7 @@ __global__ void k_ard_prepass_solids(Lat L, const int* __restrict__ l_solid, lon
                                      const double* __restrict__ C, const uint8_t* __restrict__ is_gb,
                                      const uint8_t* __restrict__ is_precip, ArdParams P,
                                      uint8_t* __restrict__ salt, double* __restrict__ dsol,
-                                     double* __restrict__ vmag) {
+                                     double* __restrict__ wpack) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_solid) return;
     long long l = l_solid[t];
@@ -74,7 +79,7 @@ __global__ void k_ard_prepass_solids(Lat L, const int* __restrict__ l_solid, lon
     }
     salt[l] = blocked;
     dsol[l] = ds;
-    vmag[l] = -ds;   // packed weight: sign bit set (-0.0 when blocked)
+    wpack[l] = -ds;   // sign bit set (-0.0 when blocked)
 }
 
 // Generic kernel: one thread per owned node (PD_ARD_Solver::step, src/pd_ard.cpp:81-190).
@@ -138,9 +143,11 @@ int pd_enqueue_ard_vmag_range(pdgpu_ctx* c, int buf, long long lo, long long hi)
     if (hi <= lo) return 0;
     long long n = hi - lo;
     if (c->dim == 2)
-        LAUNCH(c, k_ard_vmag<2>, nblocks(n, 256), 256, 0, lo, hi, c->type, VXYZ(c, buf), c->vmag);
+        LAUNCH(c, k_ard_vmag<2>, nblocks(n, 256), 256, 0, lo, hi, c->type, VXYZ(c, buf), c->cfg.D_liquid,
+               c->cfg.alpha_art_diff * c->cfg.dx, c->vmag, c->wpack);
     else
-        LAUNCH(c, k_ard_vmag<3>, nblocks(n, 256), 256, 0, lo, hi, c->type, VXYZ(c, buf), c->vmag);
+        LAUNCH(c, k_ard_vmag<3>, nblocks(n, 256), 256, 0, lo, hi, c->type, VXYZ(c, buf), c->cfg.D_liquid,
+               c->cfg.alpha_art_diff * c->cfg.dx, c->vmag, c->wpack);
     return 0;
 }
 
@@ -160,10 +167,10 @@ int pd_enqueue_ard_prepass_solids(pdgpu_ctx* c, int srcC) {
     ArdParams P = ard_params(c);
     if (c->dim == 2)
         LAUNCH(c, k_ard_prepass_solids<2>, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type,
-               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol, c->vmag);
+               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol, c->wpack);
     else
         LAUNCH(c, k_ard_prepass_solids<3>, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type,
-               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol, c->vmag);
+               c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol, c->wpack);
     return 0;
 }
 

@@ -3,17 +3,19 @@
 // Same staging scheme as ns_tile.cu (38 x 14 x 10 haloed block, 4 z-nodes per thread, sliding
 // z-window, runtime column loop: tile.cuh).  Staged per node:
 //     C      concentration
-//     w      packed weight (ard.cu): |v| >= +0 for fluid-like nodes (FLUID / INLET / OUTLET);
-//            -dsol <= -0 for a SOLID_MG node, dsol = interface diffusivity 2 D_l D_s / (D_l + D_s)
-//            (0 when salt blocked; grain-boundary / precipitate / grain class and the
-//            volume-loss decay folded in); -0 for WALL/OUTSIDE      (src/pd_ard.cpp:136-162)
+//     w      packed weight (ard.cu, k_ard_vmag): own fluid-fluid diffusivity D_l + alpha dx |v| >= +0
+//            for fluid-like nodes (FLUID / INLET / OUTLET); -dsol <= -0 for a SOLID_MG node, dsol =
+//            interface diffusivity 2 D_l D_s / (D_l + D_s) (0 when salt blocked; grain-boundary /
+//            precipitate / grain class and the volume-loss decay folded in); -0 for WALL/OUTSIDE
+//                                                                    (src/pd_ard.cpp:136-170)
 // Two staged fields = 77 KB per CTA: two CTAs per SM, so one CTA's staging overlaps the other's
-// bond loop.  With vmf = w, f = [sign bit clear], dsol = f ? 0 : -w
-// so the bond classification of src/pd_ard.cpp:120-181 becomes branch free for a FLUID row:
-//     D_ij = f_j (D_l + alpha dx max(|v_i|, |v_j|)) + dsol_j ,   f_j = [vmf_j >= 0]
+// bond loop.  For a FLUID row the bond classification of src/pd_ard.cpp:120-181 becomes
+//     D_ij = f_j ? max(w_i, w_j) : -w_j ,   f_j = [sign bit of w_j clear]
 //     diff += D_ij (C_j - C_i) w2 ;   G += f_j (C_j - C_i) e w1 ;   adv = (alpha/V_H) v_i . G
-// (WALL neighbours have f = 0, dsol = 0 and drop out).  SOLID_MG rows (2 % of the nodes)
-// are done by k_ard_solid_rows from the solid node list.
+// (WALL neighbours have f = 0, dsol = 0 and drop out).  max and the select are done on the
+// integer pipe (non-negative doubles order like their bit patterns): an FP64 max costs a DSETP
+// plus six moves/selects on sm_100a.  SOLID_MG rows (2 % of the nodes) are done by
+// k_ard_solid_rows from the solid node list.
 #include <algorithm>
 
 #include "tile.cuh"
@@ -24,29 +26,29 @@ using namespace tile;
 struct ArdTileParams {
     TileGeom g;
     int skip_wall_copy;   // WALL values of the new buffer are written by the wall-concentration BC kernel
-    double D_liquid, alpha_dx, beta, div_coeff, inv_dx;
+    double beta, div_coeff, inv_dx;
 };
 
 struct ArdAcc {
     double diff[RZ], gx[RZ], gy[RZ], gz[RZ];
 };
 
-// per bond (9 FP64 ops): dC, max, D_ff, D, D*dC, diff, f*dC, colg, gz
+// per bond: 7 FP64 ops (dC, D*dC, diff, f*dC, colg, gz + column tail) and 6 integer ops (max, select)
 template <int H>
 __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const double* __restrict__ s_w, int cb,
-                                           double dI, double dJ,
-                                           const double (&kap)[4], const double (&kz)[4], const ArdTileParams& q,
-                                           const double (&Ci)[RZ], const double (&vmi)[RZ], ArdAcc& a) {
+                                           double dI, double dJ, const double (&kap)[4], const double (&kz)[4],
+                                           const double (&Ci)[RZ], const long long (&wi)[RZ], ArdAcc& a) {
     double colg[RZ];
 #pragma unroll
     for (int t = 0; t < RZ; ++t) colg[t] = 0.0;
 #pragma unroll
     for (int zz = -H; zz < RZ + H; ++zz) {
         const int si = cb + (zz + TR) * SPLANE;
-        const double Cj = s_C[si], vmf = s_w[si];
-        const bool fluid_like = __double2hiint(vmf) >= 0;   // sign bit clear
+        const double Cj = s_C[si];
+        const long long wj = __double_as_longlong(s_w[si]);
+        const bool fluid_like = wj >= 0;                          // sign bit clear
         const double f = fluid_like ? 1.0 : 0.0;
-        const double dsj = fluid_like ? 0.0 : -vmf;
+        const long long dsj = wj ^ (long long)0x8000000000000000ull;   // -w_j = dsol of a solid neighbour
 #pragma unroll
         for (int t = 0; t < RZ; ++t) {
             const int dk = zz - t;
@@ -54,8 +56,8 @@ __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const
                 const int ak = dk < 0 ? -dk : dk;
                 const double k = kap[ak];
                 const double dC = Cj - Ci[t];
-                const double Dff = fma(q.alpha_dx, fmax(vmi[t], vmf), q.D_liquid);
-                const double D = fma(f, Dff, dsj);
+                const long long wm = wi[t] > wj ? wi[t] : wj;
+                const double D = __longlong_as_double(fluid_like ? wm : dsj);
                 a.diff[t] = fma(D * dC, k, a.diff[t]);
                 const double fd = f * dC;
                 colg[t] = fma(fd, k, colg[t]);
@@ -117,13 +119,14 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
     if (!__any_sync(0xffffffffu, any)) return;
 
     const int base = (tz * RZ * SY + ty + TR) * SX + (tx + TR);   // node t at base + (t+TR)*SPLANE
-    double Ci[RZ], vmi[RZ];
+    double Ci[RZ];
+    long long wi[RZ];     // own w as an integer: >= 0 for the FLUID nodes that are updated
     ArdAcc a;
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
         const int si = base + (t + TR) * SPLANE;
         Ci[t] = s_C[si];
-        vmi[t] = fmax(s_w[si], 0.0);
+        wi[t] = __double_as_longlong(s_w[si]);
         a.diff[t] = a.gx[t] = a.gy[t] = a.gz[t] = 0.0;
     }
 #pragma unroll 1
@@ -133,9 +136,9 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
         const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
         const double kz[4] = {T.kz[c][0], T.kz[c][1], T.kz[c][2], T.kz[c][3]};
         const int H = T.h[c];
-        if (H == 3) ard_column<3>(s_C, s_w, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
-        else if (H == 2) ard_column<2>(s_C, s_w, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
-        else ard_column<1>(s_C, s_w, cb, dI, dJ, kap, kz, q, Ci, vmi, a);
+        if (H == 3) ard_column<3>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+        else if (H == 2) ard_column<2>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+        else ard_column<1>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
     }
 
     const double dt = *d_dt;
@@ -187,7 +190,6 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
     q.g = make_geom(c);
     q.skip_wall_copy = skip_wall_copy ? 1 : 0;
     if (zb >= 0) { q.g.z_lo = zb; q.g.z_hi = ze; }
-    q.D_liquid = c->cfg.D_liquid; q.alpha_dx = c->cfg.alpha_art_diff * c->cfg.dx;
     q.beta = k.beta_lap; q.div_coeff = k.alpha / k.V_H; q.inv_dx = 1.0 / c->cfg.dx;
     const size_t smem = sizeof(double) * 2 * SN;
     static bool attr_done = false;
@@ -199,7 +201,7 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
     if (q.g.z_hi > q.g.z_lo) {
         dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + TZ - 1) / TZ);
         dim3 block(TX, TY, NZT);
-        k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->C[srcC], c->vmag, c->v[buf][0],
+        k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->C[srcC], c->wpack, c->v[buf][0],
                                                       c->v[buf][1], c->v[buf][2], c->C[dstC]);
         c->launches++;
     }

@@ -124,7 +124,7 @@ int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC) {
         add_d(c->C[oc]);
         add_b(c->type); add_b(c->phase); add_b(c->is_gb); add_b(c->is_precip);
     }
-    if (which == 3) { add_b(c->salt); add_d(c->dsol); add_d(c->vmag); }   // vmag: packed -dsol of ghost solids
+    if (which == 3) { add_b(c->salt); add_d(c->dsol); add_d(c->wpack); }   // wpack: -dsol of ghost solids
     if (which == 4 && c->moff) arrs.push_back({c->moff, 4});
     int lo = c->rank - 1, hi = c->rank + 1;
     NCCL_OK(g_nccl.GroupStart());

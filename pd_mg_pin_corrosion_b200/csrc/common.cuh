@@ -86,6 +86,7 @@ struct pdgpu_ctx {
     double* v[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     double* vmag = nullptr;         // |v| per fluid-like node, -1 otherwise (ARD artificial diffusion)
     double* dsol = nullptr;         // interface diffusivity of SOLID_MG nodes (0 elsewhere / salt blocked)
+    double* wpack = nullptr;        // packed bond weight of the tiled ARD kernel (ard.cu: k_ard_vmag)
     int cur = 0, curC = 0;          // which buffer is "current"
     int p_input = 0;                // buffer whose p is the reference's `pressure` member
 

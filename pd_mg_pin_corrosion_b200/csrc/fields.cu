@@ -34,6 +34,8 @@ int pd_alloc_fields(pdgpu_ctx* c) {
     CUDA_OK(cudaMemset(c->vmag, 0, nb));
     CUDA_OK(cudaMalloc(&c->dsol, nb));
     CUDA_OK(cudaMemset(c->dsol, 0, nb));
+    CUDA_OK(cudaMalloc(&c->wpack, nb));
+    CUDA_OK(cudaMemset(c->wpack, 0, nb));
     return 0;
 }
 
