@@ -10,7 +10,7 @@
 //                                                                    (src/pd_ard.cpp:136-170)
 // Two staged fields = 77 KB per CTA: two CTAs per SM, so one CTA's staging overlaps the other's
 // bond loop.  For a FLUID row the bond classification of src/pd_ard.cpp:120-181 becomes
-//     D_ij = f_j ? max(w_i, w_j) : -w_j ,   f_j = [sign bit of w_j clear]
+//     D_ij = | umax(w_i, w_j) |  ( = f_j ? max(w_i, w_j) : dsol_j ),   f_j = [sign bit of w_j clear]
 //     diff += D_ij (C_j - C_i) w2 ;   G += f_j (C_j - C_i) e w1 ;   adv = (alpha/V_H) v_i . G
 // (WALL neighbours have f = 0, dsol = 0 and drop out).  max and the select are done on the
 // integer pipe (non-negative doubles order like their bit patterns): an FP64 max costs a DSETP
@@ -33,11 +33,11 @@ struct ArdAcc {
     double diff[RZ], gx[RZ], gy[RZ], gz[RZ];
 };
 
-// per bond: 7 FP64 ops (dC, D*dC, diff, f*dC, colg, gz + column tail) and 6 integer ops (max, select)
+// per bond: 7 FP64 ops (dC, D*dC, diff, f*dC, colg, gz + column tail) and 4 integer ops (64-bit unsigned max)
 template <int H>
 __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const double* __restrict__ s_w, int cb,
                                            double dI, double dJ, const double (&kap)[4], const double (&kz)[4],
-                                           const double (&Ci)[RZ], const long long (&wi)[RZ], ArdAcc& a) {
+                                           const double (&Ci)[RZ], const unsigned long long (&wi)[RZ], ArdAcc& a) {
     double colg[RZ];
 #pragma unroll
     for (int t = 0; t < RZ; ++t) colg[t] = 0.0;
@@ -45,10 +45,8 @@ __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const
     for (int zz = -H; zz < RZ + H; ++zz) {
         const int si = cb + (zz + TR) * SPLANE;
         const double Cj = s_C[si];
-        const long long wj = __double_as_longlong(s_w[si]);
-        const bool fluid_like = wj >= 0;                          // sign bit clear
-        const double f = fluid_like ? 1.0 : 0.0;
-        const long long dsj = wj ^ (long long)0x8000000000000000ull;   // -w_j = dsol of a solid neighbour
+        const unsigned long long wj = (unsigned long long)__double_as_longlong(s_w[si]);
+        const double f = (int)(wj >> 32) >= 0 ? 1.0 : 0.0;        // sign bit clear: fluid-like
 #pragma unroll
         for (int t = 0; t < RZ; ++t) {
             const int dk = zz - t;
@@ -56,8 +54,10 @@ __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const
                 const int ak = dk < 0 ? -dk : dk;
                 const double k = kap[ak];
                 const double dC = Cj - Ci[t];
-                const long long wm = wi[t] > wj ? wi[t] : wj;
-                const double D = __longlong_as_double(fluid_like ? wm : dsj);
+                // unsigned max: a set sign bit (solid / wall neighbour) beats every w_i >= +0, and
+                // |.| then yields dsol_j; for a fluid-like neighbour it is max(w_i, w_j)
+                const unsigned long long wm = wi[t] > wj ? wi[t] : wj;
+                const double D = fabs(__longlong_as_double((long long)wm));
                 a.diff[t] = fma(D * dC, k, a.diff[t]);
                 const double fd = f * dC;
                 colg[t] = fma(fd, k, colg[t]);
@@ -120,13 +120,13 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
 
     const int base = (tz * RZ * SY + ty + TR) * SX + (tx + TR);   // node t at base + (t+TR)*SPLANE
     double Ci[RZ];
-    long long wi[RZ];     // own w as an integer: >= 0 for the FLUID nodes that are updated
+    unsigned long long wi[RZ];     // own w as an integer: sign bit clear for the FLUID nodes that are updated
     ArdAcc a;
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
         const int si = base + (t + TR) * SPLANE;
         Ci[t] = s_C[si];
-        wi[t] = __double_as_longlong(s_w[si]);
+        wi[t] = (unsigned long long)__double_as_longlong(s_w[si]);
         a.diff[t] = a.gx[t] = a.gy[t] = a.gz[t] = 0.0;
     }
 #pragma unroll 1
