@@ -282,6 +282,112 @@ k_outlet_sweep_mod(OutletGeom g, int RJ, const int4* __restrict__ rows, int n_ro
     }
 }
 
+// Row-walking variant (default): a group of G lanes owns one lattice row (k', j) of the outlet
+// planes at a time and follows the node i = tau - B^2 k' - B j that the level front cuts out of it;
+// the row's successor for the same group is row j + M, which the front reaches after this row has
+// left it (B M >= Nx + PF).  Per level nothing is divided or looked up: i advances by one, base
+// and neighbour count of the next G nodes of the row are prefetched one block ahead (coalesced,
+// handed to the level that needs them by a shuffle; count -1 marks a non-OUTLET lattice node), the
+// earlier half of the stencil is walked as (dj,dplane) rows with predicated, unrolled ring loads
+// (lattice-addressed ring as in k_outlet_sweep_mod), and 1/n comes from a table.
+struct RowSweepParams {
+    OutletGeom g;
+    int RJ, n_rows, M;
+    int row_start[8];      // first table row with k' + dplane >= 0, per outlet plane k'
+    int n_rcp;             // reciprocal table entries (stencil size + 1)
+};
+
+template <int G>
+__global__ void __launch_bounds__(1024, 1)
+k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __restrict__ rows,
+                    const double* __restrict__ base_v, const double* __restrict__ base_c,
+                    const int* __restrict__ cnt, double* vax, double* C, double U_in) {
+    extern __shared__ double smem[];
+    const OutletGeom& g = q.g;
+    double* ring = smem;
+    const int RI = g.ring, RJ = q.RJ;
+    int4* s_rows = (int4*)(ring + (((size_t)g.KP * RJ * RI + 1) & ~(size_t)1));   // 16-byte aligned
+    double* s_rcp = (double*)(s_rows + q.n_rows);
+    const bool is_vel = (blockIdx.x == 0);
+    const double* base = is_vel ? base_v : base_c;
+    double* out = is_vel ? vax : C;
+    for (int e = threadIdx.x; e < q.n_rows; e += blockDim.x) s_rows[e] = rows[e];
+    for (int e = threadIdx.x; e < q.n_rcp; e += blockDim.x) s_rcp[e] = e > 0 ? 1.0 / (double)e : 0.0;
+    __syncthreads();
+
+    constexpr int PF = G;                       // prefetch block = one value per lane
+    const int lane = threadIdx.x & (G - 1);
+    const int slot = threadIdx.x / G;
+    const int kp = slot / q.M, js = slot - kp * q.M;
+    const bool slot_ok = kp < g.KP;
+    const int imask = RI - 1, jmask = RJ - 1;
+    const int BM = g.B * q.M;
+    const int r0 = slot_ok ? q.row_start[kp] : q.n_rows;
+
+    int j = js;
+    int i = -g.B2 * kp - g.B * js;              // position of the level front in row j at tau = 0
+    double cur_b = 0.0, nxt_b = 0.0;
+    int cur_c = -1, nxt_c = -1;
+    auto load_block = [&](int i_first, double* b, int* c) {
+        const int ib = i_first + lane;
+        *b = 0.0; *c = -1;
+        if (ib >= 0 && ib < g.Nx) {
+            const long long d = (long long)kp * g.P + (long long)j * g.Nx + ib;
+            *b = base[d]; *c = cnt[d];
+        }
+    };
+    if (slot_ok && j < g.Ny && i > -PF) {       // rows the front has already entered at tau = 0
+        const int blk = (i >= 0 ? i / PF : -((-i + PF - 1) / PF)) * PF;
+        if (blk == i) load_block(blk, &nxt_b, &nxt_c);
+        else { load_block(blk, &cur_b, &cur_c); load_block(blk + PF, &nxt_b, &nxt_c); }
+    }
+
+    for (int tau = 0; tau <= g.tau_max; ++tau) {
+        const bool row_ok = slot_ok && j < g.Ny;
+        if (row_ok && i >= -PF && i < g.Nx && (i & (PF - 1)) == 0) {
+            cur_b = nxt_b; cur_c = nxt_c;
+            load_block(i + PF, &nxt_b, &nxt_c);
+        }
+        const double b = __shfl_sync(0xffffffffu, cur_b, i & (PF - 1), G);
+        int n = __shfl_sync(0xffffffffu, cur_c, i & (PF - 1), G);
+        const bool active = row_ok && i >= 0 && i < g.Nx;
+        if (!active) n = -1;
+        double s0 = 0.0, s1 = 0.0;
+        if (n >= 0) {
+            for (int r = r0 + lane; r < q.n_rows; r += G) {
+                const int4 row = s_rows[r];                  // dj, dplane, di_lo, di_hi
+                const int j2 = j + row.x;
+                if ((unsigned)j2 >= (unsigned)g.Ny) continue;
+                const int rb = ((kp + row.y) * RJ + (j2 & jmask)) * RI;
+                const int lo = max(i + row.z, 0), hi = min(i + row.w, g.Nx - 1);
+#pragma unroll
+                for (int u = 0; u < 7; ++u) {                // a row of the reach-3 sphere has <= 7 nodes
+                    const int i2 = lo + u;
+                    const double v = (i2 <= hi) ? ring[rb + (i2 & imask)] : 0.0;
+                    if (u & 1) s1 += v; else s0 += v;
+                }
+                for (int i2 = lo + 7; i2 <= hi; ++i2) s0 += ring[rb + (i2 & imask)];   // reach > 3
+            }
+        }
+        double sum = s0 + s1;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (active && lane == 0) {
+            double val = 0.0;
+            if (n >= 0) {
+                const double tot = b + sum;
+                if (is_vel) val = n > 0 ? tot * s_rcp[n] : U_in;   // src/boundary.cpp:113-124
+                else val = n > 0 ? tot / n : 0.0;                  // :129
+                out[g.l0 + (long long)kp * g.P + (long long)j * g.Nx + i] = val;
+            }
+            ring[(kp * RJ + (j & jmask)) * RI + (i & imask)] = val;
+        }
+        __syncthreads();
+        ++i;
+        if (i >= g.Nx && row_ok) { j += q.M; i -= BM; }
+    }
+}
+
 __global__ void k_outlet_mask(const uint8_t* __restrict__ type, long long l0, long long n, unsigned* __restrict__ mask) {
     long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w * 32 >= n) return;
@@ -347,12 +453,33 @@ int pd_outlet_setup(pdgpu_ctx* c) {
     CUDA_OK(cudaMalloc(&c->out_early, sizeof(int4) * n_early));
     CUDA_OK(cudaMemset(c->out_base_v, 0, sizeof(double) * nslab));
     CUDA_OK(cudaMemset(c->out_base_c, 0, sizeof(double) * nslab));
-    CUDA_OK(cudaMemset(c->out_cnt, 0, sizeof(int) * nslab));
+    CUDA_OK(cudaMemset(c->out_cnt, 0xFF, sizeof(int) * nslab));   // -1 = not an OUTLET node (pre-pass writes OUTLET nodes)
     CUDA_OK(cudaMemcpy(c->out_early, early.data(), sizeof(int4) * n_early, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&c->out_rows, sizeof(int4) * rows.size()));
     CUDA_OK(cudaMemcpy(c->out_rows, rows.data(), sizeof(int4) * rows.size(), cudaMemcpyHostToDevice));
     if (c->out_mod)
         CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep_mod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mod));
+    // row-walking sweep: G lanes per lattice row slot, M row slots per outlet plane
+    c->out_rows_G = 0;
+    if (c->out_mod && KP <= 8) {
+        size_t smem_rows = sizeof(double) * ((size_t)KP * RJ * ring + 1 + c->n_off + 1) + sizeof(int4) * rows.size();
+        for (int G : {8, 4}) {
+            int M = (Ny == 1) ? 1 : (Nx + G + B - 1) / B;
+            if (KP * M * G <= 1024 && smem_rows <= 220 * 1024) {
+                c->out_rows_G = G; c->out_rows_M = M; c->out_smem_rows = smem_rows;
+                break;
+            }
+        }
+        for (int kp = 0; kp < 8; ++kp) {
+            int st = 0;
+            while (st < (int)rows.size() && kp + rows[st].y < 0) ++st;
+            c->out_row_start[kp] = st;
+        }
+        if (c->out_rows_G == 8)
+            CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        if (c->out_rows_G == 4)
+            CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep_rows<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+    }
     k_outlet_mask<<<nblocks(mask_words, 256), 256, 0, c->stream>>>(c->type, c->out_l0, nslab, c->out_mask);
     CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -377,7 +504,18 @@ int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
         LAUNCH(c, k_outlet_prepass<3>, nblocks(c->n_outlet, 128), 128, 0, L, g, c->l_outlet, c->n_outlet, c->type,
                c->d_off, c->n_off, c->rho[buf], c->p[buf], VXYZ(c, buf), c->C[bufC], c->cfg.rho_f, c->out_base_v,
                c->out_base_c, c->out_cnt);
-    if (c->out_mod && c->opt_outlet_kernel >= 2)
+    if (c->out_rows_G && c->opt_outlet_kernel >= 3) {
+        RowSweepParams q;
+        q.g = g; q.RJ = c->out_RJ; q.n_rows = c->out_n_rows; q.M = c->out_rows_M; q.n_rcp = c->n_off + 1;
+        for (int kp = 0; kp < 8; ++kp) q.row_start[kp] = c->out_row_start[kp];
+        const int threads = (g.KP * q.M * c->out_rows_G + 31) / 32 * 32;
+        if (c->out_rows_G == 8)
+            LAUNCH(c, k_outlet_sweep_rows<8>, 2, threads, c->out_smem_rows, q, (const int4*)c->out_rows, c->out_base_v,
+                   c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
+        else
+            LAUNCH(c, k_outlet_sweep_rows<4>, 2, threads, c->out_smem_rows, q, (const int4*)c->out_rows, c->out_base_v,
+                   c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
+    } else if (c->out_mod && c->opt_outlet_kernel >= 2)
         LAUNCH(c, k_outlet_sweep_mod, 2, 1024, c->out_smem_mod, g, c->out_RJ, (const int4*)c->out_rows, c->out_n_rows,
                c->out_mask, c->out_mask_words, c->out_base_v, c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
     else
