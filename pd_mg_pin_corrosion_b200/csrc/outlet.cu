@@ -285,14 +285,16 @@ k_outlet_sweep_mod(OutletGeom g, int RJ, const int4* __restrict__ rows, int n_ro
 // Row-walking variant (default): a group of G lanes owns one lattice row (k', j) of the outlet
 // planes at a time and follows the node i = tau - B^2 k' - B j that the level front cuts out of it;
 // the row's successor for the same group is row j + M, which the front reaches after this row has
-// left it (B M >= Nx + PF).  Per level nothing is divided or looked up: i advances by one, base
+// left it (B M >= Nx + PF + R).  Per level nothing is divided or looked up: i advances by one, base
 // and neighbour count of the next G nodes of the row are prefetched one block ahead (coalesced,
-// handed to the level that needs them by a shuffle; count -1 marks a non-OUTLET lattice node), the
-// earlier half of the stencil is walked as (dj,dplane) rows with predicated, unrolled ring loads
-// (lattice-addressed ring as in k_outlet_sweep_mod), and 1/n comes from a table.
+// handed to the level that needs them by a shuffle; count -1 marks a non-OUTLET lattice node) and
+// 1/n comes from a table.  The ring is lattice addressed as in k_outlet_sweep_mod, but every ring
+// row is stored twice (slots s and s + RI) and the owner also writes zeros for the R virtual nodes
+// before and after its row, so a (dj,dplane) row of the earlier half of the stencil is a run of
+// <= 2R+1 consecutive shared-memory words: no wrap, no clipping, 3 instructions per bond.
 struct RowSweepParams {
     OutletGeom g;
-    int RJ, n_rows, M;
+    int RJ, n_rows, M, R;
     int row_start[8];      // first table row with k' + dplane >= 0, per outlet plane k'
     int n_rcp;             // reciprocal table entries (stencil size + 1)
 };
@@ -305,14 +307,15 @@ k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __rest
     extern __shared__ double smem[];
     const OutletGeom& g = q.g;
     double* ring = smem;
-    const int RI = g.ring, RJ = q.RJ;
-    int4* s_rows = (int4*)(ring + (((size_t)g.KP * RJ * RI + 1) & ~(size_t)1));   // 16-byte aligned
+    const int RI = g.ring, RJ = q.RJ, RW = 2 * RI;           // RW = doubled ring row
+    int4* s_rows = (int4*)(ring + (size_t)g.KP * RJ * RW);   // even number of doubles: 16-byte aligned
     double* s_rcp = (double*)(s_rows + q.n_rows);
     const bool is_vel = (blockIdx.x == 0);
     const double* base = is_vel ? base_v : base_c;
     double* out = is_vel ? vax : C;
     for (int e = threadIdx.x; e < q.n_rows; e += blockDim.x) s_rows[e] = rows[e];
     for (int e = threadIdx.x; e < q.n_rcp; e += blockDim.x) s_rcp[e] = e > 0 ? 1.0 / (double)e : 0.0;
+    for (int e = threadIdx.x; e < g.KP * RJ * RW; e += blockDim.x) ring[e] = 0.0;
     __syncthreads();
 
     constexpr int PF = G;                       // prefetch block = one value per lane
@@ -323,6 +326,7 @@ k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __rest
     const int imask = RI - 1, jmask = RJ - 1;
     const int BM = g.B * q.M;
     const int r0 = slot_ok ? q.row_start[kp] : q.n_rows;
+    const int i_end = g.Nx + q.R;               // one past the last (virtual) node of a row
 
     int j = js;
     int i = -g.B2 * kp - g.B * js;              // position of the level front in row j at tau = 0
@@ -342,7 +346,7 @@ k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __rest
         else { load_block(blk, &cur_b, &cur_c); load_block(blk + PF, &nxt_b, &nxt_c); }
     }
 
-    for (int tau = 0; tau <= g.tau_max; ++tau) {
+    for (int tau = 0; tau <= g.tau_max + q.R; ++tau) {
         const bool row_ok = slot_ok && j < g.Ny;
         if (row_ok && i >= -PF && i < g.Nx && (i & (PF - 1)) == 0) {
             cur_b = nxt_b; cur_c = nxt_c;
@@ -350,29 +354,28 @@ k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __rest
         }
         const double b = __shfl_sync(0xffffffffu, cur_b, i & (PF - 1), G);
         int n = __shfl_sync(0xffffffffu, cur_c, i & (PF - 1), G);
-        const bool active = row_ok && i >= 0 && i < g.Nx;
-        if (!active) n = -1;
+        const bool in_row = row_ok && i >= 0 && i < g.Nx;
+        if (!in_row) n = -1;
         double s0 = 0.0, s1 = 0.0;
         if (n >= 0) {
             for (int r = r0 + lane; r < q.n_rows; r += G) {
                 const int4 row = s_rows[r];                  // dj, dplane, di_lo, di_hi
                 const int j2 = j + row.x;
                 if ((unsigned)j2 >= (unsigned)g.Ny) continue;
-                const int rb = ((kp + row.y) * RJ + (j2 & jmask)) * RI;
-                const int lo = max(i + row.z, 0), hi = min(i + row.w, g.Nx - 1);
+                const double* src = ring + ((kp + row.y) * RJ + (j2 & jmask)) * RW + ((i + row.z) & imask);
+                const int w = row.w - row.z + 1;
 #pragma unroll
                 for (int u = 0; u < 7; ++u) {                // a row of the reach-3 sphere has <= 7 nodes
-                    const int i2 = lo + u;
-                    const double v = (i2 <= hi) ? ring[rb + (i2 & imask)] : 0.0;
+                    const double v = (u < w) ? src[u] : 0.0;
                     if (u & 1) s1 += v; else s0 += v;
                 }
-                for (int i2 = lo + 7; i2 <= hi; ++i2) s0 += ring[rb + (i2 & imask)];   // reach > 3
+                for (int u = 7; u < w; ++u) s0 += src[u];    // reach > 3
             }
         }
         double sum = s0 + s1;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (active && lane == 0) {
+        if (row_ok && i >= -q.R && i < i_end && lane == 0) {   // virtual nodes beside the row store 0
             double val = 0.0;
             if (n >= 0) {
                 const double tot = b + sum;
@@ -380,11 +383,13 @@ k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __rest
                 else val = n > 0 ? tot / n : 0.0;                  // :129
                 out[g.l0 + (long long)kp * g.P + (long long)j * g.Nx + i] = val;
             }
-            ring[(kp * RJ + (j & jmask)) * RI + (i & imask)] = val;
+            double* dst = ring + (kp * RJ + (j & jmask)) * RW + (i & imask);
+            dst[0] = val;
+            dst[RI] = val;
         }
         __syncthreads();
         ++i;
-        if (i >= g.Nx && row_ok) { j += q.M; i -= BM; }
+        if (i >= i_end && row_ok) { j += q.M; i -= BM; }
     }
 }
 
@@ -462,9 +467,9 @@ int pd_outlet_setup(pdgpu_ctx* c) {
     // row-walking sweep: G lanes per lattice row slot, M row slots per outlet plane
     c->out_rows_G = 0;
     if (c->out_mod && KP <= 8) {
-        size_t smem_rows = sizeof(double) * ((size_t)KP * RJ * ring + 1 + c->n_off + 1) + sizeof(int4) * rows.size();
+        size_t smem_rows = sizeof(double) * ((size_t)KP * RJ * 2 * ring + c->n_off + 1) + sizeof(int4) * rows.size();
         for (int G : {8, 4}) {
-            int M = (Ny == 1) ? 1 : (Nx + G + B - 1) / B;
+            int M = (Ny == 1) ? 1 : (Nx + G + c->R + B - 1) / B;
             if (KP * M * G <= 1024 && smem_rows <= 220 * 1024) {
                 c->out_rows_G = G; c->out_rows_M = M; c->out_smem_rows = smem_rows;
                 break;
@@ -506,7 +511,7 @@ int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
                c->out_base_c, c->out_cnt);
     if (c->out_rows_G && c->opt_outlet_kernel >= 3) {
         RowSweepParams q;
-        q.g = g; q.RJ = c->out_RJ; q.n_rows = c->out_n_rows; q.M = c->out_rows_M; q.n_rcp = c->n_off + 1;
+        q.g = g; q.RJ = c->out_RJ; q.n_rows = c->out_n_rows; q.M = c->out_rows_M; q.R = c->R; q.n_rcp = c->n_off + 1;
         for (int kp = 0; kp < 8; ++kp) q.row_start[kp] = c->out_row_start[kp];
         const int threads = (g.KP * q.M * c->out_rows_G + 31) / 32 * 32;
         if (c->out_rows_G == 8)

@@ -36,3 +36,12 @@ for st in sets:
         L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
         out.append(ms.value / 20)
     print(f"{st:40s} ns body {out[0]:.3f} ms  ard body {out[1]:.3f} ms  sum {out[0]+out[1]:.3f}", flush=True)
+# outlet BC alone (pre-pass + both sweeps)
+for ok in (3, 2):
+    grid.set_option("outlet_kernel", ok)
+    L_.check(L.pdgpu_bc_outlet(grid.ctx))
+    L_.check(L.pdgpu_timer_start(grid.ctx))
+    for _ in range(10):
+        L_.check(L.pdgpu_bc_outlet(grid.ctx))
+    L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
+    print(f"outlet_kernel={ok}: apply_outlet_bc {ms.value / 10:.3f} ms")
