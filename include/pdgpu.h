@@ -186,6 +186,16 @@ int pdgpu_step_host_chunks(pdgpu_ctx* ctx, int n_chunks, int* n_used, char* why,
 /* Timeline of the last chunked pdgpu_step_host call: per chunk (axial order) milliseconds from the
  * start of the call to { upload done, kernels done, download done }; out[3 * n_chunks]. */
 int pdgpu_step_host_trace(pdgpu_ctx* ctx, double* out, int cap, int* n_chunks);
+/* ---- Output staging (src/vtk_writer.cpp:16-146, src/coupling.cpp:242-249) ------
+ * VTKWriter::write: the ASCII ImageData snapshot of the current state, formatted ON THE DEVICE
+ * ("%g" of every value, WALL/OUTSIDE velocities zeroed, NaN/Inf/|v|<1e-300 flushed) and written to
+ * `path`; byte-identical to the reference's file for the same state. grain_id[N] and D_map[N] are
+ * host-side arrays of the driver (the solvers never read them); NULL writes -1 / 0.
+ * bytes_out = bytes of DataArray bodies, format_ms = device time of the formatting kernels. */
+int pdgpu_vti_write(pdgpu_ctx* ctx, const char* path, const int* grain_id, const double* D_map,
+                    long long* bytes_out, float* format_ms);
+/* printf("%g") of n doubles on the device into 16-byte zero-padded cells (formatter unit tests). */
+int pdgpu_format_g(pdgpu_ctx* ctx, const double* host_vals, long long n, char* host_cells16);
 /* cudaHostRegister / cudaHostUnregister of caller-owned memory (e.g. std::vector storage). */
 int pdgpu_host_register(void* ptr, size_t bytes);
 int pdgpu_host_unregister(void* ptr);

@@ -13,6 +13,7 @@
 
 #include <math.h>
 #include <omp.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -682,4 +683,57 @@ double pdo_ard_iterate(PdoGrid* g, const PdoConfig* cfg, int steps, double dt, d
         free(tmp);
     }
     return el;
+}
+
+/* ---- VTKWriter::write (src/vtk_writer.cpp:16-146) ------------------------------------------ */
+static double vti_safe(double v) {                     /* src/vtk_writer.cpp:8-14 */
+    if (isnan(v) || isinf(v)) return 0.0;
+    if (v != 0.0 && fabs(v) < 1e-300) return 0.0;
+    return v;
+}
+
+int pdo_write_vti(const PdoGrid* g, const char* path, const double* rho, const double* vel,
+                  const double* pressure, const double* Cc, const uint8_t* phase, const int* grain_id,
+                  const double* D_map, const uint8_t* is_gb, const uint8_t* is_precip) {
+    FILE* f = fopen(path, "w");
+    if (!f) return 1;
+    const int dim = g->dim;
+    const int nx = g->Nx, ny = g->Ny, nz = dim == 3 ? g->Nz : 1;
+    const long long N = g->N;
+    fprintf(f, "<?xml version=\"1.0\"?>\n");
+    fprintf(f, "<VTKFile type=\"ImageData\" version=\"1.0\" byte_order=\"LittleEndian\">\n");
+    fprintf(f, "  <ImageData WholeExtent=\"0 %d 0 %d 0 %d\" Origin=\"%g %g %g\" Spacing=\"%g %g %g\">\n",
+            nx - 1, ny - 1, nz - 1, g->origin[0], g->origin[1], dim == 3 ? g->origin[2] : 0.0, g->dx, g->dx, g->dx);
+    fprintf(f, "    <Piece Extent=\"0 %d 0 %d 0 %d\">\n", nx - 1, ny - 1, nz - 1);
+    fprintf(f, "      <PointData Scalars=\"phase\" Vectors=\"velocity\">\n");
+    fprintf(f, "        <DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n");
+    for (long long i = 0; i < N; ++i) {
+        int fict = (g->node_type[i] == PDO_WALL || g->node_type[i] == PDO_OUTSIDE);
+        double a = fict ? 0.0 : vti_safe(vel[i * dim]), b = fict ? 0.0 : vti_safe(vel[i * dim + 1]);
+        if (dim == 2) fprintf(f, "          %g %g 0\n", a, b);
+        else fprintf(f, "          %g %g %g\n", a, b, fict ? 0.0 : vti_safe(vel[i * dim + 2]));
+    }
+    fprintf(f, "        </DataArray>\n");
+#define PDO_VTI_F64(name, arr)                                                                  \
+    fprintf(f, "        <DataArray type=\"Float64\" Name=\"" name "\" format=\"ascii\">\n");    \
+    for (long long i = 0; i < N; ++i) fprintf(f, "          %g\n", vti_safe((arr) ? (arr)[i] : 0.0)); \
+    fprintf(f, "        </DataArray>\n")
+#define PDO_VTI_INT(type, name, expr)                                                           \
+    fprintf(f, "        <DataArray type=\"" type "\" Name=\"" name "\" format=\"ascii\">\n");   \
+    for (long long i = 0; i < N; ++i) fprintf(f, "          %d\n", (int)(expr));                \
+    fprintf(f, "        </DataArray>\n")
+    PDO_VTI_F64("pressure", pressure);
+    PDO_VTI_F64("density", rho);
+    PDO_VTI_F64("concentration", Cc);
+    PDO_VTI_INT("UInt8", "phase", phase[i]);
+    PDO_VTI_INT("UInt8", "node_type", g->node_type[i]);
+    PDO_VTI_INT("Int32", "grain_id", grain_id ? grain_id[i] : -1);
+    PDO_VTI_F64("D_map", D_map);
+    PDO_VTI_INT("UInt8", "is_grain_boundary", is_gb[i]);
+    PDO_VTI_INT("UInt8", "is_precipitate", is_precip[i]);
+#undef PDO_VTI_F64
+#undef PDO_VTI_INT
+    fprintf(f, "      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n");
+    fclose(f);
+    return 0;
 }

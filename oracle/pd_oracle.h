@@ -107,6 +107,12 @@ double pdo_ard_iterate(PdoGrid* g, const PdoConfig* cfg, int steps, double dt, d
                        double* rho, double* vel, double* Cc, double* C_new, const uint8_t* is_gb,
                        const uint8_t* is_precip);
 
+/* VTKWriter::write (src/vtk_writer.cpp:16-146): ASCII ImageData snapshot, `ostream << double`
+ * restated as printf("%g"). grain_id / D_map may be NULL (-1 / 0). Returns 0 on success. */
+int pdo_write_vti(const PdoGrid* g, const char* path, const double* rho, const double* vel,
+                  const double* pressure, const double* Cc, const uint8_t* phase, const int* grain_id,
+                  const double* D_map, const uint8_t* is_gb, const uint8_t* is_precip);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
         L.pdo_ard_iterate.restype = C.c_double
         L.pdo_ard_iterate.argtypes = [vp, cp, C.c_int, C.c_double, C.c_double, dp, dp, dp, dp, u8p, u8p]
         L.pdo_set_threads.argtypes = [C.c_int]
+        L.pdo_write_vti.argtypes = [vp, C.c_char_p, dp, dp, dp, dp, u8p, vp, vp, u8p, u8p]
+        L.pdo_write_vti.restype = C.c_int
         _lib = L
     return _lib
 
@@ -214,6 +216,21 @@ class PortSim:
                                     _dp(self.C), _ip(d))
         self.last_dissolved = d[:n].copy()
         return n
+
+    def write_vti(self, path: str, grain_id=None, D_map=None) -> float:
+        """VTKWriter::write restated (printf "%g"); returns seconds"""
+        import time
+        gid = None if grain_id is None else np.ascontiguousarray(grain_id, np.int32)
+        dm = None if D_map is None else np.ascontiguousarray(D_map, np.float64)
+        t0 = time.perf_counter()
+        rc = self.L.pdo_write_vti(self.g, path.encode(), _dp(self.rho), _dp(self.vel), _dp(self.pressure),
+                                  _dp(self.C), _u8(self.phase),
+                                  gid.ctypes.data_as(C.c_void_p) if gid is not None else None,
+                                  dm.ctypes.data_as(C.c_void_p) if dm is not None else None,
+                                  _u8(self.is_gb), _u8(self.is_precip))
+        if rc:
+            raise OSError(f"cannot write {path}")
+        return time.perf_counter() - t0
 
     def rebuild_tables(self):
         """after editing node_type in place (hand-built geometries)"""

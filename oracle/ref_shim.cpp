@@ -221,6 +221,15 @@ double ref_time_ard_iterate(void* h, int steps, double dt) {
     return omp_get_wtime() - t0;
 }
 
+// The reference's own VTKWriter::write (src/vtk_writer.cpp:16-146) on the current state; returns seconds.
+double ref_write_vti(void* h, const char* path) {
+    RefSim* s = S(h);
+    VTKWriter w;
+    double t0 = omp_get_wtime();
+    w.write(path, s->grid, s->fields, s->cfg);
+    return omp_get_wtime() - t0;
+}
+
 // The reference's own main(): whole-run diagnostics.csv for the 1e-6 parity check.
 int ref_main(const char* cfg_path) {
     char prog[] = "pd_corrosion";

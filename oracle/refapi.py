@@ -74,6 +74,8 @@ def _lib(dim: int) -> C.CDLL:
     lib.ref_get_config.argtypes = [vp, C.POINTER(C.c_double)]
     lib.ref_get_dims.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.ref_get_origin.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.ref_write_vti.argtypes = [vp, C.c_char_p]
+    lib.ref_write_vti.restype = C.c_double
     lib.ref_main.argtypes = [C.c_char_p]
     lib.ref_main.restype = C.c_int
     lib.ref_set_threads.argtypes = [C.c_int]
@@ -204,6 +206,10 @@ class RefSim:
         self.lib.ref_build_neighbors(self.h)
     def rebuild_tables(self):
         """after editing node_type in place: Grid::build_neighbors filters OUTSIDE only -> nothing to do"""
+
+    def write_vti(self, path: str) -> float:
+        """VTKWriter::write of the current state; returns the seconds it took"""
+        return self.lib.ref_write_vti(self.h, path.encode())
 
     def time_ns(self, n, dt) -> float: return self.lib.ref_time_ns_iterate(self.h, n, dt)
     def time_ard(self, n, dt) -> float: return self.lib.ref_time_ard_iterate(self.h, n, dt)

@@ -38,7 +38,7 @@ __device__ __forceinline__ long long block_exclusive(long long v, long long* tot
     return r;
 }
 
-__global__ void k_tile_sums(const int* __restrict__ in, long long n, long long* __restrict__ sums) {
+static __global__ void k_tile_sums(const int* __restrict__ in, long long n, long long* __restrict__ sums) {
     __shared__ long long sh[kBlock / 32];
     long long base = (long long)blockIdx.x * kTile;
     long long s = 0;
@@ -52,7 +52,7 @@ __global__ void k_tile_sums(const int* __restrict__ in, long long n, long long* 
     if (threadIdx.x == 0) sums[blockIdx.x] = total;
 }
 
-__global__ void k_scan_sums(long long* sums, long long nb, long long* grand_total) {
+static __global__ void k_scan_sums(long long* sums, long long nb, long long* grand_total) {
     __shared__ long long sh[kBlock / 32];
     __shared__ long long carry;
     if (threadIdx.x == 0) carry = 0;
@@ -70,7 +70,7 @@ __global__ void k_scan_sums(long long* sums, long long nb, long long* grand_tota
     if (threadIdx.x == 0) *grand_total = carry;
 }
 
-__global__ void k_tile_scan(const int* __restrict__ in, long long n, const long long* __restrict__ sums,
+static __global__ void k_tile_scan(const int* __restrict__ in, long long n, const long long* __restrict__ sums,
                             long long* __restrict__ out) {
     __shared__ long long sh[kBlock / 32];
     long long base = (long long)blockIdx.x * kTile;

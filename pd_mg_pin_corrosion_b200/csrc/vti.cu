@@ -1,0 +1,423 @@
+// vti.cu -- device-side formatting of the reference's VTI snapshot (src/vtk_writer.cpp:16-146).
+//
+// The reference writes every output interval (src/coupling.cpp:242-249) an ASCII ImageData file:
+// one line per node and DataArray, doubles through `ostream << double` (= printf "%g", six
+// significant digits), WALL/OUTSIDE velocities zeroed, NaN/Inf and |v| < 1e-300 flushed to 0.
+// On the CPU that is ~4 us per node; here the text is produced on the device:
+//   k_fmt_*      one thread per node formats its record into a fixed slot and stores its length
+//   scan         exclusive prefix sum of the lengths (scan.cuh)
+//   k_compact    records are packed into the contiguous text of the DataArray body
+// and only the finished text crosses PCIe. Output is byte-identical to the reference's file.
+//
+// "%g" needs the correctly rounded 6-digit decimal of a binary64 value. x = m 2^e is multiplied
+// by a 128-bit power of ten from pow10_table.inc (T 2^b <= 10^k < (T+1) 2^b): the 181-bit product
+// brackets x 10^k within m 2^(e+b), 2^-107 relative. A 53-bit value cannot come that close to a
+// 7-digit half-way point without being exactly on it, which happens only for integers
+// (x = (2N+1) 5^j 2^(j-1)) and is decided by an exact 128-bit comparison (round half to even, as
+// glibc). Anything still undecided raises the error flag of the call (never observed).
+#include <algorithm>
+#include <fstream>
+#include <sstream>
+
+#include "common.cuh"
+#include "scan.cuh"
+
+struct Pow10Entry {
+    unsigned long long hi, lo;
+    int bexp, exact;
+};
+#include "pow10_table.inc"
+
+namespace {
+
+__constant__ Pow10Entry d_pow10[PD_POW10_KMAX - PD_POW10_KMIN + 1];
+bool g_table_uploaded[64] = {false};
+
+typedef unsigned __int128 u128;
+
+// digits of |v| (normal, finite, non-zero): q in [100000, 999999], decimal exponent X with
+// |v| ~= q * 10^(X-5) correctly rounded (half to even). *flag is set if the decision was not provable.
+__device__ __forceinline__ void dec6(double av, unsigned* q_out, int* X_out, int* flag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(av);
+    const int be = (int)((bits >> 52) & 0x7ff);
+    const unsigned long long m = (bits & 0xfffffffffffffull) | (1ull << 52);   // 2^52 <= m < 2^53
+    const int e = be - 1075;                                                    // av = m 2^e
+    const int e2 = be - 1023;                                                   // floor(log2 av)
+    int X = (e2 * 78913) >> 18;                                                 // floor(e2 log10 2) <= floor(log10 av) <= that + 1
+    unsigned long long I = 0;
+    bool up = false;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        const int k = 5 - X;
+        const Pow10Entry T = d_pow10[k - PD_POW10_KMIN];
+        // P = m * (T.hi:T.lo), 192 bits p2:p1:p0
+        const unsigned long long p0 = m * T.lo;
+        const unsigned long long c0 = __umul64hi(m, T.lo);
+        const unsigned long long t1 = m * T.hi;
+        const unsigned long long p1 = t1 + c0;
+        const unsigned long long p2 = __umul64hi(m, T.hi) + (p1 < t1 ? 1ull : 0ull);
+        const int s = -(e + T.bexp);                  // value = P 2^-s, 128 < s < 192
+        const int sh = s - 128;                       // integer part = p2 >> sh
+        I = p2 >> sh;
+        if (I >= 1000000ull) { ++X; continue; }       // one decimal digit more than estimated
+        if (I < 99999ull) { --X; continue; }          // (estimate one too high: negative binary exponents)
+        // fraction F = (p2 & mask):p1:p0 against half = 2^(s-1)
+        const unsigned long long fmask = (1ull << sh) - 1ull;
+        const unsigned long long f2 = p2 & fmask;
+        const unsigned long long halfbit = 1ull << (sh - 1);
+        const bool ge_half = (f2 & halfbit) != 0;
+        const bool rest_zero = ((f2 & (halfbit - 1ull)) | p1 | p0) == 0ull;
+        if (T.exact) {
+            if (ge_half && rest_zero) up = (I & 1ull) != 0;          // exact tie: half to even
+            else up = ge_half;
+        } else if (ge_half) {
+            up = true;                                                // 10^k > T 2^b strictly
+        } else {
+            // upper bound P + m (exclusive): still below half?
+            const unsigned long long q0 = p0 + m;
+            const unsigned long long cq = q0 < p0 ? 1ull : 0ull;
+            const unsigned long long q1 = p1 + cq;
+            const unsigned long long q2 = p2 + ((cq && q1 == 0ull) ? 1ull : 0ull);
+            const bool same_int = (q2 >> sh) == I;
+            const unsigned long long g2 = q2 & fmask;
+            const bool up_ge_half = !same_int || (g2 & halfbit) != 0;
+            const bool up_is_half = same_int && (g2 & halfbit) != 0 && ((g2 & (halfbit - 1ull)) | q1 | q0) == 0ull;
+            if (!up_ge_half || up_is_half) {
+                up = false;                                           // x 10^k < upper <= half
+            } else {
+                // the bracket straddles the half-way point: only an exact tie can do that,
+                // m 2^(e+1) == (2I+1) 10^-k with -k in 1..22
+                bool tie = false;
+                if (k < 0 && -k <= 22) {
+                    u128 R = (u128)(2ull * I + 1ull);
+                    for (int t = 0; t < -k; ++t) R *= 10u;
+                    const int sl = e + 1;
+                    if (sl >= 0) {
+                        if (sl <= 70) tie = (((u128)m) << sl) == R;
+                    } else if (-sl < 64) {
+                        tie = ((m & ((1ull << (-sl)) - 1ull)) == 0ull) && ((u128)(m >> (-sl)) == R);
+                    }
+                }
+                if (tie) up = (I & 1ull) != 0;
+                else { up = true; *flag = 1; }
+            }
+        }
+        // I = 99999 is a 6-digit result only if it rounds up to 100000 (x = 10^X seen through a truncated 10^k)
+        if (I + (up ? 1ull : 0ull) < 100000ull) { --X; continue; }
+        break;
+    }
+    unsigned q = (unsigned)I + (up ? 1u : 0u);
+    if (q >= 1000000u) { q = 100000u; ++X; }
+    *q_out = q;
+    *X_out = X;
+}
+
+// printf("%g", safe_val(v)) into out (<= 13 chars); returns the length
+__device__ __forceinline__ int fmt_g(double v, char* out, int* flag) {
+    // safe_val (src/vtk_writer.cpp:8-14)
+    if (isnan(v) || isinf(v)) v = 0.0;
+    if (v != 0.0 && fabs(v) < 1e-300) v = 0.0;
+    int n = 0;
+    if (__double_as_longlong(v) < 0) out[n++] = '-';
+    if (v == 0.0) { out[n++] = '0'; return n; }
+    unsigned q;
+    int X;
+    dec6(fabs(v), &q, &X, flag);
+    char d[6];
+#pragma unroll
+    for (int t = 5; t >= 0; --t) { d[t] = (char)('0' + q % 10u); q /= 10u; }
+    int nd = 6;
+    while (nd > 1 && d[nd - 1] == '0') --nd;          // %g strips trailing zeros
+    if (X < -4 || X >= 6) {                           // exponential style
+        out[n++] = d[0];
+        if (nd > 1) {
+            out[n++] = '.';
+            for (int t = 1; t < nd; ++t) out[n++] = d[t];
+        }
+        out[n++] = 'e';
+        int ax = X;
+        if (X < 0) { out[n++] = '-'; ax = -X; } else out[n++] = '+';
+        if (ax >= 100) { out[n++] = (char)('0' + ax / 100); ax %= 100; out[n++] = (char)('0' + ax / 10); }
+        else out[n++] = (char)('0' + ax / 10);
+        out[n++] = (char)('0' + ax % 10);
+    } else if (X >= 0) {                              // fixed, integer part of X+1 digits
+        for (int t = 0; t <= X; ++t) out[n++] = d[t];
+        if (nd > X + 1) {
+            out[n++] = '.';
+            for (int t = X + 1; t < nd; ++t) out[n++] = d[t];
+        }
+    } else {                                          // 0.000ddd
+        out[n++] = '0';
+        out[n++] = '.';
+        for (int t = 0; t < -X - 1; ++t) out[n++] = '0';
+        for (int t = 0; t < nd; ++t) out[n++] = d[t];
+    }
+    return n;
+}
+
+__device__ __forceinline__ int fmt_int(int v, char* out) {
+    int n = 0;
+    unsigned u = (unsigned)v;
+    if (v < 0) { out[n++] = '-'; u = (unsigned)(-(long long)v); }
+    char tmp[10];
+    int t = 0;
+    do { tmp[t++] = (char)('0' + u % 10u); u /= 10u; } while (u);
+    while (t) out[n++] = tmp[--t];
+    return n;
+}
+
+constexpr int kIndent = 10;    // "          " in front of every record
+constexpr int SLOT_S = 32;     // scalar record slot
+constexpr int SLOT_V = 64;     // velocity record slot
+
+__device__ __forceinline__ int put_indent(char* o) {
+#pragma unroll
+    for (int t = 0; t < kIndent; ++t) o[t] = ' ';
+    return kIndent;
+}
+
+// records of a scalar double array; global node g lives at local index g + shift
+__global__ void k_fmt_scalar(const double* __restrict__ f, long long n, char* __restrict__ slots,
+                             int* __restrict__ len, int* __restrict__ flag) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    char* o = slots + t * SLOT_S;
+    int k = put_indent(o);
+    int fl = 0;
+    k += fmt_g(f[t], o + k, &fl);
+    o[k++] = '\n';
+    len[t] = k;
+    if (fl) atomicExch(flag, 1);
+}
+
+template <int DIM>
+__global__ void k_fmt_velocity(const double* __restrict__ vx, const double* __restrict__ vy,
+                               const double* __restrict__ vz, const uint8_t* __restrict__ type, long long n,
+                               char* __restrict__ slots, int* __restrict__ len, int* __restrict__ flag) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint8_t ty = type[t];
+    const bool fict = (ty == PDGPU_WALL || ty == PDGPU_OUTSIDE);     // src/vtk_writer.cpp:62
+    char* o = slots + t * SLOT_V;
+    int k = put_indent(o);
+    int fl = 0;
+    k += fmt_g(fict ? 0.0 : vx[t], o + k, &fl);
+    o[k++] = ' ';
+    k += fmt_g(fict ? 0.0 : vy[t], o + k, &fl);
+    o[k++] = ' ';
+    if (DIM == 3) k += fmt_g(fict ? 0.0 : vz[t], o + k, &fl);
+    else o[k++] = '0';
+    o[k++] = '\n';
+    len[t] = k;
+    if (fl) atomicExch(flag, 1);
+}
+
+template <typename TI>
+__global__ void k_fmt_int(const TI* __restrict__ f, long long n, char* __restrict__ slots, int* __restrict__ len) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    char* o = slots + t * SLOT_S;
+    int k = put_indent(o);
+    k += fmt_int((int)f[t], o + k);
+    o[k++] = '\n';
+    len[t] = k;
+}
+
+__global__ void k_compact_text(const char* __restrict__ slots, int slot, const int* __restrict__ len,
+                               const long long* __restrict__ pos, long long n, char* __restrict__ text) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const char* s = slots + t * slot;
+    char* d = text + pos[t];
+    const int L = len[t];
+    for (int b = 0; b < L; ++b) d[b] = s[b];
+}
+
+// raw "%g" of an array (test hook): 16-byte zero-padded cells
+__global__ void k_fmt_cells(const double* __restrict__ v, long long n, char* __restrict__ cells, int* __restrict__ flag) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    char* o = cells + t * 16;
+    int fl = 0;
+    int k = fmt_g(v[t], o, &fl);
+    for (; k < 16; ++k) o[k] = 0;
+    if (fl) atomicExch(flag, 1);
+}
+
+struct TextBuf {
+    char* slots = nullptr;
+    int* len = nullptr;
+    long long* pos = nullptr;
+    char* text = nullptr;
+    int* flag = nullptr;
+    long long n = 0;
+    void release() {
+        cudaFree(slots); cudaFree(len); cudaFree(pos); cudaFree(text); cudaFree(flag);
+        slots = text = nullptr; len = flag = nullptr; pos = nullptr;
+    }
+};
+
+int upload_table(pdgpu_ctx* c) {
+    if (c->device < 64 && g_table_uploaded[c->device]) return 0;
+    CUDA_OK(cudaMemcpyToSymbol(d_pow10, kPow10, sizeof(kPow10)));
+    if (c->device < 64) g_table_uploaded[c->device] = true;
+    return 0;
+}
+
+int alloc_buf(TextBuf* b, long long n) {
+    b->n = n;
+    CUDA_OK(cudaMalloc(&b->slots, (size_t)n * SLOT_V));
+    CUDA_OK(cudaMalloc(&b->len, sizeof(int) * n));
+    CUDA_OK(cudaMalloc(&b->pos, sizeof(long long) * (n + 1)));
+    CUDA_OK(cudaMalloc(&b->text, (size_t)n * SLOT_V));
+    CUDA_OK(cudaMalloc(&b->flag, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(b->flag, 0, sizeof(int)));
+    return 0;
+}
+
+enum ArrKind { A_VEL, A_F64, A_U8, A_I32 };
+struct ArrSpec {
+    const char* header;   // DataArray line of the reference
+    ArrKind kind;
+    const void* dev;      // device pointer (owned-node 0)
+};
+
+// formats one array into b->text; *bytes = length of the body
+int format_array(pdgpu_ctx* c, TextBuf* b, const ArrSpec& a, long long* bytes) {
+    const long long n = b->n;
+    const unsigned g = nblocks(n, 256);
+    int slot = SLOT_S;
+    switch (a.kind) {
+        case A_VEL: {
+            const long long lo = c->own_lo;
+            slot = SLOT_V;
+            if (c->dim == 2)
+                LAUNCH(c, k_fmt_velocity<2>, g, 256, 0, c->v[c->cur][0] + lo, c->v[c->cur][1] + lo, nullptr,
+                       c->type + lo, n, b->slots, b->len, b->flag);
+            else
+                LAUNCH(c, k_fmt_velocity<3>, g, 256, 0, c->v[c->cur][0] + lo, c->v[c->cur][1] + lo,
+                       c->v[c->cur][2] + lo, c->type + lo, n, b->slots, b->len, b->flag);
+            break;
+        }
+        case A_F64: LAUNCH(c, k_fmt_scalar, g, 256, 0, (const double*)a.dev, n, b->slots, b->len, b->flag); break;
+        case A_U8: LAUNCH(c, k_fmt_int<uint8_t>, g, 256, 0, (const uint8_t*)a.dev, n, b->slots, b->len); break;
+        case A_I32: LAUNCH(c, k_fmt_int<int>, g, 256, 0, (const int*)a.dev, n, b->slots, b->len); break;
+    }
+    long long total = 0;
+    PD_TRY(pdscan::exclusive_scan(c, b->len, n, b->pos, &total));
+    LAUNCH(c, k_compact_text, g, 256, 0, b->slots, slot, b->len, b->pos, n, b->text);
+    *bytes = total;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int pdgpu_format_g(pdgpu_ctx* c, const double* host_vals, long long n, char* host_cells16) {
+    CHECK_CTX(c);
+    if (!host_vals || !host_cells16 || n <= 0) PD_FAIL("pdgpu_format_g: bad arguments");
+    PD_TRY(upload_table(c));
+    double* dv = nullptr;
+    char* dc = nullptr;
+    int* df = nullptr;
+    CUDA_OK(cudaMalloc(&dv, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&dc, (size_t)16 * n));
+    CUDA_OK(cudaMalloc(&df, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(df, 0, sizeof(int), c->stream));
+    CUDA_OK(cudaMemcpyAsync(dv, host_vals, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_fmt_cells, nblocks(n, 256), 256, 0, dv, n, dc, df);
+    int flag = 0;
+    CUDA_OK(cudaMemcpyAsync(host_cells16, dc, (size_t)16 * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaMemcpyAsync(&flag, df, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(dv); cudaFree(dc); cudaFree(df);
+    if (flag) PD_FAIL("pdgpu_format_g: a rounding decision could not be proven");
+    return 0;
+}
+
+// VTKWriter::write (src/vtk_writer.cpp:16-146). grain_id / D_map are host-side arrays of the driver
+// (never read by the solvers); nullptr writes -1 / 0 like an unset Fields.
+extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_id, const double* D_map,
+                               long long* bytes_out, float* format_ms) {
+    NEED_FIELDS(c);
+    if (!path) PD_FAIL("pdgpu_vti_write: null path");
+    if (c->nranks > 1) PD_FAIL("pdgpu_vti_write: slab contexts write per-rank pieces only (not implemented)");
+    PD_TRY(pd_flush_wall_c(c));
+    PD_TRY(upload_table(c));
+    const long long n = c->own_hi - c->own_lo, lo = c->own_lo;
+    TextBuf b;
+    PD_TRY(alloc_buf(&b, n));
+    int* d_gid = nullptr;
+    double* d_dmap = nullptr;
+    CUDA_OK(cudaMalloc(&d_gid, sizeof(int) * n));
+    CUDA_OK(cudaMalloc(&d_dmap, sizeof(double) * n));
+    if (grain_id) CUDA_OK(cudaMemcpyAsync(d_gid, grain_id, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    else CUDA_OK(cudaMemsetAsync(d_gid, 0xFF, sizeof(int) * n, c->stream));
+    if (D_map) CUDA_OK(cudaMemcpyAsync(d_dmap, D_map, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    else CUDA_OK(cudaMemsetAsync(d_dmap, 0, sizeof(double) * n, c->stream));
+
+    std::ofstream out(path, std::ios::binary);
+    if (!out.is_open()) { b.release(); cudaFree(d_gid); cudaFree(d_dmap); PD_FAIL("cannot open VTI file '%s'", path); }
+    const int nx = c->Nx, ny = c->Ny, nz = (c->dim == 3) ? c->Nz : 1;
+    {   // header, formatted by the same iostream rules as the reference (src/vtk_writer.cpp:40-53)
+        std::ostringstream h;
+        h << "<?xml version=\"1.0\"?>\n";
+        h << "<VTKFile type=\"ImageData\" version=\"1.0\" byte_order=\"LittleEndian\">\n";
+        h << "  <ImageData WholeExtent=\"0 " << nx - 1 << " 0 " << ny - 1 << " 0 " << nz - 1 << "\""
+          << " Origin=\"" << c->origin[0] << " " << c->origin[1] << " " << ((c->dim == 3) ? c->origin[2] : 0.0) << "\""
+          << " Spacing=\"" << c->cfg.dx << " " << c->cfg.dx << " " << c->cfg.dx << "\">\n";
+        h << "    <Piece Extent=\"0 " << nx - 1 << " 0 " << ny - 1 << " 0 " << nz - 1 << "\">\n";
+        h << "      <PointData Scalars=\"phase\" Vectors=\"velocity\">\n";
+        out << h.str();
+    }
+    const ArrSpec arrs[] = {
+        {"        <DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n", A_VEL, nullptr},
+        {"        <DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n", A_F64, c->p[c->p_input] + lo},
+        {"        <DataArray type=\"Float64\" Name=\"density\" format=\"ascii\">\n", A_F64, c->rho[c->cur] + lo},
+        {"        <DataArray type=\"Float64\" Name=\"concentration\" format=\"ascii\">\n", A_F64, c->C[c->curC] + lo},
+        {"        <DataArray type=\"UInt8\" Name=\"phase\" format=\"ascii\">\n", A_U8, c->phase + lo},
+        {"        <DataArray type=\"UInt8\" Name=\"node_type\" format=\"ascii\">\n", A_U8, c->type + lo},
+        {"        <DataArray type=\"Int32\" Name=\"grain_id\" format=\"ascii\">\n", A_I32, d_gid},
+        {"        <DataArray type=\"Float64\" Name=\"D_map\" format=\"ascii\">\n", A_F64, d_dmap},
+        {"        <DataArray type=\"UInt8\" Name=\"is_grain_boundary\" format=\"ascii\">\n", A_U8, c->is_gb + lo},
+        {"        <DataArray type=\"UInt8\" Name=\"is_precipitate\" format=\"ascii\">\n", A_U8, c->is_precip + lo},
+    };
+    char* h_text = nullptr;
+    const size_t cap = (size_t)n * SLOT_V;
+    int rc = 0;
+    long long total_bytes = 0;
+    float ms_sum = 0.f;
+    if (cudaMallocHost(&h_text, cap) != cudaSuccess) { rc = 1; pd_set_error("pdgpu_vti_write: pinned staging allocation failed"); }
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (const ArrSpec& a : arrs) {
+        if (rc) break;
+        long long bytes = 0;
+        cudaEventRecord(e0, c->stream);
+        rc = format_array(c, &b, a, &bytes);
+        if (rc) break;
+        cudaEventRecord(e1, c->stream);
+        if (cudaMemcpyAsync(h_text, b.text, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = 1; pd_set_error("pdgpu_vti_write: copy failed"); break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        ms_sum += ms;
+        out << a.header;
+        out.write(h_text, bytes);
+        out << "        </DataArray>\n";
+        total_bytes += bytes;
+    }
+    int flag = 0;
+    if (!rc) {
+        cudaMemcpy(&flag, b.flag, sizeof(int), cudaMemcpyDeviceToHost);
+        out << "      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n";
+        out.close();
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (h_text) cudaFreeHost(h_text);
+    b.release();
+    cudaFree(d_gid); cudaFree(d_dmap);
+    if (rc) return rc;
+    if (flag) PD_FAIL("pdgpu_vti_write: a rounding decision could not be proven");
+    if (bytes_out) *bytes_out = total_bytes;
+    if (format_ms) *format_ms = ms_sum;
+    return 0;
+}

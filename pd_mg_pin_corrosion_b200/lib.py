@@ -100,6 +100,8 @@ def load() -> C.CDLL:
         "pdgpu_step_host": [vp, C.c_double, C.c_double, vp, vp, vp, C.c_int],
         "pdgpu_step_host_chunks": [vp, C.c_int, ip, C.c_char_p, C.c_int],
         "pdgpu_step_host_trace": [vp, dp, C.c_int, ip],
+        "pdgpu_vti_write": [vp, C.c_char_p, vp, vp, C.POINTER(C.c_longlong), C.POINTER(C.c_float)],
+        "pdgpu_format_g": [vp, vp, C.c_longlong, vp],
         "pdgpu_host_register": [vp, C.c_size_t], "pdgpu_host_unregister": [vp],
     }
     for name, args in sig.items():
