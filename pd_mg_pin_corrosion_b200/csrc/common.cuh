@@ -307,6 +307,7 @@ void pd_invalidate_graphs(pdgpu_ctx* c);
 int pd_refresh_eos(pdgpu_ctx* c, int buf);           // p[buf] = EOS(rho[buf]) on all local nodes
 int pd_refresh_vmag(pdgpu_ctx* c, int buf);
 int pd_enqueue_eos_range(pdgpu_ctx* c, int buf, long long lo, long long n);             // fields.cu
+int pd_enqueue_eos_to(pdgpu_ctx* c, int buf, long long lo, long long n, double* out);
 int pd_enqueue_deinterleave(pdgpu_ctx* c, const double* aos, long long lo, long long n, int buf);
 int pd_enqueue_interleave(pdgpu_ctx* c, double* aos, long long lo, long long n, int buf);
 int pd_enqueue_channel_corrections(pdgpu_ctx* c, int buf);                              // ns.cu

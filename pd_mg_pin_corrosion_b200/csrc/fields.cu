@@ -134,6 +134,14 @@ int pd_enqueue_eos_range(pdgpu_ctx* c, int buf, long long lo, long long n) {
     return 0;
 }
 
+// out[0..n) = EOS(rho[buf][lo..lo+n)) with the reference's formula (pow), without touching the shadow p
+int pd_enqueue_eos_to(pdgpu_ctx* c, int buf, long long lo, long long n, double* out) {
+    if (n <= 0) return 0;
+    PdConsts k = pd_consts(c->cfg, c->dim);
+    LAUNCH(c, k_eos, nblocks(n, 256), 256, 0, c->rho[buf] + lo, out, n, c->cfg.rho_f, c->cfg.gamma_eos, k.B_eos);
+    return 0;
+}
+
 // AoS (reference std::vector<Vec>) <-> SoA for n nodes starting at local index lo of flow buffer buf
 int pd_enqueue_deinterleave(pdgpu_ctx* c, const double* aos, long long lo, long long n, int buf) {
     if (n <= 0) return 0;

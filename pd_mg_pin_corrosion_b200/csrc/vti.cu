@@ -15,9 +15,15 @@
 // 7-digit half-way point without being exactly on it, which happens only for integers
 // (x = (2N+1) 5^j 2^(j-1)) and is decided by an exact 128-bit comparison (round half to even, as
 // glibc). Anything still undecided raises the error flag of the call (never observed).
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
-#include <fstream>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <sstream>
+#include <thread>
 
 #include "common.cuh"
 #include "scan.cuh"
@@ -309,6 +315,91 @@ int format_array(pdgpu_ctx* c, TextBuf* b, const ArrSpec& a, long long* bytes) {
     return 0;
 }
 
+// ---- pinned staging pool + writer threads of pdgpu_vti_write --------------------------------
+constexpr size_t kIoChunk = (size_t)32 << 20;
+constexpr int kIoBufs = 6, kIoWriters = 3;
+struct IoPool {
+    char* buf[kIoBufs] = {nullptr};
+    cudaEvent_t ev[kIoBufs] = {nullptr};
+};
+IoPool g_io_pool[64];
+
+int io_pool(pdgpu_ctx* c, IoPool** out) {
+    IoPool* p = &g_io_pool[c->device < 64 ? c->device : 0];
+    for (int k = 0; k < kIoBufs; ++k) {
+        if (!p->buf[k]) CUDA_OK(cudaMallocHost(&p->buf[k], kIoChunk));
+        if (!p->ev[k]) CUDA_OK(cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming));
+    }
+    *out = p;
+    return 0;
+}
+
+struct IoJob { int k; size_t len; off_t off; };
+class IoRun {
+   public:
+    IoRun(IoPool* io, int fd, int device) : io_(io), fd_(fd), device_(device) {
+        if (!io_) { err_ = true; return; }
+        for (int k = 0; k < kIoBufs; ++k) free_.push_back(k);
+        for (int w = 0; w < kIoWriters; ++w) th_.emplace_back([this] { work(); });
+    }
+    ~IoRun() { finish(); }
+    int acquire() {                               // a free staging buffer (blocks), -1 after a failure
+        std::unique_lock<std::mutex> l(m_);
+        cv_free_.wait(l, [this] { return !free_.empty() || err_; });
+        if (err_) return -1;
+        int k = free_.back();
+        free_.pop_back();
+        return k;
+    }
+    void submit(int k, size_t len, off_t off) {
+        { std::lock_guard<std::mutex> l(m_); jobs_.push_back({k, len, off}); }
+        cv_job_.notify_one();
+    }
+    void fail() { { std::lock_guard<std::mutex> l(m_); err_ = true; } cv_free_.notify_all(); }
+    bool failed() { std::lock_guard<std::mutex> l(m_); return err_; }
+    void finish() {
+        { std::lock_guard<std::mutex> l(m_); done_ = true; }
+        cv_job_.notify_all();
+        for (std::thread& t : th_) if (t.joinable()) t.join();
+        th_.clear();
+    }
+
+   private:
+    void work() {
+        cudaSetDevice(device_);
+        for (;;) {
+            IoJob j;
+            {
+                std::unique_lock<std::mutex> l(m_);
+                cv_job_.wait(l, [this] { return !jobs_.empty() || done_; });
+                if (jobs_.empty()) return;
+                j = jobs_.front();
+                jobs_.pop_front();
+            }
+            bool ok = cudaEventSynchronize(io_->ev[j.k]) == cudaSuccess;
+            size_t w = 0;
+            while (ok && w < j.len) {
+                ssize_t r = ::pwrite(fd_, io_->buf[j.k] + w, j.len - w, j.off + (off_t)w);
+                if (r <= 0) ok = false; else w += (size_t)r;
+            }
+            {
+                std::lock_guard<std::mutex> l(m_);
+                if (!ok) err_ = true;
+                free_.push_back(j.k);
+            }
+            cv_free_.notify_all();
+        }
+    }
+    IoPool* io_;
+    int fd_, device_;
+    std::mutex m_;
+    std::condition_variable cv_job_, cv_free_;
+    std::deque<IoJob> jobs_;
+    std::vector<int> free_;
+    std::vector<std::thread> th_;
+    bool done_ = false, err_ = false;
+};
+
 }  // namespace
 
 extern "C" int pdgpu_format_g(pdgpu_ctx* c, const double* host_vals, long long n, char* host_cells16) {
@@ -353,10 +444,17 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
     else CUDA_OK(cudaMemsetAsync(d_gid, 0xFF, sizeof(int) * n, c->stream));
     if (D_map) CUDA_OK(cudaMemcpyAsync(d_dmap, D_map, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
     else CUDA_OK(cudaMemsetAsync(d_dmap, 0, sizeof(double) * n, c->stream));
+    // `pressure` is written as the reference computes it, B (pow(rho/rho_f, gamma) - 1) of the density the
+    // last step started from (src/pd_ns.cpp:36-50,84), not from the Horner-evaluated shadow field the
+    // tiled kernels keep (same value to ~1e-10 relative, which is visible in the 6th digit now and then)
+    double* d_press = nullptr;
+    CUDA_OK(cudaMalloc(&d_press, sizeof(double) * n));
+    PD_TRY(pd_enqueue_eos_to(c, c->p_input, lo, n, d_press));
 
-    std::ofstream out(path, std::ios::binary);
-    if (!out.is_open()) { b.release(); cudaFree(d_gid); cudaFree(d_dmap); PD_FAIL("cannot open VTI file '%s'", path); }
+    const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) { b.release(); cudaFree(d_gid); cudaFree(d_dmap); cudaFree(d_press); PD_FAIL("cannot open VTI file '%s'", path); }
     const int nx = c->Nx, ny = c->Ny, nz = (c->dim == 3) ? c->Nz : 1;
+    std::string head;
     {   // header, formatted by the same iostream rules as the reference (src/vtk_writer.cpp:40-53)
         std::ostringstream h;
         h << "<?xml version=\"1.0\"?>\n";
@@ -366,11 +464,11 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
           << " Spacing=\"" << c->cfg.dx << " " << c->cfg.dx << " " << c->cfg.dx << "\">\n";
         h << "    <Piece Extent=\"0 " << nx - 1 << " 0 " << ny - 1 << " 0 " << nz - 1 << "\">\n";
         h << "      <PointData Scalars=\"phase\" Vectors=\"velocity\">\n";
-        out << h.str();
+        head = h.str();
     }
     const ArrSpec arrs[] = {
         {"        <DataArray type=\"Float64\" Name=\"velocity\" NumberOfComponents=\"3\" format=\"ascii\">\n", A_VEL, nullptr},
-        {"        <DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n", A_F64, c->p[c->p_input] + lo},
+        {"        <DataArray type=\"Float64\" Name=\"pressure\" format=\"ascii\">\n", A_F64, d_press},
         {"        <DataArray type=\"Float64\" Name=\"density\" format=\"ascii\">\n", A_F64, c->rho[c->cur] + lo},
         {"        <DataArray type=\"Float64\" Name=\"concentration\" format=\"ascii\">\n", A_F64, c->C[c->curC] + lo},
         {"        <DataArray type=\"UInt8\" Name=\"phase\" format=\"ascii\">\n", A_U8, c->phase + lo},
@@ -380,41 +478,57 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
         {"        <DataArray type=\"UInt8\" Name=\"is_grain_boundary\" format=\"ascii\">\n", A_U8, c->is_gb + lo},
         {"        <DataArray type=\"UInt8\" Name=\"is_precipitate\" format=\"ascii\">\n", A_U8, c->is_precip + lo},
     };
-    char* h_text = nullptr;
-    const size_t cap = (size_t)n * SLOT_V;
-    int rc = 0;
+    // The finished text leaves the device in chunks through a small pool of pinned buffers; writer
+    // threads put every chunk at its final file offset (all offsets are known from the scans), so the
+    // D2H copy of one chunk, the page-cache copies of others and the next formatting kernel overlap.
+    IoPool* io = nullptr;
+    int rc = io_pool(c, &io);
     long long total_bytes = 0;
     float ms_sum = 0.f;
-    if (cudaMallocHost(&h_text, cap) != cudaSuccess) { rc = 1; pd_set_error("pdgpu_vti_write: pinned staging allocation failed"); }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
+    IoRun run(io, fd, c->device);
+    off_t off = 0;
+    auto put_small = [&](const std::string& t) {
+        if (::pwrite(fd, t.data(), t.size(), off) != (ssize_t)t.size()) run.fail();
+        off += (off_t)t.size();
+    };
+    if (!rc) put_small(head);
     for (const ArrSpec& a : arrs) {
-        if (rc) break;
+        if (rc || run.failed()) break;
         long long bytes = 0;
         cudaEventRecord(e0, c->stream);
         rc = format_array(c, &b, a, &bytes);
         if (rc) break;
         cudaEventRecord(e1, c->stream);
-        if (cudaMemcpyAsync(h_text, b.text, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-            cudaStreamSynchronize(c->stream) != cudaSuccess) { rc = 1; pd_set_error("pdgpu_vti_write: copy failed"); break; }
+        put_small(a.header);
+        for (long long done = 0; done < bytes; done += (long long)kIoChunk) {
+            const size_t len = (size_t)std::min<long long>((long long)kIoChunk, bytes - done);
+            const int k = run.acquire();
+            if (k < 0) break;
+            if (cudaMemcpyAsync(io->buf[k], b.text + done, len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaEventRecord(io->ev[k], c->stream) != cudaSuccess) { run.fail(); break; }
+            run.submit(k, len, off + (off_t)done);
+        }
+        off += (off_t)bytes;
+        put_small("        </DataArray>\n");
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { run.fail(); break; }   // b.text is reused by the next array
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         ms_sum += ms;
-        out << a.header;
-        out.write(h_text, bytes);
-        out << "        </DataArray>\n";
         total_bytes += bytes;
     }
     int flag = 0;
     if (!rc) {
         cudaMemcpy(&flag, b.flag, sizeof(int), cudaMemcpyDeviceToHost);
-        out << "      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n";
-        out.close();
+        put_small("      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n");
     }
+    run.finish();
+    ::close(fd);
+    if (!rc && run.failed()) { rc = 1; pd_set_error("pdgpu_vti_write: writing '%s' failed", path); }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (h_text) cudaFreeHost(h_text);
     b.release();
-    cudaFree(d_gid); cudaFree(d_dmap);
+    cudaFree(d_gid); cudaFree(d_dmap); cudaFree(d_press);
     if (rc) return rc;
     if (flag) PD_FAIL("pdgpu_vti_write: a rounding decision could not be proven");
     if (bytes_out) *bytes_out = total_bytes;

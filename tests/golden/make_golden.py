@@ -64,6 +64,26 @@ def step_fixture(case: str) -> None:
     print(case, "N", r.N, "nnz", r.nnz, "dt", dt, dtc)
 
 
+def vti_fixture() -> None:
+    """sha256 of the reference's own VTKWriter::write output on a synthetic state"""
+    res = {}
+    for case in ("2d_poiseuille", "3d_small"):
+        dim, base, ov = H.CASES[case]
+        r = refapi.RefSim(dim, base, ov, threads=4)
+        st = H.synthetic_state(r.N, dim)
+        for n, v in st.items():
+            r.set(n, v)
+        r.ns_step(r.ns_compute_dt())       # `pressure` member := EOS(rho) (src/pd_ns.cpp:84)
+        path = os.path.join(tempfile.mkdtemp(), "g.vti")
+        r.write_vti(path)
+        data = open(path, "rb").read()
+        res[case] = {"sha256": hashlib.sha256(data).hexdigest(), "bytes": len(data),
+                     "pressure_sha": sha(r.get("pressure"))}
+        os.unlink(path)
+        print(case, "vti bytes", len(data))
+    json.dump(res, open(os.path.join(HERE, "vti.json"), "w"), indent=1)
+
+
 def steady_fixture() -> None:
     res = {}
     for case in ("2d_poiseuille", "2d_default"):
@@ -96,5 +116,6 @@ if __name__ == "__main__":
     for c in ("2d_default", "2d_poiseuille", "2d_offgrid", "3d_small", "3d_offgrid"):
         step_fixture(c)
     diagnostics_fixture()
+    vti_fixture()
     if "--steady" in sys.argv:
         steady_fixture()

@@ -187,3 +187,31 @@ def port_coupled_run(case: str, is_gb, is_precip):
     p = PortSim(dim, cfg, threads=4)
     p.init_fields(is_gb, is_precip)
     return coupled_run(p, cfg)
+
+
+def synthetic_state(N: int, dim: int) -> dict:
+    """Deterministic, platform-independent field values (integer hashing + exact IEEE ops only) that
+    exercise every branch of the "%g" formatter: magnitudes 1e-20..1e+20, signs, zeros, exact ties,
+    values below the 1e-300 flush threshold, NaN/Inf. Used for the VTI golden hash."""
+    i = np.arange(N, dtype=np.int64)
+    pw = np.array([float(f"1e{k}") for k in range(-20, 21)])
+
+    def field(salt: int) -> np.ndarray:
+        h = (i * 2654435761 + salt * 40503) % 1000003
+        v = (h.astype(np.float64) / 1000003.0) * pw[(i + salt) % 41]
+        v[(i + salt) % 7 == 0] *= -1.0
+        v[(i + salt) % 53 == 0] = 0.0
+        v[(i + salt) % 101 == 0] = ((i[(i + salt) % 101 == 0] % 900000) + 100000).astype(np.float64) + 0.5   # ties
+        v[(i + salt) % 211 == 0] = 1e-305
+        return v
+
+    vel = np.stack([field(1 + d) for d in range(dim)], axis=1)
+    C = field(5)
+    C[i % 997 == 0] = np.nan
+    C[i % 991 == 0] = np.inf
+    # rho / rho_f in {1/2, 1, 2}: the EOS power is exact in every libm, so `pressure` cannot differ
+    rho = np.array([500.0, 1000.0, 2000.0])[i % 3]
+    return {"rho": rho, "vel": np.ascontiguousarray(vel), "C": C,
+            "phase": (i % 2).astype(np.uint8), "is_gb": (i % 5 == 0).astype(np.uint8),
+            "is_precip": (i % 11 == 0).astype(np.uint8), "grain_id": ((i * 7919) % 60 - 1).astype(np.int32),
+            "D_map": np.abs(field(6)) * 1e-9}

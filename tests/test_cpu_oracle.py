@@ -138,3 +138,39 @@ def test_port_coupled_run_matches_reference_diagnostics():
     for col in (0, 1, 2, 4, 5):
         rel = np.abs(rows[:, col] - gold[:, col]) / np.maximum(np.abs(gold[:, col]), 1e-300)
         assert rel.max() <= 1e-6, (col, rel.max())
+
+
+# ---- VTI snapshot writer ------------------------------------------------------
+def _synthetic_port(case):
+    dim, _, _ = H.CASES[case]
+    p = H.make_port(case)
+    st = H.synthetic_state(p.N, dim)
+    p.init_fields()
+    for n in ("rho", "vel", "C", "phase", "is_gb", "is_precip"):
+        getattr(p, n)[...] = st[n]
+    p.ns_step(p.ns_compute_dt())          # pressure := EOS(rho), as the reference's member (src/pd_ns.cpp:84)
+    return p, st
+
+
+@pytest.mark.parametrize("case", ["2d_poiseuille", "3d_small"])
+def test_port_vti_matches_golden_hash(case, tmp_path):
+    """The printf("%g") restatement of VTKWriter::write reproduces the sha256 of the file the
+    reference's own writer produced for the synthetic state (tests/golden/vti.json)."""
+    gold = json.load(open(os.path.join(GOLD, "vti.json")))[case]
+    p, st = _synthetic_port(case)
+    path = str(tmp_path / "port.vti")
+    p.write_vti(path, st["grain_id"], st["D_map"])
+    data = open(path, "rb").read()
+    assert len(data) == gold["bytes"]
+    assert hashlib.sha256(data).hexdigest() == gold["sha256"]
+
+
+@pytest.mark.skipif(not refapi.have_ref(2), reason="oracle/_ref not built")
+def test_port_vti_vs_reference_writer(tmp_path):
+    ref = H.make_ref("2d_default")
+    ref.ns_iterate(40, ref.ns_compute_dt())
+    ref.ard_iterate(5, ref.ard_compute_dt())
+    ref.write_vti(str(tmp_path / "ref.vti"))
+    port = H.make_port("2d_default", state_from=ref)
+    port.write_vti(str(tmp_path / "port.vti"), ref.get("grain_id"), ref.get("D_map"))
+    assert (tmp_path / "ref.vti").read_bytes() == (tmp_path / "port.vti").read_bytes()

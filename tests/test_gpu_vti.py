@@ -108,3 +108,26 @@ def test_vti_file_is_byte_identical(case, iters, steps, tmp_path):
         diff = [(i, x, y) for i, (x, y) in enumerate(zip(la, lb)) if x != y][:8]
         raise AssertionError(f"{len(la)} vs {len(lb)} lines; first differences: {diff}")
     assert nbytes.value > 0
+
+
+@pytest.mark.parametrize("case", ["2d_poiseuille", "3d_small"])
+def test_vti_golden_hash(case, tmp_path):
+    """Device writer on the synthetic state against the sha256 of the reference writer's file
+    (tests/golden/vti.json, generated in the build container by make_golden.py)."""
+    import hashlib
+    import json
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "vti.json")))[case]
+    S, cfg, grid, fields = gpu_side(case, ref=None)
+    st = H.synthetic_state(grid.N_total, grid.dim)
+    from pd_mg_pin_corrosion_b200 import lib as L_
+    L = L_.load()
+    L_.check(L.pdgpu_fields_init(grid.ctx, st["is_gb"].ctypes.data_as(C.c_void_p), st["is_precip"].ctypes.data_as(C.c_void_p)))
+    for n in ("rho", "vel", "C", "phase"):
+        fields.set(n, st[n])
+    path = str(tmp_path / "gpu.vti")
+    L_.check(L.pdgpu_vti_write(grid.ctx, path.encode(), st["grain_id"].ctypes.data_as(C.c_void_p),
+                               st["D_map"].ctypes.data_as(C.c_void_p), None, None))
+    grid.close()
+    data = open(path, "rb").read()
+    assert len(data) == gold["bytes"]
+    assert hashlib.sha256(data).hexdigest() == gold["sha256"]
