@@ -1,7 +1,7 @@
 // host/coupling.cpp -- see coupling.h. Control flow follows src/coupling.cpp:82-302 (explicit
 // branch); every solver call is one C-ABI call into libpdgpu.so, and the corrosion steps
 // between two output points run device resident (pdgpu_ard_iterate) instead of one host call
-// per step. VTI/PVD output (src/vtk_writer.cpp) is host IO and out of scope.
+// per step. VTI snapshots are formatted on the device (pdgpu_vti_write); the PVD files are host text.
 #include "coupling.h"
 
 #include <sys/stat.h>
@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <fstream>
 #include <iomanip>
+#include <sstream>
 
 #define PD(call)                                                                  \
     do {                                                                          \
@@ -44,8 +45,49 @@ void CoupledSolver::write_diagnostics(pdgpu_ctx* ctx, double t_corr, const HostC
     ml << std::fixed << std::setprecision(6) << t_corr / 3600.0 << "," << loss << "\n";
 }
 
+static std::string make_filename(const HostConfig& cfg, const std::string& prefix, double time_s, int frame) {   // :10-18
+    std::ostringstream ss;
+    ss << cfg.output_dir << "/" << prefix << "_" << std::setw(6) << std::setfill('0') << frame << "_t" << std::fixed
+       << std::setprecision(1) << time_s << "s.vti";
+    return ss.str();
+}
+
+void PvdSeries::add_timestep(double time, const std::string& file) {   // src/vtk_writer.cpp:150-186
+    entries_.push_back({time, file});
+    if (path_.empty()) return;
+    std::ofstream out(path_);
+    if (!out.is_open()) {
+        std::fprintf(stderr, "Error: Cannot open PVD file '%s'\n", path_.c_str());
+        return;
+    }
+    std::string dir;
+    auto slash = path_.find_last_of('/');
+    if (slash != std::string::npos) dir = path_.substr(0, slash + 1);
+    out << "<?xml version=\"1.0\"?>\n<VTKFile type=\"Collection\" version=\"1.0\" byte_order=\"LittleEndian\">\n  <Collection>\n";
+    for (auto& e : entries_) {
+        std::string rel = e.second;
+        if (!dir.empty() && rel.find(dir) == 0) rel = rel.substr(dir.size());
+        out << "    <DataSet timestep=\"" << std::scientific << std::setprecision(6) << e.first << "\" file=\"" << rel
+            << "\"/>\n";
+    }
+    out << "  </Collection>\n</VTKFile>\n";
+    out.close();
+    std::printf("  Wrote PVD file: %s (%zu timesteps)\n", path_.c_str(), entries_.size());
+}
+
+void CoupledSolver::snapshot(pdgpu_ctx* ctx, const HostState& st, const HostConfig& cfg, const char* prefix, double t,
+                             PvdSeries& series, bool count_frame) {
+    if (!write_vti) return;
+    std::string fname = make_filename(cfg, prefix, t, frame_count_);
+    PD(pdgpu_vti_write(ctx, fname.c_str(), st.grain_id.data(), st.D_map.data(), nullptr, nullptr));
+    series.add_timestep(t, fname);
+    if (count_frame) frame_count_++;
+}
+
 double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, bool verbose) {
     mkdir(cfg.output_dir.c_str(), 0755);
+    writer_.set_path(cfg.output_dir + "/simulation.pvd");
+    flow_writer_.set_path(cfg.output_dir + "/flow.pvd");
     {
         std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::trunc);
         csv << "time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n";
@@ -58,6 +100,7 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
     const double n0 = (double)initial_solid_indices_.size();
     std::printf("Initial solid nodes: %zu\nUsing EXPLICIT ARD solver\n", initial_solid_indices_.size());
 
+    snapshot(ctx, st, cfg, "state", 0.0, writer_, true);   // :117-122
     double t_corr = 0.0;
     int cycle = 0;
     bool need_flow_solve = true;
@@ -72,6 +115,7 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
             PD(pdgpu_ns_solve_steady(ctx, &r, verbose ? 1 : 0));
             dissolved_since_flow_ = 0;
             need_flow_solve = false;
+            snapshot(ctx, st, cfg, "flow", t_corr, flow_writer_, true);   // :143-148
         } else {
             std::printf("  Skipping flow solve (no dissolution since last flow solve)\n");
         }
@@ -97,7 +141,10 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
             PD(pdgpu_ard_iterate(ctx, done, dt_corr));
             for (int s = 0; s < done; ++s) t_corr += dt_corr;   // same additions as the reference
             step += done;
-            if (step % every == 0) write_diagnostics(ctx, t_corr, cfg);
+            if (step % every == 0) {
+                snapshot(ctx, st, cfg, "corr", t_corr, writer_, true);   // :242-247
+                write_diagnostics(ctx, t_corr, cfg);
+            }
             if (t_corr >= cfg.T_final) break;
         }
         // phase 3 :255-290
@@ -123,6 +170,7 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
             break;
         }
     }
+    snapshot(ctx, st, cfg, "final", t_corr, writer_, false);   // :292-296
     std::printf("\n=== Simulation complete ===\n  Final time: %.1f s (%.2f h)\n", t_corr, t_corr / 3600.0);
     return t_corr;
 }

@@ -3,6 +3,7 @@
 // explicit branch :217-253), with the solvers living on the device.
 #pragma once
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "config.h"
@@ -20,14 +21,31 @@ struct HostState {
     std::vector<int> grain_id;
 };
 
+// PVD collection of the snapshots written so far, rewritten after every entry like the
+// reference's VTKWriter::add_timestep / write_pvd (src/vtk_writer.cpp:150-186).
+class PvdSeries {
+public:
+    void set_path(const std::string& p) { path_ = p; }
+    void add_timestep(double time, const std::string& file);
+private:
+    std::string path_;
+    std::vector<std::pair<double, std::string>> entries_;
+};
+
 class CoupledSolver {
 public:
     // returns the final corrosion time
     double run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, bool verbose = true);
+    bool write_vti = true;   // state_/flow_/corr_/final_ snapshots + simulation.pvd / flow.pvd (src/coupling.cpp:117-147,242-246,292-296)
 
 private:
     std::vector<int> initial_solid_indices_;
     int total_dissolved_ = 0, dissolved_since_flow_ = 0;
     double solid_C_sum(pdgpu_ctx* ctx);
     void write_diagnostics(pdgpu_ctx* ctx, double t_corr, const HostConfig& cfg);
+    // VTKWriter::write through libpdgpu.so (text formatted on the device) + PVD bookkeeping
+    void snapshot(pdgpu_ctx* ctx, const HostState& st, const HostConfig& cfg, const char* prefix, double t,
+                  PvdSeries& series, bool count_frame);
+    PvdSeries writer_, flow_writer_;
+    int frame_count_ = 0;
 };

@@ -1,7 +1,7 @@
 // host/main.cpp -- pd_corrosion_gpu: the reference's main() (src/main.cpp:129-177) over
 // libpdgpu.so. The dimension is a run-time argument instead of the PD_DIM compile-time switch.
 //
-//   pd_corrosion_gpu [config/params.cfg] [--dim 2|3] [--device N] [--dump fields.bin]
+//   pd_corrosion_gpu [config/params.cfg] [--dim 2|3] [--device N] [--dump fields.bin] [--no-vti]
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -24,10 +24,12 @@ int main(int argc, char** argv) {
     std::setvbuf(stdout, nullptr, _IONBF, 0);
     std::string cfg_path = "configs/params.cfg", dump;
     int dim = 2, device = 0;
+    bool no_vti = false;
     for (int a = 1; a < argc; ++a) {
         if (!std::strcmp(argv[a], "--dim") && a + 1 < argc) dim = std::atoi(argv[++a]);
         else if (!std::strcmp(argv[a], "--device") && a + 1 < argc) device = std::atoi(argv[++a]);
         else if (!std::strcmp(argv[a], "--dump") && a + 1 < argc) dump = argv[++a];
+        else if (!std::strcmp(argv[a], "--no-vti")) no_vti = true;
         else cfg_path = argv[a];
     }
     std::printf("=== Peridynamic Mg-Pin Corrosion Simulation (B200 path) ===\n  Dimension: %dD\n\n", dim);
@@ -78,6 +80,7 @@ int main(int argc, char** argv) {
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 
     CoupledSolver solver;
+    solver.write_vti = !no_vti;
     auto t1 = std::chrono::steady_clock::now();
     solver.run(ctx, st, cfg);
     std::printf("  [Timer] total_simulation: %.3f s\n",
