@@ -196,6 +196,11 @@ int pdgpu_vti_write(pdgpu_ctx* ctx, const char* path, const int* grain_id, const
                     long long* bytes_out, float* format_ms);
 /* printf("%g") of n doubles on the device into 16-byte zero-padded cells (formatter unit tests). */
 int pdgpu_format_g(pdgpu_ctx* ctx, const double* host_vals, long long n, char* host_cells16);
+/* Binary checkpoint / resume of the device-resident state (new: the reference cannot resume).
+ * A run continued after pdgpu_checkpoint_load on a context built from the same Config is
+ * bit-identical to the uninterrupted run. */
+int pdgpu_checkpoint_save(pdgpu_ctx* ctx, const char* path, long long* bytes_out);
+int pdgpu_checkpoint_load(pdgpu_ctx* ctx, const char* path);
 /* cudaHostRegister / cudaHostUnregister of caller-owned memory (e.g. std::vector storage). */
 int pdgpu_host_register(void* ptr, size_t bytes);
 int pdgpu_host_unregister(void* ptr);

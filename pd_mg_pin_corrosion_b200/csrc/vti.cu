@@ -15,17 +15,11 @@
 // 7-digit half-way point without being exactly on it, which happens only for integers
 // (x = (2N+1) 5^j 2^(j-1)) and is decided by an exact 128-bit comparison (round half to even, as
 // glibc). Anything still undecided raises the error flag of the call (never observed).
-#include <fcntl.h>
-#include <unistd.h>
-
 #include <algorithm>
-#include <condition_variable>
-#include <deque>
-#include <mutex>
 #include <sstream>
-#include <thread>
 
 #include "common.cuh"
+#include "iopool.cuh"
 #include "scan.cuh"
 
 struct Pow10Entry {
@@ -315,91 +309,6 @@ int format_array(pdgpu_ctx* c, TextBuf* b, const ArrSpec& a, long long* bytes) {
     return 0;
 }
 
-// ---- pinned staging pool + writer threads of pdgpu_vti_write --------------------------------
-constexpr size_t kIoChunk = (size_t)32 << 20;
-constexpr int kIoBufs = 6, kIoWriters = 3;
-struct IoPool {
-    char* buf[kIoBufs] = {nullptr};
-    cudaEvent_t ev[kIoBufs] = {nullptr};
-};
-IoPool g_io_pool[64];
-
-int io_pool(pdgpu_ctx* c, IoPool** out) {
-    IoPool* p = &g_io_pool[c->device < 64 ? c->device : 0];
-    for (int k = 0; k < kIoBufs; ++k) {
-        if (!p->buf[k]) CUDA_OK(cudaMallocHost(&p->buf[k], kIoChunk));
-        if (!p->ev[k]) CUDA_OK(cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming));
-    }
-    *out = p;
-    return 0;
-}
-
-struct IoJob { int k; size_t len; off_t off; };
-class IoRun {
-   public:
-    IoRun(IoPool* io, int fd, int device) : io_(io), fd_(fd), device_(device) {
-        if (!io_) { err_ = true; return; }
-        for (int k = 0; k < kIoBufs; ++k) free_.push_back(k);
-        for (int w = 0; w < kIoWriters; ++w) th_.emplace_back([this] { work(); });
-    }
-    ~IoRun() { finish(); }
-    int acquire() {                               // a free staging buffer (blocks), -1 after a failure
-        std::unique_lock<std::mutex> l(m_);
-        cv_free_.wait(l, [this] { return !free_.empty() || err_; });
-        if (err_) return -1;
-        int k = free_.back();
-        free_.pop_back();
-        return k;
-    }
-    void submit(int k, size_t len, off_t off) {
-        { std::lock_guard<std::mutex> l(m_); jobs_.push_back({k, len, off}); }
-        cv_job_.notify_one();
-    }
-    void fail() { { std::lock_guard<std::mutex> l(m_); err_ = true; } cv_free_.notify_all(); }
-    bool failed() { std::lock_guard<std::mutex> l(m_); return err_; }
-    void finish() {
-        { std::lock_guard<std::mutex> l(m_); done_ = true; }
-        cv_job_.notify_all();
-        for (std::thread& t : th_) if (t.joinable()) t.join();
-        th_.clear();
-    }
-
-   private:
-    void work() {
-        cudaSetDevice(device_);
-        for (;;) {
-            IoJob j;
-            {
-                std::unique_lock<std::mutex> l(m_);
-                cv_job_.wait(l, [this] { return !jobs_.empty() || done_; });
-                if (jobs_.empty()) return;
-                j = jobs_.front();
-                jobs_.pop_front();
-            }
-            bool ok = cudaEventSynchronize(io_->ev[j.k]) == cudaSuccess;
-            size_t w = 0;
-            while (ok && w < j.len) {
-                ssize_t r = ::pwrite(fd_, io_->buf[j.k] + w, j.len - w, j.off + (off_t)w);
-                if (r <= 0) ok = false; else w += (size_t)r;
-            }
-            {
-                std::lock_guard<std::mutex> l(m_);
-                if (!ok) err_ = true;
-                free_.push_back(j.k);
-            }
-            cv_free_.notify_all();
-        }
-    }
-    IoPool* io_;
-    int fd_, device_;
-    std::mutex m_;
-    std::condition_variable cv_job_, cv_free_;
-    std::deque<IoJob> jobs_;
-    std::vector<int> free_;
-    std::vector<std::thread> th_;
-    bool done_ = false, err_ = false;
-};
-
 }  // namespace
 
 extern "C" int pdgpu_format_g(pdgpu_ctx* c, const double* host_vals, long long n, char* host_cells16) {
@@ -481,13 +390,13 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
     // The finished text leaves the device in chunks through a small pool of pinned buffers; writer
     // threads put every chunk at its final file offset (all offsets are known from the scans), so the
     // D2H copy of one chunk, the page-cache copies of others and the next formatting kernel overlap.
-    IoPool* io = nullptr;
-    int rc = io_pool(c, &io);
+    pdio::IoPool* io = nullptr;
+    int rc = pdio::io_pool(c, &io);
     long long total_bytes = 0;
     float ms_sum = 0.f;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    IoRun run(io, fd, c->device);
+    pdio::IoRun run(io, fd, c->device);
     off_t off = 0;
     auto put_small = [&](const std::string& t) {
         if (::pwrite(fd, t.data(), t.size(), off) != (ssize_t)t.size()) run.fail();
@@ -502,8 +411,8 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
         if (rc) break;
         cudaEventRecord(e1, c->stream);
         put_small(a.header);
-        for (long long done = 0; done < bytes; done += (long long)kIoChunk) {
-            const size_t len = (size_t)std::min<long long>((long long)kIoChunk, bytes - done);
+        for (long long done = 0; done < bytes; done += (long long)pdio::kIoChunk) {
+            const size_t len = (size_t)std::min<long long>((long long)pdio::kIoChunk, bytes - done);
             const int k = run.acquire();
             if (k < 0) break;
             if (cudaMemcpyAsync(io->buf[k], b.text + done, len, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||

@@ -102,6 +102,7 @@ def load() -> C.CDLL:
         "pdgpu_step_host_trace": [vp, dp, C.c_int, ip],
         "pdgpu_vti_write": [vp, C.c_char_p, vp, vp, C.POINTER(C.c_longlong), C.POINTER(C.c_float)],
         "pdgpu_format_g": [vp, vp, C.c_longlong, vp],
+        "pdgpu_checkpoint_save": [vp, C.c_char_p, C.POINTER(C.c_longlong)], "pdgpu_checkpoint_load": [vp, C.c_char_p],
         "pdgpu_host_register": [vp, C.c_size_t], "pdgpu_host_unregister": [vp],
     }
     for name, args in sig.items():
