@@ -4,9 +4,10 @@
 // one line per node and DataArray, doubles through `ostream << double` (= printf "%g", six
 // significant digits), WALL/OUTSIDE velocities zeroed, NaN/Inf and |v| < 1e-300 flushed to 0.
 // On the CPU that is ~4 us per node; here the text is produced on the device:
-//   k_fmt_*      one thread per node formats its record into a fixed slot and stores its length
+//   k_rec_len    one thread per node formats its record and keeps only the length
 //   scan         exclusive prefix sum of the lengths (scan.cuh)
-//   k_compact    records are packed into the contiguous text of the DataArray body
+//   k_rec_write  a block formats its records into shared memory at their final relative positions
+//                and writes its piece of the DataArray body with aligned 16-byte stores
 // and only the finished text crosses PCIe. Output is byte-identical to the reference's file.
 //
 // "%g" needs the correctly rounded 6-digit decimal of a binary64 value. x = m 2^e is multiplied
@@ -166,8 +167,7 @@ __device__ __forceinline__ int fmt_int(int v, char* out) {
 }
 
 constexpr int kIndent = 10;    // "          " in front of every record
-constexpr int SLOT_S = 32;     // scalar record slot
-constexpr int SLOT_V = 64;     // velocity record slot
+constexpr int kMaxRec = 56;    // longest record: indent + 3 x 13 chars + 2 blanks + newline = 52
 
 __device__ __forceinline__ int put_indent(char* o) {
 #pragma unroll
@@ -175,61 +175,77 @@ __device__ __forceinline__ int put_indent(char* o) {
     return kIndent;
 }
 
-// records of a scalar double array; global node g lives at local index g + shift
-__global__ void k_fmt_scalar(const double* __restrict__ f, long long n, char* __restrict__ slots,
-                             int* __restrict__ len, int* __restrict__ flag) {
+enum RecKind { R_VEL2, R_VEL3, R_F64, R_U8, R_I32 };
+struct RecArgs {
+    const double *a, *b, *c;       // scalar field or velocity components (owned node 0)
+    const uint8_t* type;           // node types (velocity: WALL/OUTSIDE print 0, src/vtk_writer.cpp:62)
+    const void* ints;              // uint8 / int32 arrays
+};
+
+// one record (= one line of a DataArray body) of node t into o; returns its length
+template <int KIND>
+__device__ __forceinline__ int make_record(const RecArgs& A, long long t, char* o, int* fl) {
+    int k = put_indent(o);
+    if (KIND == R_VEL2 || KIND == R_VEL3) {
+        const uint8_t ty = A.type[t];
+        const bool fict = (ty == PDGPU_WALL || ty == PDGPU_OUTSIDE);
+        k += fmt_g(fict ? 0.0 : A.a[t], o + k, fl);
+        o[k++] = ' ';
+        k += fmt_g(fict ? 0.0 : A.b[t], o + k, fl);
+        o[k++] = ' ';
+        if (KIND == R_VEL3) k += fmt_g(fict ? 0.0 : A.c[t], o + k, fl);
+        else o[k++] = '0';
+    } else if (KIND == R_F64) {
+        k += fmt_g(A.a[t], o + k, fl);
+    } else if (KIND == R_U8) {
+        k += fmt_int((int)((const uint8_t*)A.ints)[t], o + k);
+    } else {
+        k += fmt_int(((const int*)A.ints)[t], o + k);
+    }
+    o[k++] = '\n';
+    return k;
+}
+
+// pass 1: record lengths (the text itself is discarded; formatting twice is cheaper than a
+// round trip of fixed-size slots through HBM)
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_rec_len(RecArgs A, long long n, int* __restrict__ len, int* __restrict__ flag) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
-    char* o = slots + t * SLOT_S;
-    int k = put_indent(o);
+    char buf[kMaxRec];
     int fl = 0;
-    k += fmt_g(f[t], o + k, &fl);
-    o[k++] = '\n';
-    len[t] = k;
+    len[t] = make_record<KIND>(A, t, buf, &fl);
     if (fl) atomicExch(flag, 1);
 }
 
-template <int DIM>
-__global__ void k_fmt_velocity(const double* __restrict__ vx, const double* __restrict__ vy,
-                               const double* __restrict__ vz, const uint8_t* __restrict__ type, long long n,
-                               char* __restrict__ slots, int* __restrict__ len, int* __restrict__ flag) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const uint8_t ty = type[t];
-    const bool fict = (ty == PDGPU_WALL || ty == PDGPU_OUTSIDE);     // src/vtk_writer.cpp:62
-    char* o = slots + t * SLOT_V;
-    int k = put_indent(o);
+// pass 2: a block formats its 256 records into shared memory at their final relative positions
+// (shifted so that shared index 0 maps to a 16-byte aligned global address) and writes the block's
+// text with aligned 16-byte stores; only the ragged ends go out bytewise
+template <int KIND>
+__global__ void __launch_bounds__(256)
+k_rec_write(RecArgs A, long long n, const long long* __restrict__ pos, char* __restrict__ text) {
+    __shared__ __align__(16) char sbuf[256 * kMaxRec + 32];
+    const long long t0 = (long long)blockIdx.x * 256, t = t0 + threadIdx.x;
+    const long long t1 = t0 + 256 < n ? t0 + 256 : n;
+    const long long base = pos[t0], end = pos[t1];
+    const int mis = (int)((unsigned long long)(text + base) & 15ull);
     int fl = 0;
-    k += fmt_g(fict ? 0.0 : vx[t], o + k, &fl);
-    o[k++] = ' ';
-    k += fmt_g(fict ? 0.0 : vy[t], o + k, &fl);
-    o[k++] = ' ';
-    if (DIM == 3) k += fmt_g(fict ? 0.0 : vz[t], o + k, &fl);
-    else o[k++] = '0';
-    o[k++] = '\n';
-    len[t] = k;
-    if (fl) atomicExch(flag, 1);
-}
-
-template <typename TI>
-__global__ void k_fmt_int(const TI* __restrict__ f, long long n, char* __restrict__ slots, int* __restrict__ len) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    char* o = slots + t * SLOT_S;
-    int k = put_indent(o);
-    k += fmt_int((int)f[t], o + k);
-    o[k++] = '\n';
-    len[t] = k;
-}
-
-__global__ void k_compact_text(const char* __restrict__ slots, int slot, const int* __restrict__ len,
-                               const long long* __restrict__ pos, long long n, char* __restrict__ text) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    const char* s = slots + t * slot;
-    char* d = text + pos[t];
-    const int L = len[t];
-    for (int b = 0; b < L; ++b) d[b] = s[b];
+    if (t < n) make_record<KIND>(A, t, sbuf + mis + (int)(pos[t] - base), &fl);
+    __syncthreads();
+    const int total = (int)(end - base);
+    char* g0 = text + base - mis;                  // 16-byte aligned, corresponds to sbuf[0]
+    const int first_full = mis ? 16 : 0;           // first chunk that lies completely inside the text
+    const int last = mis + total;                  // one past the last valid shared index
+    const int full_end = last & ~15;
+    for (int i = first_full + threadIdx.x * 16; i < full_end; i += 256 * 16)
+        *(uint4*)(g0 + i) = *(const uint4*)(sbuf + i);
+    if (mis) {
+        const int head_end = last < 16 ? last : 16;
+        for (int i = mis + threadIdx.x; i < head_end; i += 256) g0[i] = sbuf[i];
+    }
+    const int tail_begin = full_end > first_full ? full_end : (mis ? 16 : 0);
+    for (int i = tail_begin + threadIdx.x; i < last; i += 256) g0[i] = sbuf[i];
 }
 
 // raw "%g" of an array (test hook): 16-byte zero-padded cells
@@ -244,15 +260,14 @@ __global__ void k_fmt_cells(const double* __restrict__ v, long long n, char* __r
 }
 
 struct TextBuf {
-    char* slots = nullptr;
     int* len = nullptr;
     long long* pos = nullptr;
     char* text = nullptr;
     int* flag = nullptr;
     long long n = 0;
     void release() {
-        cudaFree(slots); cudaFree(len); cudaFree(pos); cudaFree(text); cudaFree(flag);
-        slots = text = nullptr; len = flag = nullptr; pos = nullptr;
+        cudaFree(len); cudaFree(pos); cudaFree(text); cudaFree(flag);
+        text = nullptr; len = flag = nullptr; pos = nullptr;
     }
 };
 
@@ -265,10 +280,9 @@ int upload_table(pdgpu_ctx* c) {
 
 int alloc_buf(TextBuf* b, long long n) {
     b->n = n;
-    CUDA_OK(cudaMalloc(&b->slots, (size_t)n * SLOT_V));
     CUDA_OK(cudaMalloc(&b->len, sizeof(int) * n));
     CUDA_OK(cudaMalloc(&b->pos, sizeof(long long) * (n + 1)));
-    CUDA_OK(cudaMalloc(&b->text, (size_t)n * SLOT_V));
+    CUDA_OK(cudaMalloc(&b->text, (size_t)n * kMaxRec + 64));
     CUDA_OK(cudaMalloc(&b->flag, sizeof(int)));
     CUDA_OK(cudaMemsetAsync(b->flag, 0, sizeof(int)));
     return 0;
@@ -282,30 +296,32 @@ struct ArrSpec {
 };
 
 // formats one array into b->text; *bytes = length of the body
-int format_array(pdgpu_ctx* c, TextBuf* b, const ArrSpec& a, long long* bytes) {
+template <int KIND>
+int format_kind(pdgpu_ctx* c, TextBuf* b, const RecArgs& A, long long* bytes) {
     const long long n = b->n;
     const unsigned g = nblocks(n, 256);
-    int slot = SLOT_S;
+    LAUNCH(c, k_rec_len<KIND>, g, 256, 0, A, n, b->len, b->flag);
+    long long total = 0;
+    PD_TRY(pdscan::exclusive_scan(c, b->len, n, b->pos, &total));
+    LAUNCH(c, k_rec_write<KIND>, g, 256, 0, A, n, b->pos, b->text);
+    *bytes = total;
+    return 0;
+}
+
+int format_array(pdgpu_ctx* c, TextBuf* b, const ArrSpec& a, long long* bytes) {
+    RecArgs A;
+    A.a = A.b = A.c = nullptr; A.type = nullptr; A.ints = nullptr;
     switch (a.kind) {
         case A_VEL: {
             const long long lo = c->own_lo;
-            slot = SLOT_V;
-            if (c->dim == 2)
-                LAUNCH(c, k_fmt_velocity<2>, g, 256, 0, c->v[c->cur][0] + lo, c->v[c->cur][1] + lo, nullptr,
-                       c->type + lo, n, b->slots, b->len, b->flag);
-            else
-                LAUNCH(c, k_fmt_velocity<3>, g, 256, 0, c->v[c->cur][0] + lo, c->v[c->cur][1] + lo,
-                       c->v[c->cur][2] + lo, c->type + lo, n, b->slots, b->len, b->flag);
-            break;
+            A.a = c->v[c->cur][0] + lo; A.b = c->v[c->cur][1] + lo; A.c = c->dim == 3 ? c->v[c->cur][2] + lo : nullptr;
+            A.type = c->type + lo;
+            return c->dim == 2 ? format_kind<R_VEL2>(c, b, A, bytes) : format_kind<R_VEL3>(c, b, A, bytes);
         }
-        case A_F64: LAUNCH(c, k_fmt_scalar, g, 256, 0, (const double*)a.dev, n, b->slots, b->len, b->flag); break;
-        case A_U8: LAUNCH(c, k_fmt_int<uint8_t>, g, 256, 0, (const uint8_t*)a.dev, n, b->slots, b->len); break;
-        case A_I32: LAUNCH(c, k_fmt_int<int>, g, 256, 0, (const int*)a.dev, n, b->slots, b->len); break;
+        case A_F64: A.a = (const double*)a.dev; return format_kind<R_F64>(c, b, A, bytes);
+        case A_U8: A.ints = a.dev; return format_kind<R_U8>(c, b, A, bytes);
+        case A_I32: A.ints = a.dev; return format_kind<R_I32>(c, b, A, bytes);
     }
-    long long total = 0;
-    PD_TRY(pdscan::exclusive_scan(c, b->len, n, b->pos, &total));
-    LAUNCH(c, k_compact_text, g, 256, 0, b->slots, slot, b->len, b->pos, n, b->text);
-    *bytes = total;
     return 0;
 }
 
