@@ -191,6 +191,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-array leg (e2e = null)")
     ap.add_argument("--e2e-chunks", type=int, default=32, help="axial chunks of the host-array step pipeline")
     ap.add_argument("--small", action="store_true", help="dx=5um params.cfg 3D (debug)")
     ap.add_argument("--csr", action="store_true",
@@ -321,8 +322,9 @@ def main() -> None:
                                    vel2d.ctypes.data_as(C.c_void_p), host["C"].ctypes.data_as(C.c_void_p),
                                    args.e2e_chunks))
 
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
+    e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
+    if e2e_steps:
+        e2e_step()
     barrier()
     L_.check(L.pdgpu_timer_start(grid.ctx))
     for _ in range(e2e_steps):
@@ -333,7 +335,7 @@ def main() -> None:
     t2 = torch.tensor([ms2.value], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = bonds_total * e2e_steps / (float(t2.item()) * 1e-3)
+    e2e_value = bonds_total * e2e_steps / (float(t2.item()) * 1e-3) if e2e_steps else None
 
     # ---- roofline of the dominant kernel (PD-NS bond kernel), timed alone with CUDA events ----
     kms = C.c_float()
