@@ -21,6 +21,12 @@
 // stream with its own download stream, while the main stream streams the chunks below it.  The arithmetic per node is that of pdgpu_ns_iterate(1) + pdgpu_ard_iterate(1); results
 // are bit-identical (tests/test_gpu_parity.py::test_step_host_*).  Geometries that do not meet
 // the chunk invariants (checked when the plan is built) run the same operators unchunked.
+//
+// Slab contexts (one rank per GPU): every rank pipelines its own slab the same way; the ghost planes
+// of the CURRENT state come straight from the host arrays, so the only exchanges left are the ones
+// of the classical loop bodies, issued once all NS chunks are done: new flow fields -> |v| of the
+// ghost planes -> salt/dsol/wpack of ghost solids; the ARD kernels of the two chunks that touch a
+// neighbour's planes (and their downloads) run after them.
 #include <algorithm>
 
 #include "common.cuh"
@@ -31,10 +37,11 @@ struct HostStep {
     int n = 1;                          // chunks (1 = unchunked)
     std::vector<int> zb;                // local plane boundaries [n+1]
     std::vector<long long> wall_lo, solid_lo;   // list offsets per chunk [n+1]
+    long long gwall_split = 0;          // ghost-plane WALL entries below / above the owned planes
     long long wall_split = 0;           // first WALL entry in an outlet plane (entries of the top chunk
                                         // before it do not depend on the outlet sweep)
     cudaStream_t s_up = nullptr, s_down = nullptr, s_down2 = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_a = nullptr, ev_x = nullptr, ev_end2 = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_a = nullptr, ev_x = nullptr, ev_end2 = nullptr, ev_sb = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_cmp, ev_down;   // per chunk: upload done, kernels done, download done
     cudaEvent_t ev_start = nullptr, ev_end = nullptr;
     double *stage_up = nullptr, *stage_down = nullptr;
@@ -53,7 +60,7 @@ void pd_host_step_free(pdgpu_ctx* c) {
     if (h->s_up) cudaStreamDestroy(h->s_up);
     if (h->s_down) cudaStreamDestroy(h->s_down);
     if (h->s_down2) cudaStreamDestroy(h->s_down2);
-    for (cudaEvent_t e : {h->ev_t0, h->ev_a, h->ev_x, h->ev_end2})
+    for (cudaEvent_t e : {h->ev_t0, h->ev_a, h->ev_x, h->ev_end2, h->ev_sb})
         if (e) cudaEventDestroy(e);
     if (h->stage_up) cudaFree(h->stage_up);
     if (h->stage_down) cudaFree(h->stage_down);
@@ -84,6 +91,20 @@ struct ListWindow {
     }
 };
 
+// narrows the ghost-plane WALL list (slab contexts)
+struct GhostWallWindow {
+    pdgpu_ctx* c;
+    int *w, *wm;
+    long long n;
+    GhostWallWindow(pdgpu_ctx* ctx, long long first, long long end)
+        : c(ctx), w(ctx->l_gwall), wm(ctx->l_gwall_mirror), n(ctx->n_gwall) {
+        c->l_gwall = w + first;
+        c->l_gwall_mirror = wm + first;
+        c->n_gwall = end - first;
+    }
+    ~GhostWallWindow() { c->l_gwall = w; c->l_gwall_mirror = wm; c->n_gwall = n; }
+};
+
 int fallback(HostStep* h, const char* why) {
     h->n = 1;
     snprintf(h->why, sizeof(h->why), "%s", why);
@@ -100,7 +121,7 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
     h->zb[1] = hi;
     h->n = 1;
     if (n_req < 2) return fallback(h, "one chunk requested");
-    if (c->nranks > 1) return fallback(h, "slab contexts exchange halos: unchunked");
+    if (c->nranks > 1 && !c->comm) return fallback(h, "slab context without communicator");
     if (c->opt_ns_kernel == 3 || c->opt_ard_kernel == 3) return fallback(h, "CSR kernels take no plane range");
     if (c->cfg.channel_flow_corrections) return fallback(h, "channel_flow_corrections");
     if (c->n_outlet > 0 && !(c->out_fast && c->opt_outlet_kernel > 0)) {
@@ -175,6 +196,13 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
             if (wm[t] >= 0 && ty[wm[t] - t0] == PDGPU_SOLID_MG)
                 return fallback(h, "a wall of the outlet planes mirrors a SOLID_MG node");
     }
+    h->gwall_split = 0;
+    if (c->n_gwall) {
+        std::vector<int> gw(c->n_gwall);
+        CUDA_OK(cudaMemcpy(gw.data(), c->l_gwall, sizeof(int) * c->n_gwall, cudaMemcpyDeviceToHost));
+        h->gwall_split = std::lower_bound(gw.begin(), gw.end(), c->own_lo,
+                                          [](int a, long long b) { return (long long)a < b; }) - gw.begin();
+    }
     h->n = n;
     h->zb = zb;
     h->wall_lo = wl;
@@ -190,7 +218,7 @@ int ensure(pdgpu_ctx* c, int n_req) {
         CUDA_OK(cudaStreamCreateWithFlags(&h->s_up, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&h->s_down, cudaStreamNonBlocking));
         CUDA_OK(cudaStreamCreateWithFlags(&h->s_down2, cudaStreamNonBlocking));
-        for (cudaEvent_t* e : {&h->ev_t0, &h->ev_a, &h->ev_x, &h->ev_end2})
+        for (cudaEvent_t* e : {&h->ev_t0, &h->ev_a, &h->ev_x, &h->ev_end2, &h->ev_sb})
             CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreate(&h->ev_start));
         CUDA_OK(cudaEventCreate(&h->ev_end));
@@ -205,7 +233,7 @@ int ensure(pdgpu_ctx* c, int n_req) {
         h->ev_cmp.push_back(b);
         h->ev_down.push_back(d);
     }
-    size_t need = (size_t)(c->own_hi - c->own_lo) * c->dim;
+    size_t need = (size_t)c->NL * c->dim;   // indexed by local node (ghost planes included)
     if (h->n > 1 && h->stage_elems < need) {
         if (h->stage_up) CUDA_OK(cudaFree(h->stage_up));
         if (h->stage_down) CUDA_OK(cudaFree(h->stage_down));
@@ -257,10 +285,21 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
     CUDA_OK(cudaStreamWaitEvent(h->s_up, h->ev_start, 0));
     CUDA_OK(cudaStreamWaitEvent(h->s_down, h->ev_start, 0));
 
+    const int T = n - 1;
+    const bool has_lo = c->nranks > 1 && c->rank > 0, has_hi = c->nranks > 1 && c->rank < c->nranks - 1;
+    // plane range a chunk moves/initialises: the end chunks of a slab take the ghost planes along
+    auto span_x = [&](int k, long long* l0, long long* cnt) {
+        int z0 = h->zb[k], z1 = h->zb[k + 1];
+        if (k == 0 && has_lo) z0 -= c->R;
+        if (k == T && has_hi) z1 += c->R;
+        *l0 = (long long)z0 * P;
+        *cnt = (long long)(z1 - z0) * P;
+    };
     // uploads, outlet end first
     for (int k = n - 1; k >= 0; --k) {
-        const long long l0 = (long long)h->zb[k] * P, cnt = (long long)(h->zb[k + 1] - h->zb[k]) * P;
-        const long long g0 = l0 + gshift, s0 = (l0 - c->own_lo) * dim;
+        long long l0, cnt;
+        span_x(k, &l0, &cnt);
+        const long long g0 = l0 + gshift, s0 = l0 * dim;
         CUDA_OK(cudaMemcpyAsync(c->rho[cur] + l0, rho + g0, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->s_up));
         CUDA_OK(cudaMemcpyAsync(h->stage_up + s0, vel + g0 * dim, sizeof(double) * cnt * dim, cudaMemcpyHostToDevice,
                                 h->s_up));
@@ -268,7 +307,7 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
         CUDA_OK(cudaEventRecord(h->ev_up[k], h->s_up));
     }
 
-    const int T = n - 1;
+    const bool use_side = c->n_outlet > 0;   // the outlet chain lives on the rank that owns the outlet
     cudaStream_t side = c->stream2;
     CUDA_OK(cudaStreamWaitEvent(h->s_down2, h->ev_start, 0));
     const bool tiles = (c->opt_ard_kernel == 1 || c->opt_ard_kernel == 2);
@@ -285,7 +324,7 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
         }
         long long l0, cnt;
         span(kd, &l0, &cnt);
-        const long long g0 = l0 + gshift, s0 = (l0 - c->own_lo) * dim;
+        const long long g0 = l0 + gshift, s0 = l0 * dim;
         PD_TRY(pd_enqueue_interleave(c, h->stage_down + s0, l0, cnt, nw));
         CUDA_OK(cudaEventRecord(h->ev_cmp[kd], st));
         CUDA_OK(cudaStreamWaitEvent(sd, h->ev_cmp[kd], 0));
@@ -300,11 +339,11 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
     for (int k = n - 1; k >= -2; --k) {
         if (k >= 0) {   // A(k): src/pd_ns.cpp:197-200 restricted to chunk k
             long long l0, cnt;
-            span(k, &l0, &cnt);
+            span_x(k, &l0, &cnt);
             CUDA_OK(cudaStreamWaitEvent(cs, h->ev_up[k], 0));
             PD_TRY(pd_enqueue_eos_range(c, cur, l0, cnt));
-            PD_TRY(pd_enqueue_deinterleave(c, h->stage_up + (l0 - c->own_lo) * dim, l0, cnt, cur));
-            if (k == T) {
+            PD_TRY(pd_enqueue_deinterleave(c, h->stage_up + l0 * dim, l0, cnt, cur));
+            if (k == T && use_side) {
                 // outlet sweep and the walls of the outlet planes: side stream; the walls below them
                 // (all that the chunk underneath reads) and the solids: main stream
                 CUDA_OK(cudaEventRecord(h->ev_t0, cs));
@@ -316,20 +355,22 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
                     PD_TRY(pd_enqueue_bc_wall(c, cur));
                 }
                 ListWindow win(c, h->wall_lo[T], h->wall_split, h->solid_lo[T], h->solid_lo[T + 1]);
-                if (k == 0) PD_TRY(pd_enqueue_bc_inlet(c, cur, sC));
                 PD_TRY(pd_enqueue_bc_wall(c, cur));
                 PD_TRY(pd_enqueue_bc_solid(c, cur));
             } else {
                 ListWindow win(c, *h, k);
                 if (k == 0) PD_TRY(pd_enqueue_bc_inlet(c, cur, sC));
+                if (k == T) PD_TRY(pd_enqueue_bc_outlet(c, cur, sC));   // (no fast sweep on this geometry)
                 PD_TRY(pd_enqueue_bc_wall(c, cur));
+                if (k == 0 && has_lo) { GhostWallWindow gw(c, 0, h->gwall_split); PD_TRY(pd_enqueue_bc_wall(c, cur, 3)); }
+                if (k == T && has_hi) { GhostWallWindow gw(c, h->gwall_split, c->n_gwall); PD_TRY(pd_enqueue_bc_wall(c, cur, 3)); }
                 PD_TRY(pd_enqueue_bc_solid(c, cur));
             }
         }
         const int kn = k + 1;
         if (kn >= 0 && kn < n) {   // N, W: src/pd_ns.cpp:201-204; B: src/coupling.cpp:232-235 + ARD pre-passes
             cudaStream_t st = cs;
-            if (kn == T) {         // after A(T-1) on the main stream, behind the sweep on the side stream
+            if (kn == T && use_side) {   // after A(T-1) on the main stream, behind the sweep on the side stream
                 CUDA_OK(cudaEventRecord(h->ev_a, cs));
                 CUDA_OK(cudaStreamWaitEvent(side, h->ev_a, 0));
                 st = side;
@@ -343,10 +384,12 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
             PD_TRY(pd_enqueue_ard_vmag_range(c, nw, (long long)h->zb[kn] * P, (long long)h->zb[kn + 1] * P));
             PD_TRY(pd_enqueue_bc_wall_conc(c, sC, true));
             PD_TRY(pd_enqueue_ard_prepass_solids(c, sC));
+            if (kn == T && use_side) CUDA_OK(cudaEventRecord(h->ev_sb, side));
         }
         const int kd = k + 2;
-        if (kd >= 0 && kd < n) {
-            if (kd >= T - 1) {     // reads |v| of the top chunk: side stream, behind everything the main
+        const bool deferred = (kd == T && has_hi) || (kd == 0 && has_lo);   // reads a neighbour rank's planes
+        if (kd >= 0 && kd < n && !deferred) {
+            if (kd >= T - 1 && use_side) {     // reads |v| of the top chunk: side stream, behind everything the main
                                    // stream has enqueued up to here (B of the chunks around it)
                 CUDA_OK(cudaEventRecord(h->ev_x, cs));
                 CUDA_OK(cudaStreamWaitEvent(side, h->ev_x, 0));
@@ -355,6 +398,18 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
                 PD_TRY(finish_chunk(kd, cs, h->s_down));
             }
         }
+    }
+    if (c->nranks > 1) {
+        // the exchanges of the classical loop bodies (src order: after wall_bc_new; inside the ARD step;
+        // after it), once per call and in the same order on every rank, chunked or not
+        if (use_side) CUDA_OK(cudaStreamWaitEvent(cs, h->ev_sb, 0));
+        PD_TRY(pd_enqueue_halo(c, 0, nw, sC));
+        if (has_lo) PD_TRY(pd_enqueue_ard_vmag_range(c, nw, 0, c->own_lo));
+        if (has_hi) PD_TRY(pd_enqueue_ard_vmag_range(c, nw, c->own_hi, c->NL));
+        PD_TRY(pd_enqueue_halo(c, 3, nw, sC));
+        if (has_hi) PD_TRY(finish_chunk(T, cs, h->s_down));
+        if (has_lo) PD_TRY(finish_chunk(0, cs, h->s_down));
+        PD_TRY(pd_enqueue_halo(c, 1, nw, dC));
     }
     CUDA_OK(cudaEventRecord(h->ev_end2, h->s_down2));
     CUDA_OK(cudaStreamWaitEvent(cs, h->ev_end2, 0));

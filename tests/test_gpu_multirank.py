@@ -23,7 +23,7 @@ def _n_gpus() -> int:
 def test_two_slabs_reproduce_one_gpu_bitwise(case):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29533",
-           os.path.join(ROOT, "tools", "multigpu_check.py"), case, "12", "6"]
+           os.path.join(ROOT, "tools", "multigpu_check.py"), case, "12", "6", "0", "6"]   # + one chunked pdgpu_step_host pass
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "bitwise=no" not in r.stdout

@@ -4,7 +4,10 @@ single-GPU fields BITWISE (same per-node arithmetic and order; only all-reduced 
 differ in the last bits).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/multigpu_check.py [case] [ns_iters] [ard_steps]
+        --master-port 29511 tools/multigpu_check.py [case] [ns_iters] [ard_steps] [dissolve_cycles] [host_chunks]
+
+host_chunks > 0 additionally runs one pdgpu_step_host pass (host arrays in/out, chunked pipeline,
+slab exchanges inside) on every rank's copy of the state and compares the owned parts.
 
 Every rank runs its slab; rank 0 additionally runs the whole domain on its own GPU and
 compares. Exit code 0 = identical.
@@ -25,7 +28,7 @@ import helpers as H  # noqa: E402
 from pd_mg_pin_corrosion_b200 import lib as L_, solver as S  # noqa: E402
 
 
-def run(grid, cfg, iters, steps, dissolve_cycles):
+def run(grid, cfg, iters, steps, dissolve_cycles, host_chunks=0):
     fields = S.Fields()
     fields.bind(grid)
     L = L_.load()
@@ -51,6 +54,10 @@ def run(grid, cfg, iters, steps, dissolve_cycles):
             dissolved.append(ard.last_dissolved.copy())
     res = ns.residual(grid)
     out = {n: fields.get(n) for n in ("rho", "vel", "C")}
+    if host_chunks:
+        used, why = S.step_host_chunks(grid, host_chunks)
+        print(f"[multigpu_check] rank {grid.rank}/{grid.nranks}: step_host chunks {used} {why}", flush=True)
+        S.step_host(grid, dt, dtc, out["rho"], out["vel"], out["C"], host_chunks)
     out["node_type"] = grid.node_type
     out["scalars"] = np.array([dt, dtc, res.num, res.den, res.v_max])
     out["dissolved"] = np.concatenate(dissolved) if dissolved else np.zeros(0, np.int32)
@@ -62,6 +69,7 @@ def main():
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
     cycles = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+    host_chunks = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -78,14 +86,14 @@ def main():
     uid = uid.cuda()
     dist.broadcast(uid, 0)
     L_.check(L.pdgpu_comm_init(grid.ctx, bytes(uid.cpu().tolist()), rank, world))
-    mine = run(grid, cfg, iters, steps, cycles)
+    mine = run(grid, cfg, iters, steps, cycles, host_chunks)
     a0, a1, P = grid.a0, grid.a1, grid.plane
     # gather the owned parts on rank 0
     ok = True
     if rank == 0:
         full = S.Grid(dim, device=local)
         full.build(cfg)
-        want = run(full, cfg, iters, steps, cycles)
+        want = run(full, cfg, iters, steps, cycles, 1 if host_chunks else 0)   # unchunked single-GPU pass
         got = {n: np.array(mine[n], copy=True) for n in ("rho", "vel", "C", "node_type")}
     for n in ("rho", "vel", "C", "node_type"):
         for r in range(1, world):
