@@ -34,10 +34,16 @@ METRIC = "pd_bond_updates_per_s_ns_plus_ard_step"
 UNIT = "bond-updates/s"
 
 
-def workload_cfg(n_gpus: int, sample: bool = False) -> tuple[Config, str]:
+def workload_cfg(n_gpus: int, sample: bool = False, big: bool = False) -> tuple[Config, str]:
     """3D params_fine (+ use_implicit = 0); tube x n_gpus for weak scaling; `sample` = the
-    same cross-section with a short tube (bounded CPU-baseline sample)."""
+    same cross-section with a short tube (bounded CPU-baseline sample); `big` = BASELINE
+    configs[4]: the params_fine tube at dx = 1 um (307x307x1407, 1.84e10 CSR-equivalent entries),
+    the SAME domain for every GPU count (strong scaling)."""
     ov = {"use_implicit": 0}
+    if big:
+        ov["dx"] = 1.0e-6
+        return (Config.load(os.path.join(ROOT, "configs", "params_fine.cfg"), ov, quiet=True),
+                "synthetic 3D tube: params_fine geometry at dx=1um (307x307x1407), strong scaling")
     base = Config.load(os.path.join(ROOT, "configs", "params_fine.cfg"), ov, quiet=True)
     if sample:
         ov.update({"L_wire": 24e-6, "L_upstream": 16e-6, "L_downstream": 16e-6})
@@ -194,6 +200,8 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-array leg (e2e = null)")
     ap.add_argument("--e2e-chunks", type=int, default=32, help="axial chunks of the host-array step pipeline")
     ap.add_argument("--small", action="store_true", help="dx=5um params.cfg 3D (debug)")
+    ap.add_argument("--big", action="store_true",
+                    help="BASELINE configs[4]: params_fine at dx=1um (132.6 M nodes), same domain at every N (strong scaling)")
     ap.add_argument("--csr", action="store_true",
                     help="also time the materialised-CSR (reference layout, HBM-bound) bond kernels")
     args = ap.parse_args()
@@ -222,7 +230,7 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     L = L_.load()
-    cfg, wname = workload_cfg(world)
+    cfg, wname = workload_cfg(world, big=args.big)
     if args.small:
         cfg = Config.load(os.path.join(ROOT, "configs", "params.cfg"), {"use_implicit": 0}, quiet=True)
         wname = "3D params.cfg (dx=5um, 67x67x287) [debug]"
@@ -406,7 +414,7 @@ def main() -> None:
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "scaling": "strong" if args.big else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic (deterministic geometry from the cfg; Poiseuille initial flow)",
                 "config": {"workload": wname, "nodes": int(N), "bond_updates_per_step": int(bonds_total),
                            "parallelism": f"z-slab x{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2",

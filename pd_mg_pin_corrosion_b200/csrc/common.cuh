@@ -112,6 +112,7 @@ struct pdgpu_ctx {
     bool out_mod = false;
     int out_RJ = 1, out_n_rows = 0;
     size_t out_smem_mod = 0;
+    int out_rows_doubled = 1;
     int out_rows_G = 0, out_rows_M = 0, out_row_start[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // row-walking sweep
     size_t out_smem_rows = 0;
     bool out_fast = false;
@@ -161,6 +162,7 @@ struct pdgpu_ctx {
     int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)
     int opt_lazy_wallc = 1;         // evaluate the wall-concentration BC only when somebody reads WALL C
     int opt_overlap = 1;            // run the outlet sweep on a side stream next to the bulk kernel
+    int opt_outlet_single_rows = 0; // force the single-row ring of the row-walking sweep (tests; large cross-sections use it anyway)
     int opt_outlet_kernel = 3;      // 0 = level-list kernel, 1 = level-addressed ring, 2 = lattice-addressed ring, 3 = row-walking
 
     // NCCL

@@ -295,6 +295,7 @@ k_outlet_sweep_mod(OutletGeom g, int RJ, const int4* __restrict__ rows, int n_ro
 struct RowSweepParams {
     OutletGeom g;
     int RJ, n_rows, M, R;
+    int doubled;           // ring rows stored twice (no wrap inside a run); 0 = single rows, wrapped reads
     int row_start[8];      // first table row with k' + dplane >= 0, per outlet plane k'
     int n_rcp;             // reciprocal table entries (stencil size + 1)
 };
@@ -307,7 +308,7 @@ k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __rest
     extern __shared__ double smem[];
     const OutletGeom& g = q.g;
     double* ring = smem;
-    const int RI = g.ring, RJ = q.RJ, RW = 2 * RI;           // RW = doubled ring row
+    const int RI = g.ring, RJ = q.RJ, RW = q.doubled ? 2 * RI : RI;   // RW = ring row pitch
     int4* s_rows = (int4*)(ring + (size_t)g.KP * RJ * RW);   // even number of doubles: 16-byte aligned
     double* s_rcp = (double*)(s_rows + q.n_rows);
     const bool is_vel = (blockIdx.x == 0);
@@ -362,14 +363,25 @@ k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __rest
                 const int4 row = s_rows[r];                  // dj, dplane, di_lo, di_hi
                 const int j2 = j + row.x;
                 if ((unsigned)j2 >= (unsigned)g.Ny) continue;
-                const double* src = ring + ((kp + row.y) * RJ + (j2 & jmask)) * RW + ((i + row.z) & imask);
+                const double* rowp = ring + ((kp + row.y) * RJ + (j2 & jmask)) * RW;
+                const int s_first = (i + row.z) & imask;
                 const int w = row.w - row.z + 1;
+                if (q.doubled) {
+                    const double* src = rowp + s_first;
 #pragma unroll
-                for (int u = 0; u < 7; ++u) {                // a row of the reach-3 sphere has <= 7 nodes
-                    const double v = (u < w) ? src[u] : 0.0;
-                    if (u & 1) s1 += v; else s0 += v;
+                    for (int u = 0; u < 7; ++u) {            // a row of the reach-3 sphere has <= 7 nodes
+                        const double v = (u < w) ? src[u] : 0.0;
+                        if (u & 1) s1 += v; else s0 += v;
+                    }
+                    for (int u = 7; u < w; ++u) s0 += src[u];    // reach > 3
+                } else {                                     // large cross-sections: single rows, wrapped
+#pragma unroll
+                    for (int u = 0; u < 7; ++u) {
+                        const double v = (u < w) ? rowp[(s_first + u) & imask] : 0.0;
+                        if (u & 1) s1 += v; else s0 += v;
+                    }
+                    for (int u = 7; u < w; ++u) s0 += rowp[(s_first + u) & imask];
                 }
-                for (int u = 7; u < w; ++u) s0 += src[u];    // reach > 3
             }
         }
         double sum = s0 + s1;
@@ -385,7 +397,7 @@ k_outlet_sweep_rows(const __grid_constant__ RowSweepParams q, const int4* __rest
             }
             double* dst = ring + (kp * RJ + (j & jmask)) * RW + (i & imask);
             dst[0] = val;
-            dst[RI] = val;
+            if (q.doubled) dst[RI] = val;
         }
         __syncthreads();
         ++i;
@@ -444,9 +456,15 @@ int pd_outlet_setup(pdgpu_ctx* c) {
         if (!rows.empty() && rows.back().x == e.y && rows.back().y == e.z && rows.back().w + 1 == e.x) rows.back().w = e.x;
         else rows.push_back(make_int4(e.y, e.z, e.x, e.x));
     }
-    int RJ = (Ny == 1) ? 1 : 64;
+    // lattice-addressed rings: the level front keeps (maxd + Nx - 1)/B + 1 rows of a plane alive
+    int RJ = 1;
+    if (Ny > 1) {
+        const int win = (maxd + Nx - 1) / B + 1;
+        RJ = 64;
+        while (RJ < win) RJ <<= 1;
+    }
     size_t smem_mod = sizeof(double) * (size_t)KP * RJ * ring + sizeof(int4) * rows.size() + sizeof(unsigned) * mask_words;
-    c->out_mod = (Ny == 1 || (maxd + Nx - 1) / B + 1 <= 64) && smem_mod <= 220 * 1024 && KP * Wj <= 2 * (1024 / 4);
+    c->out_mod = smem_mod <= 220 * 1024 && KP * Wj <= 2 * (1024 / 4);
     c->out_RJ = RJ; c->out_n_rows = (int)rows.size(); c->out_smem_mod = smem_mod;
     c->out_KP = KP; c->out_Wj = Wj; c->out_ring = ring; c->out_smem = smem; c->out_mask_words = mask_words;
     c->out_l0 = al_min * c->P;
@@ -466,15 +484,19 @@ int pd_outlet_setup(pdgpu_ctx* c) {
         CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep_mod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mod));
     // row-walking sweep: G lanes per lattice row slot, M row slots per outlet plane
     c->out_rows_G = 0;
-    if (c->out_mod && KP <= 8) {
-        size_t smem_rows = sizeof(double) * ((size_t)KP * RJ * 2 * ring + c->n_off + 1) + sizeof(int4) * rows.size();
-        for (int G : {8, 4}) {
-            int M = (Ny == 1) ? 1 : (Nx + G + c->R + B - 1) / B;
-            if (KP * M * G <= 1024 && smem_rows <= 220 * 1024) {
-                c->out_rows_G = G; c->out_rows_M = M; c->out_smem_rows = smem_rows;
-                break;
+    if (KP <= 8) {
+        for (int doubled = 1; doubled >= 0 && !c->out_rows_G; --doubled) {
+            size_t smem_rows = sizeof(double) * ((size_t)KP * RJ * (doubled ? 2 : 1) * ring + c->n_off + 1) +
+                               sizeof(int4) * rows.size();
+            for (int G : {8, 4}) {
+                int M = (Ny == 1) ? 1 : (Nx + G + c->R + B - 1) / B;
+                if (KP * M * G <= 1024 && smem_rows <= 220 * 1024) {
+                    c->out_rows_G = G; c->out_rows_M = M; c->out_smem_rows = smem_rows; c->out_rows_doubled = doubled;
+                    break;
+                }
             }
         }
+        const size_t smem_rows = c->out_smem_rows;
         for (int kp = 0; kp < 8; ++kp) {
             int st = 0;
             while (st < (int)rows.size() && kp + rows[st].y < 0) ++st;
@@ -511,7 +533,7 @@ int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
                c->out_base_c, c->out_cnt);
     if (c->out_rows_G && c->opt_outlet_kernel >= 3) {
         RowSweepParams q;
-        q.g = g; q.RJ = c->out_RJ; q.n_rows = c->out_n_rows; q.M = c->out_rows_M; q.R = c->R; q.n_rcp = c->n_off + 1;
+        q.g = g; q.RJ = c->out_RJ; q.n_rows = c->out_n_rows; q.M = c->out_rows_M; q.R = c->R; q.n_rcp = c->n_off + 1; q.doubled = (c->out_rows_doubled && !c->opt_outlet_single_rows) ? 1 : 0;
         for (int kp = 0; kp < 8; ++kp) q.row_start[kp] = c->out_row_start[kp];
         const int threads = (g.KP * q.M * c->out_rows_G + 31) / 32 * 32;
         if (c->out_rows_G == 8)

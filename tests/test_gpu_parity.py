@@ -251,6 +251,7 @@ def test_kernel_variants_agree(case):
         dict(ns_kernel=1, ard_kernel=1, outlet_kernel=2, overlap=1, graph=1),
         dict(ns_kernel=1, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1),   # default
         dict(ns_kernel=1, ard_kernel=1, outlet_kernel=3, overlap=0, graph=0),
+        dict(ns_kernel=1, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1, outlet_single_rows=1),
         dict(ns_kernel=0, ard_kernel=0, outlet_kernel=2, overlap=1, graph=1),
         dict(ns_kernel=2, ard_kernel=1, outlet_kernel=2, overlap=1, graph=1),   # z-marching NS kernel
         dict(ns_kernel=2, ard_kernel=2, outlet_kernel=2, overlap=0, graph=0),
