@@ -196,6 +196,10 @@ extern "C" int pdgpu_set_option(pdgpu_ctx* c, const char* name, int value) {
     else if (n == "outlet_kernel") c->opt_outlet_kernel = value;
     else if (n == "overlap") c->opt_overlap = value;
     else if (n == "outlet_single_rows") c->opt_outlet_single_rows = value;
+    else if (n == "outlet_rows_g") {
+        c->opt_outlet_rows_g = value;
+        if (c->grid_built && pd_outlet_setup(c)) return 1;
+    }
     else if (n == "lazy_wallc") { if (pd_flush_wall_c(c)) return 1; c->opt_lazy_wallc = value; }
     else if (n == "debug_no_halo") c->opt_debug_no_halo = value;
     else PD_FAIL("pdgpu_set_option: unknown option '%s'", name);

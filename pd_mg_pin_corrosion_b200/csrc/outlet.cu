@@ -488,7 +488,8 @@ int pd_outlet_setup(pdgpu_ctx* c) {
         for (int doubled = 1; doubled >= 0 && !c->out_rows_G; --doubled) {
             size_t smem_rows = sizeof(double) * ((size_t)KP * RJ * (doubled ? 2 : 1) * ring + c->n_off + 1) +
                                sizeof(int4) * rows.size();
-            for (int G : {8, 4}) {
+            for (int G : {4, 8, 2}) {   // 4 lanes per row measured fastest (the sweep is issue bound: fewer warps)
+                if (c->opt_outlet_rows_g && G != c->opt_outlet_rows_g) continue;
                 int M = (Ny == 1) ? 1 : (Nx + G + c->R + B - 1) / B;
                 if (KP * M * G <= 1024 && smem_rows <= 220 * 1024) {
                     c->out_rows_G = G; c->out_rows_M = M; c->out_smem_rows = smem_rows; c->out_rows_doubled = doubled;
@@ -506,6 +507,8 @@ int pd_outlet_setup(pdgpu_ctx* c) {
             CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep_rows<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
         if (c->out_rows_G == 4)
             CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep_rows<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
+        if (c->out_rows_G == 2)
+            CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep_rows<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
     }
     k_outlet_mask<<<nblocks(mask_words, 256), 256, 0, c->stream>>>(c->type, c->out_l0, nslab, c->out_mask);
     CUDA_OK(cudaFuncSetAttribute(k_outlet_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -539,8 +542,11 @@ int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
         if (c->out_rows_G == 8)
             LAUNCH(c, k_outlet_sweep_rows<8>, 2, threads, c->out_smem_rows, q, (const int4*)c->out_rows, c->out_base_v,
                    c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
-        else
+        else if (c->out_rows_G == 4)
             LAUNCH(c, k_outlet_sweep_rows<4>, 2, threads, c->out_smem_rows, q, (const int4*)c->out_rows, c->out_base_v,
+                   c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
+        else
+            LAUNCH(c, k_outlet_sweep_rows<2>, 2, threads, c->out_smem_rows, q, (const int4*)c->out_rows, c->out_base_v,
                    c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
     } else if (c->out_mod && c->opt_outlet_kernel >= 2)
         LAUNCH(c, k_outlet_sweep_mod, 2, 1024, c->out_smem_mod, g, c->out_RJ, (const int4*)c->out_rows, c->out_n_rows,

@@ -37,11 +37,13 @@ for st in sets:
         out.append(ms.value / 20)
     print(f"{st:40s} ns body {out[0]:.3f} ms  ard body {out[1]:.3f} ms  sum {out[0]+out[1]:.3f}", flush=True)
 # outlet BC alone (pre-pass + both sweeps)
-for ok in (3, 2):
+for ok, g in ((3, 8), (3, 4), (3, 2), (2, 0)):
     grid.set_option("outlet_kernel", ok)
+    if g:
+        grid.set_option("outlet_rows_g", g)
     L_.check(L.pdgpu_bc_outlet(grid.ctx))
     L_.check(L.pdgpu_timer_start(grid.ctx))
     for _ in range(10):
         L_.check(L.pdgpu_bc_outlet(grid.ctx))
     L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
-    print(f"outlet_kernel={ok}: apply_outlet_bc {ms.value / 10:.3f} ms")
+    print(f"outlet_kernel={ok} rows_g={g}: apply_outlet_bc {ms.value / 10:.3f} ms")
