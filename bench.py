@@ -176,7 +176,7 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, min(args.steps, 50))   # each step = one NS + one ARD loop body on the bounded sample (~0.1 s)
     base = cpu_reference(steps, min(args.warmup, 1))
     _, wname = workload_cfg(args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -408,7 +408,7 @@ def main() -> None:
         grid.free_neighbors()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        b = _cpu_reference(4, 1, None)
+        b = _cpu_reference(40, 2, None)   # ~4 s of host work on the bounded sample (+ ~2 s CSR build)
         cpu = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
