@@ -446,7 +446,7 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
     c->n_wall_lo = c->n_wall;
     c->solids_below_cut = true;
     if (c->n_outlet > 0 && c->out_fast) {
-        const int RZ = 4;                                  // tile::RZ
+        const int RZ = 8;                                  // tile::TZ (planes per tile)
         int zo = (int)(c->out_l0 / c->P);                  // first outlet plane (local)
         int z_lo = c->R;
         int zc = z_lo + ((zo - c->R - z_lo) / RZ) * RZ;

@@ -116,7 +116,7 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
     h->n_req = n_req;
     h->why[0] = 0;
     const int lo = c->R, nz = c->a1 - c->a0, hi = lo + nz;
-    const int TZ = 4;   // tile::TZ: chunk boundaries stay tile aligned
+    const int TZ = 8;   // tile::TZ: chunk boundaries stay tile aligned
     h->zb.assign(2, lo);
     h->zb[1] = hi;
     h->n = 1;

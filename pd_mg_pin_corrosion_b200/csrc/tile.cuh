@@ -1,10 +1,13 @@
 // tile.cuh -- shared geometry of the tiled bond kernels (ns_tile.cu, ard_tile.cu):
 // 3D, m_ratio = 3 (reach 3), full FLUID rows.
 //
-// A CTA (32 x 8 x 2 threads) stages a haloed (32+6) x (8+6) x (4+6) block in shared memory;
+// A CTA (16 x 8 x 4 threads) stages a haloed (16+6) x (8+6) x (8+6) block in shared memory;
 // thread (tx,ty,tz) owns the 2 nodes (x0+tx, y0+ty, z0+2tz..z0+2tz+1): 16 warps per SM hide the
 // FP64 and shared-memory latencies (8 warps with 4 nodes per thread reached 48 % FP64-pipe
-// utilisation, profiles/r1_notes.md).  The horizon sphere (di^2+dj^2+dk^2 <= 12, 178
+// utilisation, profiles/r1_notes.md).  A warp is two x-rows of 16 nodes: on the circular tube
+// cross-section 88 % of the lanes of a working warp own a FLUID node (82 % with 32-wide rows), and
+// 8 planes per tile amortise the 6 halo planes (measured: 32x8x4 tiles 3.24 ms, 16x16x4 2.97 ms,
+// 16x8x8 2.92 ms for the NS kernel).  The horizon sphere (di^2+dj^2+dk^2 <= 12, 178
 // offsets) is walked as 37 (di,dj) COLUMNS in a runtime loop; inside a column the window
 // slides along z, so a staged neighbour value is read from shared memory once and used for
 // up to 2 bonds.  Only the half-height H of the column (1, 2 or 3) is a compile-time
@@ -21,9 +24,9 @@
 namespace tile {
 
 constexpr int TR = 3;
-constexpr int TX = 16, TY = 16;            // threads in x, y
+constexpr int TX = 16, TY = 8;             // threads in x, y
 constexpr int RZ = 2;                      // z-nodes per thread (sliding window length)
-constexpr int NZT = 2;                     // thread layers in z
+constexpr int NZT = 4;                     // thread layers in z
 constexpr int TZ = RZ * NZT;               // z-nodes per tile
 constexpr int SX = TX + 2 * TR, SY = TY + 2 * TR, SZ = TZ + 2 * TR;
 constexpr int SPLANE = SX * SY, SN = SPLANE * SZ;
