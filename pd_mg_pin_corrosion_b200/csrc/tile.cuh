@@ -26,7 +26,10 @@ namespace tile {
 constexpr int TR = 3;
 constexpr int TX = 16, TY = 8;             // threads in x, y
 constexpr int RZ = 2;                      // z-nodes per thread (sliding window length)
-constexpr int NZT = 4;                     // thread layers in z
+#ifndef PD_TILE_NZT
+#define PD_TILE_NZT 4
+#endif
+constexpr int NZT = PD_TILE_NZT;           // thread layers in z (6 = 768 threads / 12 planes measured slower for NS: 78 registers)
 constexpr int TZ = RZ * NZT;               // z-nodes per tile
 constexpr int SX = TX + 2 * TR, SY = TY + 2 * TR, SZ = TZ + 2 * TR;
 constexpr int SPLANE = SX * SY, SN = SPLANE * SZ;
