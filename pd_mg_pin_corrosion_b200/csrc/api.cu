@@ -141,7 +141,7 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     void* ptrs[] = {c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->rho[0], c->rho[1],
                     c->p[0], c->p[1], c->C[0], c->C[1], c->v[0][0], c->v[0][1], c->v[0][2], c->v[1][0],
                     c->v[1][1], c->v[1][2], c->vmag, c->dsol, c->wpack, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,
-                    c->l_solid, c->inlet_vax, c->out_nodes, c->out_level_off, c->d_red, c->d_u64, c->d_int,
+                    c->l_solid, c->l_ssolid, c->inlet_vax, c->out_nodes, c->out_level_off, c->d_red, c->d_u64, c->d_int,
                     c->d_dissolved, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol,
                     c->l2_scratch, c->d_dt, c->stage, c->out_base_v, c->out_base_c, c->out_cnt,
                     c->out_mask, c->out_early, c->out_rows, c->l_gwall, c->l_gwall_mirror, c->moff};

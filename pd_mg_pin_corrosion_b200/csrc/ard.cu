@@ -161,15 +161,17 @@ int pd_ensure_vmag(pdgpu_ctx* c, int buf) {
     return 0;
 }
 
+// salt flag / interface diffusivity of the SURFACE solids (interior solids have no fluid-like
+// neighbour: nobody reads their entries)
 int pd_enqueue_ard_prepass_solids(pdgpu_ctx* c, int srcC) {
-    if (!c->n_solid) return 0;
+    if (!c->n_ssolid) return 0;
     Lat L = make_lat(c);
     ArdParams P = ard_params(c);
     if (c->dim == 2)
-        LAUNCH(c, k_ard_prepass_solids<2>, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type,
+        LAUNCH(c, k_ard_prepass_solids<2>, nblocks(c->n_ssolid, 128), 128, 0, L, c->l_ssolid, c->n_ssolid, c->type,
                c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol, c->wpack);
     else
-        LAUNCH(c, k_ard_prepass_solids<3>, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type,
+        LAUNCH(c, k_ard_prepass_solids<3>, nblocks(c->n_ssolid, 128), 128, 0, L, c->l_ssolid, c->n_ssolid, c->type,
                c->d_off, c->n_off, c->C[srcC], c->is_gb, c->is_precip, P, c->salt, c->dsol, c->wpack);
     return 0;
 }
@@ -244,12 +246,13 @@ static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
         // is preserved for every data dependence).
         cudaStream_t main_s = c->stream, side = c->stream2;
         const int z_hi = c->R + (c->a1 - c->a0);
+        PD_TRY(pd_enqueue_bc_outlet_prepass(c, buf, srcC));   // before the fork: see outlet.cu
         CUDA_OK(cudaEventRecord(c->ev_a, main_s));
         CUDA_OK(cudaStreamWaitEvent(side, c->ev_a, 0));
         const bool tiles = (c->opt_ard_kernel == 1 || c->opt_ard_kernel == 2);   // kernels that can skip the wall copy
         {
             StreamSwap sw(c, side);
-            PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
+            PD_TRY(pd_enqueue_bc_outlet_sweep(c, buf, srcC));
             PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0, c->NL));
             // WALL concentrations are never read by a bond (src/pd_ard.cpp:120): off the critical path
             if (tiles && !c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC, true));

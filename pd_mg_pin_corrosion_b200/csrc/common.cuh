@@ -94,6 +94,8 @@ struct pdgpu_ctx {
     int *l_wall = nullptr, *l_wall_mirror = nullptr, *l_inlet = nullptr, *l_outlet = nullptr,
         *l_solid = nullptr;
     long long n_wall = 0, n_inlet = 0, n_outlet = 0, n_solid = 0;
+    int* l_ssolid = nullptr;        // SOLID_MG nodes with a fluid-like neighbour (subset of l_solid, ascending)
+    long long n_ssolid = 0;
     // multi-GPU: WALL nodes in ghost planes + their mirrors, relative mirror offsets per node
     int *l_gwall = nullptr, *l_gwall_mirror = nullptr, *moff = nullptr;
     long long n_gwall = 0;
@@ -292,6 +294,8 @@ int pd_enqueue_bc_inlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, -1 = not applicable
 int pd_outlet_setup(pdgpu_ctx* c);
+int pd_enqueue_bc_outlet_prepass(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu: the two halves of the fast outlet BC
+int pd_enqueue_bc_outlet_sweep(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part = 0);   // part 0 all owned, 1 below the outlet planes, 2 in them, 3 ghost planes
 int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC, bool both_buffers = false, int srcC = -1);
 int pd_flush_wall_c(pdgpu_ctx* c);   // run an owed wall-concentration BC (no-op otherwise)

@@ -148,6 +148,29 @@ __global__ void k_type_flags(const uint8_t* __restrict__ type, long long own_lo,
     flag[t] = (type[own_lo + t] == want);
 }
 
+// SOLID_MG nodes with at least one fluid-like neighbour (FLUID / INLET / OUTLET): the only solids whose
+// salt flag / interface diffusivity anybody reads (src/pd_ard.cpp:61-73,140-162)
+template <int DIM>
+__global__ void k_surface_solid_flags(Lat L, const uint8_t* __restrict__ type, long long own_lo, long long own_n,
+                                      const OffEntry* __restrict__ off, int n_off, int* __restrict__ flag) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= own_n) return;
+    const long long l = own_lo + t;
+    int f = 0;
+    if (type[l] == PDGPU_SOLID_MG) {
+        const int q = (int)(l % L.P);
+        const int jj = (DIM == 3) ? q / L.Nx : 0;
+        const int ii = q - jj * L.Nx;
+        for (int o = 0; o < n_off && !f; ++o) {
+            const long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
+            if (nn < 0) continue;
+            const uint8_t tj = type[nn];
+            f = (tj == PDGPU_FLUID || tj == PDGPU_INLET || tj == PDGPU_OUTLET);
+        }
+    }
+    flag[t] = f;
+}
+
 // histogram of owned node types (block-local shared counters, one global atomic per bin)
 __global__ void k_type_hist(const uint8_t* __restrict__ type, long long own_lo, long long own_n,
                             unsigned long long* __restrict__ counts) {
@@ -373,6 +396,20 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
     PD_TRY(build_list(c, PDGPU_INLET, d_flag, d_pos, &c->l_inlet, &c->n_inlet));
     PD_TRY(build_list(c, PDGPU_OUTLET, d_flag, d_pos, &c->l_outlet, &c->n_outlet));
     PD_TRY(build_list(c, PDGPU_SOLID_MG, d_flag, d_pos, &c->l_solid, &c->n_solid));
+    {   // surface solids (the ARD salt pre-pass only needs these)
+        if (c->dim == 2)
+            LAUNCH(c, k_surface_solid_flags<2>, nblocks(own_n, 256), 256, 0, L, c->type, c->own_lo, own_n, c->d_off,
+                   c->n_off, d_flag);
+        else
+            LAUNCH(c, k_surface_solid_flags<3>, nblocks(own_n, 256), 256, 0, L, c->type, c->own_lo, own_n, c->d_off,
+                   c->n_off, d_flag);
+        long long total = 0;
+        PD_TRY(pdscan::exclusive_scan(c, d_flag, own_n, d_pos, &total));
+        if (c->l_ssolid) { CUDA_OK(cudaFree(c->l_ssolid)); c->l_ssolid = nullptr; }
+        c->n_ssolid = total;
+        CUDA_OK(cudaMalloc(&c->l_ssolid, sizeof(int) * std::max<long long>(total, 1)));
+        if (total > 0) LAUNCH(c, k_compact, nblocks(own_n, 256), 256, 0, d_flag, d_pos, c->own_lo, own_n, c->l_ssolid);
+    }
 
     // row lengths + bond counts (d_flag reused as rowlen scratch)
     LAUNCH(c, k_rowlen, nblocks(own_n, 256), 256, 0, L, c->dim, c->own_lo, own_n, c->type, c->d_off, c->n_off,

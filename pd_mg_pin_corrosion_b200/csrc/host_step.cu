@@ -36,7 +36,7 @@ struct HostStep {
     int n_req = 0;
     int n = 1;                          // chunks (1 = unchunked)
     std::vector<int> zb;                // local plane boundaries [n+1]
-    std::vector<long long> wall_lo, solid_lo;   // list offsets per chunk [n+1]
+    std::vector<long long> wall_lo, solid_lo, ssolid_lo;   // list offsets per chunk [n+1]
     long long gwall_split = 0;          // ghost-plane WALL entries below / above the owned planes
     long long wall_split = 0;           // first WALL entry in an outlet plane (entries of the top chunk
                                         // before it do not depend on the outlet sweep)
@@ -73,10 +73,13 @@ namespace {
 // narrows the WALL and SOLID lists of the context to the entries of one chunk
 struct ListWindow {
     pdgpu_ctx* c;
-    int *w, *wm, *s;
-    long long nw, ns;
-    ListWindow(pdgpu_ctx* ctx, long long w0, long long w1, long long s0, long long s1)
-        : c(ctx), w(ctx->l_wall), wm(ctx->l_wall_mirror), s(ctx->l_solid), nw(ctx->n_wall), ns(ctx->n_solid) {
+    int *w, *wm, *s, *ss;
+    long long nw, ns, nss;
+    ListWindow(pdgpu_ctx* ctx, long long w0, long long w1, long long s0, long long s1, long long q0 = 0, long long q1 = 0)
+        : c(ctx), w(ctx->l_wall), wm(ctx->l_wall_mirror), s(ctx->l_solid), ss(ctx->l_ssolid), nw(ctx->n_wall),
+          ns(ctx->n_solid), nss(ctx->n_ssolid) {
+        c->l_ssolid = ss + q0;
+        c->n_ssolid = q1 - q0;
         c->l_wall = w + w0;
         c->l_wall_mirror = wm + w0;
         c->n_wall = w1 - w0;
@@ -84,10 +87,12 @@ struct ListWindow {
         c->n_solid = s1 - s0;
     }
     ListWindow(pdgpu_ctx* ctx, const HostStep& h, int k)
-        : ListWindow(ctx, h.wall_lo[k], h.wall_lo[k + 1], h.solid_lo[k], h.solid_lo[k + 1]) {}
+        : ListWindow(ctx, h.wall_lo[k], h.wall_lo[k + 1], h.solid_lo[k], h.solid_lo[k + 1], h.ssolid_lo[k],
+                     h.ssolid_lo[k + 1]) {}
     ~ListWindow() {
         c->l_wall = w; c->l_wall_mirror = wm; c->n_wall = nw;
         c->l_solid = s; c->n_solid = ns;
+        c->l_ssolid = ss; c->n_ssolid = nss;
     }
 };
 
@@ -165,13 +170,16 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
         CUDA_OK(cudaMemcpy(wm.data(), c->l_wall_mirror, sizeof(int) * c->n_wall, cudaMemcpyDeviceToHost));
     }
     if (c->n_solid) CUDA_OK(cudaMemcpy(s.data(), c->l_solid, sizeof(int) * c->n_solid, cudaMemcpyDeviceToHost));
-    std::vector<long long> wl(n + 1), sl(n + 1);
+    std::vector<int> q(c->n_ssolid);
+    if (c->n_ssolid) CUDA_OK(cudaMemcpy(q.data(), c->l_ssolid, sizeof(int) * c->n_ssolid, cudaMemcpyDeviceToHost));
+    std::vector<long long> wl(n + 1), sl(n + 1), ql(n + 1);
     for (int k = 0; k <= n; ++k) {
         long long first = (long long)zb[k] * c->P;
         wl[k] = std::lower_bound(w.begin(), w.end(), first, [](int a, long long b) { return (long long)a < b; }) - w.begin();
         sl[k] = std::lower_bound(s.begin(), s.end(), first, [](int a, long long b) { return (long long)a < b; }) - s.begin();
+        ql[k] = std::lower_bound(q.begin(), q.end(), first, [](int a, long long b) { return (long long)a < b; }) - q.begin();
     }
-    wl[0] = 0; sl[0] = 0; wl[n] = c->n_wall; sl[n] = c->n_solid;
+    wl[0] = 0; sl[0] = 0; ql[0] = 0; wl[n] = c->n_wall; sl[n] = c->n_solid; ql[n] = c->n_ssolid;
     // a WALL node must find its mirror node inside its own chunk (same BC state as unchunked)
     for (int k = 0; k < n; ++k)
         for (long long t = wl[k]; t < wl[k + 1]; ++t) {
@@ -207,6 +215,7 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
     h->zb = zb;
     h->wall_lo = wl;
     h->solid_lo = sl;
+    h->ssolid_lo = ql;
     h->wall_split = split;
     return 0;
 }

@@ -337,11 +337,12 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
         // the new buffers.  Same arithmetic as the sequential order of src/pd_ns.cpp:196-205.
         cudaStream_t main_s = c->stream, side = c->stream2;
         const int z_hi = c->R + (c->a1 - c->a0);
+        PD_TRY(pd_enqueue_bc_outlet_prepass(c, src, c->curC));   // before the fork: see outlet.cu
         CUDA_OK(cudaEventRecord(c->ev_a, main_s));
         CUDA_OK(cudaStreamWaitEvent(side, c->ev_a, 0));
         {
             StreamSwap sw(c, side);
-            PD_TRY(pd_enqueue_bc_outlet(c, src, c->curC));
+            PD_TRY(pd_enqueue_bc_outlet_sweep(c, src, c->curC));
             PD_TRY(pd_enqueue_bc_wall(c, src, 2));
         }
         PD_TRY(pd_enqueue_bc_inlet(c, src, c->curC));

@@ -63,18 +63,38 @@ k_outlet_prepass(Lat L, OutletGeom g, const int* __restrict__ list, long long n,
     int q = (int)(l % L.P);
     int jj = (DIM == 3) ? q / L.Nx : 0;
     int ii = q - jj * L.Nx;
+    // sums in CSR order (as the reference); the loads of a batch of neighbours are issued together
     double sv = 0.0, sc = 0.0;
     int c = 0;
-    for (int o = 0; o < n_off; ++o) {
-        long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
-        if (nn < 0) continue;
-        uint8_t tj = type[nn];
-        if (tj == PDGPU_FLUID || (tj == PDGPU_OUTLET && o >= g.n_early)) {
-            sv += vax[nn];
-            sc += C[nn];
-            ++c;
-        } else if (tj == PDGPU_OUTLET) {
-            ++c;   // earlier outlet neighbour: value added by the sweep
+    constexpr int UB = 8;
+    for (int o0 = 0; o0 < n_off; o0 += UB) {
+        double rv[UB], rc[UB];
+        int kind[UB];   // 0 skip, 1 value counted now, 2 earlier OUTLET neighbour (value added by the sweep)
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int o = o0 + u;
+            long long nn = -1;
+            if (o < n_off) {
+                const OffEntry e = off[o];
+                const int ni = ii + e.di;
+                bool in = ni >= 0 && ni < L.Nx;
+                if (DIM == 3) { const int nj = jj + e.dj; in = in && nj >= 0 && nj < L.Ny; }
+                if (in) nn = l + e.lin;
+            }
+            const long long safe = nn >= 0 ? nn : l;
+            const uint8_t tj = type[safe];
+            kind[u] = 0;
+            if (nn >= 0) {
+                if (tj == PDGPU_FLUID || (tj == PDGPU_OUTLET && o >= g.n_early)) kind[u] = 1;
+                else if (tj == PDGPU_OUTLET) kind[u] = 2;
+            }
+            rv[u] = vax[safe];
+            rc[u] = C[safe];
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            if (kind[u] == 1) { sv += rv[u]; sc += rc[u]; ++c; }
+            else if (kind[u] == 2) ++c;
         }
     }
     long long d = l - g.l0;
@@ -517,15 +537,22 @@ int pd_outlet_setup(pdgpu_ctx* c) {
     return 0;
 }
 
-// returns -1 when the fast sweep is not applicable
-int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
-    if (!c->out_fast || c->opt_outlet_kernel == 0) return -1;
-    Lat L = make_lat(c);
+static OutletGeom outlet_geom(const pdgpu_ctx* c) {
     OutletGeom g;
     g.Nx = c->Nx; g.Ny = (c->dim == 3) ? c->Ny : 1; g.KP = c->out_KP; g.Wj = c->out_Wj;
     g.B = c->R + 1; g.B2 = g.B * g.B; g.ring = c->out_ring; g.n_early = c->n_off / 2;
     g.tau_max = c->out_tau_max; g.P = c->P; g.l0 = c->out_l0;
-    double* vax = c->v[buf][c->dim - 1];
+    return g;
+}
+
+// The two halves of the fast outlet BC. Loop bodies that overlap the sweep with the bulk bond kernel
+// run the pre-pass BEFORE they fork, so that the sweep kernel is the first thing the side stream has
+// ready: once the bulk kernel owns every SM the two sweep CTAs (197 KB of shared memory each) only
+// get in when it drains (measured: the whole sweep then runs after the bulk kernel).
+int pd_enqueue_bc_outlet_prepass(pdgpu_ctx* c, int buf, int bufC) {
+    if (!c->out_fast || c->opt_outlet_kernel == 0) return -1;
+    Lat L = make_lat(c);
+    OutletGeom g = outlet_geom(c);
     if (c->dim == 2)
         LAUNCH(c, k_outlet_prepass<2>, nblocks(c->n_outlet, 128), 128, 0, L, g, c->l_outlet, c->n_outlet, c->type,
                c->d_off, c->n_off, c->rho[buf], c->p[buf], VXYZ(c, buf), c->C[bufC], c->cfg.rho_f, c->out_base_v,
@@ -534,6 +561,13 @@ int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
         LAUNCH(c, k_outlet_prepass<3>, nblocks(c->n_outlet, 128), 128, 0, L, g, c->l_outlet, c->n_outlet, c->type,
                c->d_off, c->n_off, c->rho[buf], c->p[buf], VXYZ(c, buf), c->C[bufC], c->cfg.rho_f, c->out_base_v,
                c->out_base_c, c->out_cnt);
+    return 0;
+}
+
+int pd_enqueue_bc_outlet_sweep(pdgpu_ctx* c, int buf, int bufC) {
+    if (!c->out_fast || c->opt_outlet_kernel == 0) return -1;
+    OutletGeom g = outlet_geom(c);
+    double* vax = c->v[buf][c->dim - 1];
     if (c->out_rows_G && c->opt_outlet_kernel >= 3) {
         RowSweepParams q;
         q.g = g; q.RJ = c->out_RJ; q.n_rows = c->out_n_rows; q.M = c->out_rows_M; q.R = c->R; q.n_rcp = c->n_off + 1; q.doubled = (c->out_rows_doubled && !c->opt_outlet_single_rows) ? 1 : 0;
@@ -552,7 +586,13 @@ int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
         LAUNCH(c, k_outlet_sweep_mod, 2, 1024, c->out_smem_mod, g, c->out_RJ, (const int4*)c->out_rows, c->out_n_rows,
                c->out_mask, c->out_mask_words, c->out_base_v, c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
     else
-    LAUNCH(c, k_outlet_sweep, 2, 1024, c->out_smem, g, (const int4*)c->out_early, c->out_mask, c->out_mask_words,
-           c->out_base_v, c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
+        LAUNCH(c, k_outlet_sweep, 2, 1024, c->out_smem, g, (const int4*)c->out_early, c->out_mask, c->out_mask_words,
+               c->out_base_v, c->out_base_c, c->out_cnt, vax, c->C[bufC], c->cfg.U_in);
     return 0;
+}
+
+// returns -1 when the fast sweep is not applicable
+int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC) {
+    if (pd_enqueue_bc_outlet_prepass(c, buf, bufC) < 0) return -1;
+    return pd_enqueue_bc_outlet_sweep(c, buf, bufC);
 }

@@ -47,3 +47,10 @@ for ok, g in ((3, 8), (3, 4), (3, 2), (2, 0)):
         L_.check(L.pdgpu_bc_outlet(grid.ctx))
     L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
     print(f"outlet_kernel={ok} rows_g={g}: apply_outlet_bc {ms.value / 10:.3f} ms")
+for name, fn in (("inlet", L.pdgpu_bc_inlet), ("wall", L.pdgpu_bc_wall), ("solid", L.pdgpu_bc_solid)):
+    L_.check(fn(grid.ctx))
+    L_.check(L.pdgpu_timer_start(grid.ctx))
+    for _ in range(10):
+        L_.check(fn(grid.ctx))
+    L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
+    print(f"apply_{name}_bc {ms.value / 10:.3f} ms (incl. one host sync per call)")
