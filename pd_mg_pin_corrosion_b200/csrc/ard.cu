@@ -66,10 +66,27 @@ __global__ void k_ard_prepass_solids(Lat L, const int* __restrict__ l_solid, lon
     int q = (int)(l % L.P);
     int jj = (DIM == 3) ? q / L.Nx : 0;
     int ii = q - jj * L.Nx;
+    // any FLUID neighbour at or above saturation blocks the node (order-free): loads in batches of 8
     uint8_t blocked = 0;
-    for (int o = 0; o < n_off; ++o) {
-        long long nn = nbr_local(L, off[o], DIM, ii, jj, l, type);
-        if (nn >= 0 && type[nn] == PDGPU_FLUID && C[nn] >= P.C_sat) { blocked = 1; break; }
+    constexpr int UB = 8;
+    for (int o0 = 0; o0 < n_off && !blocked; o0 += UB) {
+        bool hit[UB];
+#pragma unroll
+        for (int u = 0; u < UB; ++u) {
+            const int o = o0 + u;
+            long long nn = -1;
+            if (o < n_off) {
+                const OffEntry e = off[o];
+                const int ni = ii + e.di;
+                bool in = ni >= 0 && ni < L.Nx;
+                if (DIM == 3) { const int nj = jj + e.dj; in = in && nj >= 0 && nj < L.Ny; }
+                if (in) nn = l + e.lin;
+            }
+            const long long safe = nn >= 0 ? nn : l;
+            hit[u] = nn >= 0 && type[safe] == PDGPU_FLUID && C[safe] >= P.C_sat;
+        }
+#pragma unroll
+        for (int u = 0; u < UB; ++u) blocked |= hit[u] ? 1 : 0;
     }
     double ds = 0.0;
     if (!blocked) {
