@@ -53,8 +53,6 @@ struct OffEntry {
     double dist, ex, ey, ez, vol, w1, w2;
 };
 
-constexpr int kMaxLevels = 1 << 20;
-
 // ------------------------------------------------------------------ context ---
 struct pdgpu_ctx {
     PdConfig cfg;
@@ -312,7 +310,6 @@ int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC);
 int pd_max_fluid_speed(pdgpu_ctx* c, double* vmax);
 void pd_invalidate_graphs(pdgpu_ctx* c);
 int pd_refresh_eos(pdgpu_ctx* c, int buf);           // p[buf] = EOS(rho[buf]) on all local nodes
-int pd_refresh_vmag(pdgpu_ctx* c, int buf);
 int pd_enqueue_eos_range(pdgpu_ctx* c, int buf, long long lo, long long n);             // fields.cu
 int pd_enqueue_eos_to(pdgpu_ctx* c, int buf, long long lo, long long n, double* out);
 int pd_enqueue_deinterleave(pdgpu_ctx* c, const double* aos, long long lo, long long n, int buf);

@@ -66,15 +66,6 @@ __global__ void k_eos(const double* __restrict__ rho, double* __restrict__ p, lo
     p[t] = eos_pressure(rho[t], rho0, gamma, B);
 }
 
-template <int DIM>
-__global__ void k_vmag(const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz,
-                       double* __restrict__ vmag, long long n) {
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    double s = vx[t] * vx[t] + vy[t] * vy[t];
-    if (DIM == 3) s += vz[t] * vz[t];
-    vmag[t] = sqrt(s);
-}
 
 // initialize_fields (src/main.cpp:9-127) for every local node, both buffers.
 template <int DIM>
@@ -162,13 +153,6 @@ int pd_enqueue_interleave(pdgpu_ctx* c, double* aos, long long lo, long long n, 
     return 0;
 }
 
-int pd_refresh_vmag(pdgpu_ctx* c, int buf) {
-    if (c->dim == 2)
-        LAUNCH(c, k_vmag<2>, nblocks(c->NL, 256), 256, 0, c->v[buf][0], c->v[buf][1], nullptr, c->vmag, c->NL);
-    else
-        LAUNCH(c, k_vmag<3>, nblocks(c->NL, 256), 256, 0, c->v[buf][0], c->v[buf][1], c->v[buf][2], c->vmag, c->NL);
-    return 0;
-}
 
 // persistent AoS<->SoA staging buffer (grown on demand; no cudaMalloc on the per-step path)
 static int pd_stage(pdgpu_ctx* c, size_t bytes, double** out) {
