@@ -308,7 +308,8 @@ extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
     // every WALL node from FLUID values only), unless nobody evaluates it again: keep it pending
     PD_TRY(pd_set_dt(c, 1, dt));
     PD_TRY(pd_ensure_vmag(c, c->cur));
-    bool use_graph = c->opt_graph && !(c->nranks > 1 && c->comm);
+    // opt_graph >= 2 also captures the bodies of slab contexts (NCCL send/recv inside the graph)
+    bool use_graph = c->opt_graph && (c->opt_graph >= 2 || !(c->nranks > 1 && c->comm));
     for (int it = 0; it < steps; ++it) {
         int buf = c->cur, srcC = c->curC;
         if (!use_graph) {

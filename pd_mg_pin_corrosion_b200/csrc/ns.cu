@@ -378,7 +378,8 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
 static int run_ns_body(pdgpu_ctx* c) {
     int src = c->cur;
     pd_touch_flow(c);
-    bool use_graph = c->opt_graph && !(c->nranks > 1 && c->comm);
+    // opt_graph >= 2 also captures the bodies of slab contexts (NCCL send/recv inside the graph)
+    bool use_graph = c->opt_graph && (c->opt_graph >= 2 || !(c->nranks > 1 && c->comm));
     if (!use_graph) return enqueue_ns_body(c, src);
     // the inlet/outlet BCs of the body also write C of the current concentration buffer
     // (src/boundary.cpp:31-131): one graph per (flow buffer, C buffer)
