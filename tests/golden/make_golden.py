@@ -98,9 +98,8 @@ def steady_fixture() -> None:
     json.dump(res, open(os.path.join(HERE, "steady.json"), "w"), indent=1)
 
 
-def diagnostics_fixture() -> None:
+def diagnostics_fixture(case: str = "2d_dissolve") -> None:
     """Whole run of the reference's own main() on the dissolving synthetic config."""
-    case = "2d_dissolve"
     dim, base, ov = H.CASES[case]
     tmp = tempfile.mkdtemp(prefix="pdgold_")
     ov = dict(ov, use_implicit=0, output_dir=os.path.join(tmp, "out"))
@@ -116,6 +115,7 @@ if __name__ == "__main__":
     for c in ("2d_default", "2d_poiseuille", "2d_offgrid", "3d_small", "3d_offgrid"):
         step_fixture(c)
     diagnostics_fixture()
+    diagnostics_fixture("3d_dissolve")
     vti_fixture()
     if "--steady" in sys.argv:
         steady_fixture()

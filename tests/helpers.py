@@ -28,6 +28,11 @@ CASES = {
     "2d_dissolve": (2, "params.cfg", {"D_grain": 5e-11, "D_gb": 5e-9, "C_thresh": 0.999,
                                       "corrosion_steps_per_check": 50, "flow_max_iters": 300, "T_final": 6e-4,
                                       "output_every_corr": 10}),
+    # the same in 3D on the small tube: whole-run parity with phase change + table rebuilds in 3D
+    "3d_dissolve": (3, "params.cfg", {"R_tube": 60e-6, "R_wire": 20e-6, "L_wire": 60e-6, "L_upstream": 40e-6,
+                                      "L_downstream": 40e-6, "grain_size_mean": 20e-6, "D_grain": 5e-11, "D_gb": 5e-9,
+                                      "Q_flow": 1.667e-10, "C_thresh": 0.99999, "corrosion_steps_per_check": 40,
+                                      "flow_max_iters": 400, "T_final": 6e-3, "output_every_corr": 10}),
 }
 
 

@@ -125,13 +125,15 @@ def test_port_phase_change_vs_reference():
     assert (p.node_type == 1).sum() < 1280
 
 
-def test_port_coupled_run_matches_reference_diagnostics():
+@pytest.mark.parametrize("case,geom", [("2d_dissolve", "2d_default"), ("3d_dissolve", "3d_small")])
+def test_port_coupled_run_matches_reference_diagnostics(case, geom):
     """Whole explicit coupling run (src/coupling.cpp:82-302) driven over the plain-C oracle:
     every numeric column of diagnostics.csv within 1e-6 relative of the reference's own run
-    (tests/golden/diagnostics_2d_dissolve.csv, written by the reference's main())."""
-    gold = np.loadtxt(os.path.join(GOLD, "diagnostics_2d_dissolve.csv"), delimiter=",", skiprows=1)
-    z, _ = load_gold("2d_default")   # same geometry / grains as 2d_dissolve
-    rows = H.port_coupled_run("2d_dissolve", np.unpackbits(z["is_gb"])[:19229], np.unpackbits(z["is_precip"])[:19229])
+    (tests/golden/diagnostics_<case>.csv, written by the reference's main())."""
+    gold = np.loadtxt(os.path.join(GOLD, f"diagnostics_{case}.csv"), delimiter=",", skiprows=1)
+    z, _ = load_gold(geom)   # same geometry / grains
+    n = int(z["dims"][3])
+    rows = H.port_coupled_run(case, np.unpackbits(z["is_gb"])[:n], np.unpackbits(z["is_precip"])[:n])
     rows = np.array(rows)
     assert rows.shape == gold.shape
     assert np.array_equal(rows[:, 3], gold[:, 3])                     # solid_nodes exact

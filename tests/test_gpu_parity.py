@@ -327,24 +327,26 @@ def test_step_host_chunked_is_bit_identical(case, extra, n_chunks, expect):
         assert H.rel_err(st["C"][outlet], ref.get("C")[outlet]) <= 1e-11
 
 
-def test_host_driver_whole_run_diagnostics(tmp_path):
-    """host/pd_corrosion_gpu (C++17 driver over the C ABI) on the dissolving synthetic config:
+@pytest.mark.parametrize("case", ["2d_dissolve", "3d_dissolve"])
+def test_host_driver_whole_run_diagnostics(case, tmp_path):
+    """host/pd_corrosion_gpu (C++17 driver over the C ABI) on the dissolving synthetic configs:
     every numeric column of diagnostics.csv within 1e-6 relative of the reference's own main()
-    (tests/golden/diagnostics_2d_dissolve.csv); solid-node counts exact."""
+    (tests/golden/diagnostics_<case>.csv); solid-node counts exact (the 3D case dissolves 61 nodes in two
+    checks and re-solves the flow in between)."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "host", "pd_corrosion_gpu")
     if not os.path.exists(exe):
         subprocess.check_call(["make", "-C", os.path.join(root, "host")])
-    dim, base, ov = H.CASES["2d_dissolve"]
+    dim, base, ov = H.CASES[case]
     ov = dict(ov, use_implicit=0, output_dir=str(tmp_path / "out"))
     from oracle import refapi
     cfg_path = refapi.write_cfg(base, ov, str(tmp_path / "run.cfg"))
-    r = subprocess.run([exe, cfg_path, "--dim", "2"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, cfg_path, "--dim", str(dim), "--no-vti"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     got = np.loadtxt(str(tmp_path / "out" / "diagnostics.csv"), delimiter=",", skiprows=1)
-    gold = np.loadtxt(os.path.join(root, "tests", "golden", "diagnostics_2d_dissolve.csv"), delimiter=",", skiprows=1)
+    gold = np.loadtxt(os.path.join(root, "tests", "golden", f"diagnostics_{case}.csv"), delimiter=",", skiprows=1)
     assert got.shape == gold.shape
     assert np.array_equal(got[:, 3], gold[:, 3])
     for col in (0, 1, 2, 4, 5):
@@ -410,7 +412,7 @@ def test_python_coupled_solver_whole_run(tmp_path):
     cs.log = lambda *a, **k: None
     cs.run(grid, fields, cfg)
     got = np.loadtxt(str(tmp_path / "out" / "diagnostics.csv"), delimiter=",", skiprows=1)
-    gold = np.loadtxt(os.path.join(root, "tests", "golden", "diagnostics_2d_dissolve.csv"), delimiter=",", skiprows=1)
+    gold = np.loadtxt(os.path.join(root, "tests", "golden", f"diagnostics_{case}.csv"), delimiter=",", skiprows=1)
     assert got.shape == gold.shape and np.array_equal(got[:, 3], gold[:, 3])
     for col in (0, 1, 2, 4, 5):
         rel = np.abs(got[:, col] - gold[:, col]) / np.maximum(np.abs(gold[:, col]), 1e-300)
