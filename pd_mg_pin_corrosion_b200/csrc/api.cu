@@ -196,6 +196,7 @@ extern "C" int pdgpu_set_option(pdgpu_ctx* c, const char* name, int value) {
     else if (n == "outlet_kernel") c->opt_outlet_kernel = value;
     else if (n == "overlap") c->opt_overlap = value;
     else if (n == "outlet_single_rows") c->opt_outlet_single_rows = value;
+    else if (n == "host_step_graded") c->opt_host_step_graded = value;
     else if (n == "outlet_rows_g") {
         c->opt_outlet_rows_g = value;
         if (c->grid_built && pd_outlet_setup(c)) return 1;

@@ -162,6 +162,7 @@ struct pdgpu_ctx {
     int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)
     int opt_lazy_wallc = 1;         // evaluate the wall-concentration BC only when somebody reads WALL C
     int opt_overlap = 1;            // run the outlet sweep on a side stream next to the bulk kernel
+    int opt_host_step_graded = 1;   // pdgpu_step_host: thin chunks at both ends of the slab, thick ones in the middle
     int opt_outlet_rows_g = 0;      // lanes per lattice row of the row-walking sweep: 0 = default (4 if it fits), else 2, 4 or 8
     int opt_outlet_single_rows = 0; // force the single-row ring of the row-walking sweep (tests; large cross-sections use it anyway)
     int opt_outlet_kernel = 3;      // 0 = level-list kernel, 1 = level-addressed ring, 2 = lattice-addressed ring, 3 = row-walking

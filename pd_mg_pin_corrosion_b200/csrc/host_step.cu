@@ -151,13 +151,27 @@ int build_plan(pdgpu_ctx* c, HostStep* h, int n_req) {
     }
     zt = lo + (zt - lo) / TZ * TZ;
     if (zt - lo < 2 * c->R + TZ || hi - zt <= c->R) return fallback(h, "domain too short for two chunks");
-    // lower chunks: equal thickness, tile aligned
+    // lower chunks, tile aligned: graded thickness -- thin at both ends (the first download can start
+    // after two thin chunks, the drain after the last upload is two thin chunks), thick in the middle
+    // (fewer, larger copies and kernel launches). Weights 1,1,2,2,3,4,4,... from either end.
     int n_low = std::max(1, std::min(n_req - 1, (zt - lo) / std::max(2 * c->R + TZ, TZ)));
     std::vector<int> zb;
     zb.push_back(lo);
-    for (int k = 1; k < n_low; ++k) {
-        int z = lo + (int)((long long)(zt - lo) * k / n_low) / TZ * TZ;
-        if (z - zb.back() >= 2 * c->R + TZ && zt - z >= 2 * c->R + TZ) zb.push_back(z);
+    {
+        static const int ramp[] = {1, 1, 2, 2, 3};
+        std::vector<double> wgt(n_low);
+        double tot = 0.0;
+        for (int k = 0; k < n_low; ++k) {
+            const int e = std::min(k, n_low - 1 - k);   // distance from the nearer end
+            wgt[k] = (c->opt_host_step_graded && n_low >= 8) ? (e < 5 ? ramp[e] : 4) : 1;
+            tot += wgt[k];
+        }
+        double acc = 0.0;
+        for (int k = 1; k < n_low; ++k) {
+            acc += wgt[k - 1];
+            int z = lo + (int)((double)(zt - lo) * acc / tot) / TZ * TZ;
+            if (z - zb.back() >= 2 * c->R + TZ && zt - z >= 2 * c->R + TZ) zb.push_back(z);
+        }
     }
     zb.push_back(zt);
     zb.push_back(hi);
