@@ -334,11 +334,47 @@ def diagnostics(grid: Grid) -> _l.PdDiag:
     return d
 
 
-class CoupledSolver:
-    """CoupledSolver::run, explicit branch (src/coupling.cpp:82-302). VTI output is host IO and
-    out of scope; diagnostics.csv / mass_loss.csv are written exactly as the reference does."""
+class VTKWriter:
+    """VTKWriter (src/vtk_writer.h): write() is pdgpu_vti_write -- the snapshot text is formatted on the
+    device, byte-identical to the reference's file; the PVD collection is rewritten after every entry."""
 
     def __init__(self):
+        self.pvd_entries: list[tuple[float, str]] = []
+        self.pvd_path = ""
+
+    def write(self, filename: str, grid: Grid, fields: "Fields", cfg: Config) -> None:
+        gid = None if fields.grain_id is None else np.ascontiguousarray(fields.grain_id, np.int32)
+        dmap = None if fields.D_map is None else np.ascontiguousarray(fields.D_map, np.float64)
+        _l.check(_l.load().pdgpu_vti_write(grid.ctx, filename.encode(), None if gid is None else _ptr(gid),
+                                           None if dmap is None else _ptr(dmap), None, None))
+
+    def set_pvd_path(self, path: str) -> None:
+        self.pvd_path = path
+
+    def add_timestep(self, time: float, vti_file: str) -> None:
+        self.pvd_entries.append((time, vti_file))
+        if self.pvd_path:
+            self.write_pvd(self.pvd_path)
+
+    def write_pvd(self, filename: str) -> None:   # src/vtk_writer.cpp:157-186
+        pvd_dir = filename[:filename.rfind("/") + 1] if "/" in filename else ""
+        with open(filename, "w") as out:
+            out.write('<?xml version="1.0"?>\n<VTKFile type="Collection" version="1.0" byte_order="LittleEndian">\n'
+                      "  <Collection>\n")
+            for t, f in self.pvd_entries:
+                rel = f[len(pvd_dir):] if pvd_dir and f.startswith(pvd_dir) else f
+                out.write(f'    <DataSet timestep="{t:.6e}" file="{rel}"/>\n')
+            out.write("  </Collection>\n</VTKFile>\n")
+
+
+class CoupledSolver:
+    """CoupledSolver::run, explicit branch (src/coupling.cpp:82-302): diagnostics.csv / mass_loss.csv
+    and (write_vti = True) the state_/flow_/corr_/final_ VTI series + PVD files as the reference writes
+    them."""
+
+    def __init__(self):
+        self.write_vti = False
+        self.writer, self.flow_writer, self.frame_count = VTKWriter(), VTKWriter(), 0
         self.flow_solver = PD_NS_Solver()
         self.ard_solver = PD_ARD_Solver()
         self.initial_solid_indices = np.zeros(0, np.int32)
@@ -369,9 +405,20 @@ class CoupledSolver:
         with open(os.path.join(cfg.output_dir, "mass_loss.csv"), "a") as f:
             f.write(f"{t_corr / 3600.0:.6f},{loss:.6f}\n")
 
+    def _snapshot(self, grid, fields, cfg, prefix: str, t: float, series: VTKWriter, count: bool = True) -> None:
+        if not self.write_vti:
+            return
+        fname = f"{cfg.output_dir}/{prefix}_{self.frame_count:06d}_t{t:.1f}s.vti"   # src/coupling.cpp:10-18
+        series.write(fname, grid, fields, cfg)
+        series.add_timestep(t, fname)
+        if count:
+            self.frame_count += 1
+
     def run(self, grid: Grid, fields: Fields, cfg: Config) -> float:
         cfg.check_supported()
         os.makedirs(cfg.output_dir, exist_ok=True)
+        self.writer.set_pvd_path(cfg.output_dir + "/simulation.pvd")
+        self.flow_writer.set_pvd_path(cfg.output_dir + "/flow.pvd")
         with open(os.path.join(cfg.output_dir, "diagnostics.csv"), "w") as f:
             f.write("time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n")
         with open(os.path.join(cfg.output_dir, "mass_loss.csv"), "w") as f:
@@ -382,6 +429,7 @@ class CoupledSolver:
         self.flow_solver.init(grid, cfg)
         self.ard_solver.init(grid, cfg)
         self.log("Using EXPLICIT ARD solver")
+        self._snapshot(grid, fields, cfg, "state", 0.0, self.writer)
         t_corr, cycle, need_flow_solve = 0.0, 0, True
         self.dissolved_since_flow = 0
         while t_corr < cfg.T_final:
@@ -391,6 +439,7 @@ class CoupledSolver:
                 self.flow_solver.solve_steady(fields, grid, cfg, verbose=self.log is print)
                 self.dissolved_since_flow = 0
                 need_flow_solve = False
+                self._snapshot(grid, fields, cfg, "flow", t_corr, self.flow_writer)
             vol_loss = 1.0 - self._solid_C_sum(fields) / (n0 + 1e-30)
             self.ard_solver.set_volume_loss(max(vol_loss, 0.0), grid)
             dt_corr = self.ard_solver.compute_dt(fields, grid, cfg)
@@ -412,6 +461,7 @@ class CoupledSolver:
                     t_corr += dt_corr
                 step += done
                 if step % cfg.output_every_corr == 0:
+                    self._snapshot(grid, fields, cfg, "corr", t_corr, self.writer)
                     self.write_diagnostics(grid, fields, t_corr, cfg)
                 if t_corr >= cfg.T_final:
                     break
@@ -426,5 +476,6 @@ class CoupledSolver:
             if diagnostics(grid).solid_count == 0:
                 self.log(f"\n=== All solid nodes dissolved at t={t_corr:.1f} s ===")
                 break
+        self._snapshot(grid, fields, cfg, "final", t_corr, self.writer, count=False)
         self.log("\n=== Simulation complete ===")
         return t_corr

@@ -395,13 +395,16 @@ def test_host_driver_output_files_match_reference(tmp_path):
                 assert np.allclose(xs, ys, rtol=2e-5, atol=1e-10), (f, x, y)   # fields agree to 1e-12 of their maximum
 
 
-def test_python_coupled_solver_whole_run(tmp_path):
-    """solver.CoupledSolver.run (Python mirror of the coupling loop) against the same golden CSV."""
+@pytest.mark.parametrize("case", ["2d_dissolve", "3d_dissolve"])
+def test_python_coupled_solver_whole_run(case, tmp_path):
+    """solver.CoupledSolver.run (Python mirror of the coupling loop) against the same golden CSV; with
+    write_vti it produces one state_, one final_ and a corr_ snapshot per diagnostics row."""
+    import glob
     import os
     from pd_mg_pin_corrosion_b200 import solver as S
     from pd_mg_pin_corrosion_b200.grains import GrainStructure
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    dim, cfg, _ = H.load_cfg("2d_dissolve", {"output_dir": str(tmp_path / "out")})
+    dim, cfg, _ = H.load_cfg(case, {"output_dir": str(tmp_path / "out")})
     grid = S.Grid(dim)
     grid.build(cfg)
     grains = GrainStructure().generate(grid.node_type, cfg, dim)
@@ -410,8 +413,16 @@ def test_python_coupled_solver_whole_run(tmp_path):
     S.initialize_fields(fields, grid, grains, cfg)
     cs = S.CoupledSolver()
     cs.log = lambda *a, **k: None
+    cs.write_vti = (case == "2d_dissolve")
     cs.run(grid, fields, cfg)
     got = np.loadtxt(str(tmp_path / "out" / "diagnostics.csv"), delimiter=",", skiprows=1)
+    if cs.write_vti:
+        names = sorted(os.path.basename(f) for f in glob.glob(str(tmp_path / "out" / "*.vti")))
+        assert sum(n.startswith("corr_") for n in names) == got.shape[0]
+        assert sum(n.startswith("state_") for n in names) == 1 and sum(n.startswith("final_") for n in names) == 1
+        assert sum(n.startswith("flow_") for n in names) >= 1
+        pvd = (tmp_path / "out" / "simulation.pvd").read_text()
+        assert pvd.count("<DataSet") == got.shape[0] + 2
     gold = np.loadtxt(os.path.join(root, "tests", "golden", f"diagnostics_{case}.csv"), delimiter=",", skiprows=1)
     assert got.shape == gold.shape and np.array_equal(got[:, 3], gold[:, 3])
     for col in (0, 1, 2, 4, 5):
