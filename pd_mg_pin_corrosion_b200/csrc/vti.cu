@@ -269,6 +269,14 @@ struct TextBuf {
         cudaFree(len); cudaFree(pos); cudaFree(text); cudaFree(flag);
         text = nullptr; len = flag = nullptr; pos = nullptr;
     }
+    ~TextBuf() { release(); }   // every exit path of the callers frees the device buffers
+};
+
+// device scratch array that is freed on every exit path
+template <typename T>
+struct DevArray {
+    T* p = nullptr;
+    ~DevArray() { cudaFree(p); }
 };
 
 int upload_table(pdgpu_ctx* c) {
@@ -361,10 +369,12 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
     const long long n = c->own_hi - c->own_lo, lo = c->own_lo;
     TextBuf b;
     PD_TRY(alloc_buf(&b, n));
-    int* d_gid = nullptr;
-    double* d_dmap = nullptr;
-    CUDA_OK(cudaMalloc(&d_gid, sizeof(int) * n));
-    CUDA_OK(cudaMalloc(&d_dmap, sizeof(double) * n));
+    DevArray<int> gid_buf;
+    DevArray<double> dmap_buf, press_buf;
+    CUDA_OK(cudaMalloc(&gid_buf.p, sizeof(int) * n));
+    CUDA_OK(cudaMalloc(&dmap_buf.p, sizeof(double) * n));
+    int* d_gid = gid_buf.p;
+    double* d_dmap = dmap_buf.p;
     if (grain_id) CUDA_OK(cudaMemcpyAsync(d_gid, grain_id, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     else CUDA_OK(cudaMemsetAsync(d_gid, 0xFF, sizeof(int) * n, c->stream));
     if (D_map) CUDA_OK(cudaMemcpyAsync(d_dmap, D_map, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
@@ -372,12 +382,12 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
     // `pressure` is written as the reference computes it, B (pow(rho/rho_f, gamma) - 1) of the density the
     // last step started from (src/pd_ns.cpp:36-50,84), not from the Horner-evaluated shadow field the
     // tiled kernels keep (same value to ~1e-10 relative, which is visible in the 6th digit now and then)
-    double* d_press = nullptr;
-    CUDA_OK(cudaMalloc(&d_press, sizeof(double) * n));
+    CUDA_OK(cudaMalloc(&press_buf.p, sizeof(double) * n));
+    double* d_press = press_buf.p;
     PD_TRY(pd_enqueue_eos_to(c, c->p_input, lo, n, d_press));
 
     const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) { b.release(); cudaFree(d_gid); cudaFree(d_dmap); cudaFree(d_press); PD_FAIL("cannot open VTI file '%s'", path); }
+    if (fd < 0) PD_FAIL("cannot open VTI file '%s'", path);
     const int nx = c->Nx, ny = c->Ny, nz = (c->dim == 3) ? c->Nz : 1;
     std::string head;
     {   // header, formatted by the same iostream rules as the reference (src/vtk_writer.cpp:40-53)
@@ -452,8 +462,6 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
     ::close(fd);
     if (!rc && run.failed()) { rc = 1; pd_set_error("pdgpu_vti_write: writing '%s' failed", path); }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    b.release();
-    cudaFree(d_gid); cudaFree(d_dmap); cudaFree(d_press);
     if (rc) return rc;
     if (flag) PD_FAIL("pdgpu_vti_write: a rounding decision could not be proven");
     if (bytes_out) *bytes_out = total_bytes;
