@@ -1,6 +1,6 @@
 // ard_tile.cu -- tiled fast path of the explicit PD-ARD bond kernel (3D, m_ratio = 3, full rows).
 //
-// Same staging scheme as ns_tile.cu (38 x 14 x 10 haloed block, 4 z-nodes per thread, sliding
+// Same staging scheme as ns_tile.cu (22 x 14 x 14 haloed block, 2 z-nodes per thread, sliding
 // z-window, runtime column loop: tile.cuh).  Staged per node:
 //     C      concentration
 //     w      packed weight (ard.cu, k_ard_vmag): own fluid-fluid diffusivity D_l + alpha dx |v| >= +0
