@@ -75,6 +75,70 @@ void PvdSeries::add_timestep(double time, const std::string& file) {   // src/vt
     std::printf("  Wrote PVD file: %s (%zu timesteps)\n", path_.c_str(), entries_.size());
 }
 
+// ---- driver checkpoint: plain binary, same machine ------------------------------------------------
+template <typename T>
+static void put(std::ostream& o, const T& v) { o.write((const char*)&v, sizeof(T)); }
+template <typename T>
+static void get(std::istream& i, T& v) { i.read((char*)&v, sizeof(T)); }
+
+void PvdSeries::save(std::ostream& out) const {
+    put(out, (long long)entries_.size());
+    for (auto& e : entries_) {
+        put(out, e.first);
+        put(out, (long long)e.second.size());
+        out.write(e.second.data(), (std::streamsize)e.second.size());
+    }
+}
+void PvdSeries::load(std::istream& in) {
+    long long n = 0;
+    get(in, n);
+    entries_.clear();
+    for (long long k = 0; k < n; ++k) {
+        double t; long long len;
+        get(in, t); get(in, len);
+        std::string f((size_t)len, '\0');
+        in.read(&f[0], (std::streamsize)len);
+        entries_.push_back({t, f});
+    }
+}
+
+void CoupledSolver::save_driver_state(const std::string& path, const HostState& st, double t_corr, int cycle,
+                                      bool need_flow) const {
+    std::ofstream o(path, std::ios::binary | std::ios::trunc);
+    const char magic[8] = {'P', 'D', 'D', 'R', 'V', 'C', 'K', '1'};
+    o.write(magic, 8);
+    put(o, t_corr); put(o, cycle); put(o, (int)need_flow); put(o, frame_count_); put(o, total_dissolved_);
+    put(o, dissolved_since_flow_);
+    put(o, (long long)initial_solid_indices_.size());
+    o.write((const char*)initial_solid_indices_.data(), (std::streamsize)(sizeof(int) * initial_solid_indices_.size()));
+    put(o, st.N);
+    o.write((const char*)st.node_type.data(), (std::streamsize)st.N);
+    o.write((const char*)st.D_map.data(), (std::streamsize)(sizeof(double) * st.N));
+    writer_.save(o);
+    flow_writer_.save(o);
+}
+
+bool CoupledSolver::load_driver_state(const std::string& path, HostState& st, double* t_corr, int* cycle, bool* need_flow) {
+    std::ifstream in(path, std::ios::binary);
+    char magic[8];
+    if (!in.read(magic, 8) || std::string(magic, 8) != "PDDRVCK1") return false;
+    int nf = 0;
+    long long n = 0, N = 0;
+    get(in, *t_corr); get(in, *cycle); get(in, nf); get(in, frame_count_); get(in, total_dissolved_);
+    get(in, dissolved_since_flow_);
+    *need_flow = nf != 0;
+    get(in, n);
+    initial_solid_indices_.resize((size_t)n);
+    in.read((char*)initial_solid_indices_.data(), (std::streamsize)(sizeof(int) * n));
+    get(in, N);
+    if (N != st.N) return false;
+    in.read((char*)st.node_type.data(), (std::streamsize)N);
+    in.read((char*)st.D_map.data(), (std::streamsize)(sizeof(double) * N));
+    writer_.load(in);
+    flow_writer_.load(in);
+    return (bool)in;
+}
+
 void CoupledSolver::snapshot(pdgpu_ctx* ctx, const HostState& st, const HostConfig& cfg, const char* prefix, double t,
                              PvdSeries& series, bool count_frame) {
     if (!write_vti) return;
@@ -88,23 +152,34 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
     mkdir(cfg.output_dir.c_str(), 0755);
     writer_.set_path(cfg.output_dir + "/simulation.pvd");
     flow_writer_.set_path(cfg.output_dir + "/flow.pvd");
-    {
+    const bool resuming = !resume_prefix.empty();
+    if (!resuming) {
         std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::trunc);
         csv << "time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n";
         std::ofstream ml(cfg.output_dir + "/mass_loss.csv", std::ios::trunc);
         ml << "time_h,pin_mass_loss_pct\n";
     }
-    initial_solid_indices_.clear();
-    for (long long i = 0; i < st.N; ++i)
-        if (st.node_type[i] == PDGPU_SOLID_MG) initial_solid_indices_.push_back((int)i);
-    const double n0 = (double)initial_solid_indices_.size();
-    std::printf("Initial solid nodes: %zu\nUsing EXPLICIT ARD solver\n", initial_solid_indices_.size());
-
-    snapshot(ctx, st, cfg, "state", 0.0, writer_, true);   // :117-122
     double t_corr = 0.0;
     int cycle = 0;
     bool need_flow_solve = true;
     dissolved_since_flow_ = 0;
+    if (resuming) {
+        if (!load_driver_state(resume_prefix + ".drv", st, &t_corr, &cycle, &need_flow_solve)) {
+            std::fprintf(stderr, "cannot read driver checkpoint %s.drv\n", resume_prefix.c_str());
+            std::exit(2);
+        }
+        PD(pdgpu_checkpoint_load(ctx, (resume_prefix + ".pdck").c_str()));
+        std::printf("Resumed from %s: cycle %d, t=%.6e s, %zu initial solid nodes\n", resume_prefix.c_str(), cycle, t_corr,
+                    initial_solid_indices_.size());
+    } else {
+        initial_solid_indices_.clear();
+        for (long long i = 0; i < st.N; ++i)
+            if (st.node_type[i] == PDGPU_SOLID_MG) initial_solid_indices_.push_back((int)i);
+    }
+    const double n0 = (double)initial_solid_indices_.size();
+    std::printf("Initial solid nodes: %zu\nUsing EXPLICIT ARD solver\n", initial_solid_indices_.size());
+
+    if (!resuming) snapshot(ctx, st, cfg, "state", 0.0, writer_, true);   // :117-122
     std::vector<int> dissolved(std::max<size_t>(initial_solid_indices_.size(), 1));
     while (t_corr < cfg.T_final) {
         ++cycle;
@@ -162,6 +237,14 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
             need_flow_solve = true;   // neighbour tables were rebuilt inside pdgpu_phase_change
         } else {
             std::printf("  No phase changes this cycle\n");
+        }
+        if (checkpoint_every > 0 && !checkpoint_prefix.empty() && cycle % checkpoint_every == 0) {
+            char tag[32];
+            std::snprintf(tag, sizeof(tag), "_c%04d", cycle);
+            const std::string base = checkpoint_prefix + tag;
+            PD(pdgpu_checkpoint_save(ctx, (base + ".pdck").c_str(), nullptr));
+            save_driver_state(base + ".drv", st, t_corr, cycle, need_flow_solve);
+            std::printf("  Checkpoint written: %s.pdck / .drv\n", base.c_str());
         }
         PdDiag d;
         PD(pdgpu_diag(ctx, &d));

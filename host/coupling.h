@@ -2,6 +2,7 @@
 // triggers and CSV output as the reference's CoupledSolver::run (src/coupling.cpp:82-302,
 // explicit branch :217-253), with the solvers living on the device.
 #pragma once
+#include <iosfwd>
 #include <string>
 #include <utility>
 #include <vector>
@@ -27,6 +28,8 @@ class PvdSeries {
 public:
     void set_path(const std::string& p) { path_ = p; }
     void add_timestep(double time, const std::string& file);
+    void save(std::ostream& out) const;   // driver checkpoint
+    void load(std::istream& in);
 private:
     std::string path_;
     std::vector<std::pair<double, std::string>> entries_;
@@ -36,6 +39,12 @@ class CoupledSolver {
 public:
     // returns the final corrosion time
     double run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, bool verbose = true);
+    // Restart (new; the reference cannot resume): after every `checkpoint_every` coupling cycles the device
+    // state (pdgpu_checkpoint_save) and the loop state of this driver are written to
+    // <checkpoint_prefix>_c<cycle>.pdck / .drv; `resume_prefix` continues such a pair. A resumed run appends to
+    // diagnostics.csv / mass_loss.csv and produces the rows the uninterrupted run produces.
+    std::string checkpoint_prefix, resume_prefix;
+    int checkpoint_every = 0;
     bool write_vti = true;   // state_/flow_/corr_/final_ snapshots + simulation.pvd / flow.pvd (src/coupling.cpp:117-147,242-246,292-296)
 
 private:
@@ -48,4 +57,6 @@ private:
                   PvdSeries& series, bool count_frame);
     PvdSeries writer_, flow_writer_;
     int frame_count_ = 0;
+    void save_driver_state(const std::string& path, const HostState& st, double t_corr, int cycle, bool need_flow) const;
+    bool load_driver_state(const std::string& path, HostState& st, double* t_corr, int* cycle, bool* need_flow);
 };

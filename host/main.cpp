@@ -2,6 +2,7 @@
 // libpdgpu.so. The dimension is a run-time argument instead of the PD_DIM compile-time switch.
 //
 //   pd_corrosion_gpu [config/params.cfg] [--dim 2|3] [--device N] [--dump fields.bin] [--no-vti]
+//                    [--checkpoint prefix --checkpoint-every N] [--resume prefix_cNNNN]
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -25,11 +26,16 @@ int main(int argc, char** argv) {
     std::string cfg_path = "configs/params.cfg", dump;
     int dim = 2, device = 0;
     bool no_vti = false;
+    std::string ck_prefix, resume;
+    int ck_every = 0;
     for (int a = 1; a < argc; ++a) {
         if (!std::strcmp(argv[a], "--dim") && a + 1 < argc) dim = std::atoi(argv[++a]);
         else if (!std::strcmp(argv[a], "--device") && a + 1 < argc) device = std::atoi(argv[++a]);
         else if (!std::strcmp(argv[a], "--dump") && a + 1 < argc) dump = argv[++a];
         else if (!std::strcmp(argv[a], "--no-vti")) no_vti = true;
+        else if (!std::strcmp(argv[a], "--checkpoint") && a + 1 < argc) ck_prefix = argv[++a];
+        else if (!std::strcmp(argv[a], "--checkpoint-every") && a + 1 < argc) ck_every = std::atoi(argv[++a]);
+        else if (!std::strcmp(argv[a], "--resume") && a + 1 < argc) resume = argv[++a];
         else cfg_path = argv[a];
     }
     std::printf("=== Peridynamic Mg-Pin Corrosion Simulation (B200 path) ===\n  Dimension: %dD\n\n", dim);
@@ -81,6 +87,7 @@ int main(int argc, char** argv) {
 
     CoupledSolver solver;
     solver.write_vti = !no_vti;
+    solver.checkpoint_prefix = ck_prefix; solver.checkpoint_every = ck_every; solver.resume_prefix = resume;
     auto t1 = std::chrono::steady_clock::now();
     solver.run(ctx, st, cfg);
     std::printf("  [Timer] total_simulation: %.3f s\n",

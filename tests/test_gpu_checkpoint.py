@@ -64,3 +64,30 @@ def test_checkpoint_rejects_other_configuration(tmp_path):
     (tmp_path / "junk").write_bytes(b"not a checkpoint")
     assert L.pdgpu_checkpoint_load(grid.ctx, str(tmp_path / "junk").encode()) != 0
     grid.close()
+
+
+def test_host_driver_resume_reproduces_the_tail_of_the_run(tmp_path):
+    """host/pd_corrosion_gpu --checkpoint/--resume: the rows a resumed run appends to diagnostics.csv are,
+    character for character, the rows the uninterrupted run wrote after that cycle."""
+    import os
+    import subprocess
+    from oracle import refapi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "pd_corrosion_gpu")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "host")])
+    dim, base, ov = H.CASES["2d_dissolve"]
+    ck = str(tmp_path / "ck")
+    cfg_a = refapi.write_cfg(base, dict(ov, use_implicit=0, output_dir=str(tmp_path / "a")), str(tmp_path / "a.cfg"))
+    r = subprocess.run([exe, cfg_a, "--dim", "2", "--no-vti", "--checkpoint", ck, "--checkpoint-every", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows_a = (tmp_path / "a" / "diagnostics.csv").read_text().splitlines()[1:]
+    per_cycle = ov["corrosion_steps_per_check"] // ov["output_every_corr"]
+    assert len(rows_a) >= 3 * per_cycle and os.path.exists(ck + "_c0002.pdck")
+    cfg_b = refapi.write_cfg(base, dict(ov, use_implicit=0, output_dir=str(tmp_path / "b")), str(tmp_path / "b.cfg"))
+    r = subprocess.run([exe, cfg_b, "--dim", "2", "--no-vti", "--resume", ck + "_c0002"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    rows_b = (tmp_path / "b" / "diagnostics.csv").read_text().splitlines()
+    assert rows_b == rows_a[2 * per_cycle:]
