@@ -86,6 +86,10 @@ def main():
     uid = uid.cuda()
     dist.broadcast(uid, 0)
     L_.check(L.pdgpu_comm_init(grid.ctx, bytes(uid.cpu().tolist()), rank, world))
+    for opt in os.environ.get("PDGPU_OPTIONS", "").split(","):   # e.g. PDGPU_OPTIONS=graph=2
+        if "=" in opt:
+            k, v = opt.split("=")
+            grid.set_option(k.strip(), int(v))
     mine = run(grid, cfg, iters, steps, cycles, host_chunks)
     a0, a1, P = grid.a0, grid.a1, grid.plane
     # gather the owned parts on rank 0
