@@ -156,7 +156,7 @@ struct pdgpu_ctx {
     long long launches = 0;
 
     // options
-    int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled, 2 = z-marching tiles, 3 = materialised CSR
+    int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled, 2 = z-marching tiles, 3 = materialised CSR, 4 = split (pressure / rest)
     int opt_ard_kernel = 1;
     int opt_graph = 1;
     int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)

@@ -256,6 +256,8 @@ def test_kernel_variants_agree(case):
         dict(ns_kernel=2, ard_kernel=1, outlet_kernel=2, overlap=1, graph=1),   # z-marching NS kernel
         dict(ns_kernel=2, ard_kernel=2, outlet_kernel=2, overlap=0, graph=0),
         dict(ns_kernel=3, ard_kernel=3, outlet_kernel=2, overlap=1, graph=1),   # materialised-CSR path
+        dict(ns_kernel=4, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1),   # split NS kernel (pressure / rest)
+        dict(ns_kernel=4, ard_kernel=1, outlet_kernel=3, overlap=0, graph=0),
     ]
     dt = ref.ns_compute_dt()
     results = []
