@@ -93,9 +93,11 @@ void PvdSeries::load(std::istream& in) {
     long long n = 0;
     get(in, n);
     entries_.clear();
+    if (!in || n < 0 || n > (1LL << 24)) { in.setstate(std::ios::failbit); return; }   // corrupt file
     for (long long k = 0; k < n; ++k) {
-        double t; long long len;
+        double t = 0.0; long long len = 0;
         get(in, t); get(in, len);
+        if (!in || len < 0 || len > 4096) { in.setstate(std::ios::failbit); return; }   // a file name, not a blob
         std::string f((size_t)len, '\0');
         in.read(&f[0], (std::streamsize)len);
         entries_.push_back({t, f});
@@ -104,7 +106,9 @@ void PvdSeries::load(std::istream& in) {
 
 void CoupledSolver::save_driver_state(const std::string& path, const HostState& st, double t_corr, int cycle,
                                       bool need_flow) const {
-    std::ofstream o(path, std::ios::binary | std::ios::trunc);
+    // temporary name + rename: the .drv file appears only complete, and after its .pdck partner
+    const std::string tmp = path + ".tmp";
+    std::ofstream o(tmp, std::ios::binary | std::ios::trunc);
     const char magic[8] = {'P', 'D', 'D', 'R', 'V', 'C', 'K', '1'};
     o.write(magic, 8);
     put(o, t_corr); put(o, cycle); put(o, (int)need_flow); put(o, frame_count_); put(o, total_dissolved_);
@@ -116,6 +120,9 @@ void CoupledSolver::save_driver_state(const std::string& path, const HostState& 
     o.write((const char*)st.D_map.data(), (std::streamsize)(sizeof(double) * st.N));
     writer_.save(o);
     flow_writer_.save(o);
+    o.flush();
+    o.close();
+    if (!o || std::rename(tmp.c_str(), path.c_str()) != 0) std::fprintf(stderr, "cannot write driver checkpoint %s\n", path.c_str());
 }
 
 bool CoupledSolver::load_driver_state(const std::string& path, HostState& st, double* t_corr, int* cycle, bool* need_flow) {
@@ -128,6 +135,7 @@ bool CoupledSolver::load_driver_state(const std::string& path, HostState& st, do
     get(in, dissolved_since_flow_);
     *need_flow = nf != 0;
     get(in, n);
+    if (!in || n < 0 || n > st.N) return false;   // corrupt file: never size a vector from unchecked input
     initial_solid_indices_.resize((size_t)n);
     in.read((char*)initial_solid_indices_.data(), (std::streamsize)(sizeof(int) * n));
     get(in, N);

@@ -130,6 +130,7 @@ void pd_invalidate_graphs(pdgpu_ctx* c) {
 }
 
 int pd_comm_destroy(pdgpu_ctx* c);
+void pd_tile_state_free(pdgpu_ctx* c);   // ns_stream.cu
 
 extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     if (!c) return 0;
@@ -138,9 +139,10 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     pd_invalidate_graphs(c);
     pd_host_step_free(c);
     pd_comm_destroy(c);
-    void* ptrs[] = {c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->rho[0], c->rho[1],
-                    c->p[0], c->p[1], c->C[0], c->C[1], c->v[0][0], c->v[0][1], c->v[0][2], c->v[1][0],
-                    c->v[1][1], c->v[1][2], c->vmag, c->dsol, c->wpack, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,
+    pd_tile_state_free(c);
+    for (void* p : c->raw_fields)   // padded double arrays (pd_alloc_fields)
+        if (p) cudaFree(p);
+    void* ptrs[] = {c->nbfast, c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,
                     c->l_solid, c->l_ssolid, c->inlet_vax, c->out_nodes, c->out_level_off, c->d_red, c->d_u64, c->d_int,
                     c->d_dissolved, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol,
                     c->l2_scratch, c->d_dt, c->stage, c->out_base_v, c->out_base_c, c->out_cnt,
@@ -203,6 +205,7 @@ extern "C" int pdgpu_set_option(pdgpu_ctx* c, const char* name, int value) {
     }
     else if (n == "lazy_wallc") { if (pd_flush_wall_c(c)) return 1; c->opt_lazy_wallc = value; }
     else if (n == "debug_no_halo") c->opt_debug_no_halo = value;
+    else if (n == "stream_chunk") c->opt_stream_chunk = value;
     else PD_FAIL("pdgpu_set_option: unknown option '%s'", name);
     pd_invalidate_graphs(c);
     return 0;

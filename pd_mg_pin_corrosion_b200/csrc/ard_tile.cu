@@ -18,7 +18,7 @@
 // k_ard_solid_rows from the solid node list.
 #include <algorithm>
 
-#include "tile.cuh"
+#include "stream.cuh"
 
 namespace {
 using namespace tile;
@@ -73,10 +73,72 @@ __device__ __forceinline__ void ard_column(const double* __restrict__ s_C, const
     }
 }
 
+// All-fluid fast path: every neighbour of every FLUID node of the warp is fluid-like (FLUID / INLET /
+// OUTLET; flag built by k_nbr_fluid_only), so f = 1, D_ij = max(w_i, w_j) with both >= +0, and the
+// bond classification, the sign handling and the f multiply of ard_column drop out:
+// 5 FP64 + 4 integer operations per bond.
+template <int H>
+__device__ __forceinline__ void ard_column_fluid(const double* __restrict__ s_C, const double* __restrict__ s_w, int cb,
+                                                 double dI, double dJ, const double (&kap)[4], const double (&kz)[4],
+                                                 const double (&Ci)[RZ], const unsigned long long (&wi)[RZ],
+                                                 ArdAcc& a) {
+    double colg[RZ];
+#pragma unroll
+    for (int t = 0; t < RZ; ++t) colg[t] = 0.0;
+#pragma unroll
+    for (int zz = -H; zz < RZ + H; ++zz) {
+        const int si = cb + (zz + TR) * SPLANE;
+        const double Cj = s_C[si];
+        const unsigned long long wj = (unsigned long long)__double_as_longlong(s_w[si]);
+#pragma unroll
+        for (int t = 0; t < RZ; ++t) {
+            const int dk = zz - t;
+            if (dk >= -H && dk <= H) {
+                const int ak = dk < 0 ? -dk : dk;
+                const double k = kap[ak];
+                const double dC = Cj - Ci[t];
+                const unsigned long long wm = wi[t] > wj ? wi[t] : wj;   // non-negative doubles order like their bits
+                const double D = __longlong_as_double((long long)wm);
+                a.diff[t] = fma(D * dC, k, a.diff[t]);
+                colg[t] = fma(dC, k, colg[t]);
+                if (dk > 0) a.gz[t] = fma(dC, kz[ak], a.gz[t]);
+                if (dk < 0) a.gz[t] = fma(-dC, kz[ak], a.gz[t]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < RZ; ++t) {
+        a.gx[t] = fma(dI, colg[t], a.gx[t]);
+        a.gy[t] = fma(dJ, colg[t], a.gy[t]);
+    }
+}
+
+// nbf[l] = 1 for a FLUID node whose whole horizon is fluid-like (in-box, FLUID / INLET / OUTLET)
+__global__ void __launch_bounds__(256)
+k_nbr_fluid_only(Lat L, long long own_lo, long long own_n, const uint8_t* __restrict__ type,
+                 const OffEntry* __restrict__ off, int n_off, uint8_t* __restrict__ nbf) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= own_n) return;
+    const long long l = own_lo + t;
+    uint8_t ok = 0;
+    if (type[l] == PDGPU_FLUID) {
+        const int q = (int)(l % L.P);
+        const int jj = q / L.Nx, ii = q - jj * L.Nx;
+        ok = 1;
+        for (int o = 0; o < n_off; ++o) {
+            const long long nn = nbr_local(L, off[o], 3, ii, jj, l, type);
+            if (nn < 0) { ok = 0; break; }
+            const uint8_t tj = type[nn];
+            if (!(tj == PDGPU_FLUID || tj == PDGPU_INLET || tj == PDGPU_OUTLET)) { ok = 0; break; }
+        }
+    }
+    nbf[l] = ok;
+}
+
 __global__ void __launch_bounds__(NTHREADS, 2)
 k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColTable T,
-           const double* __restrict__ d_dt, const uint8_t* __restrict__ type, const double* __restrict__ C,
-           const double* __restrict__ w_g, const double* __restrict__ vx,
+           const double* __restrict__ d_dt, const uint8_t* __restrict__ type, const uint8_t* __restrict__ nbf,
+           const double* __restrict__ C, const double* __restrict__ w_g, const double* __restrict__ vx,
            const double* __restrict__ vy, const double* __restrict__ vz, double* __restrict__ C_n) {
     extern __shared__ double sm[];
     double* s_C = sm;
@@ -89,11 +151,16 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
     const bool in_xy = gx < q.g.Nx && gy < q.g.Ny;
 
     uint8_t nty[RZ];
+    bool slow = false;   // a FLUID node of this thread has a solid / wall neighbour
 #pragma unroll
     for (int t = 0; t < RZ; ++t) {
         const int lz = zt + t;
         nty[t] = 255;
-        if (in_xy && lz < q.g.z_hi) nty[t] = type[(long long)lz * q.g.P + (long long)gy * q.g.Nx + gx];
+        if (in_xy && lz < q.g.z_hi) {
+            const long long l = (long long)lz * q.g.P + (long long)gy * q.g.Nx + gx;
+            nty[t] = type[l];
+            slow = slow || (nty[t] == PDGPU_FLUID && !nbf[l]);
+        }
     }
     // asynchronous staging (see ns_tile.cu); outside the box: C = 0, w = +0 (never used by a full row)
     for (int idx = tid; idx < SN; idx += NTHREADS) {
@@ -129,16 +196,30 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
         wi[t] = (unsigned long long)__double_as_longlong(s_w[si]);
         a.diff[t] = a.gx[t] = a.gy[t] = a.gz[t] = 0.0;
     }
+    if (__any_sync(0xffffffffu, slow)) {
 #pragma unroll 1
-    for (int c = 0; c < NCOL; ++c) {
-        const int cb = base + T.off[c];
-        const double dI = T.di[c], dJ = T.dj[c];
-        const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
-        const double kz[4] = {T.kz[c][0], T.kz[c][1], T.kz[c][2], T.kz[c][3]};
-        const int H = T.h[c];
-        if (H == 3) ard_column<3>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
-        else if (H == 2) ard_column<2>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
-        else ard_column<1>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+        for (int c = 0; c < NCOL; ++c) {
+            const int cb = base + T.off[c];
+            const double dI = T.di[c], dJ = T.dj[c];
+            const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
+            const double kz[4] = {T.kz[c][0], T.kz[c][1], T.kz[c][2], T.kz[c][3]};
+            const int H = T.h[c];
+            if (H == 3) ard_column<3>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+            else if (H == 2) ard_column<2>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+            else ard_column<1>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+        }
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < NCOL; ++c) {
+            const int cb = base + T.off[c];
+            const double dI = T.di[c], dJ = T.dj[c];
+            const double kap[4] = {T.kap[c][0], T.kap[c][1], T.kap[c][2], T.kap[c][3]};
+            const double kz[4] = {T.kz[c][0], T.kz[c][1], T.kz[c][2], T.kz[c][3]};
+            const int H = T.h[c];
+            if (H == 3) ard_column_fluid<3>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+            else if (H == 2) ard_column_fluid<2>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+            else ard_column_fluid<1>(s_C, s_w, cb, dI, dJ, kap, kz, Ci, wi, a);
+        }
     }
 
     const double dt = *d_dt;
@@ -178,13 +259,26 @@ k_ard_solid_rows(Lat L, const int* __restrict__ l_solid, long long n_solid, cons
 
 }  // namespace
 
+// nbfast flags of the owned nodes (pd_rebuild_tables: node types changed)
+int pd_build_nbfast(pdgpu_ctx* c) {
+    if (c->dim != 3) return 0;
+    if (!c->nbfast) {
+        CUDA_OK(cudaMalloc(&c->nbfast, c->NL));
+        CUDA_OK(cudaMemsetAsync(c->nbfast, 0, c->NL, c->stream));
+    }
+    const long long own_n = c->own_hi - c->own_lo;
+    Lat L = make_lat(c);
+    LAUNCH(c, k_nbr_fluid_only, nblocks(own_n, 256), 256, 0, L, c->own_lo, own_n, c->type, c->d_off, c->n_off, c->nbfast);
+    return 0;
+}
+
 // returns -1 when the tiled kernel does not apply. Expects vmag (= vmf) and dsol to be current.
 int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid,
                         bool skip_wall_copy) {
     if (!c->full_rows) return -1;
-    static ColTable T;
-    double sum_kappa = 0.0;
-    if (!build_columns(c, &T, &sum_kappa)) return -1;
+    if (pd_stream_prepare(c)) return -1;   // column table per context (stream.cuh)
+    stream::TileState* ts = pd_tile_state(c);
+    ColTable& T = ts->tcols;
     PdConsts k = pd_consts(c->cfg, c->dim);
     ArdTileParams q;
     q.g = make_geom(c);
@@ -192,16 +286,15 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
     if (zb >= 0) { q.g.z_lo = zb; q.g.z_hi = ze; }
     q.beta = k.beta_lap; q.div_coeff = k.alpha / k.V_H; q.inv_dx = 1.0 / c->cfg.dx;
     const size_t smem = sizeof(double) * 2 * SN;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ts->attr_tile_ard) {   // per context: the attribute is per device
         CUDA_OK(cudaFuncSetAttribute(k_ard_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        ts->attr_tile_ard = true;
     }
     int dstC = 1 - srcC;
     if (q.g.z_hi > q.g.z_lo) {
         dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + TZ - 1) / TZ);
         dim3 block(TX, TY, NZT);
-        k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->C[srcC], c->wpack, c->v[buf][0],
+        k_ard_tile<<<grid, block, smem, c->stream>>>(q, T, d_dt, c->type, c->nbfast, c->C[srcC], c->wpack, c->v[buf][0],
                                                       c->v[buf][1], c->v[buf][2], c->C[dstC]);
         c->launches++;
     }

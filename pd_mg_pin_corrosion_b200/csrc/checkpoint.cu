@@ -8,6 +8,7 @@
 // bit-identical to the uninterrupted one (tests/test_gpu_checkpoint.py).  Data moves through the
 // pinned staging pool of iopool.cuh in both directions.
 #include <cstring>
+#include <string>
 
 #include "common.cuh"
 #include "iopool.cuh"
@@ -24,6 +25,18 @@ struct CkHeader {
 };
 
 struct Arr { void* ptr; size_t bytes; };
+
+// Run-control members (how long, how often) may differ between the run that wrote the checkpoint
+// and the one that resumes it; everything that shapes the lattice or the physics must match.
+PdConfig physics_only(PdConfig k) {
+    k.T_final = 0.0;
+    k.flow_max_iters = 0;
+    k.corrosion_steps_per_check = 0;
+    k.output_every_flow = 0;
+    k.output_every_corr = 0;
+    k.reserved = 0;
+    return k;
+}
 
 std::vector<Arr> arrays(pdgpu_ctx* c) {
     const long long lo = c->own_lo, n = c->own_hi - c->own_lo;
@@ -55,8 +68,10 @@ extern "C" int pdgpu_checkpoint_save(pdgpu_ctx* c, const char* path, long long* 
     h.wallC_pending = c->wallC_pending ? 1 : 0; h.wallC_src = c->wallC_src;
     h.volume_loss = c->volume_loss;
     h.cfg = c->cfg;
-    const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    if (fd < 0) PD_FAIL("cannot open checkpoint file '%s'", path);
+    // written under a temporary name, synced, then renamed: a crash never leaves a torn file under `path`
+    const std::string tmp = std::string(path) + ".tmp";
+    const int fd = ::open(tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) PD_FAIL("cannot open checkpoint file '%s'", tmp.c_str());
     pdio::IoPool* io = nullptr;
     int rc = pdio::io_pool(c, &io);
     off_t off = 0;
@@ -79,8 +94,10 @@ extern "C" int pdgpu_checkpoint_save(pdgpu_ctx* c, const char* path, long long* 
         run.finish();
         if (run.failed()) rc = 1;
     }
+    if (!rc && ::fsync(fd) != 0) rc = 1;
     ::close(fd);
-    if (rc) PD_FAIL("pdgpu_checkpoint_save: writing '%s' failed", path);
+    if (!rc && ::rename(tmp.c_str(), path) != 0) rc = 1;
+    if (rc) { ::unlink(tmp.c_str()); PD_FAIL("pdgpu_checkpoint_save: writing '%s' failed", path); }
     if (bytes_out) *bytes_out = (long long)off;
     return 0;
 }
@@ -96,14 +113,19 @@ extern "C" int pdgpu_checkpoint_load(pdgpu_ctx* c, const char* path) {
         ::close(fd);
         PD_FAIL("'%s' is not a pdgpu checkpoint (version 1)", path);
     }
+    const PdConfig want = physics_only(c->cfg), have = physics_only(h.cfg);
     if (h.dim != c->dim || h.Nx != c->Nx || h.Ny != c->Ny || h.Nz != c->Nz || h.R != c->R ||
-        h.N != c->own_hi - c->own_lo || std::memcmp(&h.cfg, &c->cfg, sizeof(PdConfig)) != 0) {
+        h.N != c->own_hi - c->own_lo || std::memcmp(&have, &want, sizeof(PdConfig)) != 0) {
         ::close(fd);
         PD_FAIL("checkpoint '%s' was written for another configuration or lattice (%dD %dx%dx%d)", path, h.dim, h.Nx,
                 h.Ny, h.Nz);
     }
     pdio::IoPool* io = nullptr;
     if (pdio::io_pool(c, &io)) { ::close(fd); return 1; }
+    std::lock_guard<std::mutex> pool_guard(io->busy);
+    // from here on the device arrays are being overwritten: a failure leaves the context without fields
+    c->fields_ready = false;
+    pd_invalidate_graphs(c);
     off_t off = (off_t)sizeof(h);
     int rc = 0, k = 0;
     for (const Arr& a : arrays(c)) {

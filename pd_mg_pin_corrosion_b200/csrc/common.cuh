@@ -80,6 +80,7 @@ struct pdgpu_ctx {
 
     // per-node device arrays (local indexing, ghosts included)
     uint8_t *type = nullptr, *phase = nullptr, *is_gb = nullptr, *is_precip = nullptr, *salt = nullptr;
+    uint8_t* nbfast = nullptr;      // 1: FLUID node whose whole horizon is fluid-like (3D; ard_tile.cu fast path)
     double *rho[2] = {nullptr, nullptr}, *p[2] = {nullptr, nullptr}, *C[2] = {nullptr, nullptr};
     double* v[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     double* vmag = nullptr;         // |v| per fluid-like node, -1 otherwise (ARD artificial diffusion)
@@ -156,7 +157,7 @@ struct pdgpu_ctx {
     long long launches = 0;
 
     // options
-    int opt_ns_kernel = 1;          // 0 = generic table loop, 1 = tiled, 2 = z-marching tiles, 3 = materialised CSR, 4 = split (pressure / rest)
+    int opt_ns_kernel = 2;          // 0 = generic table loop, 1 = block tiles, 2 = z-streaming (bulk copies), 3 = materialised CSR
     int opt_ard_kernel = 1;
     int opt_graph = 1;
     int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)
@@ -181,8 +182,17 @@ struct pdgpu_ctx {
     long long g_ns_nodes[2][2] = {{0, 0}, {0, 0}}, g_ard_nodes[2][2] = {{0, 0}, {0, 0}};
 
     // host-array step (host_step.cu): chunk plan, copy streams, AoS staging
-    long long tables_epoch = 0;     // bumped by pd_rebuild_tables
+    long long tables_epoch = 0;     // bumped by pd_rebuild_tables and by option changes (pd_invalidate_graphs)
+    long long types_epoch = 0;      // bumped by pd_rebuild_tables only (node types / lists changed)
     struct HostStep* hs = nullptr;
+
+    // streaming / tiled bond kernels (stream.cuh): column tables, active tile list, per-device attributes
+    void* tile_state = nullptr;
+    int opt_stream_chunk = 0;       // planes per work item of the streaming kernels (0 = automatic)
+    // double field arrays carry `field_pad` zeroed elements in front and behind (the bulk row copies
+    // of the streaming kernels may start up to 3 rows + 4 elements outside the lattice box)
+    size_t field_pad = 0;
+    std::vector<void*> raw_fields;  // cudaMalloc bases of the padded arrays
 };
 
 // PD constants of PD_NS_Solver::init / PD_ARD_Solver::init (src/pd_ns.cpp:7-16).
@@ -289,6 +299,7 @@ __device__ __forceinline__ double warp_min(double v) {
 // ------------------------------------------------- cross-TU internal functions
 int pd_alloc_fields(pdgpu_ctx* c);
 int pd_rebuild_tables(pdgpu_ctx* c);                 // lists, mirror table, bond counts
+int pd_build_nbfast(pdgpu_ctx* c);                   // ard_tile.cu
 int pd_enqueue_bc_inlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, -1 = not applicable

@@ -6,8 +6,20 @@
 #include "common.cuh"
 #include "geom.cuh"
 
+// double arrays: zeroed, with field_pad zeroed elements in front and behind (stream.cuh)
+static int alloc_padded(pdgpu_ctx* c, double** out) {
+    const size_t n = (size_t)c->NL + 2 * c->field_pad;
+    double* raw = nullptr;
+    CUDA_OK(cudaMalloc(&raw, sizeof(double) * n));
+    CUDA_OK(cudaMemset(raw, 0, sizeof(double) * n));
+    c->raw_fields.push_back(raw);
+    *out = raw + c->field_pad;
+    return 0;
+}
+
 int pd_alloc_fields(pdgpu_ctx* c) {
-    size_t nb = sizeof(double) * (size_t)c->NL;
+    // pad: reach rows + one staged row, rounded to 32 elements (keeps the 256-byte alignment)
+    c->field_pad = ((size_t)(c->R + 1) * (size_t)c->Nx + 64 + 31) & ~(size_t)31;
     CUDA_OK(cudaMalloc(&c->type, c->NL));
     CUDA_OK(cudaMalloc(&c->phase, c->NL));
     CUDA_OK(cudaMalloc(&c->is_gb, c->NL));
@@ -19,23 +31,14 @@ int pd_alloc_fields(pdgpu_ctx* c) {
     CUDA_OK(cudaMemset(c->is_precip, 0, c->NL));
     CUDA_OK(cudaMemset(c->salt, 0, c->NL));
     for (int b = 0; b < 2; ++b) {
-        CUDA_OK(cudaMalloc(&c->rho[b], nb));
-        CUDA_OK(cudaMalloc(&c->p[b], nb));
-        CUDA_OK(cudaMalloc(&c->C[b], nb));
-        CUDA_OK(cudaMemset(c->rho[b], 0, nb));
-        CUDA_OK(cudaMemset(c->p[b], 0, nb));
-        CUDA_OK(cudaMemset(c->C[b], 0, nb));
-        for (int d = 0; d < c->dim; ++d) {
-            CUDA_OK(cudaMalloc(&c->v[b][d], nb));
-            CUDA_OK(cudaMemset(c->v[b][d], 0, nb));
-        }
+        PD_TRY(alloc_padded(c, &c->rho[b]));
+        PD_TRY(alloc_padded(c, &c->p[b]));
+        PD_TRY(alloc_padded(c, &c->C[b]));
+        for (int d = 0; d < c->dim; ++d) PD_TRY(alloc_padded(c, &c->v[b][d]));
     }
-    CUDA_OK(cudaMalloc(&c->vmag, nb));
-    CUDA_OK(cudaMemset(c->vmag, 0, nb));
-    CUDA_OK(cudaMalloc(&c->dsol, nb));
-    CUDA_OK(cudaMemset(c->dsol, 0, nb));
-    CUDA_OK(cudaMalloc(&c->wpack, nb));
-    CUDA_OK(cudaMemset(c->wpack, 0, nb));
+    PD_TRY(alloc_padded(c, &c->vmag));
+    PD_TRY(alloc_padded(c, &c->dsol));
+    PD_TRY(alloc_padded(c, &c->wpack));
     return 0;
 }
 

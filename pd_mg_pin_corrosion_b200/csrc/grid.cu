@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "geom.cuh"
 #include "scan.cuh"
+#include "stream.cuh"
 
 // ---------------------------------------------------------------- host-only ----
 static int build_stencil_host(const PdConfig& cfg, int dim, std::vector<OffEntry>& out) {
@@ -377,6 +378,7 @@ static int build_outlet_schedule(pdgpu_ctx* c) {
 int pd_rebuild_tables(pdgpu_ctx* c) {
     pd_invalidate_graphs(c);
     c->tables_epoch++;
+    c->types_epoch++;
     pd_touch_flow(c);   // node types may have changed: cached |v| is stale
     long long own_n = c->own_hi - c->own_lo;
     Lat L = make_lat(c);
@@ -500,8 +502,10 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
         }
     }
 
-    // multi-GPU sanity: owned WALL mirrors must not live in ghost planes of another rank's
-    // slab unless those are plain copies ("halo invariants").
+    PD_TRY(pd_build_nbfast(c));
+    // column tables + active tile list of the streaming / tiled bond kernels: built here, outside of
+    // any stream capture (a negative result only means that those kernels do not apply)
+    if (pd_stream_prepare(c) > 0) return 1;
     return 0;
 }
 

@@ -21,11 +21,13 @@ constexpr int kIoBufs = 6, kIoWriters = 3;
 struct IoPool {
     char* buf[kIoBufs] = {nullptr};
     cudaEvent_t ev[kIoBufs] = {nullptr};
+    std::mutex busy;   // one writer run / checkpoint load per device at a time (contexts on several host threads)
 };
 inline IoPool g_io_pool[64];
 
 inline int io_pool(pdgpu_ctx* c, IoPool** out) {
     IoPool* p = &g_io_pool[c->device < 64 ? c->device : 0];
+    std::lock_guard<std::mutex> guard(p->busy);
     for (int k = 0; k < kIoBufs; ++k) {
         if (!p->buf[k]) CUDA_OK(cudaMallocHost(&p->buf[k], kIoChunk));
         if (!p->ev[k]) CUDA_OK(cudaEventCreateWithFlags(&p->ev[k], cudaEventDisableTiming));
@@ -39,6 +41,8 @@ class IoRun {
    public:
     IoRun(IoPool* io, int fd, int device) : io_(io), fd_(fd), device_(device) {
         if (!io_) { err_ = true; return; }
+        io_->busy.lock();
+        locked_ = true;
         for (int k = 0; k < kIoBufs; ++k) free_.push_back(k);
         for (int w = 0; w < kIoWriters; ++w) th_.emplace_back([this] { work(); });
     }
@@ -62,6 +66,7 @@ class IoRun {
         cv_job_.notify_all();
         for (std::thread& t : th_) if (t.joinable()) t.join();
         th_.clear();
+        if (locked_) { io_->busy.unlock(); locked_ = false; }
     }
 
    private:
@@ -97,7 +102,7 @@ class IoRun {
     std::deque<IoJob> jobs_;
     std::vector<int> free_;
     std::vector<std::thread> th_;
-    bool done_ = false, err_ = false;
+    bool done_ = false, err_ = false, locked_ = false;
 };
 
 

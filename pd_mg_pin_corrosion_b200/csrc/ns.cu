@@ -96,15 +96,13 @@ k_ns_step_generic(Lat L, long long own_lo, long long own_n, const uint8_t* __res
 }
 
 int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze);   // ns_tile.cu
-int pd_enqueue_ns_march(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze);       // ns_march.cu
-int pd_enqueue_ns_split(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze);       // ns_split_a.cu
+int pd_enqueue_ns_stream(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze);      // ns_stream.cu
 
 int pd_enqueue_ns_step(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze) {
     if (c->opt_ns_kernel == 3) return pd_enqueue_ns_step_csr(c, src, d_dt);
     if (c->opt_ns_kernel >= 1 && c->full_rows && c->cfg.m_ratio == 3) {
-        int r = (c->opt_ns_kernel == 4)   ? pd_enqueue_ns_split(c, src, d_dt, zb, ze)
-                : (c->opt_ns_kernel >= 2) ? pd_enqueue_ns_march(c, src, d_dt, zb, ze)
-                                          : pd_enqueue_ns_step_fast(c, src, d_dt, zb, ze);
+        int r = (c->opt_ns_kernel >= 2) ? pd_enqueue_ns_stream(c, src, d_dt, zb, ze)
+                                        : pd_enqueue_ns_step_fast(c, src, d_dt, zb, ze);
         if (r >= 0) return r;   // <0: fast path not applicable -> generic
     }
     int dst = 1 - src;

@@ -17,7 +17,7 @@
 // with d = (di,dj,dk).
 #include <algorithm>
 
-#include "tile.cuh"
+#include "stream.cuh"
 
 namespace {
 using namespace tile;
@@ -193,9 +193,10 @@ k_ns_tile(const __grid_constant__ NsTileParams q, const __grid_constant__ ColTab
 // returns -1 when the tiled kernel does not apply (caller uses the generic kernel)
 int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt, int zb, int ze) {
     if (!c->full_rows) return -1;
-    static ColTable T;   // rebuilt per call: 37 columns, context independent
-    double sum_kappa = 0.0;
-    if (!build_columns(c, &T, &sum_kappa)) return -1;
+    if (pd_stream_prepare(c)) return -1;   // column table per context (stream.cuh)
+    stream::TileState* ts = pd_tile_state(c);
+    ColTable& T = ts->tcols;
+    const double sum_kappa = ts->sum_kappa;
     PdConsts k = pd_consts(c->cfg, c->dim);
     NsTileParams q;
     q.g = make_geom(c);
@@ -210,10 +211,9 @@ int pd_enqueue_ns_step_fast(pdgpu_ctx* c, int src, const double* d_dt, int zb, i
     for (int col = 0; col < tile::NCOL; ++col)
         for (int kk = 0; kk < 4; ++kk) T.aux[col][kk] = q.visc * q.inv_dx * T.kap[col][kk];
     const size_t smem = sizeof(double) * 5 * SN;
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (!ts->attr_tile_ns) {   // per context: the attribute is per device
         CUDA_OK(cudaFuncSetAttribute(k_ns_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
+        ts->attr_tile_ns = true;
     }
     int dst = 1 - src;
     dim3 grid((c->Nx + TX - 1) / TX, (c->Ny + TY - 1) / TY, ((q.g.z_hi - q.g.z_lo) + TZ - 1) / TZ);

@@ -286,13 +286,13 @@ int upload_table(pdgpu_ctx* c) {
     return 0;
 }
 
-int alloc_buf(TextBuf* b, long long n) {
+int alloc_buf(pdgpu_ctx* c, TextBuf* b, long long n) {
     b->n = n;
     CUDA_OK(cudaMalloc(&b->len, sizeof(int) * n));
     CUDA_OK(cudaMalloc(&b->pos, sizeof(long long) * (n + 1)));
     CUDA_OK(cudaMalloc(&b->text, (size_t)n * kMaxRec + 64));
     CUDA_OK(cudaMalloc(&b->flag, sizeof(int)));
-    CUDA_OK(cudaMemsetAsync(b->flag, 0, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(b->flag, 0, sizeof(int), c->stream));   // same stream as the kernels that raise it
     return 0;
 }
 
@@ -368,7 +368,7 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
     PD_TRY(upload_table(c));
     const long long n = c->own_hi - c->own_lo, lo = c->own_lo;
     TextBuf b;
-    PD_TRY(alloc_buf(&b, n));
+    PD_TRY(alloc_buf(c, &b, n));
     DevArray<int> gid_buf;
     DevArray<double> dmap_buf, press_buf;
     CUDA_OK(cudaMalloc(&gid_buf.p, sizeof(int) * n));
@@ -455,7 +455,8 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
     }
     int flag = 0;
     if (!rc) {
-        cudaMemcpy(&flag, b.flag, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpyAsync(&flag, b.flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
         put_small("      </PointData>\n    </Piece>\n  </ImageData>\n</VTKFile>\n");
     }
     run.finish();

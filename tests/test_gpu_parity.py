@@ -249,15 +249,15 @@ def test_kernel_variants_agree(case):
         dict(ns_kernel=1, ard_kernel=1, outlet_kernel=2, overlap=0, graph=1),
         dict(ns_kernel=1, ard_kernel=1, outlet_kernel=2, overlap=1, graph=0, lazy_wallc=0),
         dict(ns_kernel=1, ard_kernel=1, outlet_kernel=2, overlap=1, graph=1),
-        dict(ns_kernel=1, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1),   # default
+        dict(ns_kernel=1, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1),   # block-tile kernels
         dict(ns_kernel=1, ard_kernel=1, outlet_kernel=3, overlap=0, graph=0),
         dict(ns_kernel=1, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1, outlet_single_rows=1),
         dict(ns_kernel=0, ard_kernel=0, outlet_kernel=2, overlap=1, graph=1),
-        dict(ns_kernel=2, ard_kernel=1, outlet_kernel=2, overlap=1, graph=1),   # z-marching NS kernel
-        dict(ns_kernel=2, ard_kernel=2, outlet_kernel=2, overlap=0, graph=0),
+        dict(ns_kernel=2, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1),   # z-streaming NS kernel (default)
+        dict(ns_kernel=2, ard_kernel=1, outlet_kernel=2, overlap=0, graph=0),
+        dict(ns_kernel=2, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1, stream_chunk=8),
+        dict(ns_kernel=2, ard_kernel=1, outlet_kernel=3, overlap=0, graph=0, stream_chunk=12),
         dict(ns_kernel=3, ard_kernel=3, outlet_kernel=2, overlap=1, graph=1),   # materialised-CSR path
-        dict(ns_kernel=4, ard_kernel=1, outlet_kernel=3, overlap=1, graph=1),   # split NS kernel (pressure / rest)
-        dict(ns_kernel=4, ard_kernel=1, outlet_kernel=3, overlap=0, graph=0),
     ]
     dt = ref.ns_compute_dt()
     results = []
