@@ -144,8 +144,14 @@ int pdgpu_fields_download(pdgpu_ctx* ctx, int field, void* host_global);
 int pdgpu_fields_init(pdgpu_ctx* ctx, const uint8_t* is_gb_global, const uint8_t* is_precip_global);
 int pdgpu_swap_flow(pdgpu_ctx* ctx);                 /* Fields::swap_buffers       */
 int pdgpu_swap_C(pdgpu_ctx* ctx);                    /* std::swap(C, C_new), coupling.cpp:238 */
-/* out[t] = field[idx[t]] for scalar double fields (ordered host sums, coupling.cpp:32-38) */
+/* out[t] = field[idx[t]] for scalar double fields (ordered host sums, coupling.cpp:32-38).
+ * Slab contexts: COLLECTIVE -- every rank passes the same index list and receives every value
+ * (each node is read by its owner), so that all ranks form the same ordered sum. */
 int pdgpu_gather(pdgpu_ctx* ctx, int field, const int* idx_global, long long n, double* out);
+/* Slab contexts: COLLECTIVE download of the WHOLE global array on every rank (host mirrors of the
+ * coupling loop: node types for the initial-solid list of src/coupling.cpp:95-103, final fields).
+ * One rank: same as pdgpu_fields_download. */
+int pdgpu_fields_download_all(pdgpu_ctx* ctx, int field, void* host_global);
 
 /* ---- boundary operators (src/boundary.h:6-13) ---------------------------------------- */
 int pdgpu_bc_inlet(pdgpu_ctx* ctx);                  /* apply_inlet_bc               */
@@ -214,6 +220,9 @@ int pdgpu_comm_uid_bytes(void);
 int pdgpu_comm_get_uid(void* uid_out);               /* rank 0; broadcast by the caller */
 int pdgpu_comm_init(pdgpu_ctx* ctx, const void* uid, int rank, int nranks);
 int pdgpu_halo_exchange(pdgpu_ctx* ctx, int which);  /* 0: rho,vel,p   1: C   2: all (incl. _new) */
+/* Host scalars of the coupling loop combined over the ranks (op 0 sum, 1 max, 2 min), e.g. the
+ * dissolved-node count of a check (src/coupling.cpp:256-275). No-op for one rank. n <= 1024. */
+int pdgpu_comm_allreduce(pdgpu_ctx* ctx, double* host_vals, int n, int op);
 
 /* ---- instrumentation --------------------------------------------------------------------- */
 int pdgpu_timer_start(pdgpu_ctx* ctx);               /* cudaEventRecord on the ctx stream */

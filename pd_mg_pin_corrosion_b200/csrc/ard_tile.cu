@@ -97,8 +97,10 @@ __device__ __forceinline__ void ard_column_fluid(const double* __restrict__ s_C,
                 const int ak = dk < 0 ? -dk : dk;
                 const double k = kap[ak];
                 const double dC = Cj - Ci[t];
-                const unsigned long long wm = wi[t] > wj ? wi[t] : wj;   // non-negative doubles order like their bits
-                const double D = __longlong_as_double((long long)wm);
+                // FP64 compare + two selects: one instruction less than the 64-bit integer max, and this
+                // kernel is issue bound with the FP64 pipe half idle
+                const double wid = __longlong_as_double((long long)wi[t]), wjd = __longlong_as_double((long long)wj);
+                const double D = wid > wjd ? wid : wjd;
                 a.diff[t] = fma(D * dC, k, a.diff[t]);
                 colg[t] = fma(dC, k, colg[t]);
                 if (dk > 0) a.gz[t] = fma(dC, kz[ak], a.gz[t]);

@@ -98,6 +98,28 @@ int pd_comm_allreduce(pdgpu_ctx* c, double* d_buf, int n, int op) {
     return 0;
 }
 
+// In-place merge over ranks of a device buffer in which every element is non-zero on at most one rank
+// (elements of `elem` = 1, 4 or 8 bytes): an INTEGER sum, so that the merged array is the owners' bytes
+// exactly (a floating-point sum would turn -0.0 into +0.0).
+int pd_comm_allreduce_bytes(pdgpu_ctx* c, void* d_buf, size_t bytes, int elem) {
+    if (!c->comm) return 0;
+    ncclDataType_t ty = elem == 8 ? ncclUint64 : elem == 4 ? ncclUint32 : ncclUint8;
+    NCCL_OK(g_nccl.AllReduce(d_buf, d_buf, bytes / (size_t)elem, ty, ncclSum, (ncclComm_t)c->comm, c->stream));
+    return 0;
+}
+
+// Host scalars combined over the ranks of a slab run (op 0 sum, 1 max, 2 min); no-op for one rank.
+extern "C" int pdgpu_comm_allreduce(pdgpu_ctx* c, double* host_vals, int n, int op) {
+    CHECK_CTX(c);
+    if (!host_vals || n < 0 || n > 1024) PD_FAIL("pdgpu_comm_allreduce: bad arguments");
+    if (c->nranks == 1 || !c->comm || n == 0) return 0;
+    CUDA_OK(cudaMemcpyAsync(c->d_red, host_vals, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    PD_TRY(pd_comm_allreduce(c, c->d_red, n, op));
+    CUDA_OK(cudaMemcpyAsync(host_vals, c->d_red, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // Exchange the `reach` boundary planes of the listed arrays with both axial neighbours.
 //   which 0: rho, p, v[dim] of flow buffer `buf`        (after an NS step + wall_new)
 //   which 1: C of buffer `bufC`                          (after an ARD step)
@@ -128,20 +150,24 @@ int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC) {
     if (which == 4 && c->moff) arrs.push_back({c->moff, 4});
     int lo = c->rank - 1, hi = c->rank + 1;
     NCCL_OK(g_nccl.GroupStart());
+    // a failing call inside the group must still close it (an open group swallows every later call)
+    ncclResult_t bad = ncclSuccess;
+    auto keep = [&](ncclResult_t r) { if (r != ncclSuccess && bad == ncclSuccess) bad = r; };
     for (const Arr& a : arrs) {
         char* base = (char*)a.p;
         size_t nb = (size_t)hp * a.bytes;
         // offsets from pdgpu_slab_layout: send_lo, recv_lo, send_hi, recv_hi
         if (lo >= 0) {
-            NCCL_OK(g_nccl.Send(base + (size_t)c->halo_off[0] * a.bytes, nb, ncclUint8, lo, comm, c->stream));
-            NCCL_OK(g_nccl.Recv(base + (size_t)c->halo_off[1] * a.bytes, nb, ncclUint8, lo, comm, c->stream));
+            keep(g_nccl.Send(base + (size_t)c->halo_off[0] * a.bytes, nb, ncclUint8, lo, comm, c->stream));
+            keep(g_nccl.Recv(base + (size_t)c->halo_off[1] * a.bytes, nb, ncclUint8, lo, comm, c->stream));
         }
         if (hi < c->nranks) {
-            NCCL_OK(g_nccl.Send(base + (size_t)c->halo_off[2] * a.bytes, nb, ncclUint8, hi, comm, c->stream));
-            NCCL_OK(g_nccl.Recv(base + (size_t)c->halo_off[3] * a.bytes, nb, ncclUint8, hi, comm, c->stream));
+            keep(g_nccl.Send(base + (size_t)c->halo_off[2] * a.bytes, nb, ncclUint8, hi, comm, c->stream));
+            keep(g_nccl.Recv(base + (size_t)c->halo_off[3] * a.bytes, nb, ncclUint8, hi, comm, c->stream));
         }
     }
-    NCCL_OK(g_nccl.GroupEnd());
+    keep(g_nccl.GroupEnd());
+    if (bad != ncclSuccess) PD_FAIL("halo exchange (which=%d) failed: %s", which, g_nccl.GetErrorString(bad));
     return 0;
 }
 

@@ -332,6 +332,7 @@ int pd_enqueue_ns_step_csr(pdgpu_ctx* c, int src, const double* d_dt);          
 int pd_enqueue_ard_step_csr(pdgpu_ctx* c, int buf, int srcC, const double* d_dt);       // csr_path.cu
 int pd_set_dt(pdgpu_ctx* c, int slot, double value);
 int pd_comm_allreduce(pdgpu_ctx* c, double* d_buf, int n, int op);   // op 0 sum, 1 max
+int pd_comm_allreduce_bytes(pdgpu_ctx* c, void* d_buf, size_t bytes, int elem);   // in-place sum, elem = 1, 4 or 8 bytes
 #define NEED_FIELDS(c)                                                                       \
     do {                                                                                     \
         NEED_GRID(c);                                                                        \

@@ -104,12 +104,13 @@ __global__ void k_init_fields(GeomParams g, Lat L, long long NL, PdConfig cfg, d
     else { vy0[l] = 0.0; vy1[l] = 0.0; vz0[l] = vax; vz1[l] = vax; }
 }
 
+// out[t] = f[idx[t]] for nodes this context OWNS, 0 otherwise (a slab context sums the vectors of all ranks)
 __global__ void k_gather(const double* __restrict__ f, const int* __restrict__ idx, long long n,
-                         long long halo_shift, long long NL, double* __restrict__ out) {
+                         long long halo_shift, long long own_lo, long long own_hi, double* __restrict__ out) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     long long l = (long long)idx[t] - halo_shift;
-    out[t] = (l >= 0 && l < NL) ? f[l] : 0.0;
+    out[t] = (l >= own_lo && l < own_hi) ? f[l] : 0.0;
 }
 
 // --------------------------------------------------------------- host side ----
@@ -267,9 +268,48 @@ extern "C" int pdgpu_fields_download(pdgpu_ctx* c, int field, void* host) {
     return 0;
 }
 
+// Collective download for slab contexts: every rank receives the WHOLE global array (each rank
+// contributes its owned planes to a zeroed global-size device buffer, NCCL sums them).
+extern "C" int pdgpu_fields_download_all(pdgpu_ctx* c, int field, void* host) {
+    NEED_GRID(c);
+    if (c->nranks == 1 || !c->comm) return pdgpu_fields_download(c, field, host);
+    if (field == PDGPU_F_C || field == PDGPU_F_C_NEW) PD_TRY(pd_flush_wall_c(c));
+    if (!host) PD_FAIL("pdgpu_fields_download_all: null host array");
+    FieldRef r;
+    PD_TRY(field_ref(c, field, &r));
+    const long long n_own = c->own_hi - c->own_lo, goff = (long long)c->a0 * c->P;
+    const size_t per = (size_t)r.elem * r.comps, total = (size_t)c->N_total * per;
+    char* g = nullptr;
+    CUDA_OK(cudaMalloc(&g, total));
+    CUDA_OK(cudaMemsetAsync(g, 0, total, c->stream));
+    if (r.comps == 1) {
+        CUDA_OK(cudaMemcpyAsync(g + goff * r.elem, (const char*)r.ptr[0] + c->own_lo * r.elem, (size_t)n_own * r.elem,
+                                cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        double* dst = (double*)g + goff * r.comps;
+        const long long lo = c->own_lo;
+        if (c->dim == 2)
+            LAUNCH(c, k_interleave<2>, nblocks(n_own, 256), 256, 0, dst, n_own, (const double*)r.ptr[0] + lo,
+                   (const double*)r.ptr[1] + lo, nullptr);
+        else
+            LAUNCH(c, k_interleave<3>, nblocks(n_own, 256), 256, 0, dst, n_own, (const double*)r.ptr[0] + lo,
+                   (const double*)r.ptr[1] + lo, (const double*)r.ptr[2] + lo);
+    }
+    int rc = pd_comm_allreduce_bytes(c, g, total, r.elem);
+    if (!rc && cudaMemcpyAsync(host, g, total, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) rc = 1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) rc = 1;
+    cudaFree(g);
+    if (rc) PD_FAIL("pdgpu_fields_download_all failed: %s", pdgpu_last_error());
+    return 0;
+}
+
 extern "C" int pdgpu_fields_init(pdgpu_ctx* c, const uint8_t* is_gb, const uint8_t* is_precip) {
     NEED_GRID(c);
     c->cur = 0; c->curC = 0; c->p_input = 0;
+    c->wallC_pending = false; c->wallC_src = 0;   // a reused context starts like a fresh one
+    c->volume_loss = 0.0;
+    pd_touch_flow(c);
+    pd_invalidate_graphs(c);
     c->fields_ready = true;   // allow the flag uploads below
     if (is_gb) PD_TRY(pdgpu_fields_upload(c, PDGPU_F_IS_GB, is_gb));
     else CUDA_OK(cudaMemsetAsync(c->is_gb, 0, c->NL, c->stream));
@@ -318,7 +358,11 @@ extern "C" int pdgpu_gather(pdgpu_ctx* c, int field, const int* idx, long long n
     CUDA_OK(cudaMalloc(&d_out, sizeof(double) * n));
     CUDA_OK(cudaMemcpyAsync(d_idx, idx, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     long long halo_shift = (long long)(c->a0 - c->R) * c->P;
-    LAUNCH(c, k_gather, nblocks(n, 256), 256, 0, (const double*)r.ptr[0], d_idx, n, halo_shift, c->NL, d_out);
+    LAUNCH(c, k_gather, nblocks(n, 256), 256, 0, (const double*)r.ptr[0], d_idx, n, halo_shift, c->own_lo, c->own_hi,
+           d_out);
+    // slab contexts: collective -- every rank passes the same index list and receives every value
+    // (each node has exactly one owner; the merge is an integer sum of the bit patterns)
+    if (c->nranks > 1 && c->comm) PD_TRY(pd_comm_allreduce_bytes(c, d_out, sizeof(double) * (size_t)n, 8));
     CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaFree(d_idx));

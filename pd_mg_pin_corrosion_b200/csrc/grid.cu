@@ -463,10 +463,23 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
         CUDA_OK(cudaStreamSynchronize(c->stream));
         CUDA_OK(cudaFree(gflag));
         CUDA_OK(cudaFree(gpos));
-        if (bad[0] || bad[1])
-            PD_FAIL("slab boundary of rank %d is within %d planes of the inlet/outlet ghost planes (%d wall mirrors, "
-                    "%d inlet/outlet nodes fall into ghost planes): use fewer ranks or a longer tube",
-                    c->rank, c->R, bad[0], bad[1]);
+        // every rank must take the same decision: a rank that returned alone would leave the others
+        // hanging in their next collective
+        double worst[2] = {(double)bad[0], (double)bad[1]};
+        {
+            c->h_red[0] = worst[0]; c->h_red[1] = worst[1];
+            CUDA_OK(cudaMemcpyAsync(c->d_red, c->h_red, sizeof(double) * 2, cudaMemcpyHostToDevice, c->stream));
+            PD_TRY(pd_comm_allreduce(c, c->d_red, 2, 1));
+            CUDA_OK(cudaMemcpyAsync(c->h_red, c->d_red, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_OK(cudaStreamSynchronize(c->stream));
+            worst[0] = c->h_red[0]; worst[1] = c->h_red[1];
+        }
+        if (worst[0] > 0.0 || worst[1] > 0.0) {
+            cudaFree(d_flag); cudaFree(d_pos); cudaFree(d_counts);
+            PD_FAIL("a slab boundary is within %d planes of the inlet/outlet planes (rank %d: %d wall mirrors, %d "
+                    "inlet/outlet nodes fall into ghost planes; worst rank %d / %d): use fewer ranks or a longer tube",
+                    c->R, c->rank, bad[0], bad[1], (int)worst[0], (int)worst[1]);
+        }
     }
     // inlet velocity table
     if (c->inlet_vax) { CUDA_OK(cudaFree(c->inlet_vax)); c->inlet_vax = nullptr; }

@@ -65,6 +65,45 @@ class Grid:
         self.origin_x, self.origin_y, self.origin_z = i.origin[0], i.origin[1], i.origin[2]
         self.a0, self.a1, self.plane = i.a0, i.a1, i.plane
 
+    # -- z-slab runs: one process per GPU (the reference has no distributed layer) --
+    def comm_init(self, uid: bytes) -> None:
+        """Join the NCCL communicator of the slab run; `uid` comes from rank 0's comm_uid()."""
+        _l.check(_l.load().pdgpu_comm_init(self.ctx, uid, self.rank, self.nranks))
+        self._refresh()
+
+    @staticmethod
+    def comm_uid() -> bytes:
+        L = _l.load()
+        buf = (C.c_ubyte * L.pdgpu_comm_uid_bytes())()
+        _l.check(L.pdgpu_comm_get_uid(buf))
+        return bytes(buf)
+
+    def comm_init_torch(self) -> None:
+        """comm_init with the id broadcast over an initialised torch.distributed process group."""
+        import torch
+        import torch.distributed as dist
+        nb = _l.load().pdgpu_comm_uid_bytes()
+        dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.zeros(nb, dtype=torch.uint8, device=dev)
+        if self.rank == 0:
+            t = torch.tensor(list(self.comm_uid()), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0)
+        self.comm_init(bytes(t.cpu().tolist()))
+
+    def allreduce(self, vals, op: str = "sum") -> np.ndarray:
+        """Host scalars combined over the ranks (no-op for one rank)."""
+        a = np.ascontiguousarray(np.atleast_1d(vals), np.float64).copy()
+        _l.check(_l.load().pdgpu_comm_allreduce(self.ctx, a.ctypes.data_as(C.POINTER(C.c_double)), a.size,
+                                                {"sum": 0, "max": 1, "min": 2}[op]))
+        return a
+
+    @property
+    def node_type_all(self) -> np.ndarray:
+        """Node types of the WHOLE grid on every rank (collective for slab contexts)."""
+        out = np.full(self.N_total, _l.OUTSIDE, np.uint8)
+        _l.check(_l.load().pdgpu_fields_download_all(self.ctx, _l.F_NODE_TYPE, _ptr(out)))
+        return out
+
     def set_node_types(self, node_type: np.ndarray) -> None:
         """Hand-built geometry (tests/test_implicit.cpp:737-772 style)."""
         nt = np.ascontiguousarray(node_type, np.uint8)
@@ -172,6 +211,14 @@ class Fields:
         _l.check(_l.load().pdgpu_fields_download(g.ctx, _FIELD_IDS[name], _ptr(out)))
         return out
 
+    def get_all(self, name: str) -> np.ndarray:
+        """The whole global array on every rank (collective for slab contexts)."""
+        g = self._grid
+        shape = (g.N_total, g.dim) if name in ("vel", "vel_new") else (g.N_total,)
+        out = np.zeros(shape, np.uint8 if name in _U8 else np.float64)
+        _l.check(_l.load().pdgpu_fields_download_all(g.ctx, _FIELD_IDS[name], _ptr(out)))
+        return out
+
     def set(self, name: str, value) -> None:
         g = self._grid
         shape = (g.N_total, g.dim) if name in ("vel", "vel_new") else (g.N_total,)
@@ -218,7 +265,7 @@ def initialize_fields(fields: Fields, grid: Grid, grains, cfg: Config) -> None:
     _l.check(_l.load().pdgpu_fields_init(grid.ctx, _ptr(gb) if gb is not None else None,
                                          _ptr(pr) if pr is not None else None))
     if fields.D_map is not None:   # host-only output field
-        nt = grid.node_type
+        nt = grid.node_type_all if grid.nranks > 1 else grid.node_type
         D = np.zeros(grid.N_total)
         D[(nt == _l.FLUID) | (nt == _l.INLET) | (nt == _l.OUTLET)] = cfg.D_liquid
         if gb is not None:
@@ -392,11 +439,13 @@ class CoupledSolver:
         return s
 
     def write_diagnostics(self, grid: Grid, fields: Fields, t_corr: float, cfg: Config) -> None:
-        d = diagnostics(grid)
+        d = diagnostics(grid)                      # reductions over all ranks
         n0 = len(self.initial_solid_indices)
-        loss = (1.0 - self._solid_C_sum(fields) / (n0 + 1e-30)) * 100.0
+        loss = (1.0 - self._solid_C_sum(fields) / (n0 + 1e-30)) * 100.0   # collective gather, same sum on every rank
         if loss < 0.0:
             loss = 0.0
+        if grid.rank != 0:
+            return
         self.log(f"  t={t_corr:.1f} s ({t_corr / 3600.0:.2f} h)  pin_mass_loss={loss:.2f}%  solid={d.solid_count}"
                  f"  v_max={d.v_max:.3e}  C_max_fluid={d.C_max_fluid:.4f}")
         with open(os.path.join(cfg.output_dir, "diagnostics.csv"), "a") as f:
@@ -415,15 +464,24 @@ class CoupledSolver:
             self.frame_count += 1
 
     def run(self, grid: Grid, fields: Fields, cfg: Config) -> float:
+        """One rank per GPU when grid.nranks > 1 (z-slabs, comm_init done by the caller): every rank runs
+        this loop, the reductions inside the library span all ranks, rank 0 writes the files."""
         cfg.check_supported()
-        os.makedirs(cfg.output_dir, exist_ok=True)
-        self.writer.set_pvd_path(cfg.output_dir + "/simulation.pvd")
-        self.flow_writer.set_pvd_path(cfg.output_dir + "/flow.pvd")
-        with open(os.path.join(cfg.output_dir, "diagnostics.csv"), "w") as f:
-            f.write("time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n")
-        with open(os.path.join(cfg.output_dir, "mass_loss.csv"), "w") as f:
-            f.write("time_h,pin_mass_loss_pct\n")
-        self.initial_solid_indices = np.nonzero(grid.node_type == _l.SOLID_MG)[0].astype(np.int32)
+        root = grid.rank == 0
+        if grid.nranks > 1:
+            if self.write_vti:
+                raise ValueError("CoupledSolver: VTI snapshots are written by single-GPU runs only")
+            if not root:
+                self.log = lambda *a, **k: None
+        if root:
+            os.makedirs(cfg.output_dir, exist_ok=True)
+            self.writer.set_pvd_path(cfg.output_dir + "/simulation.pvd")
+            self.flow_writer.set_pvd_path(cfg.output_dir + "/flow.pvd")
+            with open(os.path.join(cfg.output_dir, "diagnostics.csv"), "w") as f:
+                f.write("time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n")
+            with open(os.path.join(cfg.output_dir, "mass_loss.csv"), "w") as f:
+                f.write("time_h,pin_mass_loss_pct\n")
+        self.initial_solid_indices = np.nonzero(grid.node_type_all == _l.SOLID_MG)[0].astype(np.int32)
         n0 = len(self.initial_solid_indices)
         self.log(f"Initial solid nodes: {n0}")
         self.flow_solver.init(grid, cfg)
@@ -436,7 +494,7 @@ class CoupledSolver:
             cycle += 1
             self.log(f"\n=== Coupling cycle {cycle}, t={t_corr:.1f} s ({t_corr / 3600.0:.2f} h) ===")
             if need_flow_solve:
-                self.flow_solver.solve_steady(fields, grid, cfg, verbose=self.log is print)
+                self.flow_solver.solve_steady(fields, grid, cfg, verbose=self.log is print and root)
                 self.dissolved_since_flow = 0
                 need_flow_solve = False
                 self._snapshot(grid, fields, cfg, "flow", t_corr, self.flow_writer)
@@ -465,7 +523,8 @@ class CoupledSolver:
                     self.write_diagnostics(grid, fields, t_corr, cfg)
                 if t_corr >= cfg.T_final:
                     break
-            n_dissolved = self.ard_solver.apply_phase_change(fields, grid, cfg)
+            n_dissolved = self.ard_solver.apply_phase_change(fields, grid, cfg)   # this rank's slab
+            n_dissolved = int(grid.allreduce([n_dissolved], "sum")[0])            # all ranks take the same branch
             self.total_dissolved += n_dissolved
             self.dissolved_since_flow += n_dissolved
             if n_dissolved > 0:
