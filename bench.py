@@ -25,6 +25,12 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# CPU-baseline protocol: OpenMP threads pinned. libgomp reads this when it is loaded
+# (numpy / torch / the oracle library), so it is set before any of them is imported -- but only in the
+# one process that times the CPU path: under torchrun every rank would pin its main thread to the same
+# core (measured: 5.4 -> 8.6 ms per step at N = 2).
+if int(os.environ.get("WORLD_SIZE", "1")) == 1 or ("reference" in sys.argv and os.environ.get("RANK", "0") == "0"):
+    os.environ.setdefault("OMP_PROC_BIND", "true")
 
 import numpy as np  # noqa: E402
 
@@ -132,61 +138,129 @@ def cpu_reference(steps: int, warmup: int, threads: int | None = None) -> dict:
         return _cpu_reference(steps, warmup, threads)
 
 
+def _thread_sweep(nproc: int) -> list[int]:
+    """{1, nproc/2, nproc-1, nproc}"""
+    return sorted({1, max(1, nproc // 2), max(1, nproc - 1), nproc})
+
+
 def _cpu_reference(steps: int, warmup: int, threads: int | None = None) -> dict:
-    """The reference's own OpenMP path (oracle/_ref, else the plain-C port) on the host cores,
-    on the bounded sample of the workload. Test/baseline infrastructure only."""
+    """The reference's own OpenMP path (oracle/_ref, else the plain-C port) on the host cores, on the
+    bounded sample of the workload: thread sweep {1, nproc/2, nproc-1, nproc} with OMP_PROC_BIND=true,
+    best figure reported with its thread count. Test/baseline infrastructure only."""
     from oracle import refapi
     cfg, name = workload_cfg(1, sample=True)
-    cores = threads or os.cpu_count() or 1
+    nproc = os.cpu_count() or 1
+    sweep = [threads] if threads else _thread_sweep(nproc)
     ov = {"L_wire": cfg.L_wire, "L_upstream": cfg.L_upstream, "L_downstream": cfg.L_downstream}
     t_build = time.time()
     if refapi.have_ref(3):
-        sim = refapi.RefSim(3, "params_fine.cfg", ov, threads=cores)
+        sim = refapi.RefSim(3, "params_fine.cfg", ov, threads=max(sweep))
         kind = "reference"
         nt = sim.get("node_type")
         rowlen = np.diff(sim.get("nbr_offset").astype(np.int64))
+        set_threads = sim.lib.ref_set_threads
     else:
         from oracle.portapi import PortSim
-        sim = PortSim(3, cfg, threads=cores)
+        sim = PortSim(3, cfg, threads=max(sweep))
         sim.init_fields()
         kind = "port"
         nt = sim.node_type
         rowlen = np.diff(sim.csr()[0])
+        set_threads = sim.L.pdo_set_threads
     t_build = time.time() - t_build
     ns_bonds = int(rowlen[nt == 0].sum())
     ard_bonds = int(rowlen[(nt == 0) | (nt == 1)].sum())
     dt = sim.ns_compute_dt()
     dtc = sim.ard_compute_dt()
-    for _ in range(warmup):
-        sim.ns_iterate(1, dt)
-        sim.ard_iterate(1, dtc)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        sim.ns_iterate(1, dt)
-        sim.ard_iterate(1, dtc)
-    el = time.perf_counter() - t0
-    value = (ns_bonds + ard_bonds) * steps / el
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{name}: {ns_bonds + ard_bonds} bond-updates/step, {steps} steps in {el:.2f} s "
+    runs = []
+    for thr in sweep:
+        if set_threads is not None:
+            set_threads(int(thr))
+        # steps scaled so that every sweep point costs about the same wall time
+        k = max(2, int(round(steps * thr / max(sweep))))
+        for _ in range(warmup):
+            sim.ns_iterate(1, dt)
+            sim.ard_iterate(1, dtc)
+        t0 = time.perf_counter()
+        for _ in range(k):
+            sim.ns_iterate(1, dt)
+            sim.ard_iterate(1, dtc)
+        el = time.perf_counter() - t0
+        runs.append({"threads": int(thr), "steps": k, "seconds": el, "value": (ns_bonds + ard_bonds) * k / el})
+    best = max(runs, key=lambda r: r["value"])
+    sweep_txt = ", ".join(f"{r['threads']} thr: {r['value'] / 1e9:.3f} G/s" for r in runs)
+    return {"value": best["value"], "unit": UNIT, "cores": best["threads"], "kind": kind,
+            "sample": f"{name}: {ns_bonds + ard_bonds} bond-updates/step, {best['steps']} steps in "
+                      f"{best['seconds']:.2f} s at {best['threads']} of {nproc} host threads, OMP_PROC_BIND="
+                      f"{os.environ.get('OMP_PROC_BIND', 'unset')}; sweep [{sweep_txt}] "
                       f"(+{t_build:.1f} s grid/CSR build, untimed)",
-            "ms_per_step": 1e3 * el / steps}
+            "ms_per_step": 1e3 * best["seconds"] / best["steps"], "sweep": runs, "nproc": nproc}
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 50))   # each step = one NS + one ARD loop body on the bounded sample (~0.1 s)
-    base = cpu_reference(steps, min(args.warmup, 1))
+    steps = max(2, min(args.steps, 50))   # each step = one NS + one ARD loop body on the bounded sample (~0.1 s at 16 threads)
+    base = cpu_reference(steps, min(args.warmup, 1))   # thread sweep, best figure (SURVEY.md 8d)
     _, wname = workload_cfg(args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic (deterministic geometry from the cfg; Poiseuille initial flow)",
             "config": {"workload": wname, "measured_on": base["sample"]},
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "sweep", "nproc")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def slab_parity(S, L_, dist, local: int, rank: int, world: int) -> dict:
+    """In-run check of the multi-GPU path (the driver's test box has one GPU): 3D params.cfg (dx = 5 um,
+    67x67x287) advanced by 6 NS + 3 ARD loop bodies on `world` z-slabs and, on rank 0, on one GPU; the
+    SHA-256 of every rank's owned planes of rho / vel / C must equal that of the same planes of the
+    single-GPU run (same per-node arithmetic and order: SURVEY.md 8e)."""
+    import hashlib
+    L = L_.load()
+    cfg = Config.load(os.path.join(ROOT, "configs", "params.cfg"), {"use_implicit": 0}, quiet=True)
+
+    def advance(grid):
+        f = S.Fields()
+        f.bind(grid)
+        L_.check(L.pdgpu_fields_init(grid.ctx, None, None))
+        ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
+        ns.init(grid, cfg)
+        ard.init(grid, cfg)
+        dt = ns.compute_dt(f, grid, cfg)
+        ns.iterate(f, grid, cfg, 6, dt)
+        dtc = ard.compute_dt(f, grid, cfg)
+        ard.iterate(f, grid, cfg, 3, dtc)
+        return {n: f.get(n) for n in ("rho", "vel", "C")}
+
+    def digest(arrs, a0, a1, P):
+        h = hashlib.sha256()
+        for n in ("rho", "vel", "C"):
+            h.update(np.ascontiguousarray(arrs[n][a0 * P:a1 * P]).tobytes())
+        return h.hexdigest()
+
+    g = S.Grid(3, device=local, rank=rank, nranks=world)
+    g.build(cfg)
+    g.comm_init_torch()
+    mine = (g.a0, g.a1, digest(advance(g), g.a0, g.a1, g.plane))
+    P = g.plane
+    g.close()
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    out = None
+    if rank == 0:
+        one = S.Grid(3, device=local)
+        one.build(cfg)
+        ref = advance(one)
+        one.close()
+        bad = [r for r, (a0, a1, d) in enumerate(parts) if digest(ref, a0, a1, P) != d]
+        out = {"slab_parity": "bitwise" if not bad else f"MISMATCH on ranks {bad}",
+               "slab_parity_case": f"3D params.cfg (dx=5um, 67x67x287), 6 NS + 3 ARD loop bodies, {world} z-slabs vs 1 GPU, "
+                                   "sha-256 of the owned planes of rho/vel/C"}
+    return out
 
 
 # -------------------------------------------------------------------- our arm ---------
@@ -237,16 +311,7 @@ def main() -> None:
     grid = S.Grid(3, device=local, rank=rank, nranks=world)
     grid.build(cfg)
     if world > 1:
-        nb = L.pdgpu_comm_uid_bytes()
-        uid = torch.zeros(nb, dtype=torch.uint8)
-        if rank == 0:
-            buf = (C.c_ubyte * nb)()
-            L_.check(L.pdgpu_comm_get_uid(buf))
-            uid = torch.tensor(list(buf), dtype=torch.uint8)
-        uid = uid.cuda()
-        dist.broadcast(uid, 0)
-        ub = bytes(uid.cpu().tolist())
-        L_.check(L.pdgpu_comm_init(grid.ctx, ub, rank, world))
+        grid.comm_init_torch()
     for opt in os.environ.get("PDGPU_OPTIONS", "").split(","):   # e.g. PDGPU_OPTIONS=debug_no_halo=1,graph=0
         if "=" in opt:
             k, v = opt.split("=")
@@ -357,37 +422,52 @@ def main() -> None:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
-    # algorithmic bytes (reference CSR formulation): 44 B per bond-update
-    # + 65 B per updated FLUID node (read rho,v,type; write rho_new,v_new)
+    # The offset-table kernels do not stream a CSR: their DRAM traffic is the compulsory field traffic
+    # (~1.6 GB per launch, a few % of the HBM peak) and the binding resource is the FP64 pipe.  `frac` is
+    # therefore the FP64 fraction: executed useful FP64 work over the DFMA peak measured on this device.
+    # The reference-layout (CSR) algorithmic-byte view of SURVEY.md 8d is kept beside it as csr_equiv_*.
     alg_bytes = info.ns_bonds * 44 + int(info.counts[0]) * 65
-    achieved = alg_bytes / (kms.value * 1e-3) / 1e9
-    traffic = None
+    csr_equiv = alg_bytes / (kms.value * 1e-3) / 1e9
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ns_kernel_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ns_kernel_traffic.json")))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     except (OSError, ValueError):
         pass
     fp64_peak = C.c_double()
     fp64_peak3 = C.c_double()
     L_.check(L.pdgpu_fp64_peak(grid.ctx, C.byref(fp64_peak)))
     L_.check(L.pdgpu_fp64_peak3(grid.ctx, C.byref(fp64_peak3)))
-    # FP64 work of the tiled NS kernel: 10 DFMA-class ops per bond + 5 per staged neighbour read
-    # (1.68 bonds per read on average) = 13 ops per bond, counted as 2 flop each
-    ns_flops = info.ns_bonds * 13.0 * 2.0
-    fp64_view = {"achieved_tflops": ns_flops / (kms.value * 1e-3) / 1e12, "peak_tflops": fp64_peak.value,
-                 "frac": ns_flops / (kms.value * 1e-3) / 1e12 / fp64_peak.value,
-                 "peak_tflops_3_register_sources": fp64_peak3.value,
-                 "peak_source": "pdgpu_fp64_peak / pdgpu_fp64_peak3: DFMA micro-benchmarks on this device "
-                                "(one register source + constants; three distinct register sources)",
-                 "model": "13 executed FP64 ops per bond-update (tiled kernel), 2 flop per op"}
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "pd-ns bond kernel", "kernel_ms": kms.value,
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "model": "reference CSR layout: 44 B/bond-update + 65 B/FLUID node (SURVEY.md 8d); the "
-                         "offset-table kernel does not stream a CSR, so frac can exceed 1 -- see DESIGN.md",
+    # FP64 work of the NS bond kernel: 10 DFMA-class ops per bond + 4 per staged neighbour value
+    # (1.75 bonds per staged value) = 12.3 ops per bond-update, 2 flop each
+    ops_per_bond = 10.0 + 4.0 / 1.75
+    ns_flops = info.ns_bonds * ops_per_bond * 2.0
+    achieved_tf = ns_flops / (kms.value * 1e-3) / 1e12
+    streaming = grid.info.m == 3
+    roofline = {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak.value, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp64_peak.value,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "pd-ns bond kernel (k_ns_stream)" if streaming else "pd-ns bond kernel (generic)",
+                "kernel_ms": kms.value,
+                "peak_source": "pdgpu_fp64_peak: DFMA micro-benchmark on this device in this run (MEASURED_PEAKS.json "
+                               "holds HBM and bf16 figures only)",
+                "peak_tflops_3_register_sources": fp64_peak3.value,
+                "model": f"{ops_per_bond:.1f} useful FP64 ops per bond-update x 2 flop x {info.ns_bonds} bond-updates per launch; "
+                         "tensor cores unused (no dense contraction)",
+                "csr_equiv_gbs": csr_equiv, "csr_equiv_frac": csr_equiv / peak, "hbm_peak_gbs": peak,
+                "hbm_peak_source": peak_src,
+                "csr_equiv_model": "reference CSR layout, 44 B/bond-update + 65 B/FLUID node (SURVEY.md 8d): what the "
+                                   "same launch would stream from HBM in the reference's data layout; > 1 because the "
+                                   "offset-table formulation removes that stream",
+                "algorithmic_bytes_per_launch": alg_bytes,
                 "ns_bond_updates_per_s": info.ns_bonds / (kms.value * 1e-3),
                 "ard_kernel_ms": kms_ard.value,
-                "ard_bond_updates_per_s": info.ard_bonds / (kms_ard.value * 1e-3),
-                "fp64": fp64_view}
+                "ard_kernel_what": "ARD bond kernels alone (FLUID tiles + SOLID_MG rows); pre-passes and exchanges untimed",
+                "ard_bond_updates_per_s": info.ard_bonds / (kms_ard.value * 1e-3)}
+
+    parity = None
+    if world > 1:
+        parity = slab_parity(S, L_, dist, local, rank, world)
 
     csr_view = None
     if args.csr and world == 1:
@@ -403,13 +483,13 @@ def main() -> None:
                     "ns_bond_updates_per_s": info.ns_bonds / (kc.value * 1e-3),
                     "achieved_gbs": csr_bytes / (kc.value * 1e-3) / 1e9, "frac_of_hbm_peak": csr_bytes / (kc.value * 1e-3) / 1e9 / peak,
                     "what": "k_ns_step_csr: one warp per row streaming the reference CSR layout"}
-        grid.set_option("ns_kernel", 1)
+        grid.set_option("ns_kernel", 2)
         grid.set_option("ard_kernel", 1)
         grid.free_neighbors()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         b = _cpu_reference(40, 2, None)   # ~4 s of host work on the bounded sample (+ ~2 s CSR build)
-        cpu = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu = {k: b[k] for k in ("value", "unit", "cores", "kind", "sample", "sweep", "nproc")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -418,7 +498,12 @@ def main() -> None:
                 "data": "synthetic (deterministic geometry from the cfg; Poiseuille initial flow)",
                 "config": {"workload": wname, "nodes": int(N), "bond_updates_per_step": int(bonds_total),
                            "parallelism": f"z-slab x{world}", "l2": "per-step working set (>1 GB) exceeds the 126 MB L2",
-                           "ns_kernel": "tile" if grid.info.m == 3 else "generic"},
+                           "ns_kernel": "z-streaming tiles" if grid.info.m == 3 else "generic",
+                           "grains": "none (is_gb / is_precip = 0: the flags only select the interface diffusivity "
+                                     "of wire-surface bonds)",
+                           "elided": ["wall_conc_bc (lazy): apply_wall_concentration_bc writes WALL C, which no bond "
+                                      "reads (src/pd_ard.cpp:120); device-resident runs evaluate it when WALL C is "
+                                      "observed (download / VTI / checkpoint), not every step"]},
                 "clocks": clocks, "gpu_launches": int(launches.value),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
@@ -426,6 +511,8 @@ def main() -> None:
                         "what": "pinned host rho/vel/C -> pdgpu_step_host (H2D, NS body + ARD body, D2H "
                                 "pipelined over axial chunks), every step"},
                 "roofline": roofline}
+        if parity is not None:
+            line.update(parity)
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if csr_view is not None:

@@ -34,8 +34,9 @@ void CoupledSolver::write_diagnostics(pdgpu_ctx* ctx, double t_corr, const HostC
     PdDiag d;
     PD(pdgpu_diag(ctx, &d));
     double n0 = (double)initial_solid_indices_.size();
-    double loss = (1.0 - solid_C_sum(ctx) / (n0 + 1e-30)) * 100.0;
+    double loss = (1.0 - solid_C_sum(ctx) / (n0 + 1e-30)) * 100.0;   // collective gather: same sum on every rank
     if (loss < 0.0) loss = 0.0;
+    if (rank != 0) return;
     std::printf("  t=%.1f s (%.2f h)  pin_mass_loss=%.2f%%  solid=%lld  v_max=%.3e  C_max_fluid=%.4f\n", t_corr,
                 t_corr / 3600.0, loss, d.solid_count, d.v_max, d.C_max_fluid);
     std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::app);
@@ -158,10 +159,12 @@ void CoupledSolver::snapshot(pdgpu_ctx* ctx, const HostState& st, const HostConf
 
 double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, bool verbose) {
     mkdir(cfg.output_dir.c_str(), 0755);
-    writer_.set_path(cfg.output_dir + "/simulation.pvd");
-    flow_writer_.set_path(cfg.output_dir + "/flow.pvd");
+    if (rank == 0) {
+        writer_.set_path(cfg.output_dir + "/simulation.pvd");
+        flow_writer_.set_path(cfg.output_dir + "/flow.pvd");
+    }
     const bool resuming = !resume_prefix.empty();
-    if (!resuming) {
+    if (!resuming && rank == 0) {
         std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::trunc);
         csv << "time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n";
         std::ofstream ml(cfg.output_dir + "/mass_loss.csv", std::ios::trunc);
@@ -195,7 +198,7 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
         if (need_flow_solve) {   // phase 1 :136-151
             std::printf("  Flow re-solve triggered (%d nodes dissolved since last flow solve)\n", dissolved_since_flow_);
             PdSteadyResult r;
-            PD(pdgpu_ns_solve_steady(ctx, &r, verbose ? 1 : 0));
+            PD(pdgpu_ns_solve_steady(ctx, &r, verbose && rank == 0 ? 1 : 0));
             dissolved_since_flow_ = 0;
             need_flow_solve = false;
             snapshot(ctx, st, cfg, "flow", t_corr, flow_writer_, true);   // :143-148
@@ -232,13 +235,19 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
         }
         // phase 3 :255-290
         int n_dissolved = 0;
-        PD(pdgpu_phase_change(ctx, &n_dissolved, dissolved.data(), (int)dissolved.size()));
+        PD(pdgpu_phase_change(ctx, &n_dissolved, dissolved.data(), (int)dissolved.size()));   // this rank's slab
+        const int n_local = n_dissolved;
+        if (nranks > 1) {   // all ranks take the same branch below
+            double tot = (double)n_dissolved;
+            PD(pdgpu_comm_allreduce(ctx, &tot, 1, 0));
+            n_dissolved = (int)tot;
+        }
         total_dissolved_ += n_dissolved;
         dissolved_since_flow_ += n_dissolved;
         if (n_dissolved > 0) {
             std::printf("  Phase change: %d nodes dissolved (total: %d, since flow: %d)\n", n_dissolved,
                         total_dissolved_, dissolved_since_flow_);
-            for (int t = 0; t < n_dissolved; ++t) {   // host mirrors used for output only
+            for (int t = 0; t < n_local; ++t) {   // host mirrors used for output only (this rank's nodes)
                 st.node_type[dissolved[t]] = PDGPU_FLUID;
                 st.D_map[dissolved[t]] = cfg.D_liquid;
             }

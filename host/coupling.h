@@ -45,6 +45,7 @@ public:
     // diagnostics.csv / mass_loss.csv and produces the rows the uninterrupted run produces.
     std::string checkpoint_prefix, resume_prefix;
     int checkpoint_every = 0;
+    int rank = 0, nranks = 1;   // z-slab runs: every rank runs the loop on its slab, rank 0 writes the files
     bool write_vti = true;   // state_/flow_/corr_/final_ snapshots + simulation.pvd / flow.pvd (src/coupling.cpp:117-147,242-246,292-296)
 
 private:

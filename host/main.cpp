@@ -3,11 +3,23 @@
 //
 //   pd_corrosion_gpu [config/params.cfg] [--dim 2|3] [--device N] [--dump fields.bin] [--no-vti]
 //                    [--checkpoint prefix --checkpoint-every N] [--resume prefix_cNNNN]
+//
+// z-slab runs (BASELINE config 4: the coupled run at 1/2/4/8 GPUs): start one process per GPU with
+// RANK / WORLD_SIZE / LOCAL_RANK in the environment, e.g.
+//   python -m torch.distributed.run --no-python --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 ...
+//       ... host/pd_corrosion_gpu cfg --dim 3 --no-vti
+// Rank 0 creates the NCCL id and publishes it as <output_dir>/.pdgpu_uid.<MASTER_PORT>; every rank runs
+// the coupling loop on its slab, rank 0 writes diagnostics.csv / mass_loss.csv.
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <vector>
 
 #include "config.h"
 #include "coupling.h"
@@ -21,10 +33,39 @@
         }                                                                         \
     } while (0)
 
+static int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+// NCCL unique id from rank 0 to the others through a file (no MPI / torch in this driver)
+static int exchange_uid(const std::string& path, int rank, std::vector<unsigned char>& uid) {
+    if (rank == 0) {
+        if (pdgpu_comm_get_uid(uid.data()) != 0) return 1;
+        const std::string tmp = path + ".tmp";
+        FILE* f = std::fopen(tmp.c_str(), "wb");
+        if (!f) return 1;
+        std::fwrite(uid.data(), 1, uid.size(), f);
+        std::fclose(f);
+        return std::rename(tmp.c_str(), path.c_str()) != 0;
+    }
+    for (int tries = 0; tries < 6000; ++tries) {   // up to 10 minutes
+        FILE* f = std::fopen(path.c_str(), "rb");
+        if (f) {
+            size_t got = std::fread(uid.data(), 1, uid.size(), f);
+            std::fclose(f);
+            if (got == uid.size()) return 0;
+        }
+        usleep(100000);
+    }
+    return 1;
+}
+
 int main(int argc, char** argv) {
     std::setvbuf(stdout, nullptr, _IONBF, 0);
+    const int rank = env_int("RANK", 0), nranks = env_int("WORLD_SIZE", 1);
     std::string cfg_path = "configs/params.cfg", dump;
-    int dim = 2, device = 0;
+    int dim = 2, device = env_int("LOCAL_RANK", 0);
     bool no_vti = false;
     std::string ck_prefix, resume;
     int ck_every = 0;
@@ -38,7 +79,10 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[a], "--resume") && a + 1 < argc) resume = argv[++a];
         else cfg_path = argv[a];
     }
-    std::printf("=== Peridynamic Mg-Pin Corrosion Simulation (B200 path) ===\n  Dimension: %dD\n\n", dim);
+    if (rank != 0 && !std::freopen("/dev/null", "w", stdout)) return 1;   // rank 0 reports
+    std::printf("=== Peridynamic Mg-Pin Corrosion Simulation (B200 path) ===\n  Dimension: %dD\n", dim);
+    if (nranks > 1) std::printf("  z-slabs: %d ranks (one GPU each)\n", nranks);
+    std::printf("\n");
     auto t0 = std::chrono::steady_clock::now();
     HostConfig cfg;
     cfg.load(cfg_path);
@@ -49,9 +93,25 @@ int main(int argc, char** argv) {
     }
     PdConfig pod = cfg.to_pod();
     pdgpu_ctx* ctx = nullptr;
-    PD(pdgpu_create(&pod, dim, device, &ctx));
+    if (nranks > 1 && (!no_vti || !ck_prefix.empty() || !resume.empty())) {
+        std::fprintf(stderr, "z-slab runs write no VTI snapshots / checkpoints yet: pass --no-vti\n");
+        return 1;
+    }
+    PD(pdgpu_create_slab(&pod, dim, device, rank, nranks, &ctx));
     std::printf("Building grid...\n");
     PD(pdgpu_grid_build(ctx));
+    if (nranks > 1) {
+        mkdir(cfg.output_dir.c_str(), 0755);
+        std::vector<unsigned char> uid((size_t)pdgpu_comm_uid_bytes());
+        const char* port = std::getenv("MASTER_PORT");
+        const std::string uid_path = cfg.output_dir + "/.pdgpu_uid." + (port ? port : "0");
+        if (rank == 0) std::remove(uid_path.c_str());
+        if (exchange_uid(uid_path, rank, uid)) {
+            std::fprintf(stderr, "rank %d: cannot exchange the NCCL id through %s\n", rank, uid_path.c_str());
+            return 2;
+        }
+        PD(pdgpu_comm_init(ctx, uid.data(), rank, nranks));
+    }
     PdGridInfo gi;
     PD(pdgpu_grid_info(ctx, &gi));
     std::printf("Grid: Nx=%d Ny=%d Nz=%d  N_total=%lld\n", gi.Nx, gi.Ny, gi.Nz, gi.N_total);
@@ -62,7 +122,7 @@ int main(int argc, char** argv) {
     HostState st;
     st.dim = dim; st.Nx = gi.Nx; st.Ny = gi.Ny; st.Nz = gi.Nz; st.N = gi.N_total;
     st.node_type.resize(st.N);
-    PD(pdgpu_fields_download(ctx, PDGPU_F_NODE_TYPE, st.node_type.data()));
+    PD(pdgpu_fields_download_all(ctx, PDGPU_F_NODE_TYPE, st.node_type.data()));   // whole grid on every rank
 
     std::printf("Generating grain structure...\n");
     GrainParams gp;
@@ -86,6 +146,7 @@ int main(int argc, char** argv) {
                 std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 
     CoupledSolver solver;
+    solver.rank = rank; solver.nranks = nranks;
     solver.write_vti = !no_vti;
     solver.checkpoint_prefix = ck_prefix; solver.checkpoint_every = ck_every; solver.resume_prefix = resume;
     auto t1 = std::chrono::steady_clock::now();
@@ -95,9 +156,10 @@ int main(int argc, char** argv) {
 
     if (!dump.empty()) {   // raw binary state: N, dim, then rho, vel[N][dim], C (FP64)
         std::vector<double> rho(st.N), vel((size_t)st.N * dim), C(st.N);
-        PD(pdgpu_fields_download(ctx, PDGPU_F_RHO, rho.data()));
-        PD(pdgpu_fields_download(ctx, PDGPU_F_VEL, vel.data()));
-        PD(pdgpu_fields_download(ctx, PDGPU_F_C, C.data()));
+        PD(pdgpu_fields_download_all(ctx, PDGPU_F_RHO, rho.data()));   // collective for slab runs
+        PD(pdgpu_fields_download_all(ctx, PDGPU_F_VEL, vel.data()));
+        PD(pdgpu_fields_download_all(ctx, PDGPU_F_C, C.data()));
+        if (rank != 0) { PD(pdgpu_destroy(ctx)); return 0; }
         std::ofstream f(dump, std::ios::binary);
         long long hdr[2] = {st.N, dim};
         f.write((const char*)hdr, sizeof(hdr));

@@ -160,6 +160,9 @@ int pdgpu_bc_wall(pdgpu_ctx* ctx);                   /* apply_wall_bc           
 int pdgpu_bc_wall_new(pdgpu_ctx* ctx);               /* apply_wall_bc_new            */
 int pdgpu_bc_wall_conc(pdgpu_ctx* ctx);              /* apply_wall_concentration_bc  */
 int pdgpu_bc_solid(pdgpu_ctx* ctx);                  /* apply_solid_surface_bc       */
+/* smooth_boundary_concentration (src/boundary.cpp:332-376; called after every implicit ARD step,
+ * src/coupling.cpp:186): in place, in the reference's index order. */
+int pdgpu_bc_smooth_conc(pdgpu_ctx* ctx);
 
 /* ---- PD_NS_Solver (src/pd_ns.h:9-17) --------------------------------------------------- */
 int pdgpu_ns_compute_dt(pdgpu_ctx* ctx, double* dt);

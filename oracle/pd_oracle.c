@@ -366,6 +366,31 @@ void pdo_wall_conc_bc(const PdoGrid* g, double* Cc) {
     }
 }
 
+/* src/boundary.cpp:332-376: in place, sequential index order (what the reference produces when the
+ * affected planes fall into one OpenMP chunk; the GPU kernel sweeps planes in the same order) */
+void pdo_smooth_conc(const PdoGrid* g, const PdoConfig* cfg, double* Cc) {
+    const int ax = g->dim == 2 ? 1 : 2;
+    const double y_min = -cfg->L_upstream, y_max = cfg->L_wire + cfg->L_downstream, delta = cfg->delta;
+    for (long long n = 0; n < g->N; ++n) {
+        if (g->node_type[n] != PDO_FLUID) continue;
+        int i, j, k;
+        ijk(g, n, &i, &j, &k);
+        const int a = ax == 1 ? j : k;
+        const double y = fma((double)a, g->dx, g->origin[ax]);      /* src/grid.cpp:88-92, contracted */
+        const int near_in = (y - y_min < delta), near_out = (y_max - y < delta);
+        if (!near_in && !near_out) continue;
+        double s = 0.0;
+        int cnt = 0;
+        for (int o = 0; o < g->n_off; ++o) {
+            const int dax = g->off_d[3 * o + ax];
+            if (!((near_out && dax < 0) || (near_in && dax > 0))) continue;   /* yj < y  <=>  axial offset < 0 */
+            long long nn = nbr(g, i, j, k, o);
+            if (nn >= 0 && g->node_type[nn] == PDO_FLUID) { s += Cc[nn]; ++cnt; }
+        }
+        if (cnt > 0) Cc[n] = s / cnt;
+    }
+}
+
 /* src/boundary.cpp:381-390 */
 void pdo_solid_bc(const PdoGrid* g, double* vel) {
     int dim = g->dim;

@@ -79,6 +79,8 @@ void pdo_inlet_bc(const PdoGrid* g, const PdoConfig* cfg, double* rho, double* v
 void pdo_outlet_bc(const PdoGrid* g, const PdoConfig* cfg, double* rho, double* vel, double* Cc);
 void pdo_wall_bc(const PdoGrid* g, const PdoConfig* cfg, double* rho, double* vel);
 void pdo_wall_conc_bc(const PdoGrid* g, double* Cc);
+/* smooth_boundary_concentration (src/boundary.cpp:332-376) */
+void pdo_smooth_conc(const PdoGrid* g, const PdoConfig* cfg, double* Cc);
 void pdo_solid_bc(const PdoGrid* g, double* vel);
 
 /* PD-NS (src/pd_ns.cpp:36-180). */

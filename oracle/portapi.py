@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         L.pdo_wall_bc.argtypes = [vp, cp, dp, dp]
         L.pdo_wall_conc_bc.argtypes = [vp, dp]
         L.pdo_solid_bc.argtypes = [vp, dp]
+        L.pdo_smooth_conc.argtypes = [vp, cp, dp]
         L.pdo_max_fluid_speed.restype = C.c_double
         L.pdo_max_fluid_speed.argtypes = [vp, dp]
         L.pdo_ns_compute_dt.restype = C.c_double
@@ -179,6 +180,7 @@ class PortSim:
     def wall_bc_new(self): self.L.pdo_wall_bc(self.g, self.c, _dp(self.rho_new), _dp(self.vel_new))
     def wall_conc_bc(self): self.L.pdo_wall_conc_bc(self.g, _dp(self.C))
     def solid_bc(self): self.L.pdo_solid_bc(self.g, _dp(self.vel))
+    def smooth_conc(self): self.L.pdo_smooth_conc(self.g, self.c, _dp(self.C))
     def ns_compute_dt(self): return self.L.pdo_ns_compute_dt(self.g, self.c, _dp(self.vel))
     def ard_compute_dt(self): return self.L.pdo_ard_compute_dt(self.g, self.c, _dp(self.vel))
 

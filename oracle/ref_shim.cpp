@@ -165,6 +165,7 @@ void ref_apply_wall_concentration_bc(void* h) {
     apply_wall_concentration_bc(S(h)->fields, S(h)->grid, S(h)->cfg);
 }
 void ref_apply_solid_surface_bc(void* h) { apply_solid_surface_bc(S(h)->fields, S(h)->grid); }
+void ref_smooth_boundary_concentration(void* h) { smooth_boundary_concentration(S(h)->fields, S(h)->grid, S(h)->cfg); }
 void ref_update_node_types(void* h) { update_node_types_after_dissolution(S(h)->grid, S(h)->fields); }
 
 // ---- PD-NS --------------------------------------------------------------------

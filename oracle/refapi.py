@@ -64,6 +64,7 @@ def _lib(dim: int) -> C.CDLL:
                  "ref_fields_init", "ref_apply_inlet_bc", "ref_apply_outlet_bc",
                  "ref_apply_wall_bc", "ref_apply_wall_bc_new",
                  "ref_apply_wall_concentration_bc", "ref_apply_solid_surface_bc",
+                 "ref_smooth_boundary_concentration",
                  "ref_update_node_types", "ref_ns_init", "ref_swap_flow", "ref_ard_init",
                  "ref_swap_C"):
         getattr(lib, name).restype = None
@@ -190,6 +191,7 @@ class RefSim:
     def wall_bc_new(self): self.lib.ref_apply_wall_bc_new(self.h)
     def wall_conc_bc(self): self.lib.ref_apply_wall_concentration_bc(self.h)
     def solid_bc(self): self.lib.ref_apply_solid_surface_bc(self.h)
+    def smooth_conc(self): self.lib.ref_smooth_boundary_concentration(self.h)
     def ns_compute_dt(self) -> float: return self.lib.ref_ns_compute_dt(self.h)
     def ns_step(self, dt): self.lib.ref_ns_step(self.h, dt)
     def ns_iterate(self, n, dt): self.lib.ref_ns_iterate(self.h, n, dt)

@@ -5,6 +5,7 @@
 // write p = EOS(rho) (the pressure field is kept as a shadow of rho, which removes the
 // reference's separate compute_pressure pass, src/pd_ns.cpp:36-50).
 #include "common.cuh"
+#include "geom.cuh"
 
 // ---------------------------------------------------------------- inlet --------
 // apply_inlet_bc (src/boundary.cpp:31-75): prescribed Poiseuille velocity, rho = mean rho of
@@ -290,6 +291,66 @@ int pd_flush_wall_c(pdgpu_ctx* c) {
     if (!c->wallC_pending) return 0;
     c->wallC_pending = false;
     return pd_enqueue_bc_wall_conc(c, 1 - c->wallC_src, true, c->wallC_src);
+}
+
+// smooth_boundary_concentration (src/boundary.cpp:332-376, implicit branch src/coupling.cpp:186): FLUID
+// nodes within delta of the inlet / outlet end of the fluid column take the mean C of their FLUID
+// neighbours on the interior side (lower planes at the outlet end, higher planes at the inlet end).
+// The reference updates C IN PLACE in index order: an outlet-side node reads lower planes that were
+// already smoothed, an inlet-side node reads higher planes that are still untouched.  Both are
+// reproduced by sweeping the affected planes in ascending axial order, one launch per plane (nodes
+// of one plane never read each other: same-plane neighbours are not "deeper in the interior").
+template <int DIM>
+__global__ void k_bc_smooth_plane(Lat L, long long plane_lo, int near_in, int near_out,
+                                  const uint8_t* __restrict__ type, const OffEntry* __restrict__ off, int n_off,
+                                  double* __restrict__ C) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= L.P) return;
+    const long long l = plane_lo + q;
+    if (type[l] != PDGPU_FLUID) return;
+    const int jj = (DIM == 3) ? (int)(q / L.Nx) : 0;
+    const int ii = (int)(q - (long long)jj * L.Nx);
+    double s = 0.0;
+    int cnt = 0;
+    for (int o = 0; o < n_off; ++o) {           // CSR order: the sum is bit-identical to the reference's
+        const OffEntry e = off[o];
+        const int dax = (DIM == 3) ? e.dk : e.dj;
+        if (!((near_out && dax < 0) || (near_in && dax > 0))) continue;
+        const int ni = ii + e.di;
+        if (ni < 0 || ni >= L.Nx) continue;
+        if (DIM == 3) { const int nj = jj + e.dj; if (nj < 0 || nj >= L.Ny) continue; }
+        const long long nn = l + e.lin;
+        if (type[nn] == PDGPU_FLUID) { s += C[nn]; ++cnt; }
+    }
+    if (cnt > 0) C[l] = s / cnt;
+}
+
+int pd_enqueue_bc_smooth(pdgpu_ctx* c, int bufC) {
+    Lat L = make_lat(c);
+    const double y_min = -c->cfg.L_upstream, y_max = c->cfg.L_wire + c->cfg.L_downstream, delta = c->cfg.delta;
+    const double o_ax = (c->dim == 2) ? c->origin[1] : c->origin[2];
+    for (int a = c->a0; a < c->a1; ++a) {       // ascending axial order = the reference's index order
+        const double y = geom_coord(o_ax, a, c->cfg.dx);
+        const int near_in = (y - y_min < delta), near_out = (y_max - y < delta);
+        if (!near_in && !near_out) continue;
+        const long long plane_lo = (long long)(a - c->a0 + c->R) * c->P;
+        if (c->dim == 2)
+            LAUNCH(c, k_bc_smooth_plane<2>, nblocks(c->P, 128), 128, 0, L, plane_lo, near_in, near_out, c->type,
+                   c->d_off, c->n_off, c->C[bufC]);
+        else
+            LAUNCH(c, k_bc_smooth_plane<3>, nblocks(c->P, 128), 128, 0, L, plane_lo, near_in, near_out, c->type,
+                   c->d_off, c->n_off, c->C[bufC]);
+    }
+    return 0;
+}
+
+extern "C" int pdgpu_bc_smooth_conc(pdgpu_ctx* c) {
+    NEED_FIELDS(c);
+    PD_TRY(pd_flush_wall_c(c));
+    PD_TRY(pd_enqueue_bc_smooth(c, c->curC));
+    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 1, c->cur, c->curC));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 extern "C" int pdgpu_bc_wall_conc(pdgpu_ctx* c) {

@@ -19,7 +19,7 @@ using namespace stream;
 constexpr int NF = 5;                       // rho, p, vx, vy, vz
 constexpr int MSLOT = NF * MFS;             // doubles per plane slot
 constexpr int NACC = 8;                     // accumulators per node
-constexpr size_t NS_STREAM_SMEM = sizeof(double) * ((size_t)MRING * MSLOT + (size_t)2 * NACC * MGROUP) + 32;
+constexpr size_t NS_STREAM_SMEM = sizeof(double) * ((size_t)MRING * MSLOT + (size_t)2 * NACC * MGROUP) + 48;
 
 struct NsStreamParams {
     double rho_f, gamma, B;
@@ -32,6 +32,7 @@ struct NsStreamParams {
     int nchunks, ntiles;
     int par_p, par_x;      // P & 1, Nx & 1
     const int* tiles;
+    int* work;             // work-item counter of this launch (zeroed before the launch)
     const double* f[NF];
     double* o[NF];
 };
@@ -164,6 +165,7 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
     double* comb = sm + MRING * MSLOT;
     unsigned long long* full = (unsigned long long*)(comb + 2 * NACC * MGROUP);
     unsigned long long* empty = full + 2;
+    volatile int* next_item = (volatile int*)(empty + 2);   // [2]: work item of sequence number n in slot n & 1
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -172,6 +174,7 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
         mbar_init(&empty[0], MTHREADS / 32);
         mbar_init(&empty[1], MTHREADS / 32);
         mbar_fence_init();
+        next_item[0] = atomicAdd(q.work, 1);
     }
     __syncthreads();
     const int n_items = q.ntiles * q.nchunks;
@@ -183,7 +186,14 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
     const int ctr = (ty + TR) * MPITCH + (tx + TR);   // in-plane offset of the thread's own (x, y)
     unsigned k0 = 0;
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // Work items are handed out dynamically (atomic counter): CTAs that start late -- the outlet sweep
+    // of the side stream holds two SMs while this kernel starts -- simply take fewer items.  Thread 0
+    // fetches item n+1 at the start of item n; the other warps read it when they finish item n, which
+    // they cannot do before thread 0's arrivals on the full barriers of item n (after the fetch).
+    for (unsigned seq = 0;; ++seq) {
+        const int item = next_item[seq & 1];
+        if (item >= n_items) break;
+        if (tid == 0) next_item[(seq + 1) & 1] = atomicAdd(q.work, 1);
         const NsItem it = ns_item(q, item);
         const int gx = it.x0 + tx, gy = it.y0 + ty;
         const bool in_xy = gx < q.Nx && gy < q.Ny;
@@ -362,6 +372,7 @@ void pd_tile_state_free(pdgpu_ctx* c) {
     stream::TileState* s = (stream::TileState*)c->tile_state;
     if (!s) return;
     if (s->d_tiles) cudaFree(s->d_tiles);
+    if (s->d_work) cudaFree(s->d_work);
     delete s;
     c->tile_state = nullptr;
 }
@@ -372,6 +383,7 @@ int pd_stream_prepare(pdgpu_ctx* c) {
     s->epoch = c->types_epoch;
     s->cols_ok = false;
     if (c->dim != 3) return -1;
+    if (!s->d_work) CUDA_OK(cudaMalloc(&s->d_work, sizeof(int) * 16));   // here: never inside a stream capture
     if (!tile::build_columns(c, &s->tcols, &s->sum_kappa)) return -1;
     if (!build_stream_cols(s->tcols, &s->cols)) return -1;
     const int ntx = (c->Nx + TX - 1) / TX, nty = (c->Ny + TY - 1) / TY;
@@ -437,6 +449,9 @@ int pd_enqueue_ns_stream(pdgpu_ctx* c, int src, const double* d_dt, int zb, int 
     }
     const long long items = (long long)q.ntiles * q.nchunks;
     const unsigned grid = (unsigned)std::min<long long>(items, s->sm_count);
+    // one counter per launch in flight (the two plane ranges of a loop body run on two streams)
+    q.work = s->d_work + (s->work_seq++ & 15);
+    CUDA_OK(cudaMemsetAsync(q.work, 0, sizeof(int), c->stream));
     k_ns_stream<<<grid, MTHREADS, NS_STREAM_SMEM, c->stream>>>(q, K, d_dt, c->type);
     c->launches++;
     return 0;

@@ -63,6 +63,8 @@ struct TileState {
     long long epoch = -1;       // tables_epoch the tile list was built for
     int* d_tiles = nullptr;     // active (bx | by << 16) tiles: columns with a non-OUTSIDE node
     int ntiles = 0;
+    int* d_work = nullptr;      // work-item counters of the persistent kernels (one per launch in flight)
+    unsigned work_seq = 0;
     int sm_count = 0;
     bool attr_ns = false, attr_ard = false, attr_tile_ns = false, attr_tile_ard = false;
     bool cols_ok = false;

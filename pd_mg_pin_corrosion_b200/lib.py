@@ -83,7 +83,7 @@ def load() -> C.CDLL:
         "pdgpu_fields_init": [vp, vp, vp], "pdgpu_swap_flow": [vp], "pdgpu_swap_C": [vp],
         "pdgpu_gather": [vp, C.c_int, vp, C.c_longlong, vp],
         "pdgpu_bc_inlet": [vp], "pdgpu_bc_outlet": [vp], "pdgpu_bc_wall": [vp], "pdgpu_bc_wall_new": [vp],
-        "pdgpu_bc_wall_conc": [vp], "pdgpu_bc_solid": [vp],
+        "pdgpu_bc_wall_conc": [vp], "pdgpu_bc_solid": [vp], "pdgpu_bc_smooth_conc": [vp],
         "pdgpu_ns_compute_dt": [vp, dp], "pdgpu_ns_step": [vp, C.c_double],
         "pdgpu_ns_iterate": [vp, C.c_int, C.c_double], "pdgpu_ns_residual": [vp, C.POINTER(PdResidual)],
         "pdgpu_ns_solve_steady": [vp, C.POINTER(PdSteadyResult), C.c_int],

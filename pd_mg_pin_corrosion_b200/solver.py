@@ -281,6 +281,7 @@ def apply_wall_bc(f: Fields, g: Grid, cfg: Config) -> None: _l.check(_l.load().p
 def apply_wall_bc_new(f: Fields, g: Grid, cfg: Config) -> None: _l.check(_l.load().pdgpu_bc_wall_new(g.ctx))
 def apply_wall_concentration_bc(f: Fields, g: Grid, cfg: Config) -> None: _l.check(_l.load().pdgpu_bc_wall_conc(g.ctx))
 def apply_solid_surface_bc(f: Fields, g: Grid) -> None: _l.check(_l.load().pdgpu_bc_solid(g.ctx))
+def smooth_boundary_concentration(f: Fields, g: Grid, cfg: Config) -> None: _l.check(_l.load().pdgpu_bc_smooth_conc(g.ctx))
 
 
 def update_node_types_after_dissolution(g: Grid, f: Fields) -> None:

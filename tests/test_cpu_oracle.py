@@ -85,6 +85,12 @@ def test_port_vs_compiled_reference(case):
         getattr(p, op)()
         for f in ("rho", "vel", "C"):
             assert H.rel_err(getattr(p, f), r.get(f)) <= 1e-15, (op, f)
+    # smooth_boundary_concentration (implicit-branch BC): in place and order dependent;
+    # the port's sequential sweep must equal the reference (4 OpenMP threads) bit for bit, twice over
+    for _ in range(2):
+        r.smooth_conc()
+        p.smooth_conc()
+        assert np.array_equal(p.C, r.get("C")), "smooth_conc"
     dt = r.ns_compute_dt()
     assert p.ns_compute_dt() == dt
     r.ns_step(dt)

@@ -108,6 +108,23 @@ def test_boundary_operators(case):
         assert_fields(fields, ref, ("rho", "vel", "C", "rho_new", "vel_new"))
 
 
+@pytest.mark.parametrize("case", ["2d_default", "2d_offgrid", "3d_small", "3d_default"])
+def test_smooth_boundary_concentration_bit_exact(case):
+    """smooth_boundary_concentration (src/boundary.cpp:332-376): in-place sweep in the
+    reference's index order; sums run in CSR order, so C must be reproduced bit for bit. Applied twice:
+    the second pass reads the first pass's output (order dependence at the outlet end)."""
+    ref = H.make_ref(case)
+    H.perturbed_state(ref, seed=7)
+    S, cfg, grid, fields = gpu_side(case, ref=ref)
+    before = fields.get("C")
+    for _ in range(2):
+        ref.smooth_conc()
+        S.smooth_boundary_concentration(fields, grid, cfg)
+        got, want = fields.get("C"), ref.get("C")
+        assert np.array_equal(got, want), float(np.abs(got - want).max())
+    assert not np.array_equal(before, fields.get("C"))   # the operator did something
+
+
 @pytest.mark.parametrize("case", ["2d_default", "2d_poiseuille", "2d_offgrid", "3d_small", "3d_default"])
 def test_ns_step_and_dt(case):
     ref = H.make_ref(case)
