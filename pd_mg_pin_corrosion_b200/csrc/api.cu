@@ -101,11 +101,14 @@ extern "C" int pdgpu_create_slab(const PdConfig* cfg, int dim, int device, int r
     int prio_least = 0, prio_greatest = 0;
     CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     CUDA_OK(cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_greatest));
+    CUDA_OK(cudaStreamCreateWithPriority(&c->stream3, cudaStreamNonBlocking, prio_greatest));
     CUDA_OK(cudaEventCreate(&c->ev_t0));
     CUDA_OK(cudaEventCreate(&c->ev_t1));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&c->ev_c, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_d, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&c->ev_e, cudaEventDisableTiming));
     CUDA_OK(cudaMalloc(&c->d_red, sizeof(double) * 8192));
     CUDA_OK(cudaMallocHost(&c->h_red, sizeof(double) * 64));
     CUDA_OK(cudaMalloc(&c->d_u64, sizeof(unsigned long long) * 16));
@@ -155,8 +158,11 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->ev_c) cudaEventDestroy(c->ev_c);
+    if (c->ev_d) cudaEventDestroy(c->ev_d);
+    if (c->ev_e) cudaEventDestroy(c->ev_e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->stream3) cudaStreamDestroy(c->stream3);
     delete c;
     return 0;
 }
@@ -197,6 +203,7 @@ extern "C" int pdgpu_set_option(pdgpu_ctx* c, const char* name, int value) {
     else if (n == "graph") c->opt_graph = value;
     else if (n == "outlet_kernel") c->opt_outlet_kernel = value;
     else if (n == "overlap") c->opt_overlap = value;
+    else if (n == "comm_overlap") c->opt_comm_overlap = value;
     else if (n == "outlet_single_rows") c->opt_outlet_single_rows = value;
     else if (n == "host_step_graded") c->opt_host_step_graded = value;
     else if (n == "outlet_rows_g") {

@@ -255,49 +255,77 @@ extern "C" int pdgpu_ard_step(pdgpu_ctx* c, double dt) {
     return 0;
 }
 
-// explicit coupling-loop body (src/coupling.cpp:232-238)
+// explicit coupling-loop body (src/coupling.cpp:232-238).  Same arithmetic and dependence order as
+// the sequential body; schedule as in enqueue_ns_body (ns.cu):
+//  * outlet rank: sweep + |v| of the outlet planes + the z-tiles that see outlet planes on the side stream;
+//  * slab contexts: the chain  {weights of ghost solids} -> {boundary tiles + SOLID_MG rows} -> {C of
+//    the boundary planes}  runs on a third stream next to the interior tiles, which read owned planes only.
 static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
-    if (pd_can_overlap(c)) {
-        // fork/join as in the NS body: the outlet sweep and the few z-tiles that see outlet
-        // planes run on the side stream next to the bulk tiles (src/coupling.cpp:232-238 order
-        // is preserved for every data dependence).
-        cudaStream_t main_s = c->stream, side = c->stream2;
-        const int z_hi = c->R + (c->a1 - c->a0);
+    cudaStream_t main_s = c->stream, side = c->stream2, comm = c->stream3;
+    const bool fork = pd_can_overlap(c);
+    const bool slab = c->nranks > 1 && c->comm;
+    const bool ovl = pd_comm_overlap(c);
+    const bool lower = slab && c->rank > 0, upper = slab && c->rank < c->nranks - 1;
+    const int z_lo = c->R, z_hi = c->R + (c->a1 - c->a0), W = c->R;
+    const bool tiles = (c->opt_ard_kernel == 1 || c->opt_ard_kernel == 2);   // kernels that can skip the wall copy
+    const double* d_dt = c->d_dt + 1;
+    const bool skipw = tiles && fork;   // the side stream's wall-concentration BC writes WALL C of both buffers
+
+    if (fork) {
         PD_TRY(pd_enqueue_bc_outlet_prepass(c, buf, srcC));   // before the fork: see outlet.cu
         CUDA_OK(cudaEventRecord(c->ev_a, main_s));
         CUDA_OK(cudaStreamWaitEvent(side, c->ev_a, 0));
-        const bool tiles = (c->opt_ard_kernel == 1 || c->opt_ard_kernel == 2);   // kernels that can skip the wall copy
+        StreamSwap sw(c, side);
+        PD_TRY(pd_enqueue_bc_outlet_sweep(c, buf, srcC));
+        PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0, c->NL));
+        // WALL concentrations are never read by a bond (src/pd_ard.cpp:120): off the critical path
+        if (tiles && !c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC, true));
+    }
+    PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
+    if (!fork) {
+        PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
+        if (!c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
+        if (c->n_outlet) PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0_any, c->NL));   // outlet velocities just changed
+    } else if (!tiles && !c->opt_lazy_wallc) {
+        PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
+    }
+    PD_TRY(pd_enqueue_ard_prepass_solids(c, srcC));
+    if (slab && !ovl) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));   // salt flags + weights of ghost solids
+    if (fork) CUDA_OK(cudaEventRecord(c->ev_b, main_s));
+
+    int i0 = z_lo, i1 = fork ? c->z_cut : z_hi;
+    if (ovl) {
+        CUDA_OK(cudaEventRecord(c->ev_d, main_s));
+        CUDA_OK(cudaStreamWaitEvent(comm, c->ev_d, 0));
         {
-            StreamSwap sw(c, side);
-            PD_TRY(pd_enqueue_bc_outlet_sweep(c, buf, srcC));
-            PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0, c->NL));
-            // WALL concentrations are never read by a bond (src/pd_ard.cpp:120): off the critical path
-            if (tiles && !c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC, true));
+            StreamSwap sw(c, comm);
+            PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));
+            bool solids_done = false;
+            if (lower) {
+                PD_TRY(pd_enqueue_ard_main(c, buf, srcC, d_dt, z_lo, z_lo + W, true, skipw));
+                solids_done = true;
+            }
+            if (upper) PD_TRY(pd_enqueue_ard_main(c, buf, srcC, d_dt, z_hi - W, z_hi, !solids_done, skipw));
+            PD_TRY(pd_enqueue_halo(c, 1, buf, 1 - srcC));
         }
-        PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
-        if (!tiles && !c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
-        PD_TRY(pd_enqueue_ard_prepass_solids(c, srcC));
-        if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));
-        CUDA_OK(cudaEventRecord(c->ev_b, main_s));
-        PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, c->R, c->z_cut, false, tiles));
+        CUDA_OK(cudaEventRecord(c->ev_e, comm));
+        if (lower) i0 = z_lo + W;
+        if (upper) i1 = z_hi - W;
+    }
+    // SOLID_MG rows: with the boundary chain (ovl); else with the top tiles of the outlet rank (they may read
+    // OUTLET C of the sweep) or with the only launch there is
+    PD_TRY(pd_enqueue_ard_main(c, buf, srcC, d_dt, i0, i1, !ovl && !fork, skipw));
+    if (fork) {
         CUDA_OK(cudaStreamWaitEvent(side, c->ev_b, 0));
         {
             StreamSwap sw(c, side);
-            PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, c->z_cut, z_hi, true, tiles));
+            PD_TRY(pd_enqueue_ard_main(c, buf, srcC, d_dt, c->z_cut, z_hi, !ovl, skipw));
         }
         CUDA_OK(cudaEventRecord(c->ev_c, side));
         CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_c, 0));
-        if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 1, buf, 1 - srcC));
-        return 0;
     }
-    PD_TRY(pd_enqueue_bc_inlet(c, buf, srcC));
-    PD_TRY(pd_enqueue_bc_outlet(c, buf, srcC));
-    if (!c->opt_lazy_wallc) PD_TRY(pd_enqueue_bc_wall_conc(c, srcC));
-    if (c->n_outlet) PD_TRY(pd_enqueue_ard_vmag_range(c, buf, c->out_l0_any, c->NL));   // outlet velocities just changed
-    PD_TRY(pd_enqueue_ard_prepass_solids(c, srcC));
-    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 3, buf, srcC));
-    PD_TRY(pd_enqueue_ard_main(c, buf, srcC, c->d_dt + 1, -1, -1, true));
-    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 1, buf, 1 - srcC));
+    if (ovl) CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_e, 0));
+    else if (slab) PD_TRY(pd_enqueue_halo(c, 1, buf, 1 - srcC));
     return 0;
 }
 

@@ -206,6 +206,17 @@ int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC) {
     return 0;
 }
 
+int pd_enqueue_bc_wall_range(pdgpu_ctx* c, int buf, long long first, long long n) {
+    if (n <= 0) return 0;
+    if (c->dim == 2)
+        LAUNCH(c, k_bc_wall<2>, nblocks(n, 256), 256, 0, c->l_wall + first, c->l_wall_mirror + first, n, c->rho[buf],
+               c->p[buf], VXYZ(c, buf), c->cfg.rho_f);
+    else
+        LAUNCH(c, k_bc_wall<3>, nblocks(n, 256), 256, 0, c->l_wall + first, c->l_wall_mirror + first, n, c->rho[buf],
+               c->p[buf], VXYZ(c, buf), c->cfg.rho_f);
+    return 0;
+}
+
 int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part) {
     if (part == 3) {   // ghost-plane walls of a slab (refreshed locally like their owner does)
         if (!c->n_gwall) return 0;

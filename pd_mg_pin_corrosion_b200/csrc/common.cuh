@@ -70,8 +70,8 @@ struct pdgpu_ctx {
     double origin[3] = {0, 0, 0};
     bool grid_built = false, fields_ready = false;
 
-    cudaStream_t stream = nullptr, stream2 = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;   // main, outlet side stream, slab boundary / exchange stream
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr, ev_e = nullptr;
 
     // stencil
     int n_off = 0;
@@ -124,6 +124,9 @@ struct pdgpu_ctx {
     // overlap of the outlet sweep with the bulk bond kernel: walls below the first outlet plane,
     // first local plane whose stencil touches an outlet plane (tile aligned), -1 = no overlap
     long long n_wall_lo = 0;
+    // slab contexts: walls in the `reach` owned planes next to the lower / upper neighbour are
+    // l_wall[0, n_wall_b0) and l_wall[n_wall_b1, n_wall) (0 / n_wall without that neighbour)
+    long long n_wall_b0 = 0, n_wall_b1 = 0;
     int z_cut = -1;
     bool solids_below_cut = true;
 
@@ -163,6 +166,7 @@ struct pdgpu_ctx {
     int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)
     int opt_lazy_wallc = 1;         // evaluate the wall-concentration BC only when somebody reads WALL C
     int opt_overlap = 1;            // run the outlet sweep on a side stream next to the bulk kernel
+    int opt_comm_overlap = 1;       // slab contexts: boundary planes first, halo exchange next to the interior kernels
     int opt_host_step_graded = 1;   // pdgpu_step_host: thin chunks at both ends of the slab, thick ones in the middle
     int opt_outlet_rows_g = 0;      // lanes per lattice row of the row-walking sweep: 0 = default (4 if it fits), else 2, 4 or 8
     int opt_outlet_single_rows = 0; // force the single-row ring of the row-walking sweep (tests; large cross-sections use it anyway)
@@ -306,6 +310,7 @@ int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, 
 int pd_outlet_setup(pdgpu_ctx* c);
 int pd_enqueue_bc_outlet_prepass(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu: the two halves of the fast outlet BC
 int pd_enqueue_bc_outlet_sweep(pdgpu_ctx* c, int buf, int bufC);
+int pd_enqueue_bc_wall_range(pdgpu_ctx* c, int buf, long long first, long long n);   // l_wall[first, first+n)
 int pd_enqueue_bc_wall(pdgpu_ctx* c, int buf, int part = 0);   // part 0 all owned, 1 below the outlet planes, 2 in them, 3 ghost planes
 int pd_enqueue_bc_wall_conc(pdgpu_ctx* c, int bufC, bool both_buffers = false, int srcC = -1);
 int pd_flush_wall_c(pdgpu_ctx* c);   // run an owed wall-concentration BC (no-op otherwise)
@@ -347,6 +352,15 @@ struct StreamSwap {
     StreamSwap(pdgpu_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { ctx->stream = s; }
     ~StreamSwap() { c->stream = saved; }
 };
+// slab contexts: compute the boundary planes first and exchange them while the interior runs
+inline bool pd_comm_overlap(const pdgpu_ctx* c) {
+    if (!(c->nranks > 1 && c->comm && c->opt_comm_overlap && !c->opt_debug_no_halo)) return false;
+    if (c->dim != 3 || !c->full_rows || c->cfg.m_ratio != 3 || c->cfg.channel_flow_corrections) return false;
+    if (c->opt_ns_kernel < 1 || c->opt_ns_kernel > 2 || c->opt_ard_kernel < 1 || c->opt_ard_kernel > 2) return false;
+    if (c->a1 - c->a0 < 8 * c->R) return false;
+    if (c->n_outlet > 0 && (c->z_cut < 0 || c->z_cut < 6 * c->R || !c->solids_below_cut)) return false;
+    return true;
+}
 inline bool pd_can_overlap(const pdgpu_ctx* c) {
     return c->opt_overlap && c->z_cut > 0 && c->n_outlet > 0 && c->out_fast && c->opt_outlet_kernel > 0 &&
            c->opt_ns_kernel != 3 && c->opt_ard_kernel != 3;   // the CSR kernels take no plane range

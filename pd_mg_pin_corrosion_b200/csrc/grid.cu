@@ -516,6 +516,17 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
     }
 
     PD_TRY(pd_build_nbfast(c));
+    // slab contexts: wall-list ranges of the boundary planes (exchanged while the interior is computed)
+    c->n_wall_b0 = 0;
+    c->n_wall_b1 = c->n_wall;
+    if (c->nranks > 1 && c->n_wall) {
+        std::vector<int> w(c->n_wall);
+        CUDA_OK(cudaMemcpy(w.data(), c->l_wall, sizeof(int) * c->n_wall, cudaMemcpyDeviceToHost));
+        const long long lo_end = (long long)(2 * c->R) * c->P;                     // local planes [R, 2R)
+        const long long hi_beg = (long long)(c->R + (c->a1 - c->a0) - c->R) * c->P;   // last R owned planes
+        if (c->rank > 0) c->n_wall_b0 = std::lower_bound(w.begin(), w.end(), (int)lo_end) - w.begin();
+        if (c->rank < c->nranks - 1) c->n_wall_b1 = std::lower_bound(w.begin(), w.end(), (int)hi_beg) - w.begin();
+    }
     // column tables + active tile list of the streaming / tiled bond kernels: built here, outside of
     // any stream capture (a negative result only means that those kernels do not apply)
     if (pd_stream_prepare(c) > 0) return 1;

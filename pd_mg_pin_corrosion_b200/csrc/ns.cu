@@ -329,28 +329,58 @@ int pd_enqueue_channel_corrections(pdgpu_ctx* c, int buf) {
 
 // one iteration of solve_steady without the convergence block (src/pd_ns.cpp:196-205):
 // reads buffer `src`, leaves the new state (with wall mirror applied) in 1-src.
+//
+// Same arithmetic and the same order for every data dependence as the sequential loop body; the
+// schedule forks where the dependences allow it:
+//  * outlet rank (pd_can_overlap): the in-place outlet sweep is a long dependent chain on two SMs and
+//    only the top few planes depend on it -> side stream = sweep, outlet-plane walls, top z-tiles;
+//    main stream = inlet, lower walls, solid, bulk z-tiles.
+//  * slab contexts (pd_comm_overlap): the 2*reach planes next to each neighbour and the walls of the
+//    `reach` planes that are sent are computed first; their exchange then runs on a third stream next
+//    to the interior tiles.  (A wall's mirror lies within `reach` planes and never in a ghost plane --
+//    checked in pd_rebuild_tables -- so the boundary walls only read planes computed before them.)
 static int enqueue_ns_body(pdgpu_ctx* c, int src) {
-    if (pd_can_overlap(c)) {
-        // The in-place outlet sweep is a long dependent chain on two SMs; only the top few
-        // planes depend on it.  Fork: side stream = outlet sweep, outlet-plane walls, top z-tiles;
-        // main stream = inlet, lower walls, solid, bulk z-tiles.  Join before the wall mirror of
-        // the new buffers.  Same arithmetic as the sequential order of src/pd_ns.cpp:196-205.
-        cudaStream_t main_s = c->stream, side = c->stream2;
-        const int z_hi = c->R + (c->a1 - c->a0);
+    cudaStream_t main_s = c->stream, side = c->stream2, comm = c->stream3;
+    const bool fork = pd_can_overlap(c);
+    const bool slab = c->nranks > 1 && c->comm;
+    const bool ovl = pd_comm_overlap(c);
+    const bool lower = slab && c->rank > 0, upper = slab && c->rank < c->nranks - 1;
+    const int z_lo = c->R, z_hi = c->R + (c->a1 - c->a0), W = 2 * c->R;
+    const int dst = 1 - src;
+
+    // ---- boundary operators on the current buffers
+    if (fork) {
         PD_TRY(pd_enqueue_bc_outlet_prepass(c, src, c->curC));   // before the fork: see outlet.cu
         CUDA_OK(cudaEventRecord(c->ev_a, main_s));
         CUDA_OK(cudaStreamWaitEvent(side, c->ev_a, 0));
+        StreamSwap sw(c, side);
+        PD_TRY(pd_enqueue_bc_outlet_sweep(c, src, c->curC));
+        PD_TRY(pd_enqueue_bc_wall(c, src, 2));
+    }
+    PD_TRY(pd_enqueue_bc_inlet(c, src, c->curC));
+    if (!fork) PD_TRY(pd_enqueue_bc_outlet(c, src, c->curC));
+    PD_TRY(pd_enqueue_bc_wall(c, src, fork ? 1 : 0));
+    PD_TRY(pd_enqueue_bc_wall(c, src, 3));
+    PD_TRY(pd_enqueue_bc_solid(c, src));
+    if (fork) CUDA_OK(cudaEventRecord(c->ev_b, main_s));
+
+    // ---- bond kernel
+    int i0 = z_lo, i1 = fork ? c->z_cut : z_hi;   // plane range of the main stream's bulk launch
+    if (ovl) {
+        if (lower) { PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt, z_lo, z_lo + W)); i0 = z_lo + W; }
+        if (upper) { PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt, z_hi - W, z_hi)); i1 = z_hi - W; }
+        PD_TRY(pd_enqueue_bc_wall_range(c, dst, 0, c->n_wall_b0));
+        PD_TRY(pd_enqueue_bc_wall_range(c, dst, c->n_wall_b1, c->n_wall - c->n_wall_b1));
+        CUDA_OK(cudaEventRecord(c->ev_d, main_s));
+        CUDA_OK(cudaStreamWaitEvent(comm, c->ev_d, 0));
         {
-            StreamSwap sw(c, side);
-            PD_TRY(pd_enqueue_bc_outlet_sweep(c, src, c->curC));
-            PD_TRY(pd_enqueue_bc_wall(c, src, 2));
+            StreamSwap sw(c, comm);
+            PD_TRY(pd_enqueue_halo(c, 0, dst, c->curC));
         }
-        PD_TRY(pd_enqueue_bc_inlet(c, src, c->curC));
-        PD_TRY(pd_enqueue_bc_wall(c, src, 1));
-        PD_TRY(pd_enqueue_bc_wall(c, src, 3));
-        PD_TRY(pd_enqueue_bc_solid(c, src));
-        CUDA_OK(cudaEventRecord(c->ev_b, main_s));
-        PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt, c->R, c->z_cut));
+        CUDA_OK(cudaEventRecord(c->ev_e, comm));
+    }
+    PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt, i0, i1));
+    if (fork) {
         CUDA_OK(cudaStreamWaitEvent(side, c->ev_b, 0));
         {
             StreamSwap sw(c, side);
@@ -358,20 +388,16 @@ static int enqueue_ns_body(pdgpu_ctx* c, int src) {
         }
         CUDA_OK(cudaEventRecord(c->ev_c, side));
         CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_c, 0));
-        PD_TRY(pd_enqueue_bc_wall(c, 1 - src));
-        PD_TRY(pd_enqueue_channel_corrections(c, 1 - src));
-        if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 0, 1 - src, c->curC));
-        return 0;
     }
-    PD_TRY(pd_enqueue_bc_inlet(c, src, c->curC));
-    PD_TRY(pd_enqueue_bc_outlet(c, src, c->curC));
-    PD_TRY(pd_enqueue_bc_wall(c, src));
-    PD_TRY(pd_enqueue_bc_wall(c, src, 3));
-    PD_TRY(pd_enqueue_bc_solid(c, src));
-    PD_TRY(pd_enqueue_ns_step(c, src, c->d_dt));
-    PD_TRY(pd_enqueue_bc_wall(c, 1 - src));
-    PD_TRY(pd_enqueue_channel_corrections(c, 1 - src));
-    if (c->nranks > 1 && c->comm) PD_TRY(pd_enqueue_halo(c, 0, 1 - src, c->curC));
+    // ---- wall mirror of the new buffers, exchange
+    if (ovl) {
+        PD_TRY(pd_enqueue_bc_wall_range(c, dst, c->n_wall_b0, c->n_wall_b1 - c->n_wall_b0));
+        CUDA_OK(cudaStreamWaitEvent(main_s, c->ev_e, 0));
+    } else {
+        PD_TRY(pd_enqueue_bc_wall(c, dst));
+        PD_TRY(pd_enqueue_channel_corrections(c, dst));
+        if (slab) PD_TRY(pd_enqueue_halo(c, 0, dst, c->curC));
+    }
     return 0;
 }
 
