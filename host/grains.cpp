@@ -59,6 +59,16 @@ struct Lattice {
 }  // namespace
 
 void GrainStructure::generate(const PdConfig& cfg, const GrainParams& gp, int dim, const uint8_t* type, int seed) {
+    generate_impl(cfg, gp, dim, type, seed, nullptr);
+}
+// same draws, lattice passes on the device (pdgpu_grains_voronoi / pdgpu_grains_grow_precip)
+int GrainStructure::generate_device(pdgpu_ctx* ctx, const PdConfig& cfg, const GrainParams& gp, int dim,
+                                    const uint8_t* type, int seed) {
+    return generate_impl(cfg, gp, dim, type, seed, ctx);
+}
+
+int GrainStructure::generate_impl(const PdConfig& cfg, const GrainParams& gp, int dim, const uint8_t* type, int seed,
+                                  pdgpu_ctx* ctx) {
     Lattice L;
     L.dim = dim;
     L.dx = cfg.dx;
@@ -72,7 +82,7 @@ void GrainStructure::generate(const PdConfig& cfg, const GrainParams& gp, int di
     std::vector<int> solid;
     for (int n = 0; n < N; ++n)
         if (type[n] == SOLID) solid.push_back(n);
-    if (solid.empty()) return;                                               // :25-29
+    if (solid.empty()) return 0;                                             // :25-29
 
     double cell = std::pow(cfg.dx, dim);
     double grain_vol = dim == 2 ? PI / 4.0 * gp.grain_size_mean * gp.grain_size_mean
@@ -84,6 +94,11 @@ void GrainStructure::generate(const PdConfig& cfg, const GrainParams& gp, int di
     std::vector<double> seeds(3 * (size_t)n_grains);
     for (int g = 0; g < n_grains; ++g) L.pos(solid[pick(rng)], &seeds[3 * (size_t)g]);
 
+    if (ctx) {   // Voronoi, boundaries and dilation on the device
+        if (pdgpu_grains_voronoi(ctx, seeds.data(), n_grains, gp.gb_width_cells, grain_id.data(),
+                                 is_grain_boundary.data()) != 0)
+            return 1;
+    } else {
     for (int n : solid) {                                                    // Voronoi :56-70
         double p[3];
         L.pos(n, p);
@@ -113,6 +128,7 @@ void GrainStructure::generate(const PdConfig& cfg, const GrainParams& gp, int di
         }
         is_grain_boundary.swap(next);
     }
+    }
     if (gp.precip_fraction > 0.0) {                                          // precipitates :119-175
         std::vector<int> interior;
         for (int n : solid)
@@ -127,7 +143,12 @@ void GrainStructure::generate(const PdConfig& cfg, const GrainParams& gp, int di
         std::shuffle(interior.begin(), interior.end(), rng);
         n_seeds = std::min(n_seeds, (int)interior.size());
         for (int s = 0; s < n_seeds; ++s) is_precipitate[interior[s]] = 1;
-        if (gp.precip_cluster_cells > 0) {
+        if (gp.precip_cluster_cells > 0 && ctx) {
+            std::vector<uint8_t> seeds_flag = is_precipitate;
+            if (pdgpu_grains_grow_precip(ctx, is_grain_boundary.data(), seeds_flag.data(), gp.precip_cluster_cells,
+                                         is_precipitate.data()) != 0)
+                return 1;
+        } else if (gp.precip_cluster_cells > 0) {
             double cluster_r = gp.precip_cluster_cells * cfg.dx;
             std::vector<uint8_t> grown = is_precipitate;
             for (int n : solid) {
@@ -142,6 +163,7 @@ void GrainStructure::generate(const PdConfig& cfg, const GrainParams& gp, int di
             is_precipitate.swap(grown);
         }
     }
+    return 0;
 }
 
 extern "C" int pdhost_generate_grains(const PdConfig* cfg, double grain_size_mean, double precip_fraction,
@@ -154,6 +176,23 @@ extern "C" int pdhost_generate_grains(const PdConfig* cfg, double grain_size_mea
     gp.gb_width_cells = gb_width_cells; gp.precip_cluster_cells = precip_cluster_cells;
     GrainStructure gs;
     gs.generate(*cfg, gp, dim, node_type, seed);
+    return pdhost_copy_out(gs, grain_id, is_gb, is_precip, n_grains);
+}
+
+extern "C" int pdhost_generate_grains_device(pdgpu_ctx* ctx, const PdConfig* cfg, double grain_size_mean,
+                                             double precip_fraction, int gb_width_cells, int precip_cluster_cells,
+                                             int dim, const uint8_t* node_type, int seed, int* grain_id,
+                                             uint8_t* is_gb, uint8_t* is_precip, int* n_grains) {
+    if (!ctx || !cfg || !node_type || (dim != 2 && dim != 3)) return 1;
+    GrainParams gp;
+    gp.grain_size_mean = grain_size_mean; gp.precip_fraction = precip_fraction;
+    gp.gb_width_cells = gb_width_cells; gp.precip_cluster_cells = precip_cluster_cells;
+    GrainStructure gs;
+    if (gs.generate_device(ctx, *cfg, gp, dim, node_type, seed) != 0) return 2;
+    return pdhost_copy_out(gs, grain_id, is_gb, is_precip, n_grains);
+}
+
+int pdhost_copy_out(const GrainStructure& gs, int* grain_id, uint8_t* is_gb, uint8_t* is_precip, int* n_grains) {
     size_t N = gs.grain_id.size();
     for (size_t n = 0; n < N; ++n) {
         if (grain_id) grain_id[n] = gs.grain_id[n];

@@ -20,7 +20,21 @@ struct GrainStructure {
     std::vector<uint8_t> is_grain_boundary, is_precipitate;
     int n_grains = 0;
     void generate(const PdConfig& cfg, const GrainParams& gp, int dim, const uint8_t* node_type, int seed = 42);
+    // the same structure with the O(N_solid * n_grains) Voronoi pass, the boundary passes and the cluster
+    // growth on the device; 0 on success
+    int generate_device(pdgpu_ctx* ctx, const PdConfig& cfg, const GrainParams& gp, int dim, const uint8_t* node_type,
+                        int seed = 42);
+
+private:
+    int generate_impl(const PdConfig& cfg, const GrainParams& gp, int dim, const uint8_t* node_type, int seed,
+                      pdgpu_ctx* ctx);
 };
+int pdhost_copy_out(const GrainStructure& gs, int* grain_id, uint8_t* is_gb, uint8_t* is_precip, int* n_grains);
+
+extern "C" int pdhost_generate_grains_device(pdgpu_ctx* ctx, const PdConfig* cfg, double grain_size_mean,
+                                             double precip_fraction, int gb_width_cells, int precip_cluster_cells,
+                                             int dim, const uint8_t* node_type, int seed, int* grain_id,
+                                             uint8_t* is_gb, uint8_t* is_precip, int* n_grains);
 
 extern "C" int pdhost_generate_grains(const PdConfig* cfg, double grain_size_mean, double precip_fraction,
                                       int gb_width_cells, int precip_cluster_cells, int dim,

@@ -2,7 +2,7 @@
 // libpdgpu.so. The dimension is a run-time argument instead of the PD_DIM compile-time switch.
 //
 //   pd_corrosion_gpu [config/params.cfg] [--dim 2|3] [--device N] [--dump fields.bin] [--no-vti]
-//                    [--checkpoint prefix --checkpoint-every N] [--resume prefix_cNNNN]
+//                    [--checkpoint prefix --checkpoint-every N] [--resume prefix_cNNNN] [--host-grains]
 //
 // z-slab runs (BASELINE config 4: the coupled run at 1/2/4/8 GPUs): start one process per GPU with
 // RANK / WORLD_SIZE / LOCAL_RANK in the environment, e.g.
@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
     const int rank = env_int("RANK", 0), nranks = env_int("WORLD_SIZE", 1);
     std::string cfg_path = "configs/params.cfg", dump;
     int dim = 2, device = env_int("LOCAL_RANK", 0);
-    bool no_vti = false;
+    bool no_vti = false, host_grains = false;
     std::string ck_prefix, resume;
     int ck_every = 0;
     for (int a = 1; a < argc; ++a) {
@@ -74,6 +74,7 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[a], "--device") && a + 1 < argc) device = std::atoi(argv[++a]);
         else if (!std::strcmp(argv[a], "--dump") && a + 1 < argc) dump = argv[++a];
         else if (!std::strcmp(argv[a], "--no-vti")) no_vti = true;
+        else if (!std::strcmp(argv[a], "--host-grains")) host_grains = true;
         else if (!std::strcmp(argv[a], "--checkpoint") && a + 1 < argc) ck_prefix = argv[++a];
         else if (!std::strcmp(argv[a], "--checkpoint-every") && a + 1 < argc) ck_every = std::atoi(argv[++a]);
         else if (!std::strcmp(argv[a], "--resume") && a + 1 < argc) resume = argv[++a];
@@ -129,8 +130,16 @@ int main(int argc, char** argv) {
     gp.grain_size_mean = cfg.grain_size_mean; gp.precip_fraction = cfg.precip_fraction;
     gp.gb_width_cells = cfg.gb_width_cells; gp.precip_cluster_cells = cfg.precip_cluster_cells;
     GrainStructure grains;
-    grains.generate(pod, gp, dim, st.node_type.data());
-    std::printf("Grain generation: %d grains\n", grains.n_grains);
+    auto tg = std::chrono::steady_clock::now();
+    if (host_grains) {
+        grains.generate(pod, gp, dim, st.node_type.data());
+    } else if (grains.generate_device(ctx, pod, gp, dim, st.node_type.data()) != 0) {   // lattice passes on the device
+        std::fprintf(stderr, "libpdgpu: grain generation failed: %s\n", pdgpu_last_error());
+        return 2;
+    }
+    std::printf("Grain generation: %d grains (%s passes)\n  [Timer] grain_generation: %.3f s\n", grains.n_grains,
+                host_grains ? "host" : "device",
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count());
     st.grain_id = grains.grain_id;
 
     std::printf("Initializing fields...\n");

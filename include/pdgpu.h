@@ -218,6 +218,17 @@ int pdgpu_host_unregister(void* ptr);
 int pdgpu_phase_change(pdgpu_ctx* ctx, int* n_dissolved, int* dissolved_global, int cap);
 int pdgpu_diag(pdgpu_ctx* ctx, PdDiag* out);
 
+/* ---- GrainStructure::generate on device (src/grains.cpp:55-107,152-166) -------
+ * The lattice passes of the grain generator: nearest-seed Voronoi assignment of every SOLID_MG node
+ * (brute force over the seeds), grain-boundary detection over the immediate neighbours and
+ * gb_width_cells dilation passes; then the ball growth of clustered precipitates.  The random draws
+ * (seed picks, shuffle) stay with the caller: host/grains.cpp keeps the reference's libstdc++ RNG call
+ * sequence and calls these two.  Outputs are WHOLE global arrays on every rank (collective for slabs). */
+int pdgpu_grains_voronoi(pdgpu_ctx* ctx, const double* seeds_xyz, int n_grains, int gb_width_cells,
+                         int* grain_id_global, uint8_t* is_gb_global);
+int pdgpu_grains_grow_precip(pdgpu_ctx* ctx, const uint8_t* is_gb_global, const uint8_t* seed_flags_global,
+                             int cluster_cells, uint8_t* is_precip_global);
+
 /* ---- multi-GPU: one process per GPU, z-slabs, NCCL halo exchange ------------------------ */
 int pdgpu_comm_uid_bytes(void);
 int pdgpu_comm_get_uid(void* uid_out);               /* rank 0; broadcast by the caller */

@@ -27,6 +27,8 @@ def _load() -> C.CDLL:
         L.pdhost_generate_grains.argtypes = [C.POINTER(PdConfig), C.c_double, C.c_double, C.c_int, C.c_int, C.c_int,
                                              C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                              C.POINTER(C.c_int)]
+        L.pdhost_generate_grains_device.restype = C.c_int
+        L.pdhost_generate_grains_device.argtypes = [C.c_void_p] + L.pdhost_generate_grains.argtypes
         _lib = L
     return _lib
 
@@ -36,7 +38,10 @@ class GrainStructure:
         self.grain_id = self.is_grain_boundary = self.is_precipitate = None
         self.n_grains = 0
 
-    def generate(self, node_type: np.ndarray, cfg: Config, dim: int, seed: int = 42) -> "GrainStructure":
+    def generate(self, node_type: np.ndarray, cfg: Config, dim: int, seed: int = 42, grid=None) -> "GrainStructure":
+        """grid = a built solver.Grid: the Voronoi / grain-boundary / cluster passes run on its device
+        (pdgpu_grains_voronoi, pdgpu_grains_grow_precip; collective for slab grids), the random draws stay
+        on the host in the reference's order. Same arrays either way."""
         L = _load()
         nt = np.ascontiguousarray(node_type, np.uint8)
         N = nt.size
@@ -45,12 +50,13 @@ class GrainStructure:
         self.is_precipitate = np.zeros(N, np.uint8)
         s = cfg.to_struct()
         n = C.c_int()
-        rc = L.pdhost_generate_grains(C.byref(s), cfg.grain_size_mean, cfg.precip_fraction, cfg.gb_width_cells,
-                                      cfg.precip_cluster_cells, dim, nt.ctypes.data_as(C.c_void_p), seed,
-                                      self.grain_id.ctypes.data_as(C.c_void_p),
-                                      self.is_grain_boundary.ctypes.data_as(C.c_void_p),
-                                      self.is_precipitate.ctypes.data_as(C.c_void_p), C.byref(n))
+        args = (C.byref(s), cfg.grain_size_mean, cfg.precip_fraction, cfg.gb_width_cells,
+                cfg.precip_cluster_cells, dim, nt.ctypes.data_as(C.c_void_p), seed,
+                self.grain_id.ctypes.data_as(C.c_void_p), self.is_grain_boundary.ctypes.data_as(C.c_void_p),
+                self.is_precipitate.ctypes.data_as(C.c_void_p), C.byref(n))
+        rc = L.pdhost_generate_grains(*args) if grid is None else L.pdhost_generate_grains_device(grid.ctx, *args)
         if rc != 0:
-            raise RuntimeError("pdhost_generate_grains failed")
+            from . import lib as _l
+            raise RuntimeError("grain generation failed: " + _l.load().pdgpu_last_error().decode(errors="replace"))
         self.n_grains = n.value
         return self

@@ -93,6 +93,8 @@ def load() -> C.CDLL:
         "pdgpu_comm_get_uid": [vp], "pdgpu_comm_init": [vp, vp, C.c_int, C.c_int],
         "pdgpu_halo_exchange": [vp, C.c_int],
         "pdgpu_comm_allreduce": [vp, dp, C.c_int, C.c_int],
+        "pdgpu_grains_voronoi": [vp, vp, C.c_int, C.c_int, vp, vp],
+        "pdgpu_grains_grow_precip": [vp, vp, vp, C.c_int, vp],
         "pdgpu_fields_download_all": [vp, C.c_int, vp],
         "pdgpu_timer_start": [vp], "pdgpu_timer_stop": [vp, C.POINTER(C.c_float)],
         "pdgpu_launch_count": [vp, C.POINTER(C.c_longlong), C.c_int],

@@ -108,6 +108,26 @@ def test_boundary_operators(case):
         assert_fields(fields, ref, ("rho", "vel", "C", "rho_new", "vel_new"))
 
 
+@pytest.mark.parametrize("case,extra", [("3d_default", None), ("2d_default", {"gb_width_cells": 2, "precip_cluster_cells": 2}),
+                                        ("3d_small", {"gb_width_cells": 1, "precip_cluster_cells": 1, "precip_fraction": 0.2}),
+                                        ("2d_offgrid", None), ("3d_offgrid", {"gb_width_cells": 2})])
+def test_device_grain_generation_bit_exact(case, extra):
+    """GrainStructure::generate with the Voronoi / boundary / dilation / cluster passes on the device
+    (src/grains.cpp:55-107,152-166) against the reference: grain ids and both flag arrays
+    bit for bit (nearest-seed ties resolve like the reference's strict `<`)."""
+    from pd_mg_pin_corrosion_b200.grains import GrainStructure
+    ref = H.make_ref(case, extra)
+    dim, cfg, _ = H.load_cfg(case, extra)
+    S, cfg2, grid, fields = gpu_side(case, extra, ref=ref, upload=False)
+    g = GrainStructure().generate(ref.get("node_type"), cfg, dim, grid=grid)
+    h = GrainStructure().generate(ref.get("node_type"), cfg, dim)          # host path
+    for name, want in (("grain_id", ref.get("grain_id")), ("is_grain_boundary", ref.get("is_gb")),
+                       ("is_precipitate", ref.get("is_precip"))):
+        assert np.array_equal(getattr(g, name), want), name
+        assert np.array_equal(getattr(h, name), want), name
+    assert g.n_grains == h.n_grains and int(g.is_grain_boundary.sum()) > 0
+
+
 @pytest.mark.parametrize("case", ["2d_default", "2d_offgrid", "3d_small", "3d_default"])
 def test_smooth_boundary_concentration_bit_exact(case):
     """smooth_boundary_concentration (src/boundary.cpp:332-376): in-place sweep in the
