@@ -146,8 +146,10 @@ k_ard_tile(const __grid_constant__ ArdTileParams q, const __grid_constant__ ColT
     double* s_C = sm;
     double* s_w = sm + SN;
 
-    const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
-    const int tid = (tz * TY + ty) * TX + tx;
+    // warp w owns row pair w >> 2 and thread layer w & 3: the four warps of a row pair sit on the four SM
+    // sub-partitions (warp id mod 4), so a row pair without FLUID nodes (tube rim) idles none of them
+    const int tid = (threadIdx.z * TY + threadIdx.y) * TX + threadIdx.x;
+    const int tx = tid & (TX - 1), ty = 2 * (tid >> 7) + ((tid >> 4) & 1), tz = (tid >> 5) & 3;
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = q.g.z_lo + blockIdx.z * TZ;
     const int gx = x0 + tx, gy = y0 + ty, zt = z0 + tz * RZ;   // first z-node of this thread
     const bool in_xy = gx < q.g.Nx && gy < q.g.Ny;

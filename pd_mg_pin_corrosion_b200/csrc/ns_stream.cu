@@ -178,9 +178,14 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
     }
     __syncthreads();
     const int n_items = q.ntiles * q.nchunks;
-    const int grp = tid >> 8, t = tid & (MGROUP - 1);
-    const int tx = t & (TX - 1), ty = (t >> 4) & (TY - 1), tz = t >> 7;
-    const int pair_bar = 1 + ((tid >> 5) & 7);        // named barrier of this warp and its partner in the other group
+    // Warp w owns the row pair w >> 2 of the tile, column group (w >> 1) & 1 and thread layer w & 1.  The four
+    // warps of a row pair therefore sit on the four different SM sub-partitions (warp id mod 4): a row pair
+    // without FLUID nodes (tube rim) thins every sub-partition out by one warp instead of idling one of them.
+    const int warp = tid >> 5, lane = tid & 31;
+    const int grp = (warp >> 1) & 1, tz = warp & 1;
+    const int tx = lane & (TX - 1), ty = 2 * (warp >> 2) + (lane >> 4);
+    const int t = (tz * TY + ty) * TX + tx;           // node-owning thread index inside a column group
+    const int pair_bar = 1 + 2 * (warp >> 2) + tz;    // named barrier of this warp and its partner in the other group
     const double dt = *d_dt;
     const double vW = q.visc * q.W2;
     const int ctr = (ty + TR) * MPITCH + (tx + TR);   // in-plane offset of the thread's own (x, y)

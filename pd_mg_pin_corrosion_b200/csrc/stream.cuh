@@ -121,16 +121,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     const unsigned addr = smem_u32(bar);
     unsigned done = 0;
     for (unsigned spins = 0; !done; ++spins) {
+        // try_wait suspends the thread in hardware for up to the hinted time (ns) before it reports
+        // failure: a waiting warp leaves the issue slots to the warps that feed the FP64 pipe
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
             "selp.u32 %0, 1, 0, p;\n"
             "}\n"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(2000u)
             : "memory");
-        if (!done && spins > (1u << 28)) asm volatile("trap;\n");
+        if (!done && spins > (1u << 24)) asm volatile("trap;\n");
     }
 }
 // one non-blocking poll of the phase with the given parity
