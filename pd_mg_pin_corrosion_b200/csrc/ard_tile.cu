@@ -276,6 +276,16 @@ int pd_build_nbfast(pdgpu_ctx* c) {
     return 0;
 }
 
+// SOLID_MG rows of the tiled / streaming kernels (all solids of the list, any plane)
+int pd_enqueue_ard_solid_rows(pdgpu_ctx* c, int srcC, const double* d_dt) {
+    if (!c->n_solid) return 0;
+    PdConsts k = pd_consts(c->cfg, c->dim);
+    Lat L = make_lat(c);
+    LAUNCH(c, k_ard_solid_rows, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type, c->d_off,
+           c->n_off, d_dt, k.beta_lap, c->C[srcC], c->dsol, c->C[1 - srcC]);
+    return 0;
+}
+
 // returns -1 when the tiled kernel does not apply. Expects vmag (= vmf) and dsol to be current.
 int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid,
                         bool skip_wall_copy) {
@@ -302,10 +312,6 @@ int pd_enqueue_ard_tile(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int
                                                       c->v[buf][1], c->v[buf][2], c->C[dstC]);
         c->launches++;
     }
-    if (c->n_solid && do_solid) {
-        Lat L = make_lat(c);
-        LAUNCH(c, k_ard_solid_rows, nblocks(c->n_solid, 128), 128, 0, L, c->l_solid, c->n_solid, c->type, c->d_off,
-               c->n_off, d_dt, k.beta_lap, c->C[srcC], c->dsol, c->C[dstC]);
-    }
+    if (c->n_solid && do_solid) PD_TRY(pd_enqueue_ard_solid_rows(c, srcC, d_dt));
     return 0;
 }

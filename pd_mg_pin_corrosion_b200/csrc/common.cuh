@@ -161,7 +161,7 @@ struct pdgpu_ctx {
 
     // options
     int opt_ns_kernel = 2;          // 0 = generic table loop, 1 = block tiles, 2 = z-streaming (bulk copies), 3 = materialised CSR
-    int opt_ard_kernel = 1;
+    int opt_ard_kernel = 1;         // 0 = generic, 1 = block tiles, 3 = materialised CSR
     int opt_graph = 1;
     int opt_debug_no_halo = 0;      // skip per-step halo exchanges (timing experiments; results are wrong)
     int opt_lazy_wallc = 1;         // evaluate the wall-concentration BC only when somebody reads WALL C
@@ -304,6 +304,7 @@ __device__ __forceinline__ double warp_min(double v) {
 int pd_alloc_fields(pdgpu_ctx* c);
 int pd_rebuild_tables(pdgpu_ctx* c);                 // lists, mirror table, bond counts
 int pd_build_nbfast(pdgpu_ctx* c);                   // ard_tile.cu
+int pd_enqueue_ard_solid_rows(pdgpu_ctx* c, int srcC, const double* d_dt);   // ard_tile.cu
 int pd_enqueue_bc_inlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet(pdgpu_ctx* c, int buf, int bufC);
 int pd_enqueue_bc_outlet_fast(pdgpu_ctx* c, int buf, int bufC);   // outlet.cu, -1 = not applicable

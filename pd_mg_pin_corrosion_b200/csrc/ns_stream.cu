@@ -25,14 +25,7 @@ struct NsStreamParams {
     double rho_f, gamma, B;
     double c_div, dens_diff, visc, rho_lo, rho_hi, W2, inv_dx, md_scale;
     int gamma_is_7;
-    int Nx, Ny;
-    long long P;
-    int zb, ze;            // local plane range of this launch
-    int zc;                // planes per work item (multiple of MS)
-    int nchunks, ntiles;
-    int par_p, par_x;      // P & 1, Nx & 1
-    const int* tiles;
-    int* work;             // work-item counter of this launch (zeroed before the launch)
+    StreamGeom g;          // lattice, plane range, work items (stream.cuh)
     const double* f[NF];
     double* o[NF];
 };
@@ -122,32 +115,6 @@ __device__ __forceinline__ void ns_columns(const double* __restrict__ ring, cons
     }
 }
 
-// Work item decoding.
-struct NsItem {
-    int x0, y0, z0, len, nsteps, np;
-    long long ebase;
-};
-__device__ __forceinline__ NsItem ns_item(const NsStreamParams& q, int item) {
-    NsItem it;
-    const int ch = item / q.ntiles;
-    const int tl = q.tiles[item - ch * q.ntiles];
-    it.x0 = (tl & 0xffff) * TX;
-    it.y0 = (tl >> 16) * TY;
-    it.z0 = q.zb + ch * q.zc;
-    it.len = min(q.zc, q.ze - it.z0);
-    it.nsteps = (it.len + MS - 1) / MS;
-    it.np = it.len + 2 * TR;       // staged planes z0-3 .. z0+len+2
-    it.ebase = (long long)(it.z0 - TR) * q.P + (long long)(it.y0 - TR) * q.Nx + (it.x0 - TR);
-    return it;
-}
-
-// One 16-byte piece of a staged row that this thread copies for every plane of the item.
-struct CopyDesc {
-    const double* src;   // field + first element of the piece in staged plane 0 (not yet aligned down)
-    int dst;             // offset inside a plane slot; < 0: no piece
-    int par;             // (element index of the row start in plane 0) & 1
-};
-
 // Synchronisation is point to point only, so the 16 warps drift apart and the integer / memory
 // phases of some overlap the FP64 loops of the others:
 //   full[2]   copies of a step's planes have landed: every thread arrives through
@@ -174,10 +141,10 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
         mbar_init(&empty[0], MTHREADS / 32);
         mbar_init(&empty[1], MTHREADS / 32);
         mbar_fence_init();
-        next_item[0] = atomicAdd(q.work, 1);
+        next_item[0] = atomicAdd(q.g.work, 1);
     }
     __syncthreads();
-    const int n_items = q.ntiles * q.nchunks;
+    const int n_items = q.g.ntiles * q.g.nchunks;
     // Warp w owns the row pair w >> 2 of the tile, column group (w >> 1) & 1 and thread layer w & 1.  The four
     // warps of a row pair therefore sit on the four different SM sub-partitions (warp id mod 4): a row pair
     // without FLUID nodes (tube rim) thins every sub-partition out by one warp instead of idling one of them.
@@ -198,13 +165,13 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
     for (unsigned seq = 0;; ++seq) {
         const int item = next_item[seq & 1];
         if (item >= n_items) break;
-        if (tid == 0) next_item[(seq + 1) & 1] = atomicAdd(q.work, 1);
-        const NsItem it = ns_item(q, item);
+        if (tid == 0) next_item[(seq + 1) & 1] = atomicAdd(q.g.work, 1);
+        const StreamItem it = stream_item(q.g, item);
         const int gx = it.x0 + tx, gy = it.y0 + ty;
-        const bool in_xy = gx < q.Nx && gy < q.Ny;
-        const long long lxy = (long long)gy * q.Nx + gx;
+        const bool in_xy = gx < q.g.Nx && gy < q.g.Ny;
+        const long long lxy = (long long)gy * q.g.Nx + gx;
         // alignment parity of the thread's own row in window plane 0 (4 s and 2 tz are even)
-        const int c0 = (int)(it.ebase & 1) ^ (((ty + TR) & 1) & q.par_x);
+        const int c0 = (int)(it.ebase & 1) ^ (((ty + TR) & 1) & q.g.par_x);
 
         // this thread's pieces of a staged plane: 5 fields x 14 rows x 12 pieces = 840 per plane
         CopyDesc cd[2];
@@ -214,7 +181,7 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
             const int row = j / (MPITCH / 2), cc = j - row * (MPITCH / 2);
             const int f = row / MROWS, r = row - f * MROWS;
             const double* base = f == 0 ? q.f[0] : f == 1 ? q.f[1] : f == 2 ? q.f[2] : f == 3 ? q.f[3] : q.f[4];
-            const long long e = it.ebase + (long long)r * q.Nx;
+            const long long e = it.ebase + (long long)r * q.g.Nx;
             cd[d].src = base + e + 2 * cc;
             cd[d].par = (int)(e & 1);
             cd[d].dst = j < NF * MROWS * (MPITCH / 2) ? f * MFS + r * MPITCH + 2 * cc : -1;
@@ -224,9 +191,9 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
         auto issue = [&](int pl_lo, int pl_hi, unsigned long long* bar) {
             pl_hi = min(pl_hi, it.np);
             for (int pl = pl_lo; pl < pl_hi; ++pl) {
-                const long long poff = (long long)pl * q.P;
+                const long long poff = (long long)pl * q.g.P;
                 const int slot = (pl % MRING) * MSLOT;
-                const int pp = pl & q.par_p;
+                const int pp = pl & q.g.par_p;
 #pragma unroll
                 for (int d = 0; d < 2; ++d)
                     if (cd[d].dst >= 0) cp_async16(ring + slot + cd[d].dst, cd[d].src + poff - (cd[d].par ^ pp));
@@ -242,7 +209,7 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
 #pragma unroll
         for (int tn = 0; tn < RZ; ++tn) {
             const int rel = 2 * tz + tn;
-            nty[tn] = (in_xy && rel < it.len) ? type[(long long)(it.z0 + rel) * q.P + lxy] : (uint8_t)255;
+            nty[tn] = (in_xy && rel < it.len) ? type[(long long)(it.z0 + rel) * q.g.P + lxy] : (uint8_t)255;
         }
 
         for (int s = 0; s < it.nsteps; ++s) {
@@ -257,7 +224,7 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
 #pragma unroll
             for (int tn = 0; tn < RZ; ++tn) {
                 const int rel = MS * (s + 1) + 2 * tz + tn;
-                nty[tn] = (in_xy && rel < it.len) ? type[(long long)(it.z0 + rel) * q.P + lxy] : (uint8_t)255;
+                nty[tn] = (in_xy && rel < it.len) ? type[(long long)(it.z0 + rel) * q.g.P + lxy] : (uint8_t)255;
             }
             // ring offsets of the thread's window planes (4 s + 2 tz + q)
             int po[RZ + 2 * TR];
@@ -278,8 +245,8 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
             // the column range is selected by a branch so that the loop counter -- and with it every
             // weight operand (uniform registers) -- stays warp-uniform for the compiler
             if (warp_any) {
-                if (grp == 0) ns_columns(ring, po, T, T.beg[0], T.mid[0], ctr, c0, q.par_x, q.par_p, q.c_div, a);
-                else ns_columns(ring, po, T, T.beg[1], T.mid[1], ctr, c0, q.par_x, q.par_p, q.c_div, a);
+                if (grp == 0) ns_columns(ring, po, T, T.beg[0], T.mid[0], ctr, c0, q.g.par_x, q.g.par_p, q.c_div, a);
+                else ns_columns(ring, po, T, T.beg[1], T.mid[1], ctr, c0, q.g.par_x, q.g.par_p, q.c_div, a);
             }
             // middle of the step: request the planes of step s+1.  Their slots held the first planes of
             // step s-1, which every warp has normally left by now (the wait only holds a warp that runs
@@ -290,14 +257,14 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
                 issue(MWIN + MS * s, MWIN + MS * (s + 1), &full[(k + 1) & 1]);
             }
             if (warp_any) {
-                if (grp == 0) ns_columns(ring, po, T, T.mid[0], T.end[0], ctr, c0, q.par_x, q.par_p, q.c_div, a);
-                else ns_columns(ring, po, T, T.mid[1], T.end[1], ctr, c0, q.par_x, q.par_p, q.c_div, a);
+                if (grp == 0) ns_columns(ring, po, T, T.mid[0], T.end[0], ctr, c0, q.g.par_x, q.g.par_p, q.c_div, a);
+                else ns_columns(ring, po, T, T.mid[1], T.end[1], ctr, c0, q.g.par_x, q.g.par_p, q.c_div, a);
             }
             // own values of the node this thread finalises (z-node `grp` of the pair): window plane TR + grp
             double own[NF];
             {
                 // window plane TR + grp: TR is odd, so plane TR + 0 is an odd and TR + 1 an even window plane
-                const double* sp = ring + (grp ? po[TR + 1] + ctr + c0 : po[TR] + ctr + (c0 ^ q.par_p));
+                const double* sp = ring + (grp ? po[TR + 1] + ctr + c0 : po[TR] + ctr + (c0 ^ q.g.par_p));
 #pragma unroll
                 for (int f = 0; f < NF; ++f) own[f] = sp[f * MFS];
             }
@@ -317,7 +284,7 @@ k_ns_stream(const __grid_constant__ NsStreamParams q, const __grid_constant__ St
                 named_bar_sync(pair_bar, 64);   // sums of this step are visible
             }
             if (my_type != 255) {
-                const long long l = (long long)(it.z0 + rel_own) * q.P + lxy;
+                const long long l = (long long)(it.z0 + rel_own) * q.g.P + lxy;
                 if (my_type == PDGPU_FLUID) {
                     const double* cr = comb + ((1 - grp) * NACC) * MGROUP + t;
 #define PD_MINE(x) (grp ? x[1] : x[0])
@@ -418,25 +385,25 @@ int pd_enqueue_ns_stream(pdgpu_ctx* c, int src, const double* d_dt, int zb, int 
     stream::TileState* s = pd_tile_state(c);
     PdConsts k = pd_consts(c->cfg, c->dim);
     NsStreamParams q;
-    q.zb = zb >= 0 ? zb : c->R;
-    q.ze = zb >= 0 ? ze : c->R + (c->a1 - c->a0);
-    if (q.ze <= q.zb || s->ntiles == 0) return 0;
+    q.g.zb = zb >= 0 ? zb : c->R;
+    q.g.ze = zb >= 0 ? ze : c->R + (c->a1 - c->a0);
+    if (q.g.ze <= q.g.zb || s->ntiles == 0) return 0;
     q.rho_f = c->cfg.rho_f; q.gamma = c->cfg.gamma_eos; q.B = k.B_eos;
     q.c_div = k.alpha * k.inv_VH; q.dens_diff = k.dens_diff_coeff; q.visc = c->cfg.mu_f * k.beta_lap;
     q.rho_lo = 0.5 * c->cfg.rho_f; q.rho_hi = 2.0 * c->cfg.rho_f;
     q.inv_dx = 1.0 / c->cfg.dx;
     q.W2 = s->sum_kappa * q.inv_dx;
     q.gamma_is_7 = (c->cfg.gamma_eos == 7.0);
-    q.Nx = c->Nx; q.Ny = c->Ny; q.P = c->P;
-    q.par_p = (int)(c->P & 1); q.par_x = c->Nx & 1;
-    q.tiles = s->d_tiles; q.ntiles = s->ntiles;
+    q.g.Nx = c->Nx; q.g.Ny = c->Ny; q.g.P = c->P;
+    q.g.par_p = (int)(c->P & 1); q.g.par_x = c->Nx & 1;
+    q.g.tiles = s->d_tiles; q.g.ntiles = s->ntiles;
     // planes per work item: long chunks amortise the 10-plane fill, short ones balance the CTAs;
     // aim at >= 6 items per CTA
-    const int planes = q.ze - q.zb;
+    const int planes = q.g.ze - q.g.zb;
     int zc = c->opt_stream_chunk > 0 ? c->opt_stream_chunk : 32;
     while (zc > 8 && (long long)s->ntiles * ((planes + zc - 1) / zc) < 6LL * s->sm_count) zc -= 4;
-    q.zc = zc;
-    q.nchunks = (planes + zc - 1) / zc;
+    q.g.zc = zc;
+    q.g.nchunks = (planes + zc - 1) / zc;
     const int dst = 1 - src;
     q.f[0] = c->rho[src]; q.f[1] = c->p[src]; q.f[2] = c->v[src][0]; q.f[3] = c->v[src][1]; q.f[4] = c->v[src][2];
     q.o[0] = c->rho[dst]; q.o[1] = c->p[dst]; q.o[2] = c->v[dst][0]; q.o[3] = c->v[dst][1]; q.o[4] = c->v[dst][2];
@@ -452,11 +419,11 @@ int pd_enqueue_ns_stream(pdgpu_ctx* c, int src, const double* d_dt, int zb, int 
         CUDA_OK(cudaFuncSetAttribute(k_ns_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NS_STREAM_SMEM));
         s->attr_ns = true;
     }
-    const long long items = (long long)q.ntiles * q.nchunks;
+    const long long items = (long long)q.g.ntiles * q.g.nchunks;
     const unsigned grid = (unsigned)std::min<long long>(items, s->sm_count);
     // one counter per launch in flight (the two plane ranges of a loop body run on two streams)
-    q.work = s->d_work + (s->work_seq++ & 15);
-    CUDA_OK(cudaMemsetAsync(q.work, 0, sizeof(int), c->stream));
+    q.g.work = s->d_work + (s->work_seq++ & 15);
+    CUDA_OK(cudaMemsetAsync(q.g.work, 0, sizeof(int), c->stream));
     k_ns_stream<<<grid, MTHREADS, NS_STREAM_SMEM, c->stream>>>(q, K, d_dt, c->type);
     c->launches++;
     return 0;

@@ -103,7 +103,46 @@ inline bool build_stream_cols(const tile::ColTable& T0, StreamCols* S) {
     return n == NCOL;
 }
 
+// lattice, plane range and work items of one launch of a streaming kernel
+struct StreamGeom {
+    int Nx, Ny;
+    long long P;
+    int zb, ze;            // local plane range of this launch
+    int zc;                // planes per work item
+    int nchunks, ntiles;   // work items = ntiles * nchunks, chunk-major
+    int par_p, par_x;      // P & 1, Nx & 1 (row alignment parity)
+    const int* tiles;      // (x0 / TX) | (y0 / TY) << 16 of the active tiles
+    int* work;             // work-item counter of this launch (zeroed before the launch)
+};
+
+// one work item: tile column (x0, y0) x planes [z0, z0 + len)
+struct StreamItem {
+    int x0, y0, z0, len, nsteps, np;
+    long long ebase;       // element index of staged (row 0, plane 0) = (x0-3, y0-3, z0-3)
+};
+
+// One 16-byte piece of a staged row that a thread copies for every plane of the item.
+struct CopyDesc {
+    const double* src;   // field + first element of the piece in staged plane 0 (not yet aligned down)
+    int dst;             // offset inside a plane slot; < 0: no piece
+    int par;             // (element index of the row start in plane 0) & 1
+};
+
 #ifdef __CUDACC__
+__device__ __forceinline__ StreamItem stream_item(const StreamGeom& g, int item) {
+    StreamItem it;
+    const int ch = item / g.ntiles;
+    const int tl = g.tiles[item - ch * g.ntiles];
+    it.x0 = (tl & 0xffff) * TX;
+    it.y0 = (tl >> 16) * TY;
+    it.z0 = g.zb + ch * g.zc;
+    it.len = min(g.zc, g.ze - it.z0);
+    it.nsteps = (it.len + MS - 1) / MS;
+    it.np = it.len + 2 * TR;       // staged planes z0-3 .. z0+len+2
+    it.ebase = (long long)(it.z0 - TR) * g.P + (long long)(it.y0 - TR) * g.Nx + (it.x0 - TR);
+    return it;
+}
+
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
