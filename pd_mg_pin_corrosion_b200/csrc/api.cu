@@ -147,7 +147,7 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
         if (p) cudaFree(p);
     void* ptrs[] = {c->nbfast, c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,
                     c->l_solid, c->l_ssolid, c->inlet_vax, c->out_nodes, c->out_level_off, c->d_red, c->d_u64, c->d_int,
-                    c->d_dissolved, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol,
+                    c->d_dissolved, c->d_dissolved_rho, c->csr_off, c->csr_idx, c->csr_dist, c->csr_evec, c->csr_vol,
                     c->l2_scratch, c->d_dt, c->stage, c->out_base_v, c->out_base_c, c->out_cnt,
                     c->out_mask, c->out_early, c->out_rows, c->l_gwall, c->l_gwall_mirror, c->moff};
     for (void* p : ptrs)

@@ -376,11 +376,12 @@ __global__ void k_phase_change(const int* __restrict__ l_solid, long long n_soli
                                double* __restrict__ p, double* __restrict__ vx, double* __restrict__ vy,
                                double* __restrict__ vz, double C_thresh, double rho_f, uint8_t* __restrict__ salt,
                                double* __restrict__ dsol, int* __restrict__ count, int* __restrict__ out,
-                               long long cap) {
+                               double* __restrict__ out_rho_old, long long cap) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_solid) return;
     int l = l_solid[t];
     if (phase[l] == 0 && type[l] == PDGPU_SOLID_MG && C[l] < C_thresh) {
+        const double rho_before = rho[l];   // the reference's `pressure` member keeps EOS(rho_before) until the next NS step
         phase[l] = 1;
         type[l] = PDGPU_FLUID;
         rho[l] = rho_f;
@@ -390,8 +391,9 @@ __global__ void k_phase_change(const int* __restrict__ l_solid, long long n_soli
         C[l] = C_thresh;
         salt[l] = 0;
         dsol[l] = 0.0;
+        const double rho_old = rho_before;
         int pos = atomicAdd(count, 1);
-        if (pos < cap) out[pos] = l;
+        if (pos < cap) { out[pos] = l; out_rho_old[pos] = rho_old; }
     }
 }
 
@@ -405,7 +407,9 @@ extern "C" int pdgpu_phase_change(pdgpu_ctx* c, int* n_dissolved, int* dissolved
     if (c->n_solid > 0) {
         if (c->dissolved_cap < c->n_solid) {
             if (c->d_dissolved) CUDA_OK(cudaFree(c->d_dissolved));
+            if (c->d_dissolved_rho) CUDA_OK(cudaFree(c->d_dissolved_rho));
             CUDA_OK(cudaMalloc(&c->d_dissolved, sizeof(int) * c->n_solid));
+            CUDA_OK(cudaMalloc(&c->d_dissolved_rho, sizeof(double) * c->n_solid));
             c->dissolved_cap = c->n_solid;
         }
         CUDA_OK(cudaMemsetAsync(c->d_int, 0, sizeof(int), c->stream));
@@ -413,16 +417,20 @@ extern "C" int pdgpu_phase_change(pdgpu_ctx* c, int* n_dissolved, int* dissolved
         if (c->dim == 2)
             LAUNCH(c, k_phase_change<2>, nblocks(c->n_solid, 256), 256, 0, c->l_solid, c->n_solid, c->type, c->phase,
                    c->C[bc], c->rho[b], c->p[b], VXYZ(c, b), c->cfg.C_thresh, c->cfg.rho_f, c->salt, c->dsol, c->d_int, c->d_dissolved,
-                   c->dissolved_cap);
+                   c->d_dissolved_rho, c->dissolved_cap);
         else
             LAUNCH(c, k_phase_change<3>, nblocks(c->n_solid, 256), 256, 0, c->l_solid, c->n_solid, c->type, c->phase,
                    c->C[bc], c->rho[b], c->p[b], VXYZ(c, b), c->cfg.C_thresh, c->cfg.rho_f, c->salt, c->dsol, c->d_int, c->d_dissolved,
-                   c->dissolved_cap);
+                   c->d_dissolved_rho, c->dissolved_cap);
         CUDA_OK(cudaMemcpyAsync(&n, c->d_int, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_OK(cudaStreamSynchronize(c->stream));
         if (n > 0) {
             h.resize(n);
             CUDA_OK(cudaMemcpy(h.data(), c->d_dissolved, sizeof(int) * n, cudaMemcpyDeviceToHost));
+            // stale `pressure` of the dissolved nodes for snapshots written before the next NS step (vti.cu)
+            std::vector<double> r(n);
+            CUDA_OK(cudaMemcpy(r.data(), c->d_dissolved_rho, sizeof(double) * n, cudaMemcpyDeviceToHost));
+            for (int t = 0; t < n; ++t) { c->stale_p_idx.push_back(h[t]); c->stale_p_rho.push_back(r[t]); }
             std::sort(h.begin(), h.end());
         }
     }

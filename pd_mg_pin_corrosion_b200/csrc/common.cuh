@@ -136,6 +136,11 @@ struct pdgpu_ctx {
     unsigned long long* d_u64 = nullptr;
     int* d_int = nullptr;
     int* d_dissolved = nullptr;
+    double* d_dissolved_rho = nullptr;   // density of the dissolved nodes before the phase change
+    // nodes dissolved since the last NS step: the reference's `pressure` member still holds EOS(old density)
+    // there (apply_phase_change does not touch it, src/pd_ard.cpp:193-212); snapshots reproduce that
+    std::vector<int> stale_p_idx;
+    std::vector<double> stale_p_rho;
     long long dissolved_cap = 0;
 
     // materialised CSR (optional)
@@ -322,6 +327,8 @@ int pd_enqueue_ard_prepass_solids(pdgpu_ctx* c, int srcC);
 int pd_enqueue_ard_vmag_range(pdgpu_ctx* c, int buf, long long lo, long long hi);
 int pd_ensure_vmag(pdgpu_ctx* c, int buf);
 inline void pd_touch_flow(pdgpu_ctx* c) { c->flow_epoch++; }
+// an NS step recomputes the pressure of every node (src/pd_ns.cpp:79): nothing stale is left
+inline void pd_pressure_recomputed(pdgpu_ctx* c) { c->stale_p_idx.clear(); c->stale_p_rho.clear(); }
 int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid,
                         bool skip_wall_copy = false);
 int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC);

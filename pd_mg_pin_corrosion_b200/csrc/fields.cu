@@ -308,6 +308,7 @@ extern "C" int pdgpu_fields_init(pdgpu_ctx* c, const uint8_t* is_gb, const uint8
     c->cur = 0; c->curC = 0; c->p_input = 0;
     c->wallC_pending = false; c->wallC_src = 0;   // a reused context starts like a fresh one
     c->volume_loss = 0.0;
+    pd_pressure_recomputed(c);
     pd_touch_flow(c);
     pd_invalidate_graphs(c);
     c->fields_ready = true;   // allow the flag uploads below

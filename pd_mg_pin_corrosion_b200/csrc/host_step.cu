@@ -439,7 +439,7 @@ extern "C" int pdgpu_step_host(pdgpu_ctx* c, double dt_ns, double dt_ard, double
     CUDA_OK(cudaEventRecord(h->ev_end, h->s_down));
     CUDA_OK(cudaStreamWaitEvent(cs, h->ev_end, 0));
     // std::swap(rho, rho_new) ... (src/pd_ns.cpp:325) and std::swap(C, C_new) (src/coupling.cpp:239)
-    c->p_input = cur;
+    c->p_input = cur; pd_pressure_recomputed(c);
     c->cur = nw;
     c->curC = dC;
     pd_touch_flow(c);

@@ -265,7 +265,7 @@ extern "C" int pdgpu_ns_step(pdgpu_ctx* c, double dt) {
     pd_touch_flow(c);
     PD_TRY(pd_set_dt(c, 0, dt));
     PD_TRY(pd_enqueue_ns_step(c, c->cur, c->d_dt));
-    c->p_input = c->cur;
+    c->p_input = c->cur; pd_pressure_recomputed(c);
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -435,7 +435,7 @@ extern "C" int pdgpu_ns_iterate(pdgpu_ctx* c, int iters, double dt) {
     PD_TRY(pd_set_dt(c, 0, dt));
     for (int it = 0; it < iters; ++it) {
         PD_TRY(run_ns_body(c));
-        c->p_input = c->cur;
+        c->p_input = c->cur; pd_pressure_recomputed(c);
         c->cur = 1 - c->cur;
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
@@ -490,7 +490,7 @@ extern "C" int pdgpu_ns_solve_steady(pdgpu_ctx* c, PdSteadyResult* out, int verb
     const int max_iters = c->cfg.flow_max_iters;
     for (iter = 1; iter <= max_iters; ++iter) {
         PD_TRY(run_ns_body(c));
-        c->p_input = c->cur;
+        c->p_input = c->cur; pd_pressure_recomputed(c);
         if (iter <= 10 || iter % 100 == 0) {   // :273-322
             PD_TRY(pdgpu_ns_residual(c, &res));
             if (res.has_nan) {

@@ -385,6 +385,21 @@ extern "C" int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_
     CUDA_OK(cudaMalloc(&press_buf.p, sizeof(double) * n));
     double* d_press = press_buf.p;
     PD_TRY(pd_enqueue_eos_to(c, c->p_input, lo, n, d_press));
+    if (!c->stale_p_idx.empty()) {   // nodes dissolved since the last NS step keep their pre-dissolution pressure
+        const PdConsts kc = pd_consts(c->cfg, c->dim);
+        std::vector<double> pv(c->stale_p_idx.size());
+        for (size_t t = 0; t < pv.size(); ++t) {
+            double ratio = c->stale_p_rho[t] / c->cfg.rho_f;          // src/pd_ns.cpp:44-48
+            ratio = std::min(std::max(ratio, 0.5), 2.0);
+            pv[t] = kc.B_eos * (std::pow(ratio, c->cfg.gamma_eos) - 1.0);
+        }
+        for (size_t t = 0; t < pv.size(); ++t) {
+            const long long l = c->stale_p_idx[t];
+            if (l >= lo && l < lo + n)
+                CUDA_OK(cudaMemcpyAsync(d_press + (l - lo), &pv[t], sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        }
+        CUDA_OK(cudaStreamSynchronize(c->stream));   // pv lives on this stack frame
+    }
 
     const int fd = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fd < 0) PD_FAIL("cannot open VTI file '%s'", path);
