@@ -10,8 +10,12 @@ from pd_mg_pin_corrosion_b200 import lib as L_, solver as S   # noqa: E402
 from pd_mg_pin_corrosion_b200.config import Config            # noqa: E402
 
 small = "--small" in sys.argv
+big = "--big" in sys.argv   # params_fine cross-section at dx = 1 um (307 x 307), short tube
 sets = [a for a in sys.argv[1:] if not a.startswith("--")] or ["overlap=1"]
-cfg = Config.load(os.path.join(ROOT, "configs", "params.cfg" if small else "params_fine.cfg"), {"use_implicit": 0}, quiet=True)
+ov = {"use_implicit": 0}
+if big:
+    ov.update({"dx": 1.0e-6, "L_wire": 60e-6, "L_upstream": 40e-6, "L_downstream": 40e-6})
+cfg = Config.load(os.path.join(ROOT, "configs", "params.cfg" if small else "params_fine.cfg"), ov, quiet=True)
 L = L_.load()
 grid = S.Grid(3)
 grid.build(cfg)
