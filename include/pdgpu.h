@@ -218,6 +218,27 @@ int pdgpu_host_unregister(void* ptr);
 int pdgpu_phase_change(pdgpu_ctx* ctx, int* n_dissolved, int* dissolved_global, int cap);
 int pdgpu_diag(pdgpu_ctx* ctx, PdDiag* out);
 
+/* ---- PD_ARD_ImplicitSolver (src/pd_ard_implicit.h:12-40), matrix-free ---------------
+ * assemble(): salt-layer flags + interface diffusivities from the current C (once per coupling cycle,
+ *   src/coupling.cpp:166); the operator M itself is never stored.
+ * compute_adaptive_dt(): src/pd_ard_implicit.cpp:438-487 (implicit_dt_fraction, implicit_dt_max of Config).
+ * step(): solves (I - dt M) C_new = C_old + dt bc_rhs with restarted GMRES on the device, clamps to
+ *   [0, C_solid_init] and stores into the current C (:371-429). precond: 0 none, 1 Jacobi, 2 forward sweep
+ *   over the axial planes. The reference's own solver is Eigen's GMRES + IncompleteLUT (tolerance 1e-10,
+ *   restart 50, 200 iterations).
+ * matvec / rhs: y = (I - dt M) x and b for GLOBAL host vectors (inspection, tests). Single-GPU contexts. */
+typedef struct PdLinSolveInfo {
+    int iters, converged;
+    double rel_res;               /* ||b - A x|| / ||b|| of the returned iterate */
+    int pad;
+} PdLinSolveInfo;
+int pdgpu_implicit_assemble(pdgpu_ctx* ctx);
+int pdgpu_implicit_compute_dt(pdgpu_ctx* ctx, double dt_fraction, double dt_max, double* dt);
+int pdgpu_implicit_step(pdgpu_ctx* ctx, double dt, double tol, int restart, int max_iters, int precond,
+                        PdLinSolveInfo* info);
+int pdgpu_implicit_matvec(pdgpu_ctx* ctx, double dt, const double* x_global, double* y_global);
+int pdgpu_implicit_rhs(pdgpu_ctx* ctx, double dt, double* b_global);
+
 /* ---- GrainStructure::generate on device (src/grains.cpp:55-107,152-166) -------
  * The lattice passes of the grain generator: nearest-seed Voronoi assignment of every SOLID_MG node
  * (brute force over the seeds), grain-boundary detection over the immediate neighbours and

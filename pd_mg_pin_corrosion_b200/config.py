@@ -81,7 +81,7 @@ class Config:
     output_every_flow: int = 2000
     output_every_corr: int = 100
     output_dir: str = "output"
-    # Implicit solver keys: parsed for file compatibility; the implicit branch is out of scope
+    # Implicit branch (src/config.h:72-80): matrix-free operator + GMRES on the device (solver.PD_ARD_ImplicitSolver)
     use_implicit: int = 1
     implicit_dt_fraction: float = 0.5
     implicit_dt_max: float = 60.0
@@ -161,8 +161,6 @@ class Config:
     def check_supported(self) -> None:
         if self.use_amr:
             raise ValueError("use_amr = 1 is out of scope (uniform-grid hot path only)")
-        if self.use_implicit:
-            raise ValueError("use_implicit = 1 (Eigen/GMRES branch) is out of scope; set use_implicit = 0")
 
     def describe(self, dim: int) -> str:
         """Config::print (src/config.cpp:114-139)."""

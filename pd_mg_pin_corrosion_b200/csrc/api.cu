@@ -27,7 +27,6 @@ extern "C" int pdgpu_create_slab(const PdConfig* cfg, int dim, int device, int r
                                  pdgpu_ctx** out) {
     if (!cfg || !out) PD_FAIL("pdgpu_create: null argument");
     if (dim != 2 && dim != 3) PD_FAIL("pdgpu_create: dim must be 2 or 3 (PD_DIM, src/utils.h:8-12)");
-    if (cfg->use_implicit) PD_FAIL("pdgpu_create: use_implicit = 1 (Eigen/GMRES branch) is out of scope; set use_implicit = 0");
     if (cfg->m_ratio < 1 || cfg->m_ratio > 5) PD_FAIL("pdgpu_create: m_ratio must be in [1,5]");
     if (!(cfg->dx > 0.0) || !(cfg->delta > 0.0)) PD_FAIL("pdgpu_create: dx/delta must be positive (run compute_derived)");
     int ndev = 0;
@@ -134,6 +133,7 @@ void pd_invalidate_graphs(pdgpu_ctx* c) {
 
 int pd_comm_destroy(pdgpu_ctx* c);
 void pd_tile_state_free(pdgpu_ctx* c);   // ns_stream.cu
+void pd_implicit_free(pdgpu_ctx* c);     // implicit.cu
 
 extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     if (!c) return 0;
@@ -143,6 +143,7 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     pd_host_step_free(c);
     pd_comm_destroy(c);
     pd_tile_state_free(c);
+    pd_implicit_free(c);
     for (void* p : c->raw_fields)   // padded double arrays (pd_alloc_fields)
         if (p) cudaFree(p);
     void* ptrs[] = {c->nbfast, c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,

@@ -197,6 +197,7 @@ struct pdgpu_ctx {
 
     // streaming / tiled bond kernels (stream.cuh): column tables, active tile list, per-device attributes
     void* tile_state = nullptr;
+    void* impl_state = nullptr;     // implicit ARD branch (implicit.cu)
     int opt_stream_chunk = 0;       // planes per work item of the streaming kernels (0 = automatic)
     // double field arrays carry `field_pad` zeroed elements in front and behind (the bulk row copies
     // of the streaming kernels may start up to 3 rows + 4 elements outside the lattice box)

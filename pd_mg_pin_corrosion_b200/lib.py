@@ -41,6 +41,10 @@ class PdDiag(C.Structure):
     _fields_ = [("solid_count", C.c_longlong), ("v_max", C.c_double), ("C_max_fluid", C.c_double)]
 
 
+class PdLinSolveInfo(C.Structure):
+    _fields_ = [("iters", C.c_int), ("converged", C.c_int), ("rel_res", C.c_double), ("pad", C.c_int)]
+
+
 class PdGpuError(RuntimeError):
     pass
 
@@ -93,6 +97,9 @@ def load() -> C.CDLL:
         "pdgpu_comm_get_uid": [vp], "pdgpu_comm_init": [vp, vp, C.c_int, C.c_int],
         "pdgpu_halo_exchange": [vp, C.c_int],
         "pdgpu_comm_allreduce": [vp, dp, C.c_int, C.c_int],
+        "pdgpu_implicit_assemble": [vp], "pdgpu_implicit_compute_dt": [vp, C.c_double, C.c_double, dp],
+        "pdgpu_implicit_step": [vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(PdLinSolveInfo)],
+        "pdgpu_implicit_matvec": [vp, C.c_double, vp, vp], "pdgpu_implicit_rhs": [vp, C.c_double, vp],
         "pdgpu_grains_voronoi": [vp, vp, C.c_int, C.c_int, vp, vp],
         "pdgpu_grains_grow_precip": [vp, vp, vp, C.c_int, vp],
         "pdgpu_fields_download_all": [vp, C.c_int, vp],

@@ -376,6 +376,55 @@ class PD_ARD_Solver:
         return n.value
 
 
+class PD_ARD_ImplicitSolver:
+    """PD_ARD_ImplicitSolver (src/pd_ard_implicit.h:12-40): backward Euler with the bond operator applied
+    matrix-free on the device and a restarted GMRES. The reference solves the same system with
+    Eigen's GMRES + IncompleteLUT (tolerance 1e-10, restart 50, 200 iterations)."""
+
+    def __init__(self, tol: float = 1e-10, restart: int = 50, max_iters: int = 2000, precond: int = 2):
+        self.tol, self.restart, self.max_iters, self.precond = tol, restart, max_iters, precond
+        self.volume_loss_fraction = 0.0
+        self.last = None
+
+    def init(self, grid: Grid, cfg: Config) -> None:
+        pass
+
+    def set_volume_loss(self, vl: float, grid: Grid | None = None) -> None:
+        self.volume_loss_fraction = vl
+        if grid is not None:
+            _l.check(_l.load().pdgpu_ard_set_volume_loss(grid.ctx, vl))
+
+    def assemble(self, fields: Fields, grid: Grid, cfg: Config) -> None:
+        _l.check(_l.load().pdgpu_ard_set_volume_loss(grid.ctx, self.volume_loss_fraction))
+        _l.check(_l.load().pdgpu_implicit_assemble(grid.ctx))
+
+    def compute_adaptive_dt(self, fields: Fields, grid: Grid, cfg: Config) -> float:
+        dt = C.c_double()
+        _l.check(_l.load().pdgpu_implicit_compute_dt(grid.ctx, cfg.implicit_dt_fraction, cfg.implicit_dt_max, C.byref(dt)))
+        return dt.value
+
+    def step(self, fields: Fields, grid: Grid, cfg: Config, dt: float) -> int:
+        info = _l.PdLinSolveInfo()
+        _l.check(_l.load().pdgpu_implicit_step(grid.ctx, dt, self.tol, self.restart, self.max_iters, self.precond,
+                                               C.byref(info)))
+        self.last = info
+        return 1
+
+    def matvec(self, grid: Grid, dt: float, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.zeros_like(x)
+        _l.check(_l.load().pdgpu_implicit_matvec(grid.ctx, dt, _ptr(x), _ptr(y)))
+        return y
+
+    def rhs(self, grid: Grid, dt: float) -> np.ndarray:
+        b = np.zeros(grid.N_total)
+        _l.check(_l.load().pdgpu_implicit_rhs(grid.ctx, dt, _ptr(b)))
+        return b
+
+    def apply_phase_change(self, fields: Fields, grid: Grid, cfg: Config) -> int:
+        return PD_ARD_Solver.apply_phase_change(self, fields, grid, cfg)   # same rule (src/pd_ard_implicit.cpp:540-561)
+
+
 def diagnostics(grid: Grid) -> _l.PdDiag:
     d = _l.PdDiag()
     _l.check(_l.load().pdgpu_diag(grid.ctx, C.byref(d)))
@@ -425,6 +474,8 @@ class CoupledSolver:
         self.writer, self.flow_writer, self.frame_count = VTKWriter(), VTKWriter(), 0
         self.flow_solver = PD_NS_Solver()
         self.ard_solver = PD_ARD_Solver()
+        self.ard_implicit_solver = PD_ARD_ImplicitSolver()
+        self.total_implicit_steps = 0
         self.initial_solid_indices = np.zeros(0, np.int32)
         self.total_dissolved = 0
         self.dissolved_since_flow = 0
@@ -438,6 +489,12 @@ class CoupledSolver:
         for v in vals.tolist():
             s += v
         return s
+
+    @staticmethod
+    def _any_solid_below(grid: Grid, fields: Fields, cfg: Config) -> bool:
+        nt = grid.node_type
+        Cc = fields.get("C")
+        return bool(((nt == _l.SOLID_MG) & (Cc < cfg.C_thresh)).any())
 
     def write_diagnostics(self, grid: Grid, fields: Fields, t_corr: float, cfg: Config) -> None:
         d = diagnostics(grid)                      # reductions over all ranks
@@ -487,7 +544,10 @@ class CoupledSolver:
         self.log(f"Initial solid nodes: {n0}")
         self.flow_solver.init(grid, cfg)
         self.ard_solver.init(grid, cfg)
-        self.log("Using EXPLICIT ARD solver")
+        implicit = bool(cfg.use_implicit)
+        if implicit and grid.nranks > 1:
+            raise ValueError("CoupledSolver: the implicit branch runs on single-GPU grids only")
+        self.log("Using IMPLICIT ARD solver (matrix-free GMRES)" if implicit else "Using EXPLICIT ARD solver")
         self._snapshot(grid, fields, cfg, "state", 0.0, self.writer)
         t_corr, cycle, need_flow_solve = 0.0, 0, True
         self.dissolved_since_flow = 0
@@ -500,6 +560,42 @@ class CoupledSolver:
                 need_flow_solve = False
                 self._snapshot(grid, fields, cfg, "flow", t_corr, self.flow_writer)
             vol_loss = 1.0 - self._solid_C_sum(fields) / (n0 + 1e-30)
+            if implicit:   # src/coupling.cpp:154-216
+                imp = self.ard_implicit_solver
+                imp.set_volume_loss(max(vol_loss, 0.0), grid)
+                imp.assemble(fields, grid, cfg)                     # once per coupling cycle
+                implicit_step, t_cycle_start, dissolution = 0, t_corr, False
+                while implicit_step < cfg.corrosion_steps_per_check and t_corr < cfg.T_final and not dissolution:
+                    dt_impl = imp.compute_adaptive_dt(fields, grid, cfg)
+                    apply_inlet_bc(fields, grid, cfg)
+                    apply_outlet_bc(fields, grid, cfg)
+                    apply_wall_concentration_bc(fields, grid, cfg)
+                    imp.step(fields, grid, cfg, dt_impl)
+                    smooth_boundary_concentration(fields, grid, cfg)
+                    t_corr += dt_impl
+                    implicit_step += 1
+                    self.total_implicit_steps += 1
+                    if self.total_implicit_steps % cfg.diagnostic_every == 0:
+                        self.write_diagnostics(grid, fields, t_corr, cfg)
+                    if self.total_implicit_steps % cfg.implicit_output_every == 0:
+                        self._snapshot(grid, fields, cfg, "corr", t_corr, self.writer)
+                    # any solid node below the threshold ends the cycle (src/coupling.cpp:206-211)
+                    dissolution = self._any_solid_below(grid, fields, cfg)
+                self.log(f"  Implicit cycle: {implicit_step} steps, t={t_cycle_start:.2f} to {t_corr:.2f} s "
+                         f"({t_corr / 3600.0:.4f} h); last solve {imp.last.iters} iterations, "
+                         f"|res| = {imp.last.rel_res:.2e}")
+                n_dissolved = imp.apply_phase_change(fields, grid, cfg)
+                self.total_dissolved += n_dissolved
+                self.dissolved_since_flow += n_dissolved
+                if n_dissolved > 0:
+                    self.log(f"  Phase change: {n_dissolved} nodes dissolved (total: {self.total_dissolved})")
+                    need_flow_solve = True
+                else:
+                    self.log("  No phase changes this cycle")
+                if diagnostics(grid).solid_count == 0:
+                    self.log(f"\n=== All solid nodes dissolved at t={t_corr:.1f} s ===")
+                    break
+                continue
             self.ard_solver.set_volume_loss(max(vol_loss, 0.0), grid)
             dt_corr = self.ard_solver.compute_dt(fields, grid, cfg)
             self.log(f"  Corrosion dt = {dt_corr:.4e} s")
