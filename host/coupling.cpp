@@ -188,7 +188,8 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
             if (st.node_type[i] == PDGPU_SOLID_MG) initial_solid_indices_.push_back((int)i);
     }
     const double n0 = (double)initial_solid_indices_.size();
-    std::printf("Initial solid nodes: %zu\nUsing EXPLICIT ARD solver\n", initial_solid_indices_.size());
+    std::printf("Initial solid nodes: %zu\nUsing %s ARD solver\n", initial_solid_indices_.size(),
+                cfg.use_implicit ? "IMPLICIT (matrix-free GMRES)" : "EXPLICIT");
 
     if (!resuming) snapshot(ctx, st, cfg, "state", 0.0, writer_, true);   // :117-122
     std::vector<int> dissolved(std::max<size_t>(initial_solid_indices_.size(), 1));
@@ -205,10 +206,35 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
         } else {
             std::printf("  Skipping flow solve (no dissolution since last flow solve)\n");
         }
-        // phase 2, explicit :217-253
         double vol_loss = 1.0 - solid_C_sum(ctx) / (n0 + 1e-30);
         if (vol_loss < 0.0) vol_loss = 0.0;
         PD(pdgpu_ard_set_volume_loss(ctx, vol_loss));
+        if (cfg.use_implicit) {   // phase 2, implicit :154-216 (operator matrix-free on the device, GMRES)
+            PD(pdgpu_implicit_assemble(ctx));                       // once per coupling cycle
+            int implicit_step = 0, below = 0;
+            const double t_cycle_start = t_corr;
+            PdLinSolveInfo info = {0, 0, 0.0, 0};
+            while (implicit_step < cfg.corrosion_steps_per_check && t_corr < cfg.T_final && below == 0) {
+                double dt_impl = 0.0;
+                PD(pdgpu_implicit_compute_dt(ctx, cfg.implicit_dt_fraction, cfg.implicit_dt_max, &dt_impl));
+                PD(pdgpu_bc_inlet(ctx));
+                PD(pdgpu_bc_outlet(ctx));
+                PD(pdgpu_bc_wall_conc(ctx));
+                PD(pdgpu_implicit_step(ctx, dt_impl, 1e-10, 50, 2000, 2, &info));
+                std::printf("    Linear solve: GMRES %d iters, |res|=%.2e%s\n", info.iters, info.rel_res,
+                            info.converged ? "" : "  (NOT converged)");
+                PD(pdgpu_bc_smooth_conc(ctx));
+                t_corr += dt_impl;
+                ++implicit_step;
+                ++total_implicit_steps_;
+                if (total_implicit_steps_ % cfg.diagnostic_every == 0) write_diagnostics(ctx, t_corr, cfg);
+                if (total_implicit_steps_ % cfg.implicit_output_every == 0) snapshot(ctx, st, cfg, "corr", t_corr, writer_, true);
+                PD(pdgpu_solid_below_thresh(ctx, &below));
+            }
+            std::printf("  Implicit cycle: %d steps, t=%.2f to %.2f s (%.4f h)\n", implicit_step, t_cycle_start, t_corr,
+                        t_corr / 3600.0);
+        } else {
+        // phase 2, explicit :217-253
         double dt_corr = 0.0;
         PD(pdgpu_ard_compute_dt(ctx, &dt_corr));
         std::printf("  Corrosion dt = %.4e s\n", dt_corr);
@@ -232,6 +258,7 @@ double CoupledSolver::run(pdgpu_ctx* ctx, HostState& st, const HostConfig& cfg, 
                 write_diagnostics(ctx, t_corr, cfg);
             }
             if (t_corr >= cfg.T_final) break;
+        }
         }
         // phase 3 :255-290
         int n_dissolved = 0;

@@ -50,7 +50,7 @@ public:
 
 private:
     std::vector<int> initial_solid_indices_;
-    int total_dissolved_ = 0, dissolved_since_flow_ = 0;
+    int total_dissolved_ = 0, dissolved_since_flow_ = 0, total_implicit_steps_ = 0;
     double solid_C_sum(pdgpu_ctx* ctx);
     void write_diagnostics(pdgpu_ctx* ctx, double t_corr, const HostConfig& cfg);
     // VTKWriter::write through libpdgpu.so (text formatted on the device) + PVD bookkeeping

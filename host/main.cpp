@@ -88,8 +88,12 @@ int main(int argc, char** argv) {
     HostConfig cfg;
     cfg.load(cfg_path);
     cfg.print(dim);
-    if (cfg.use_implicit || cfg.use_amr) {
-        std::fprintf(stderr, "use_implicit = 1 / use_amr = 1 are out of scope of the GPU path (set use_implicit = 0)\n");
+    if (cfg.use_amr) {
+        std::fprintf(stderr, "use_amr = 1 is out of scope of the GPU path\n");
+        return 1;
+    }
+    if (cfg.use_implicit && nranks > 1) {
+        std::fprintf(stderr, "the implicit branch runs on one GPU only (set use_implicit = 0 for z-slab runs)\n");
         return 1;
     }
     PdConfig pod = cfg.to_pod();

@@ -232,6 +232,8 @@ typedef struct PdLinSolveInfo {
     double rel_res;               /* ||b - A x|| / ||b|| of the returned iterate */
     int pad;
 } PdLinSolveInfo;
+/* SOLID_MG nodes with C < C_thresh (all ranks): the implicit cycle ends at the first one (src/coupling.cpp:206-211) */
+int pdgpu_solid_below_thresh(pdgpu_ctx* ctx, int* count);
 int pdgpu_implicit_assemble(pdgpu_ctx* ctx);
 int pdgpu_implicit_compute_dt(pdgpu_ctx* ctx, double dt_fraction, double dt_max, double* dt);
 int pdgpu_implicit_step(pdgpu_ctx* ctx, double dt, double tol, int restart, int max_iters, int precond,

@@ -453,6 +453,36 @@ extern "C" int pdgpu_phase_change(pdgpu_ctx* c, int* n_dissolved, int* dissolved
     return 0;
 }
 
+// number of SOLID_MG nodes whose concentration has fallen below C_thresh (the implicit coupling cycle ends
+// at the first one, src/coupling.cpp:206-211)
+__global__ void k_count_below(const int* __restrict__ l_solid, long long n, const uint8_t* __restrict__ type,
+                              const double* __restrict__ C, double C_thresh, int* __restrict__ count) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const int l = l_solid[t];
+    if (type[l] == PDGPU_SOLID_MG && C[l] < C_thresh) atomicAdd(count, 1);
+}
+
+extern "C" int pdgpu_solid_below_thresh(pdgpu_ctx* c, int* count) {
+    NEED_FIELDS(c);
+    if (!count) PD_FAIL("pdgpu_solid_below_thresh: null output");
+    int n = 0;
+    if (c->n_solid > 0) {
+        CUDA_OK(cudaMemsetAsync(c->d_int, 0, sizeof(int), c->stream));
+        LAUNCH(c, k_count_below, nblocks(c->n_solid, 256), 256, 0, c->l_solid, c->n_solid, c->type, c->C[c->curC],
+               c->cfg.C_thresh, c->d_int);
+        CUDA_OK(cudaMemcpyAsync(&n, c->d_int, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    if (c->nranks > 1 && c->comm) {
+        double v = (double)n;
+        PD_TRY(pdgpu_comm_allreduce(c, &v, 1, 0));
+        n = (int)v;
+    }
+    *count = n;
+    return 0;
+}
+
 // Reductions of write_diagnostics (src/coupling.cpp:20-49): solid count, max |v| and max C
 // over FLUID nodes. All order-free (integer count, max of non-negative doubles).
 template <int DIM>

@@ -97,6 +97,7 @@ def load() -> C.CDLL:
         "pdgpu_comm_get_uid": [vp], "pdgpu_comm_init": [vp, vp, C.c_int, C.c_int],
         "pdgpu_halo_exchange": [vp, C.c_int],
         "pdgpu_comm_allreduce": [vp, dp, C.c_int, C.c_int],
+        "pdgpu_solid_below_thresh": [vp, ip],
         "pdgpu_implicit_assemble": [vp], "pdgpu_implicit_compute_dt": [vp, C.c_double, C.c_double, dp],
         "pdgpu_implicit_step": [vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(PdLinSolveInfo)],
         "pdgpu_implicit_matvec": [vp, C.c_double, vp, vp], "pdgpu_implicit_rhs": [vp, C.c_double, vp],

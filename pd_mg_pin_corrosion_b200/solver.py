@@ -492,9 +492,9 @@ class CoupledSolver:
 
     @staticmethod
     def _any_solid_below(grid: Grid, fields: Fields, cfg: Config) -> bool:
-        nt = grid.node_type
-        Cc = fields.get("C")
-        return bool(((nt == _l.SOLID_MG) & (Cc < cfg.C_thresh)).any())
+        n = C.c_int()
+        _l.check(_l.load().pdgpu_solid_below_thresh(grid.ctx, C.byref(n)))
+        return n.value > 0
 
     def write_diagnostics(self, grid: Grid, fields: Fields, t_corr: float, cfg: Config) -> None:
         d = diagnostics(grid)                      # reductions over all ranks

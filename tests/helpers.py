@@ -187,6 +187,81 @@ def coupled_run(sim, cfg, log=None):
     return rows
 
 
+def coupled_run_implicit(sim, cfg, is_gb, is_precip, log=None):
+    """CoupledSolver::run, IMPLICIT branch (src/coupling.cpp:154-216) over the plain-C port (flow solve,
+    BCs, smoother, phase change) and the numpy/scipy restatement of PD_ARD_ImplicitSolver with the exact
+    sparse solve in place of Eigen's GMRES. Returns the diagnostics.csv rows."""
+    from oracle.implicit_oracle import ImplicitOracle
+    nt0 = sim.get("node_type")
+    solid0 = np.nonzero(nt0 == 1)[0]
+    n0 = len(solid0)
+    rows = []
+
+    def solid_sum():
+        s = 0.0
+        for v in sim.get("C")[solid0].tolist():
+            s += v
+        return s
+
+    def diagnostics(t):
+        nt = sim.get("node_type")
+        loss = max((1.0 - solid_sum() / (n0 + 1e-30)) * 100.0, 0.0)
+        fl = nt == 0
+        v = sim.get("vel")[fl]
+        vmax = float(np.sqrt((v * v).sum(1)).max()) if fl.any() else 0.0
+        cmax = float(max(sim.get("C")[fl].max(), 0.0)) if fl.any() else 0.0
+        rows.append([float(f"{x:.6e}") for x in [t, t / 3600.0, loss, float((nt == 1).sum()), vmax, cmax]])
+
+    def solve_steady():
+        dt = sim.ns_compute_dt()
+        it = 1
+        while it <= cfg.flow_max_iters:
+            sim.inlet_bc(); sim.outlet_bc(); sim.wall_bc(); sim.solid_bc()
+            sim.ns_step(dt)
+            sim.wall_bc_new()
+            if it <= 10 or it % 100 == 0:
+                fl = sim.get("node_type") == 0
+                v, vn = sim.get("vel")[fl], sim.get("vel_new")[fl]
+                num, den = float(((vn - v) ** 2).sum()), float((v ** 2).sum())
+                eps = np.sqrt(num / den) if den > 1e-30 else np.sqrt(num)
+                if eps < cfg.flow_conv_tol and it > 100:
+                    break
+            sim.swap_flow()
+            if it % 200 == 0:
+                dt = sim.ns_compute_dt()
+            it += 1
+
+    t_corr, need_flow, total_steps = 0.0, True, 0
+    while t_corr < cfg.T_final:
+        if need_flow:
+            solve_steady()
+            need_flow = False
+        orc = ImplicitOracle(sim.dim, sim.Nx, sim.Ny, sim.Nz, sim.get("node_type"), sim.off_d, sim.off_dist,
+                             sim.off_evec, sim.off_vol, cfg)
+        orc.volume_loss = max(1.0 - solid_sum() / (n0 + 1e-30), 0.0)
+        orc.assemble(sim.get("C"), sim.get("vel"), is_gb, is_precip)
+        step, dissolved = 0, False
+        while step < cfg.corrosion_steps_per_check and t_corr < cfg.T_final and not dissolved:
+            dt = orc.adaptive_dt(sim.get("C"), cfg.implicit_dt_fraction, cfg.implicit_dt_max)
+            sim.inlet_bc(); sim.outlet_bc(); sim.wall_conc_bc()
+            sim.set("C", orc.step(sim.get("C"), dt))
+            sim.smooth_conc()
+            t_corr += dt
+            step += 1
+            total_steps += 1
+            if total_steps % cfg.diagnostic_every == 0:
+                diagnostics(t_corr)
+            nt = sim.get("node_type")
+            dissolved = bool(((nt == 1) & (sim.get("C") < cfg.C_thresh)).any())
+        n = sim.phase_change()
+        if n > 0:
+            sim.rebuild_neighbors()
+            need_flow = True
+        if (sim.get("node_type") == 1).sum() == 0:
+            break
+    return rows
+
+
 def port_coupled_run(case: str, is_gb, is_precip):
     dim, cfg, _ = load_cfg(case)
     p = PortSim(dim, cfg, threads=4)
