@@ -1,17 +1,18 @@
-// stream.cuh -- shared machinery of the z-streaming bond kernels (ns_stream.cu, ard_stream.cu):
+// stream.cuh -- machinery of the z-streaming NS bond kernel (ns_stream.cu):
 // 3D, m_ratio = 3 (reach 3), full FLUID rows.
 //
 // A persistent CTA owns a 16 x 8 column of lattice nodes and STREAMS along z through a chunk of
 // planes in steps of 4 planes.  The haloed planes ((16+6) x (8+6) values per field) live in a
 // ring of 14 plane slots in shared memory: 10 planes are read by the current step while the 4
-// planes of the step after the next one arrive.  Planes are moved by the bulk-copy engine
-// (cp.async.bulk global -> shared, UBLKCP in SASS, one 192-byte row per copy, completion counted
-// on an mbarrier) -- no thread holds registers or issues per-element copies for staging, and the
-// transfer of step s+1 / s+2 overlaps the FP64 work of step s.  Every staged plane is read from
+// planes of the next step arrive.  Planes are moved by 16-byte cp.async (LDGSTS.128 in SASS; every
+// thread requests its share, ~6.6 copies per step, in the middle of its bond loop) with completion
+// counted on an mbarrier (cp.async.mbarrier.arrive.noinc), so the transfer of step s+1 overlaps
+// the FP64 work of step s.  (Bulk row copies -- cp.async.bulk / UBLKCP -- were measured and lost:
+// they issue through uniform registers, ~50 cycles per 192-byte row; profiles/r2_notes.md.)  Every staged plane is read from
 // L2 once per chunk: 2.4x read amplification (in-plane halo only) instead of 4.2x for the
 // block-per-CTA kernels (tile.cuh).
 //
-// Row alignment.  cp.async.bulk needs 16-byte aligned addresses; with an odd lattice pitch (157
+// Row alignment.  16-byte copies need 16-byte aligned addresses; with an odd lattice pitch (157
 // at params_fine) the first element of a staged row is 16-byte aligned only for every other
 // (row, plane).  Each row copy therefore starts at the even element at or below the row start and
 // moves 24 doubles; the row's data begin at element `par` = (element index & 1) of the slot row.

@@ -44,10 +44,9 @@ def test_struct_roundtrip():
 
 
 def test_out_of_scope_branches_are_rejected():
-    c = Config.load(os.path.join(H.CONFIG_DIR, "params.cfg"), quiet=True)   # as shipped: implicit
-    with pytest.raises(ValueError, match="use_implicit"):
-        c.check_supported()
-    c = Config.load(None, {"use_implicit": 0, "use_amr": 1}, quiet=True)
+    c = Config.load(os.path.join(H.CONFIG_DIR, "params.cfg"), quiet=True)   # as shipped: implicit (built)
+    c.check_supported()
+    c = Config.load(None, {"use_amr": 1}, quiet=True)
     with pytest.raises(ValueError, match="use_amr"):
         c.check_supported()
 

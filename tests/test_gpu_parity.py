@@ -264,14 +264,15 @@ def test_phase_change_sets_bit_exact():
 
 def test_errors_are_loud():
     from pd_mg_pin_corrosion_b200 import lib as L, solver as S
-    dim, cfg, _ = H.load_cfg("2d_default", {"use_implicit": 1})
-    with pytest.raises(ValueError):
+    dim, cfg, _ = H.load_cfg("2d_default", {"use_amr": 1})
+    with pytest.raises(ValueError, match="use_amr"):
         S.Grid(2).build(cfg)
+    cfg.use_amr = 0
     s = cfg.to_struct()
     import ctypes as C
     ctx = C.c_void_p()
-    assert L.load().pdgpu_create(C.byref(s), 2, 0, C.byref(ctx)) != 0
-    assert b"use_implicit" in L.load().pdgpu_last_error()
+    assert L.load().pdgpu_create(C.byref(s), 4, 0, C.byref(ctx)) != 0          # dim must be 2 or 3
+    assert b"dim" in L.load().pdgpu_last_error()
 
 
 @pytest.mark.parametrize("case", ["3d_small", "3d_default"])
