@@ -134,6 +134,7 @@ void pd_invalidate_graphs(pdgpu_ctx* c) {
 int pd_comm_destroy(pdgpu_ctx* c);
 void pd_tile_state_free(pdgpu_ctx* c);   // ns_stream.cu
 void pd_implicit_free(pdgpu_ctx* c);     // implicit.cu
+void pd_ns2d_free(pdgpu_ctx* c);         // ns2d.cu
 
 extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     if (!c) return 0;
@@ -144,6 +145,7 @@ extern "C" int pdgpu_destroy(pdgpu_ctx* c) {
     pd_comm_destroy(c);
     pd_tile_state_free(c);
     pd_implicit_free(c);
+    pd_ns2d_free(c);
     for (void* p : c->raw_fields)   // padded double arrays (pd_alloc_fields)
         if (p) cudaFree(p);
     void* ptrs[] = {c->nbfast, c->d_off, c->type, c->phase, c->is_gb, c->is_precip, c->salt, c->l_wall, c->l_wall_mirror, c->l_inlet, c->l_outlet,
@@ -214,6 +216,7 @@ extern "C" int pdgpu_set_option(pdgpu_ctx* c, const char* name, int value) {
     else if (n == "lazy_wallc") { if (pd_flush_wall_c(c)) return 1; c->opt_lazy_wallc = value; }
     else if (n == "debug_no_halo") c->opt_debug_no_halo = value;
     else if (n == "stream_chunk") c->opt_stream_chunk = value;
+    else if (n == "ns2d") c->opt_ns2d = value;
     else PD_FAIL("pdgpu_set_option: unknown option '%s'", name);
     pd_invalidate_graphs(c);
     return 0;

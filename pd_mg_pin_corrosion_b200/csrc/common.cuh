@@ -198,6 +198,8 @@ struct pdgpu_ctx {
     // streaming / tiled bond kernels (stream.cuh): column tables, active tile list, per-device attributes
     void* tile_state = nullptr;
     void* impl_state = nullptr;     // implicit ARD branch (implicit.cu)
+    void* ns2d_state = nullptr;     // persistent 2D flow loop (ns2d.cu)
+    int opt_ns2d = 1;               // 2D, one rank: run batches of NS loop bodies as one persistent kernel
     int opt_stream_chunk = 0;       // planes per work item of the streaming kernels (0 = automatic)
     // double field arrays carry `field_pad` zeroed elements in front and behind (the bulk row copies
     // of the streaming kernels may start up to 3 rows + 4 elements outside the lattice box)
@@ -333,6 +335,9 @@ inline void pd_pressure_recomputed(pdgpu_ctx* c) { c->stale_p_idx.clear(); c->st
 int pd_enqueue_ard_main(pdgpu_ctx* c, int buf, int srcC, const double* d_dt, int zb, int ze, bool do_solid,
                         bool skip_wall_copy = false);
 int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC);
+int pd_ns2d_prepare(pdgpu_ctx* c);                   // ns2d.cu
+bool pd_ns2d_ok(const pdgpu_ctx* c);
+int pd_enqueue_ns2d(pdgpu_ctx* c, int src, int iters);
 int pd_max_fluid_speed(pdgpu_ctx* c, double* vmax);
 void pd_invalidate_graphs(pdgpu_ctx* c);
 int pd_refresh_eos(pdgpu_ctx* c, int buf);           // p[buf] = EOS(rho[buf]) on all local nodes

@@ -530,6 +530,7 @@ int pd_rebuild_tables(pdgpu_ctx* c) {
     // column tables + active tile list of the streaming / tiled bond kernels: built here, outside of
     // any stream capture (a negative result only means that those kernels do not apply)
     if (pd_stream_prepare(c) > 0) return 1;
+    if (pd_ns2d_prepare(c)) return 1;     // persistent 2D flow loop (ns2d.cu)
     return 0;
 }
 

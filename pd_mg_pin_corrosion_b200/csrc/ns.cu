@@ -433,6 +433,18 @@ static int run_ns_body(pdgpu_ctx* c) {
 extern "C" int pdgpu_ns_iterate(pdgpu_ctx* c, int iters, double dt) {
     NEED_FIELDS(c);
     PD_TRY(pd_set_dt(c, 0, dt));
+    if (pd_ns2d_ok(c)) {   // 2D: batches of loop bodies as one persistent kernel (ns2d.cu)
+        for (int done = 0; done < iters;) {
+            const int n = std::min(iters - done, 500);
+            pd_touch_flow(c);
+            PD_TRY(pd_enqueue_ns2d(c, c->cur, n));
+            c->cur ^= (n - 1) & 1;             // buffer the last body read
+            c->p_input = c->cur; pd_pressure_recomputed(c);
+            c->cur = 1 - c->cur;
+            done += n;
+        }
+        iters = 0;
+    }
     for (int it = 0; it < iters; ++it) {
         PD_TRY(run_ns_body(c));
         c->p_input = c->cur; pd_pressure_recomputed(c);
@@ -488,8 +500,18 @@ extern "C" int pdgpu_ns_solve_steady(pdgpu_ctx* c, PdSteadyResult* out, int verb
     PdResidual res;
     memset(&res, 0, sizeof(res));
     const int max_iters = c->cfg.flow_max_iters;
+    const bool fused = pd_ns2d_ok(c);   // 2D: the bodies up to the next convergence poll are one kernel (ns2d.cu)
     for (iter = 1; iter <= max_iters; ++iter) {
-        PD_TRY(run_ns_body(c));
+        if (fused) {
+            int n = 1;
+            if (iter > 10) n = std::min(100 - (iter - 1) % 100, max_iters - iter + 1);
+            pd_touch_flow(c);
+            PD_TRY(pd_enqueue_ns2d(c, c->cur, n));
+            c->cur ^= (n - 1) & 1;             // buffer the last body read; the swaps in between happened in the kernel
+            iter += n - 1;
+        } else {
+            PD_TRY(run_ns_body(c));
+        }
         c->p_input = c->cur; pd_pressure_recomputed(c);
         if (iter <= 10 || iter % 100 == 0) {   // :273-322
             PD_TRY(pdgpu_ns_residual(c, &res));

@@ -168,6 +168,12 @@ class Grid:
     def set_option(self, name: str, value: int) -> None:
         _l.check(_l.load().pdgpu_set_option(self.ctx, name.encode(), value))
 
+    def launch_count(self, reset: bool = False) -> int:
+        """kernels (and graph nodes) this context has launched since the last reset"""
+        n = C.c_longlong()
+        _l.check(_l.load().pdgpu_launch_count(self.ctx, C.byref(n), 1 if reset else 0))
+        return n.value
+
     def close(self) -> None:
         if self.ctx:
             _l.load().pdgpu_destroy(self.ctx)

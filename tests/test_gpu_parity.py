@@ -320,6 +320,62 @@ def test_kernel_variants_agree(case):
             assert H.rel_err(res[n], ref.get(n)) <= TOL, (opts, n, "vs oracle")
 
 
+@pytest.mark.parametrize("case,extra", [
+    ("2d_default", None), ("2d_offgrid", None), ("2d_poiseuille", {"channel_flow_corrections": 1}),
+    ("2d_default", {"m_ratio": 2}), ("2d_default", {"m_ratio": 4}), ("2d_dissolve", None)])
+def test_2d_persistent_flow_loop(case, extra):
+    """2D: batches of NS loop bodies as one persistent cooperative kernel (csrc/ns2d.cu: BCs, Gauss-Seidel
+    outlet recurrence, wall mirror folded into the staging, bond sums, channel corrections, two grid barriers
+    per iteration) against one launch per operator (ns2d = 0) and against the oracle -- after 1, 2 and 57 loop
+    bodies from a perturbed state (both buffers: the state a later swap exposes must match too)."""
+    ref = H.make_ref(case, extra)
+    H.perturbed_state(ref, seed=7)
+    dt = ref.ns_compute_dt()
+    names = ("rho", "vel", "C", "rho_new", "vel_new")
+    done = 0
+    sides = []
+    for ns2d in (1, 0):
+        S, cfg, grid, fields = gpu_side(case, extra, ref=ref, upload=True)
+        grid.set_option("ns2d", ns2d)
+        ns = S.PD_NS_Solver(); ns.init(grid, cfg)
+        sides.append((S, cfg, grid, fields, ns))
+    for iters in (1, 2, 57):
+        out = []
+        for S, cfg, grid, fields, ns in sides:
+            n0 = grid.launch_count()
+            ns.iterate(fields, grid, cfg, iters, dt)
+            out.append(({n: fields.get(n) for n in names}, grid.launch_count() - n0))
+        ref.ns_iterate(iters, dt)
+        done += iters
+        assert out[0][1] <= 3 and out[1][1] >= 5 * iters, (out[0][1], out[1][1])   # dt upload + one kernel per batch
+        for n in names:
+            assert H.rel_err(out[0][0][n], out[1][0][n]) <= 1e-13, (case, done, n, "persistent vs per-operator")
+        if not (extra and "channel_flow_corrections" in extra):   # (the oracle applies those in solve_steady only)
+            for n in ("rho", "vel", "C"):
+                assert H.rel_err(out[0][0][n], ref.get(n)) <= TOL, (case, done, n, "vs oracle")
+    for _, _, grid, _, _ in sides:
+        grid.close()
+
+
+@pytest.mark.parametrize("case", ["2d_default", "2d_poiseuille"])
+def test_2d_solve_steady_persistent(case):
+    """solve_steady through the persistent kernel: same iteration count, same residual and the same fields as
+    the per-operator path (flow_max_iters capped so the test stays short)."""
+    extra = {"flow_max_iters": 700}
+    res = []
+    for ns2d in (1, 0):
+        S, cfg, grid, fields = gpu_side(case, extra, ref=None)
+        grid.set_option("ns2d", ns2d)
+        ns = S.PD_NS_Solver(); ns.init(grid, cfg)
+        it = ns.solve_steady(fields, grid, cfg, verbose=False)
+        res.append((it, ns.last.eps, ns.last.status, {n: fields.get(n) for n in ("rho", "vel", "C", "rho_new", "vel_new")}))
+        grid.close()
+    assert res[0][0] == res[1][0] and res[0][2] == res[1][2]
+    assert abs(res[0][1] - res[1][1]) <= 1e-9 * abs(res[1][1])
+    for n, a in res[0][3].items():
+        assert H.rel_err(a, res[1][3][n]) <= 1e-12, n
+
+
 @pytest.mark.parametrize("case,extra,n_chunks,expect", [
     ("3d_small", None, 3, 2), ("3d_default", None, 8, 8), ("3d_default", None, 16, 12),
     ("2d_default", None, 6, 4), ("2d_dissolve", None, 4, 3),
