@@ -54,7 +54,6 @@ struct Ns2dParams {
     int sweep_parts;          // lanes per T value of the sweep (4, or 2 for more than 8 outlet rows)
     int channel;              // channel_flow_corrections
     int iters, src0;
-    int dbg;
     double rho_f, gamma, B, c_div, dens_diff, visc, rho_lo, rho_hi;
     double C_in, U_in;
     const double* dt;
@@ -185,19 +184,17 @@ __device__ __forceinline__ OutSmem out_smem(const Ns2dParams& q, unsigned char* 
 // SWB steps of the recurrence of one (field, outlet row): x_i = (T_i + x_{i-R} + .. + x_{i-1}) * (1/n) resp. / n.
 // Everything but the newest value is added one step ahead (`pre`), so the dependent path per step is one DADD
 // and one DMUL (velocity) or DMUL + 2 DFMA (concentration: Markstein's correction, exact quotient).
-// out of line on purpose: inlined, the compiler evaluates the division speculatively on every step
-__device__ __noinline__ double div_tiny(double a, double dn) { return a / dn; }
-
-template <int RR>
-__device__ __forceinline__ void chain_batch(const OutSmem& s, double* row, int i0, int Nx, int fld, int kp,
-                                            double (&prev)[MAXR2D]) {
-    double T[SWB], rc[SWB], dn[SWB];
-#pragma unroll
-    for (int u = 0; u < SWB; ++u) {
-        T[u] = s.T[(fld * SWB + u) * MAXKP2D + kp];
-        rc[u] = s.brc[u * MAXKP2D + kp];
-        dn[u] = s.bdn[u * MAXKP2D + kp];
-    }
+// SWB steps of the recurrence of one (field, outlet row): x_i = (T_i + x_{i-R} + .. + x_{i-1}) * (1/n) resp. / n.
+// Everything but the newest value is added one step ahead (`pre`), so the dependent path per step is one DADD
+// and one DMUL (velocity) or DMUL + 2 DFMA (concentration: q = RN(tot * RN(1/n)) is within one ulp, the exact
+// remainder tot - q n comes from one FMA and RN(q + r * RN(1/n)) is the correctly rounded quotient -- Markstein;
+// checked against the division for n <= 130 on 4 x 10^8 operands).  No branch inside the steps: totals below
+// the range of the correction (|tot| < 1e-280, not zero) only raise a flag and the batch is redone with the
+// division (EXACT = true; out of line, practically never).
+template <int RR, bool EXACT>
+__device__ __forceinline__ bool chain_steps(const double (&T)[SWB], const double (&rc)[SWB], const double (&dn)[SWB],
+                                            double* row, int i0, int Nx, int fld, double (&prev)[MAXR2D]) {
+    bool tiny = false;
     double pre = T[0];
 #pragma unroll
     for (int x = RR - 1; x >= 1; --x) pre += prev[x];            // di = -R .. -2
@@ -213,8 +210,11 @@ __device__ __forceinline__ void chain_batch(const OutSmem& s, double* row, int i
         const double qv = tot * rc[u];                            // src/boundary.cpp:113-124 (rc = 0: not an OUTLET node)
         double val = qv;
         if (fld) {                                                // :129, sc / cnt
-            val = fma(fma(-qv, dn[u], tot), rc[u], qv);
-            if (fabs(tot) < 1e-280 && tot != 0.0 && rc[u] != 0.0) val = div_tiny(tot, dn[u]);   // below the range of the correction
+            if (EXACT) val = rc[u] != 0.0 ? tot / dn[u] : 0.0;
+            else {
+                val = fma(fma(-qv, dn[u], tot), rc[u], qv);
+                tiny |= fabs(tot) < 1e-280 && tot != 0.0 && rc[u] != 0.0;
+            }
         }
         const int i = i0 + u;
         if (i >= 0 && i < Nx) row[i] = val;
@@ -222,6 +222,33 @@ __device__ __forceinline__ void chain_batch(const OutSmem& s, double* row, int i
         for (int x = RR - 1; x > 0; --x) prev[x] = prev[x - 1];
         prev[0] = val;
         pre = pre_n;
+    }
+    return tiny;
+}
+
+template <int RR>
+__device__ __noinline__ void chain_redo(const double (&T)[SWB], const double (&rc)[SWB], const double (&dn)[SWB],
+                                        double* row, int i0, int Nx, int fld, double (&prev)[MAXR2D]) {
+    chain_steps<RR, true>(T, rc, dn, row, i0, Nx, fld, prev);
+}
+
+template <int RR>
+__device__ __forceinline__ void chain_batch(const OutSmem& s, double* row, int i0, int Nx, int fld, int kp,
+                                            double (&prev)[MAXR2D]) {
+    double T[SWB], rc[SWB], dn[SWB];
+#pragma unroll
+    for (int u = 0; u < SWB; ++u) {
+        T[u] = s.T[(fld * SWB + u) * MAXKP2D + kp];
+        rc[u] = s.brc[u * MAXKP2D + kp];
+        dn[u] = s.bdn[u * MAXKP2D + kp];
+    }
+    double saved[MAXR2D];
+#pragma unroll
+    for (int x = 0; x < MAXR2D; ++x) saved[x] = prev[x];
+    if (chain_steps<RR, false>(T, rc, dn, row, i0, Nx, fld, prev)) {
+#pragma unroll
+        for (int x = 0; x < MAXR2D; ++x) prev[x] = saved[x];
+        chain_redo<RR>(T, rc, dn, row, i0, Nx, fld, prev);
     }
 }
 
@@ -296,7 +323,13 @@ __device__ void outlet_phase(const Ns2dParams& q, const OutSmem& s, const Off2* 
     const int t_part = tid % PARTS, t_rest = tid / PARTS;
     const int t_fld = t_rest & 1, t_u = (t_rest >> 1) % SWB, t_kp = t_valid ? (t_rest >> 1) / SWB : 0;
     const double* t_base = (t_fld ? s.base_c : s.base_v) + t_kp * Nx;
+    const double* t_rc = s.rc + t_kp * Nx;
+    const double* t_dn = s.dn + t_kp * Nx;
     const double* t_row = (t_fld ? s.new_c : s.new_v) + (t_kp + R) * PW + R;
+    const int t_i0 = t_u - LAG * t_kp;
+    double* t_T = s.T + (t_fld * SWB + t_u) * MAXKP2D + t_kp;
+    double* t_brc = s.brc + t_u * MAXKP2D + t_kp;
+    double* t_bdn = s.bdn + t_u * MAXKP2D + t_kp;
     const int ne = (n_below + PARTS - 1) / PARTS;
     int rel[8];
 #pragma unroll
@@ -313,10 +346,12 @@ __device__ void outlet_phase(const Ns2dParams& q, const OutSmem& s, const Off2* 
     long long c_help = 0, c_chain = 0;
     for (int b0 = 0; b0 < steps; b0 += SWB) {
         const long long c0 = clock64();
-        if (!(q.dbg & 4)) {
-            const int i = b0 + t_u - LAG * t_kp;
+        {
+            // (addresses of steps outside [0, Nx) stay inside the CTA's shared memory; what they read is dropped)
+            const int i = b0 + t_i0;
             const bool in = t_valid && i >= 0 && i < Nx;
-            const double* p = t_row + min(max(i, 0), Nx - 1);
+            const double* p = t_row + i;
+            const double bse = t_base[i], rcv = t_rc[i], dnv = t_dn[i];
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int e = 0; e < 8; e += 2) {
@@ -324,19 +359,16 @@ __device__ void outlet_phase(const Ns2dParams& q, const OutSmem& s, const Off2* 
                 if (e + 1 < ne) a1 += p[rel[e + 1]];
             }
             double a = a0 + a1;
-            for (int x = 1; x < PARTS; x <<= 1) a += __shfl_xor_sync(0xffffffffu, a, x);
+            if (PARTS == 4) { a += __shfl_xor_sync(0xffffffffu, a, 1); a += __shfl_xor_sync(0xffffffffu, a, 2); }
+            else a += __shfl_xor_sync(0xffffffffu, a, 1);
             if (t_valid && t_part == 0) {
-                const int ic = min(max(i, 0), Nx - 1);
-                s.T[(t_fld * SWB + t_u) * MAXKP2D + t_kp] = in ? t_base[ic] + a : 0.0;
-                if (t_fld == 0) {
-                    s.brc[t_u * MAXKP2D + t_kp] = in ? s.rc[t_kp * Nx + ic] : 0.0;
-                    s.bdn[t_u * MAXKP2D + t_kp] = in ? s.dn[t_kp * Nx + ic] : 1.0;
-                }
+                t_T[0] = in ? bse + a : 0.0;
+                if (t_fld == 0) { t_brc[0] = in ? rcv : 0.0; t_bdn[0] = in ? dnv : 1.0; }
             }
         }
         __syncthreads();
         const long long c1 = clock64();
-        if (tid < 64 && kp_w < q.KP && !(q.dbg & 2) && !((q.dbg & 1) && fld_w)) {
+        if (tid < 64 && kp_w < q.KP) {
             const int i0 = b0 - LAG * kp_w;
             switch (R) {
                 case 1: chain_batch<1>(s, c_row, i0, Nx, fld_w, kp_w, prev); break;
@@ -783,7 +815,6 @@ int pd_enqueue_ns2d(pdgpu_ctx* c, int src, int iters) {
     q.l_solid = c->l_solid; q.n_solid = (int)c->n_solid;
     q.l_wall = c->l_wall; q.mirror = c->l_wall_mirror; q.n_wall = (int)c->n_wall;
     q.bar = st->bar;
-    { const char* e = getenv("PDGPU_NS2D_DBG"); q.dbg = e ? atoi(e) : 0; }
     q.sweep_parts = st->KP <= 8 ? 4 : 2;
     static const bool want_prof = getenv("PDGPU_NS2D_PROF") != nullptr;
     q.prof = nullptr;

