@@ -265,6 +265,10 @@ int pdgpu_comm_allreduce(pdgpu_ctx* ctx, double* host_vals, int n, int op);
 int pdgpu_timer_start(pdgpu_ctx* ctx);               /* cudaEventRecord on the ctx stream */
 int pdgpu_timer_stop(pdgpu_ctx* ctx, float* ms);     /* record + synchronize + elapsed    */
 int pdgpu_launch_count(pdgpu_ctx* ctx, long long* launches, int reset);
+/* Kernel selection (defaults in parentheses; every variant gives the same results, tests/test_gpu_parity.py):
+ * ns_kernel (2) 0 generic / 1 block tiles / 2 z-streaming / 3 materialised CSR; ard_kernel (1) 0 / 1 / 3;
+ * outlet_kernel (3); overlap (1); comm_overlap (1); graph (1); lazy_wallc (1); stream_chunk (0 = auto);
+ * ns2d (1): 2D, one rank -- the NS loop bodies between two convergence polls as one persistent kernel. */
 int pdgpu_set_option(pdgpu_ctx* ctx, const char* name, int value);
 int pdgpu_flush_l2(pdgpu_ctx* ctx);                  /* write a > L2-sized scratch buffer */
 /* kernel-only timing of the dominant kernel: average ms of `reps` launches of the NS

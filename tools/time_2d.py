@@ -1,5 +1,5 @@
 """2D solve_steady timing (BASELINE configs 1-2): loop body per iteration under option sets, whole
-solve_steady wall time.  usage: python tools/time_2d.py [--fine] [--solve] "graph=1" "graph=0" ..."""
+solve_steady wall time.  usage: python tools/time_2d.py [--fine | --cfg=params_poiseuille.cfg] [--solve] "ns2d=1" "ns2d=0" ..."""
 import ctypes as C
 import os
 import sys
@@ -11,12 +11,16 @@ from pd_mg_pin_corrosion_b200 import lib as L_, solver as S   # noqa: E402
 from pd_mg_pin_corrosion_b200.config import Config            # noqa: E402
 
 fine = "--fine" in sys.argv
+cfg_name = "params_fine.cfg" if fine else "params.cfg"
+for a in sys.argv[1:]:
+    if a.startswith("--cfg="):
+        cfg_name = a[6:]
 sets = [a for a in sys.argv[1:] if not a.startswith("--")] or ["graph=1"]
-cfg = Config.load(os.path.join(ROOT, "configs", "params_fine.cfg" if fine else "params.cfg"), {}, quiet=True)
+cfg = Config.load(os.path.join(ROOT, "configs", cfg_name), {}, quiet=True)
 L = L_.load()
 grid = S.Grid(2)
 grid.build(cfg)
-print(f"2D lattice {grid.Nx} x {grid.Ny} = {grid.N_total} nodes", flush=True)
+print(f"{cfg_name}: 2D lattice {grid.Nx} x {grid.Ny} = {grid.N_total} nodes", flush=True)
 fields = S.Fields(); fields.bind(grid)
 L_.check(L.pdgpu_fields_init(grid.ctx, None, None))
 ns = S.PD_NS_Solver(); ns.init(grid, cfg)
