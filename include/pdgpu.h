@@ -261,6 +261,41 @@ int pdgpu_halo_exchange(pdgpu_ctx* ctx, int which);  /* 0: rho,vel,p   1: C   2:
  * dissolved-node count of a check (src/coupling.cpp:256-275). No-op for one rank. n <= 1024. */
 int pdgpu_comm_allreduce(pdgpu_ctx* ctx, double* host_vals, int n, int op);
 
+/* ---- two-level AMR grid (2D like the reference) ------------------------------
+ * Replaces Grid::build_amr / build_neighbors_celllist / update_fictitious (src/grid.cpp:352-842) and the AMR
+ * branches of the explicit solvers and BCs (src/pd_ns.cpp:18-33,328; src/pd_ard.cpp:17-31,86,130;
+ * src/boundary.cpp:185-201). The grid build is host code (no device needed until pdamr_device_init);
+ * every array it produces is bit-identical to the reference's. amr_ratio / amr_buffer: src/config.h:86-88. */
+typedef struct pdamr_ctx pdamr_ctx;
+typedef struct PdAmrInfo {
+    long long N_total, n_fine, n_coarse, n_fict, nnz, n_fict_entries;   /* nnz = -1 before build_neighbors */
+    long long counts[7];                                                 /* per NodeType, FICTITIOUS = 6 */
+    double origin[2], dx_coarse, delta_coarse;
+} PdAmrInfo;
+int pdamr_create(const PdConfig* cfg, int amr_ratio, double amr_buffer, pdamr_ctx** out);
+int pdamr_build(pdamr_ctx* ctx);                 /* Grid::build_amr */
+int pdamr_build_neighbors(pdamr_ctx* ctx);       /* Grid::build_neighbors_celllist (+ wall-mirror table, outlet levels) */
+int pdamr_info(pdamr_ctx* ctx, PdAmrInfo* out);
+/* host copies: pos [N][2], node_type (u8), dx_local, delta_local, grid_level (int), fict_offset [N+1], fict_source,
+ * fict_weight, nbr_offset [N+1], nbr_index, nbr_dist, nbr_evec [nnz][2], nbr_vol, wall_mirror (int, -2: not a WALL) */
+int pdamr_get(pdamr_ctx* ctx, const char* name, void* out);
+int pdamr_device_init(pdamr_ctx* ctx, int device);   /* uploads the tables, allocates the fields; needs a B200 */
+/* fields by the reference's names: rho, vel [N][2], pressure, C, rho_new, vel_new, C_new, phase, is_gb, is_precip */
+int pdamr_field_set(pdamr_ctx* ctx, const char* name, const void* src);
+int pdamr_field_get(pdamr_ctx* ctx, const char* name, void* dst);
+int pdamr_update_fictitious(pdamr_ctx* ctx);     /* Grid::update_fictitious: IDW of C, rho, pressure, vel */
+int pdamr_bc(pdamr_ctx* ctx, int which);         /* 0 inlet, 1 outlet, 2 wall, 3 solid, 4 wall conc., 5 wall (new buffers) */
+int pdamr_ns_compute_dt(pdamr_ctx* ctx, double* dt);
+int pdamr_ns_step(pdamr_ctx* ctx, double dt);    /* compute_pressure + step -> new buffers (no swap) */
+int pdamr_ns_iterate(pdamr_ctx* ctx, int iters, double dt);   /* loop bodies of solve_steady incl. the IDW update */
+int pdamr_ns_solve_steady(pdamr_ctx* ctx, PdSteadyResult* out, int verbose);
+int pdamr_ard_set_volume_loss(pdamr_ctx* ctx, double vl);
+int pdamr_ard_compute_dt(pdamr_ctx* ctx, double* dt);
+int pdamr_ard_step(pdamr_ctx* ctx, double dt);
+int pdamr_ard_iterate(pdamr_ctx* ctx, int steps, double dt);
+int pdamr_phase_change(pdamr_ctx* ctx, int* n_dissolved);
+int pdamr_destroy(pdamr_ctx* ctx);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 int pdgpu_timer_start(pdgpu_ctx* ctx);               /* cudaEventRecord on the ctx stream */
 int pdgpu_timer_stop(pdgpu_ctx* ctx, float* ms);     /* record + synchronize + elapsed    */

@@ -9,6 +9,7 @@
 // What it wraps (reference file:line):
 //   Config::load / compute_derived            src/config.cpp:16,98
 //   Grid::build / build_neighbors             src/grid.cpp:29,157
+//   Grid::build_amr / build_neighbors_celllist / update_fictitious   src/grid.cpp:352,660,802
 //   GrainStructure::generate                  src/grains.cpp:9   (forced 1 thread)
 //   initialize_fields (static in main.cpp)    src/main.cpp:9
 //   apply_*_bc                                src/boundary.cpp:31,88,288,292,302,381
@@ -97,6 +98,11 @@ void ref_get_config(void* h, double* out) {
 int ref_config_len() { return 39; }
 
 void ref_grid_build(void* h) { S(h)->grid.build(S(h)->cfg); }
+// two-level AMR grid (src/grid.cpp:352-842): what main() calls with use_amr = 1 (src/main.cpp:151-154)
+void ref_grid_build_amr(void* h) { S(h)->grid.build_amr(S(h)->cfg); }
+void ref_build_neighbors_celllist(void* h) { S(h)->grid.build_neighbors_celllist(S(h)->cfg); }
+void ref_update_fictitious(void* h) { S(h)->grid.update_fictitious(S(h)->fields); }
+long long ref_fict_entries(void* h) { return (long long)S(h)->grid.fict_source.size(); }
 void ref_build_neighbors(void* h) { S(h)->grid.build_neighbors(); }
 
 void ref_generate_grains(void* h) {
@@ -141,6 +147,12 @@ void* ref_ptr(void* h, const char* name) {
     if (n == "nbr_dist") return g.nbr_dist.data();
     if (n == "nbr_evec") return g.nbr_evec.data();
     if (n == "nbr_vol") return g.nbr_vol.data();
+    if (n == "dx_local") return g.dx_local.data();
+    if (n == "delta_local") return g.delta_local.data();
+    if (n == "grid_level") return g.grid_level.data();
+    if (n == "fict_offset") return g.fict_offset.data();
+    if (n == "fict_source") return g.fict_source.data();
+    if (n == "fict_weight") return g.fict_weight.data();
     if (n == "rho") return f.rho.data();
     if (n == "vel") return f.vel.data();
     if (n == "pressure") return f.pressure.data();
@@ -187,6 +199,21 @@ void ref_ns_iterate(void* h, int iters, double dt) {
         s->ns.step(s->fields, s->grid, s->cfg, dt);
         apply_wall_bc_new(s->fields, s->grid, s->cfg);
         s->fields.swap_buffers();
+    }
+}
+
+// The same loop body on the AMR grid: solve_steady refreshes the FICTITIOUS nodes after the swap (:328).
+void ref_ns_iterate_amr(void* h, int iters, double dt) {
+    RefSim* s = S(h);
+    for (int it = 0; it < iters; ++it) {
+        apply_inlet_bc(s->fields, s->grid, s->cfg);
+        apply_outlet_bc(s->fields, s->grid, s->cfg);
+        apply_wall_bc(s->fields, s->grid, s->cfg);
+        apply_solid_surface_bc(s->fields, s->grid);
+        s->ns.step(s->fields, s->grid, s->cfg, dt);
+        apply_wall_bc_new(s->fields, s->grid, s->cfg);
+        s->fields.swap_buffers();
+        s->grid.update_fictitious(s->fields);
     }
 }
 

@@ -54,7 +54,7 @@ def _lib(dim: int) -> C.CDLL:
     for name in ("ref_time_ns_iterate", "ref_time_ard_iterate"):
         getattr(lib, name).restype = C.c_double
         getattr(lib, name).argtypes = [vp, C.c_int, C.c_double]
-    for name in ("ref_ns_iterate", "ref_ard_iterate"):
+    for name in ("ref_ns_iterate", "ref_ard_iterate", "ref_ns_iterate_amr"):
         getattr(lib, name).restype = None
         getattr(lib, name).argtypes = [vp, C.c_int, C.c_double]
     for name in ("ref_ns_step", "ref_ard_step", "ref_ard_set_volume_loss"):
@@ -66,12 +66,14 @@ def _lib(dim: int) -> C.CDLL:
                  "ref_apply_wall_concentration_bc", "ref_apply_solid_surface_bc",
                  "ref_smooth_boundary_concentration",
                  "ref_update_node_types", "ref_ns_init", "ref_swap_flow", "ref_ard_init",
-                 "ref_swap_C"):
+                 "ref_swap_C", "ref_grid_build_amr", "ref_build_neighbors_celllist", "ref_update_fictitious"):
         getattr(lib, name).restype = None
         getattr(lib, name).argtypes = [vp]
     for name in ("ref_ns_solve_steady", "ref_ard_phase_change", "ref_n_grains"):
         getattr(lib, name).restype = C.c_int
         getattr(lib, name).argtypes = [vp]
+    lib.ref_fict_entries.restype = C.c_longlong
+    lib.ref_fict_entries.argtypes = [vp]
     lib.ref_get_config.argtypes = [vp, C.POINTER(C.c_double)]
     lib.ref_get_dims.argtypes = [vp, C.POINTER(C.c_longlong)]
     lib.ref_get_origin.argtypes = [vp, C.POINTER(C.c_double)]
@@ -121,9 +123,19 @@ class RefSim:
         self.lib.ref_get_config(self.h, buf)
         self.cfg = dict(zip(CONFIG_FIELDS, list(buf)))
         self.N = 0
+        self.amr = False                  # the last `use_amr = ...` line wins, as in the reference parser
+        with open(self.cfg_path) as f:
+            for line in f:
+                k, _, v = line.partition("=")
+                if k.strip() == "use_amr":
+                    self.amr = bool(int(v.split("#")[0].strip()))
         if build:
-            self.lib.ref_grid_build(self.h)
-            self.lib.ref_build_neighbors(self.h)
+            if self.amr:      # src/main.cpp:151-154
+                self.lib.ref_grid_build_amr(self.h)
+                self.lib.ref_build_neighbors_celllist(self.h)
+            else:
+                self.lib.ref_grid_build(self.h)
+                self.lib.ref_build_neighbors(self.h)
             self._dims()
             if fields:
                 self.lib.ref_generate_grains(self.h)
@@ -164,12 +176,15 @@ class RefSim:
         "phase": (np.uint8, "N"), "grain_id": (np.int32, "N"), "is_gb": (np.uint8, "N"),
         "is_precip": (np.uint8, "N"), "rho_new": (np.float64, "N"),
         "vel_new": (np.float64, "N,DIM"), "C_new": (np.float64, "N"),
+        "dx_local": (np.float64, "N"), "delta_local": (np.float64, "N"), "grid_level": (np.int32, "N"),
+        "fict_offset": (np.int32, "N+1"), "fict_source": (np.int32, "NF"), "fict_weight": (np.float64, "NF"),
     }
 
     def arr(self, name: str) -> np.ndarray:
         dt, shp = self._SPEC[name]
         self._dims()
-        dims = {"N": self.N, "N+1": self.N + 1, "NNZ": self.nnz, "DIM": self.dim}
+        dims = {"N": self.N, "N+1": self.N + 1, "NNZ": self.nnz, "DIM": self.dim,
+                "NF": int(self.lib.ref_fict_entries(self.h))}
         shape = tuple(dims[s] for s in shp.split(","))
         ptr = self.lib.ref_ptr(self.h, name.encode())
         if not ptr or 0 in shape:
@@ -194,7 +209,8 @@ class RefSim:
     def smooth_conc(self): self.lib.ref_smooth_boundary_concentration(self.h)
     def ns_compute_dt(self) -> float: return self.lib.ref_ns_compute_dt(self.h)
     def ns_step(self, dt): self.lib.ref_ns_step(self.h, dt)
-    def ns_iterate(self, n, dt): self.lib.ref_ns_iterate(self.h, n, dt)
+    def ns_iterate(self, n, dt): (self.lib.ref_ns_iterate_amr if self.amr else self.lib.ref_ns_iterate)(self.h, n, dt)
+    def update_fictitious(self): self.lib.ref_update_fictitious(self.h)
     def ns_solve_steady(self) -> int: return self.lib.ref_ns_solve_steady(self.h)
     def swap_flow(self): self.lib.ref_swap_flow(self.h)
     def ard_set_volume_loss(self, v): self.lib.ref_ard_set_volume_loss(self.h, v)

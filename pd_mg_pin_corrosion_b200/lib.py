@@ -37,6 +37,13 @@ class PdSteadyResult(C.Structure):
                 ("poiseuille_l2", C.c_double), ("poiseuille_nodes", C.c_int), ("pad", C.c_int)]
 
 
+class PdAmrInfo(C.Structure):
+    _fields_ = [("N_total", C.c_longlong), ("n_fine", C.c_longlong), ("n_coarse", C.c_longlong),
+                ("n_fict", C.c_longlong), ("nnz", C.c_longlong), ("n_fict_entries", C.c_longlong),
+                ("counts", C.c_longlong * 7), ("origin", C.c_double * 2), ("dx_coarse", C.c_double),
+                ("delta_coarse", C.c_double)]
+
+
 class PdDiag(C.Structure):
     _fields_ = [("solid_count", C.c_longlong), ("v_max", C.c_double), ("C_max_fluid", C.c_double)]
 
@@ -116,6 +123,15 @@ def load() -> C.CDLL:
         "pdgpu_format_g": [vp, vp, C.c_longlong, vp],
         "pdgpu_checkpoint_save": [vp, C.c_char_p, C.POINTER(C.c_longlong)], "pdgpu_checkpoint_load": [vp, C.c_char_p],
         "pdgpu_host_register": [vp, C.c_size_t], "pdgpu_host_unregister": [vp],
+        "pdamr_create": [cfgp, C.c_int, C.c_double, C.POINTER(vp)], "pdamr_build": [vp], "pdamr_build_neighbors": [vp],
+        "pdamr_info": [vp, C.POINTER(PdAmrInfo)], "pdamr_get": [vp, C.c_char_p, vp],
+        "pdamr_device_init": [vp, C.c_int], "pdamr_field_set": [vp, C.c_char_p, vp], "pdamr_field_get": [vp, C.c_char_p, vp],
+        "pdamr_update_fictitious": [vp], "pdamr_bc": [vp, C.c_int],
+        "pdamr_ns_compute_dt": [vp, dp], "pdamr_ns_step": [vp, C.c_double], "pdamr_ns_iterate": [vp, C.c_int, C.c_double],
+        "pdamr_ns_solve_steady": [vp, C.POINTER(PdSteadyResult), C.c_int],
+        "pdamr_ard_set_volume_loss": [vp, C.c_double], "pdamr_ard_compute_dt": [vp, dp],
+        "pdamr_ard_step": [vp, C.c_double], "pdamr_ard_iterate": [vp, C.c_int, C.c_double],
+        "pdamr_phase_change": [vp, ip], "pdamr_destroy": [vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

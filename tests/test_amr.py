@@ -1,0 +1,153 @@
+"""Two-level AMR grid.  CPU part: the host-side grid build of libpdgpu.so against the UNMODIFIED
+reference (oracle/_ref: Grid::build_amr / build_neighbors_celllist, src/grid.cpp:352-796) -- every array bit for
+bit.  GPU part: update_fictitious, the BCs, the explicit NS / ARD loop bodies, solve_steady and the phase change
+on that grid against the reference, 1e-12 of the field maximum (same summation order: CSR order)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import refapi
+from pd_mg_pin_corrosion_b200.config import Config
+
+import helpers as H
+
+needs_ref = pytest.mark.skipif(not refapi.have_ref(2), reason="oracle/_ref not built")
+TOL = 1e-12
+
+AMR_CASES = {
+    "amr_default": ("params.cfg", {"use_amr": 1, "amr_ratio": 3, "amr_buffer": 50e-6}),
+    "amr_ratio2": ("params.cfg", {"use_amr": 1, "amr_ratio": 2, "amr_buffer": 40e-6, "dx": 4.0e-6}),
+    "amr_shipped": ("params_amr.cfg", {}),
+    "amr_offgrid": ("params.cfg", {"use_amr": 1, "amr_ratio": 3, "amr_buffer": 47e-6, "dx": 4.3e-6, "R_tube": 151e-6,
+                                   "R_wire": 33e-6, "L_wire": 207e-6, "L_upstream": 260e-6, "L_downstream": 310e-6}),
+}
+GEOM = ["pos", "node_type", "dx_local", "delta_local", "grid_level", "fict_offset", "fict_source", "fict_weight",
+        "nbr_offset", "nbr_index", "nbr_dist", "nbr_evec", "nbr_vol"]
+
+
+def both(case, fields=False, extra=None):
+    from pd_mg_pin_corrosion_b200.amr import AmrGrid
+    base, ov = AMR_CASES[case]
+    ov = dict(ov, use_implicit=0, **(extra or {}))
+    ref = refapi.RefSim(2, base, ov, threads=1, build=True, fields=fields)
+    cfg = Config.load(os.path.join(H.CONFIG_DIR, base), ov, quiet=True)
+    g = AmrGrid(cfg)
+    g.build_amr()
+    g.build_neighbors_celllist()
+    return ref, cfg, g
+
+
+@needs_ref
+@pytest.mark.parametrize("case", list(AMR_CASES))
+def test_amr_grid_build_bit_exact(case):
+    ref, cfg, g = both(case)
+    i = g.info
+    assert (i.N_total, i.nnz, i.n_fict_entries) == (ref.N, ref.nnz, ref.lib.ref_fict_entries(ref.h))
+    assert list(i.counts) == np.bincount(ref.get("node_type"), minlength=7).tolist()
+    assert i.n_fict > 0 and i.n_fine > 0 and i.n_coarse > 0
+    for name in GEOM:
+        a, b = g.get(name), ref.get(name)
+        assert a.shape == b.shape, name
+        assert np.array_equal(a, b), (case, name, int((a != b).sum()))
+    assert (ref.origin[0], ref.origin[1]) == (i.origin[0], i.origin[1])
+
+
+@needs_ref
+def test_amr_wall_mirror_table():
+    """index trick: rho[i] = i + 0.25, apply_wall_bc on the reference, read the WALL nodes"""
+    ref, cfg, g = both("amr_default", fields=True)
+    N = ref.N
+    ref.set("rho", np.arange(N) + 0.25)
+    ref.wall_bc()
+    nt = ref.get("node_type")
+    got = g.get("wall_mirror")
+    rho = ref.get("rho")
+    walls = np.nonzero(nt == 2)[0]
+    assert walls.size > 0 and np.all(got[nt != 2] == -2)
+    for n in walls:
+        m = got[n]
+        expect = (m + 0.25) if m >= 0 else cfg.rho_f
+        assert rho[n] == expect, (n, m, rho[n])
+
+
+def gpu_pair(case, extra=None):
+    ref, cfg, g = both(case, fields=True, extra=extra)
+    g.device_init(0)
+    for n in ("rho", "vel", "C", "rho_new", "vel_new", "C_new", "phase", "is_gb", "is_precip"):
+        g.set_field(n, ref.get(n))
+    return ref, cfg, g
+
+
+def assert_close(g, ref, names, tol=TOL):
+    for n in names:
+        a, b = g.get_field(n), ref.get(n)
+        e = H.rel_err(a, b)
+        assert e <= tol, f"{n}: rel err {e:.3e}"
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("case", ["amr_default", "amr_ratio2", "amr_offgrid"])
+def test_amr_operators_match_reference(case):
+    ref, cfg, g = gpu_pair(case)
+    H.perturbed_state(ref, seed=3)
+    for n in ("rho", "vel", "C", "rho_new", "vel_new", "C_new"):
+        g.set_field(n, ref.get(n))
+    for op in ("inlet_bc", "outlet_bc", "wall_bc", "solid_bc", "wall_conc_bc"):
+        getattr(ref, op)(); getattr(g, op)()
+        assert_close(g, ref, ("rho", "vel", "C"))
+    ref.update_fictitious(); g.update_fictitious()
+    assert_close(g, ref, ("rho", "vel", "C", "pressure"))
+    dt = ref.ns_compute_dt()
+    assert abs(g.ns_compute_dt() - dt) <= 1e-15 * dt
+    ref.ns_step(dt); g.ns_step(dt)
+    assert_close(g, ref, ("rho_new", "vel_new", "pressure"))
+    ref.wall_bc_new(); g.wall_bc_new()
+    assert_close(g, ref, ("rho_new", "vel_new"))
+    dtc = ref.ard_compute_dt()
+    assert abs(g.ard_compute_dt() - dtc) <= 1e-15 * dtc
+    ref.ard_step(dtc); g.ard_step(dtc)
+    assert_close(g, ref, ("C_new",))
+    g.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("case", ["amr_default", "amr_ratio2"])
+def test_amr_loop_bodies_match_reference(case):
+    ref, cfg, g = gpu_pair(case)
+    dt = ref.ns_compute_dt()
+    ref.ns_iterate(40, dt); g.ns_iterate(40, dt)
+    assert_close(g, ref, ("rho", "vel", "C", "pressure"))
+    dtc = ref.ard_compute_dt()
+    ref.ard_iterate(25, dtc); g.ard_iterate(25, dtc)
+    assert_close(g, ref, ("rho", "vel", "C"))
+    g.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_amr_solve_steady_and_phase_change():
+    extra = {"flow_max_iters": 300, "D_grain": 5e-11, "D_gb": 5e-9, "C_thresh": 0.999}
+    ref, cfg, g = gpu_pair("amr_default", extra)
+    it_ref = ref.ns_solve_steady()
+    r = g.ns_solve_steady()
+    assert r.iters == it_ref
+    assert_close(g, ref, ("rho", "vel", "rho_new", "vel_new"), tol=1e-11)
+    ref.update_fictitious(); g.update_fictitious()          # src/coupling.cpp:139
+    dtc = ref.ard_compute_dt()
+    total = 0
+    for _ in range(6):
+        ref.ard_iterate(40, dtc); g.ard_iterate(40, dtc)
+        n_ref, n = ref.phase_change(), g.phase_change()
+        assert n == n_ref
+        total += n
+        if n_ref:
+            ref.lib.ref_update_node_types(ref.h)
+            ref.lib.ref_build_neighbors_celllist(ref.h)
+        assert np.array_equal(g.get_field("node_type"), ref.get("node_type"))
+        assert np.array_equal(g.get_field("phase"), ref.get("phase"))
+        assert_close(g, ref, ("rho", "vel", "C"), tol=1e-11)
+    assert total > 0, "the synthetic diffusivities must dissolve nodes"
+    g.close()
