@@ -131,3 +131,104 @@ class AmrGrid:
             self.close()
         except Exception:
             pass
+
+
+def initialize_fields(grid: AmrGrid, is_gb, is_precip) -> None:
+    """initialize_fields (src/main.cpp:9-126) on the AMR cloud: Poiseuille profile on FLUID / INLET nodes,
+    C = C_solid_init on the wire, FICTITIOUS nodes at rest; new buffers = current buffers."""
+    cfg = grid.cfg
+    nt = grid.get("node_type")
+    x = grid.get("pos")[:, 0]
+    N = grid.N_total
+    rr = np.minimum((x * x) / (cfg.R_tube * cfg.R_tube), 1.0)
+    v_ax = 1.5 * cfg.U_in * (1.0 - rr)
+    rho = np.full(N, cfg.rho_f)
+    rho[nt == 5] = 0.0
+    vel = np.zeros((N, 2))
+    flow = (nt == 0) | (nt == 3)
+    vel[flow, 1] = v_ax[flow]
+    Cc = np.zeros(N)
+    Cc[nt == 0] = cfg.C_liquid_init
+    Cc[nt == 3] = cfg.C_liquid_init
+    Cc[nt == 4] = cfg.C_liquid_init
+    Cc[nt == 1] = cfg.C_solid_init
+    phase = np.ones(N, np.uint8)
+    phase[nt == 1] = 0
+    for name, val in (("rho", rho), ("rho_new", rho), ("vel", vel), ("vel_new", vel), ("C", Cc), ("C_new", Cc),
+                      ("phase", phase), ("is_gb", np.asarray(is_gb, np.uint8)),
+                      ("is_precip", np.asarray(is_precip, np.uint8))):
+        grid.set_field(name, val)
+
+
+class AmrCoupledSolver:
+    """CoupledSolver::run with use_amr = 1, explicit ARD branch (src/coupling.cpp:82-302): flow solve when the
+    geometry changed + IDW refresh of the FICTITIOUS nodes (:138-139), corrosion sub-steps with the frozen flow,
+    phase change, diagnostics rows (:20-68) every output_every_corr steps.  Returns the rows; writes
+    <output_dir>/diagnostics.csv when `out_dir` is given.  (Snapshots of the cloud are VTU files in the
+    reference -- not written here.)"""
+
+    def __init__(self, log=None):
+        self.log = log or (lambda *a, **k: None)
+        self.rows: list[list[float]] = []
+
+    def _diag(self, grid: AmrGrid, t: float, solid0: np.ndarray) -> None:
+        nt = grid.get_field("node_type")
+        Cc = grid.get_field("C")
+        s = 0.0
+        for v in Cc[solid0].tolist():          # ordered sum (src/coupling.cpp:32-38)
+            s += v
+        loss = max((1.0 - s / (len(solid0) + 1e-30)) * 100.0, 0.0)
+        fl = nt == 0
+        v = grid.get_field("vel")[fl]
+        vmax = float(np.sqrt((v * v).sum(1)).max()) if fl.any() else 0.0
+        cmax = float(max(Cc[fl].max(), 0.0)) if fl.any() else 0.0
+        self.rows.append([t, t / 3600.0, loss, float((nt == 1).sum()), vmax, cmax])
+
+    def run(self, grid: AmrGrid, out_dir: str | None = None) -> list[list[float]]:
+        cfg = grid.cfg
+        solid0 = np.nonzero(grid.get_field("node_type") == 1)[0]
+        n0 = len(solid0)
+        t_corr, need_flow, cycle = 0.0, True, 0
+        while t_corr < cfg.T_final:
+            cycle += 1
+            if need_flow:
+                r = grid.ns_solve_steady()
+                grid.update_fictitious()
+                self.log(f"cycle {cycle}: flow solve {r.iters} iterations, eps {r.eps:.3e}")
+                need_flow = False
+            s = 0.0
+            for v in grid.get_field("C")[solid0].tolist():
+                s += v
+            grid.ard_set_volume_loss(max(1.0 - s / (n0 + 1e-30), 0.0))
+            dtc = grid.ard_compute_dt()
+            step = 0
+            every = int(cfg.output_every_corr)
+            while step < cfg.corrosion_steps_per_check:
+                # device-resident batches between two diagnostics rows
+                n = min(every - step % every, cfg.corrosion_steps_per_check - step)
+                done = 0
+                while done < n:                  # t_corr advances per step (:237) and ends the cycle (:248)
+                    t_corr += dtc
+                    done += 1
+                    if t_corr >= cfg.T_final:
+                        break
+                grid.ard_iterate(done, dtc)
+                step += done
+                if done == n and step % every == 0:
+                    self._diag(grid, t_corr, solid0)
+                if t_corr >= cfg.T_final:
+                    break
+            n_diss = grid.phase_change()
+            if n_diss > 0:
+                need_flow = True
+            self.log(f"cycle {cycle}: t = {t_corr:.4e} s, {n_diss} nodes dissolved")
+            if (grid.get_field("node_type") == 1).sum() == 0:
+                break
+        if out_dir is not None:
+            import os
+            os.makedirs(out_dir, exist_ok=True)
+            with open(os.path.join(out_dir, "diagnostics.csv"), "w") as f:
+                f.write("time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n")
+                for row in self.rows:
+                    f.write(f"{row[0]:.6e},{row[1]:.6e},{row[2]:.6e},{int(row[3])},{row[4]:.6e},{row[5]:.6e}\n")
+        return self.rows

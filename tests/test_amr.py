@@ -151,3 +151,36 @@ def test_amr_solve_steady_and_phase_change():
         assert_close(g, ref, ("rho", "vel", "C"), tol=1e-11)
     assert total > 0, "the synthetic diffusivities must dissolve nodes"
     g.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_amr_whole_coupled_run_matches_reference_main(tmp_path):
+    """CoupledSolver::run with use_amr = 1 (explicit branch) through the reference's own main() -- grid build,
+    grains, flow solve, IDW refresh, corrosion cycles with dissolution and flow re-solves -- against
+    amr.AmrCoupledSolver on the device: diagnostics.csv rows within 1e-6, identical solid counts."""
+    from pd_mg_pin_corrosion_b200 import amr as A
+    base, ov = AMR_CASES["amr_default"]
+    ov = dict(ov, use_implicit=0, D_grain=5e-11, D_gb=5e-9, C_thresh=0.999, corrosion_steps_per_check=50,
+              flow_max_iters=300, T_final=6e-4, output_every_corr=10, output_dir=str(tmp_path / "ref"))
+    cfg_path = refapi.write_cfg(base, ov, str(tmp_path / "amr.cfg"))
+    refapi._lib(2).ref_set_threads(1)
+    assert refapi.run_reference_main(2, cfg_path) == 0
+    gold = np.loadtxt(tmp_path / "ref" / "diagnostics.csv", delimiter=",", skiprows=1, ndmin=2)
+    assert gold.shape[0] >= 5 and gold[-1, 3] < gold[0, 3] + 1, "the run must dissolve nodes"
+    ref = refapi.RefSim(2, base, ov, threads=1, build=True, fields=True)      # same grains (seed 42)
+    cfg = Config.load(os.path.join(H.CONFIG_DIR, base), ov, quiet=True)
+    g = A.AmrGrid(cfg)
+    g.build_amr(); g.build_neighbors_celllist(); g.device_init(0)
+    A.initialize_fields(g, ref.get("is_gb"), ref.get("is_precip"))
+    for n in ("rho", "vel", "C", "phase"):
+        assert np.array_equal(g.get_field(n), ref.get(n)), n        # initialize_fields itself
+    rows = np.array(A.AmrCoupledSolver().run(g, str(tmp_path / "gpu")))
+    assert rows.shape == gold.shape
+    assert np.array_equal(rows[:, 3], gold[:, 3])
+    for col in (0, 1, 2, 4, 5):
+        rel = np.abs(rows[:, col] - gold[:, col]) / np.maximum(np.abs(gold[:, col]), 1e-300)
+        assert rel.max() <= 1e-6, (col, float(rel.max()))
+    got = np.loadtxt(tmp_path / "gpu" / "diagnostics.csv", delimiter=",", skiprows=1, ndmin=2)
+    assert got.shape == gold.shape
+    g.close()
