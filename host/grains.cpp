@@ -202,3 +202,95 @@ int pdhost_copy_out(const GrainStructure& gs, int* grain_id, uint8_t* is_gb, uin
     if (n_grains) *n_grains = gs.n_grains;
     return 0;
 }
+
+// ---- point cloud (two-level AMR grid, csrc/amr.cu) --------------------------------------------------------
+// The reference's generator is written against grid.pos and the CSR (src/grains.cpp:16-179), so on the AMR
+// cloud it runs unchanged; here the same passes take the arrays pdamr_get returns (2D): positions, node types,
+// CSR offsets / indices / distances.  Same libstdc++ RNG calls in the same order.
+extern "C" int pdhost_generate_grains_cloud(const PdConfig* cfg, double grain_size_mean, double precip_fraction,
+                                            int gb_width_cells, int precip_cluster_cells, int N, const double* pos,
+                                            const uint8_t* type, const int* nbr_off, const int* nbr_idx,
+                                            const double* nbr_dist, int seed, int* grain_id, uint8_t* is_gb,
+                                            uint8_t* is_precip, int* n_grains_out) {
+    if (!cfg || !pos || !type || !nbr_off || !nbr_idx || !nbr_dist || !grain_id || !is_gb || !is_precip) return 1;
+    for (int n = 0; n < N; ++n) { grain_id[n] = -1; is_gb[n] = 0; is_precip[n] = 0; }
+    if (n_grains_out) *n_grains_out = 0;
+    std::vector<int> solid;
+    for (int n = 0; n < N; ++n)
+        if (type[n] == SOLID) solid.push_back(n);
+    if (solid.empty()) return 0;
+    auto dist = [&](int a, const double* b) {           // norm(p - q), src/utils.h:16-24 (fma chain, sqrt)
+        double s = 0.0;
+        for (int d = 0; d < 2; ++d) {
+            const double t = pos[2 * a + d] - b[d];
+            s = std::fma(t, t, s);
+        }
+        return std::sqrt(s);
+    };
+    const double cell = std::pow(cfg->dx, 2);
+    const double grain_area = PI / 4.0 * grain_size_mean * grain_size_mean;
+    const int n_grains = std::max(1, (int)std::round(solid.size() * cell / grain_area));
+    if (n_grains_out) *n_grains_out = n_grains;
+    std::mt19937 rng(seed);
+    std::uniform_int_distribution<int> pick(0, (int)solid.size() - 1);
+    std::vector<double> seeds(2 * (size_t)n_grains);
+    for (int g = 0; g < n_grains; ++g) {
+        const int si = solid[pick(rng)];
+        seeds[2 * g] = pos[2 * si]; seeds[2 * g + 1] = pos[2 * si + 1];
+    }
+    for (int ni : solid) {                               // Voronoi, first strictly smaller distance wins
+        double best = std::numeric_limits<double>::max();
+        int bg = 0;
+        for (int g = 0; g < n_grains; ++g) {
+            const double d = dist(ni, &seeds[2 * g]);
+            if (d < best) { best = d; bg = g; }
+        }
+        grain_id[ni] = bg;
+    }
+    const double gb_cutoff = std::sqrt(2.0) * cfg->dx * 1.01;
+    for (int ni : solid)
+        for (int q = nbr_off[ni]; q < nbr_off[ni + 1]; ++q) {
+            const int nj = nbr_idx[q];
+            if (nbr_dist[q] > gb_cutoff) continue;
+            if (type[nj] == SOLID && grain_id[nj] != grain_id[ni]) { is_gb[ni] = 1; break; }
+        }
+    for (int pass = 0; pass < gb_width_cells; ++pass) {
+        std::vector<uint8_t> nw(is_gb, is_gb + N);
+        for (int ni : solid) {
+            if (is_gb[ni]) continue;
+            for (int q = nbr_off[ni]; q < nbr_off[ni + 1]; ++q) {
+                if (nbr_dist[q] > gb_cutoff) continue;
+                if (is_gb[nbr_idx[q]]) { nw[ni] = 1; break; }
+            }
+        }
+        std::copy(nw.begin(), nw.end(), is_gb);
+    }
+    if (precip_fraction > 0.0) {
+        std::vector<int> interior;
+        for (int ni : solid)
+            if (!is_gb[ni]) interior.push_back(ni);
+        double cells_per_cluster = 1.0;
+        if (precip_cluster_cells > 0) {
+            const double r = precip_cluster_cells;
+            cells_per_cluster = PI * r * r;
+        }
+        int n_seeds = (int)(interior.size() * precip_fraction / cells_per_cluster);
+        n_seeds = std::max(1, n_seeds);
+        std::shuffle(interior.begin(), interior.end(), rng);
+        n_seeds = std::min(n_seeds, (int)interior.size());
+        for (int p = 0; p < n_seeds; ++p) is_precip[interior[p]] = 1;
+        if (precip_cluster_cells > 0) {
+            const double cluster_r = precip_cluster_cells * cfg->dx;
+            std::vector<uint8_t> seed_mark(is_precip, is_precip + N);
+            for (int ni : solid) {
+                if (is_gb[ni] || seed_mark[ni]) continue;
+                for (int p = 0; p < n_seeds; ++p) {
+                    const int si = interior[p];
+                    const double q[2] = {pos[2 * si], pos[2 * si + 1]};
+                    if (dist(ni, q) <= cluster_r) { is_precip[ni] = 1; break; }
+                }
+            }
+        }
+    }
+    return 0;
+}

@@ -40,3 +40,10 @@ extern "C" int pdhost_generate_grains(const PdConfig* cfg, double grain_size_mea
                                       int gb_width_cells, int precip_cluster_cells, int dim,
                                       const uint8_t* node_type, int seed, int* grain_id, uint8_t* is_gb,
                                       uint8_t* is_precip, int* n_grains);
+
+// the same generator on the AMR point cloud (arrays of pdamr_get; 2D)
+extern "C" int pdhost_generate_grains_cloud(const PdConfig* cfg, double grain_size_mean, double precip_fraction,
+                                            int gb_width_cells, int precip_cluster_cells, int N, const double* pos,
+                                            const uint8_t* type, const int* nbr_off, const int* nbr_idx,
+                                            const double* nbr_dist, int seed, int* grain_id, uint8_t* is_gb,
+                                            uint8_t* is_precip, int* n_grains);

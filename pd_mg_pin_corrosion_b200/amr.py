@@ -133,6 +133,36 @@ class AmrGrid:
             pass
 
 
+def generate_grains(grid: AmrGrid, seed: int = 42):
+    """GrainStructure::generate (src/grains.cpp:9-179) on the cloud: the reference's generator works on grid.pos and
+    the CSR, so it runs unchanged with use_amr = 1; same passes and libstdc++ RNG calls here (host/grains.cpp).
+    Returns (grain_id, is_grain_boundary, is_precipitate, n_grains)."""
+    from . import grains as _g
+    L = _g._load()
+    if not hasattr(L, "_cloud_bound"):
+        L.pdhost_generate_grains_cloud.restype = C.c_int
+        L.pdhost_generate_grains_cloud.argtypes = [C.c_void_p,
+                                                   C.c_double, C.c_double, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5 + \
+                                                  [C.c_int] + [C.c_void_p] * 3 + [C.POINTER(C.c_int)]
+        L._cloud_bound = True
+    cfg = grid.cfg
+    N = grid.N_total
+    pos, nt = grid.get("pos"), grid.get("node_type")
+    off, idx, dist = grid.get("nbr_offset"), grid.get("nbr_index"), grid.get("nbr_dist")
+    gid = np.full(N, -1, np.int32)
+    gb = np.zeros(N, np.uint8)
+    pr = np.zeros(N, np.uint8)
+    n = C.c_int()
+    s = cfg.to_struct()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = L.pdhost_generate_grains_cloud(C.byref(s), cfg.grain_size_mean, cfg.precip_fraction, int(cfg.gb_width_cells),
+                                        int(cfg.precip_cluster_cells), N, p(pos), p(nt), p(off), p(idx), p(dist), seed,
+                                        p(gid), p(gb), p(pr), C.byref(n))
+    if rc != 0:
+        raise RuntimeError("grain generation on the AMR cloud failed")
+    return gid, gb, pr, n.value
+
+
 def initialize_fields(grid: AmrGrid, is_gb, is_precip) -> None:
     """initialize_fields (src/main.cpp:9-126) on the AMR cloud: Poiseuille profile on FLUID / INLET nodes,
     C = C_solid_init on the wire, FICTITIOUS nodes at rest; new buffers = current buffers."""

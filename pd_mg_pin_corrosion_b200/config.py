@@ -90,7 +90,7 @@ class Config:
     newton_tol: float = 1.0e-8
     newton_max_iter: int = 20
     channel_flow_corrections: int = 0
-    # AMR keys: parsed, unsupported (use_amr must stay 0)
+    # AMR keys (amr.AmrGrid; the uniform-lattice Grid needs use_amr = 0)
     use_amr: int = 0
     amr_ratio: int = 3
     amr_buffer: float = 50.0e-6
@@ -160,7 +160,8 @@ class Config:
 
     def check_supported(self) -> None:
         if self.use_amr:
-            raise ValueError("use_amr = 1 is out of scope (uniform-grid hot path only)")
+            raise ValueError("use_amr = 1: the two-level AMR cloud is built by amr.AmrGrid (2D, explicit branch), "
+                             "not by the uniform-lattice Grid")
 
     def describe(self, dim: int) -> str:
         """Config::print (src/config.cpp:114-139)."""

@@ -49,6 +49,7 @@ struct pdamr_ctx {
     std::vector<double> nbr_dist, nbr_evec, nbr_vol;    // evec [nnz][2]
     std::vector<int> mirror;            // per node: WALL -> mirror node or -1; others -2
     std::vector<int> out_nodes, out_level_off;          // OUTLET nodes by Gauss-Seidel level
+    std::vector<int> out_list, out_ord_level, out_eoff, out_eidx;   // ascending OUTLET nodes, their levels, earlier OUTLET neighbours (ordinals)
     bool built = false, nbrs = false;
 
     // device
@@ -57,6 +58,8 @@ struct pdamr_ctx {
     uint8_t *d_type = nullptr, *d_phase = nullptr, *d_gb = nullptr, *d_precip = nullptr, *d_salt = nullptr;
     int *d_off = nullptr, *d_idx = nullptr, *d_foff = nullptr, *d_fsrc = nullptr, *d_mirror = nullptr;
     int *d_out_nodes = nullptr, *d_out_level_off = nullptr, *d_int = nullptr;
+    int *d_out_list = nullptr, *d_out_ord_level = nullptr, *d_out_eoff = nullptr, *d_out_eidx = nullptr, *d_out_cnt = nullptr;
+    double *d_out_bv = nullptr, *d_out_bc = nullptr;
     double *d_dist = nullptr, *d_evec = nullptr, *d_vol = nullptr, *d_fw = nullptr, *d_pos = nullptr, *d_delta = nullptr;
     double *rho[2] = {nullptr, nullptr}, *vel[2] = {nullptr, nullptr}, *C[2] = {nullptr, nullptr}, *p = nullptr;
     double* d_red = nullptr;
@@ -308,6 +311,22 @@ static void amr_tables(pdamr_ctx* c) {
     c->out_nodes.assign(outs.size(), 0);
     std::vector<int> fill(c->out_level_off.begin(), c->out_level_off.end() - 1);
     for (int n : outs) c->out_nodes[fill[lvl[n]]++] = n;
+    // fast sweep: ordinals of the OUTLET nodes, per node the ordinals of its EARLIER outlet neighbours
+    std::vector<int> ord(N, -1);
+    for (size_t t = 0; t < outs.size(); ++t) ord[outs[t]] = (int)t;
+    c->out_list = outs;
+    c->out_ord_level.resize(outs.size());          // level of each OUTLET node, by ordinal
+    for (size_t t = 0; t < outs.size(); ++t) c->out_ord_level[t] = lvl[outs[t]];
+    c->out_eoff.assign(outs.size() + 1, 0);
+    c->out_eidx.clear();
+    for (size_t t = 0; t < outs.size(); ++t) {
+        const int n = outs[t];
+        for (int q = c->nbr_off[n]; q < c->nbr_off[n + 1]; ++q) {
+            const int j = c->nbr_idx[q];
+            if (j < n && c->type[j] == T_OUTLET) c->out_eidx.push_back(ord[j]);
+        }
+        c->out_eoff[t + 1] = (int)c->out_eidx.size();
+    }
 }
 
 // Grid::build_neighbors_celllist (src/grid.cpp:660-796)
@@ -489,6 +508,55 @@ __global__ void __launch_bounds__(256) k_amr_outlet(AmrDev g, const int* __restr
                 vel[2 * i + 1] = U_in;
                 C[i] = 0.0;
             }
+        }
+        __syncthreads();
+    }
+}
+
+// The same sweep split like the lattice path (outlet.cu): a parallel pre-pass sums the FLUID neighbours and the
+// LATER outlet neighbours (old values), the sequential part only adds the already swept EARLIER outlet
+// neighbours, which live in shared memory.
+__global__ void k_amr_outlet_prepass(AmrDev g, const int* __restrict__ list, int n_out, double* rho, double* vel,
+                                     const double* C, double rho_f, double* __restrict__ bv, double* __restrict__ bc,
+                                     int* __restrict__ cnt) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_out) return;
+    const int i = list[t];
+    double sv = 0.0, sc = 0.0;
+    int c = 0;
+    for (int q = g.off[i]; q < g.off[i + 1]; ++q) {
+        const int j = g.idx[q];
+        const uint8_t tj = g.type[j];
+        if (tj == T_FLUID || (tj == T_OUTLET && j > i)) { sv += vel[2 * j + 1]; sc += C[j]; ++c; }
+        else if (tj == T_OUTLET) ++c;
+    }
+    bv[t] = sv; bc[t] = sc; cnt[t] = c;
+    rho[i] = rho_f;
+    vel[2 * i] = 0.0;
+}
+// one thread per OUTLET node (n_out <= 1024): level, pre-pass sums and the list of earlier neighbours are loaded
+// once; the level loop only touches shared memory
+__global__ void __launch_bounds__(1024)
+k_amr_outlet_sweep(const int* __restrict__ list, const int* __restrict__ level_of, int n_levels, int n_out,
+                   const int* __restrict__ eoff, const int* __restrict__ eidx, int n_e, const double* __restrict__ bv,
+                   const double* __restrict__ bc, const int* __restrict__ cnt, double* vel, double* C, double U_in) {
+    extern __shared__ double sm[];
+    double* nv = sm;
+    double* ncc = sm + n_out;
+    int* s_e = (int*)(sm + 2 * n_out);
+    const int t = threadIdx.x;
+    for (int e = t; e < n_e; e += blockDim.x) s_e[e] = eidx[e];
+    int lvl = -1, e0 = 0, e1 = 0, n = 0, node = 0;
+    double sv = 0.0, sc = 0.0;
+    if (t < n_out) { lvl = level_of[t]; e0 = eoff[t]; e1 = eoff[t + 1]; n = cnt[t]; sv = bv[t]; sc = bc[t]; node = list[t]; }
+    __syncthreads();
+    for (int l = 0; l < n_levels; ++l) {
+        if (lvl == l) {
+            for (int e = e0; e < e1; ++e) { sv += nv[s_e[e]]; sc += ncc[s_e[e]]; }
+            const double v = n > 0 ? sv * (1.0 / n) : U_in, cc = n > 0 ? sc / n : 0.0;
+            nv[t] = v; ncc[t] = cc;
+            vel[2 * node + 1] = v;
+            C[node] = cc;
         }
         __syncthreads();
     }
@@ -699,6 +767,13 @@ int upload_tables(pdamr_ctx* c) {
     PD_TRY(up(&c->d_mirror, c->mirror));
     PD_TRY(up(&c->d_out_nodes, c->out_nodes));
     PD_TRY(up(&c->d_out_level_off, c->out_level_off));
+    PD_TRY(up(&c->d_out_list, c->out_list)); PD_TRY(up(&c->d_out_ord_level, c->out_ord_level));
+    PD_TRY(up(&c->d_out_eoff, c->out_eoff)); PD_TRY(up(&c->d_out_eidx, c->out_eidx));
+    const size_t no = std::max<size_t>(c->out_list.size(), 1);
+    if (c->d_out_bv) { CUDA_OK(cudaFree(c->d_out_bv)); CUDA_OK(cudaFree(c->d_out_bc)); CUDA_OK(cudaFree(c->d_out_cnt)); }
+    CUDA_OK(cudaMalloc(&c->d_out_bv, sizeof(double) * no));
+    CUDA_OK(cudaMalloc(&c->d_out_bc, sizeof(double) * no));
+    CUDA_OK(cudaMalloc(&c->d_out_cnt, sizeof(int) * no));
     return 0;
 }
 
@@ -753,7 +828,9 @@ extern "C" int pdamr_destroy(pdamr_ctx* c) {
         cudaSetDevice(c->device);
         for (void* q : {(void*)c->d_type, (void*)c->d_phase, (void*)c->d_gb, (void*)c->d_precip, (void*)c->d_salt,
                         (void*)c->d_off, (void*)c->d_idx, (void*)c->d_foff, (void*)c->d_fsrc, (void*)c->d_mirror,
-                        (void*)c->d_out_nodes, (void*)c->d_out_level_off, (void*)c->d_int, (void*)c->d_dist,
+                        (void*)c->d_out_nodes, (void*)c->d_out_level_off, (void*)c->d_int, (void*)c->d_out_list,
+                        (void*)c->d_out_ord_level, (void*)c->d_out_eoff, (void*)c->d_out_eidx, (void*)c->d_out_cnt,
+                        (void*)c->d_out_bv, (void*)c->d_out_bc, (void*)c->d_dist,
                         (void*)c->d_evec, (void*)c->d_vol, (void*)c->d_fw, (void*)c->d_pos, (void*)c->d_delta,
                         (void*)c->rho[0], (void*)c->rho[1], (void*)c->vel[0], (void*)c->vel[1], (void*)c->C[0],
                         (void*)c->C[1], (void*)c->p, (void*)c->d_red})
@@ -819,11 +896,24 @@ static int enqueue_bc(pdamr_ctx* c, int which, int buf) {   // 0 inlet, 1 outlet
     switch (which) {
         case 0: k_amr_inlet<<<nb(N, 128), 128, 0, c->stream>>>(g, c->d_pos, c->rho[buf], c->vel[buf], c->C[c->curC], k.R_tube,
                                                                k.U_in, k.rho_f, k.C_liquid_init); break;
-        case 1: if (!c->out_nodes.empty())
-                    k_amr_outlet<<<1, 256, 0, c->stream>>>(g, c->d_out_nodes, c->d_out_level_off,
-                                                           (int)c->out_level_off.size() - 1, c->rho[buf], c->vel[buf],
-                                                           c->C[c->curC], k.rho_f, k.U_in);
-                break;
+        case 1: {
+            const int n_out = (int)c->out_list.size(), n_levels = (int)c->out_level_off.size() - 1;
+            if (!n_out) break;
+            const int n_e = (int)c->out_eidx.size();
+            const size_t smem = sizeof(double) * 2 * n_out + sizeof(int) * n_e;
+            if (n_out <= 1024 && smem <= 48 * 1024) {
+                k_amr_outlet_prepass<<<nb(n_out, 128), 128, 0, c->stream>>>(g, c->d_out_list, n_out, c->rho[buf], c->vel[buf],
+                                                                            c->C[c->curC], k.rho_f, c->d_out_bv, c->d_out_bc,
+                                                                            c->d_out_cnt);
+                k_amr_outlet_sweep<<<1, 1024, smem, c->stream>>>(c->d_out_list, c->d_out_ord_level, n_levels, n_out,
+                                                                 c->d_out_eoff, c->d_out_eidx, n_e, c->d_out_bv, c->d_out_bc,
+                                                                 c->d_out_cnt, c->vel[buf], c->C[c->curC], k.U_in);
+            } else {
+                k_amr_outlet<<<1, 256, 0, c->stream>>>(g, c->d_out_nodes, c->d_out_level_off, n_levels, c->rho[buf],
+                                                       c->vel[buf], c->C[c->curC], k.rho_f, k.U_in);
+            }
+            break;
+        }
         case 2: k_amr_wall<<<nb(N, 128), 128, 0, c->stream>>>(N, c->d_mirror, c->rho[buf], c->vel[buf], k.rho_f); break;
         case 3: k_amr_solid<<<nb(N, 128), 128, 0, c->stream>>>(N, c->d_type, c->vel[buf]); break;
         default: k_amr_wall_conc<<<nb(N, 128), 128, 0, c->stream>>>(g, c->C[c->curC]); break;

@@ -71,6 +71,20 @@ def test_amr_wall_mirror_table():
         assert rho[n] == expect, (n, m, rho[n])
 
 
+@needs_ref
+@pytest.mark.parametrize("case,extra", [("amr_default", None), ("amr_shipped", None),
+                                        ("amr_ratio2", {"gb_width_cells": 1, "precip_cluster_cells": 2})])
+def test_amr_grain_generation_bit_exact(case, extra):
+    """GrainStructure::generate on the cloud (positions + CSR, same RNG draws) against the reference"""
+    from pd_mg_pin_corrosion_b200 import amr as A
+    ref, cfg, g = both(case, fields=True, extra=extra)
+    gid, gb, pr, n = A.generate_grains(g)
+    assert n == ref.lib.ref_n_grains(ref.h) and n > 1
+    assert np.array_equal(gid, ref.get("grain_id"))
+    assert np.array_equal(gb, ref.get("is_gb")) and gb.sum() > 0
+    assert np.array_equal(pr, ref.get("is_precip")) and pr.sum() > 0
+
+
 def gpu_pair(case, extra=None):
     ref, cfg, g = both(case, fields=True, extra=extra)
     g.device_init(0)
@@ -172,8 +186,9 @@ def test_amr_whole_coupled_run_matches_reference_main(tmp_path):
     cfg = Config.load(os.path.join(H.CONFIG_DIR, base), ov, quiet=True)
     g = A.AmrGrid(cfg)
     g.build_amr(); g.build_neighbors_celllist(); g.device_init(0)
-    A.initialize_fields(g, ref.get("is_gb"), ref.get("is_precip"))
-    for n in ("rho", "vel", "C", "phase"):
+    _, gb, pr, _ = A.generate_grains(g)                 # standalone: own grains (bit-exact, tested above)
+    A.initialize_fields(g, gb, pr)
+    for n in ("rho", "vel", "C", "phase", "is_gb", "is_precip"):
         assert np.array_equal(g.get_field(n), ref.get(n)), n        # initialize_fields itself
     rows = np.array(A.AmrCoupledSolver().run(g, str(tmp_path / "gpu")))
     assert rows.shape == gold.shape
