@@ -100,6 +100,11 @@ int pdgpu_device_count(int* count);
 int pdgpu_grid_extents(const PdConfig* cfg, int dim, int* Nx, int* Ny, int* Nz, double origin[3]);
 /* Balanced z-slab [a0,a1) of `rank` among `nranks` over n_axial planes. */
 int pdgpu_partition(int n_axial, int nranks, int rank, int* a0, int* a1);
+/* what pdgpu_create_slab uses: equal COST per rank -- planes within reach of the wire carry a measured surcharge
+ * (the ARD kernel's general body, solid rows), so the wire slabs get slightly fewer planes. Deterministic in
+ * (cfg, dim, nranks); env PDGPU_SLAB_PIN_COST = 0 gives equal plane counts. */
+int pdgpu_partition_balanced(const PdConfig* cfg, int dim, int nranks, int rank, int* a0, int* a1);
+int pdgpu_slab_layout_range(int a0, int a1, long long plane, int reach, long long* out);
 /* Local layout of a z-slab (what the halo exchange uses): out[0..9] = a0, a1, local planes,
  * local nodes, own_lo, own_hi, send_lo, recv_lo, send_hi, recv_hi (node offsets into a local
  * array; a halo block is reach*plane nodes). New: the reference has no distributed layer. */

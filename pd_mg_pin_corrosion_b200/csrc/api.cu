@@ -51,14 +51,14 @@ extern "C" int pdgpu_create_slab(const PdConfig* cfg, int dim, int device, int r
     c->P = (dim == 2) ? c->Nx : (long long)c->Nx * c->Ny;
     c->N_total = (long long)c->Nx * c->Ny * c->Nz;
     c->R = cfg->m_ratio;
-    if (pdgpu_partition(c->Na, nranks, rank, &c->a0, &c->a1)) { delete c; return 1; }
+    if (pdgpu_partition_balanced(cfg, dim, nranks, rank, &c->a0, &c->a1)) { delete c; return 1; }
     if (nranks > 1 && (c->a1 - c->a0) < 2 * c->R + 2) {
         int planes = c->a1 - c->a0;
         delete c;
         PD_FAIL("pdgpu_create_slab: slab of %d planes is thinner than 2*reach+2", planes);
     }
     long long lay[10];
-    if (pdgpu_slab_layout(c->Na, c->P, c->R, nranks, rank, lay)) { delete c; return 1; }
+    if (pdgpu_slab_layout_range(c->a0, c->a1, c->P, c->R, lay)) { delete c; return 1; }
     c->nlp = (int)lay[2];
     c->NL = lay[3];
     c->own_lo = lay[4];

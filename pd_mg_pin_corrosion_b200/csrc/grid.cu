@@ -58,6 +58,53 @@ extern "C" int pdgpu_partition(int n_axial, int nranks, int rank, int* a0, int* 
     return 0;
 }
 
+// Cost-balanced partition of the axial planes (z-slabs of a slab context).  Planes within reach of the wire cost
+// more than bulk-fluid planes: the ARD bond kernel takes its general (solid / wall aware) body there and the
+// solid rows and the salt pre-pass live there -- measured on 8 x B200 (profiles/r2_bench_n8_per_rank.txt): NS + ARD
+// 4.32 ms on a slab inside the wire region against 4.15 ms on a fluid-only slab of the same 701 planes, i.e. +4.1 %
+// per plane.  With equal plane counts the wire slabs set the step time of every rank; equal COST gives them ~3 %
+// fewer planes (4 x B200, profiles/r2b_bench_n4_*: 4.825 ms per step against 4.871 ms; the residual imbalance of
+// that run put the surcharge at 4.8 %).  Deterministic in (cfg, dim, nranks): every rank computes the same boundaries.
+// PDGPU_SLAB_PIN_COST overrides the surcharge (0 = equal plane counts).
+static double pin_surcharge() {
+    static const double w = [] {
+        const char* e = getenv("PDGPU_SLAB_PIN_COST");
+        return e ? atof(e) : 0.048;
+    }();
+    return w;
+}
+extern "C" int pdgpu_partition_balanced(const PdConfig* cfg, int dim, int nranks, int rank, int* a0, int* a1) {
+    if (!cfg || !a0 || !a1 || (dim != 2 && dim != 3)) PD_FAIL("pdgpu_partition_balanced: bad arguments");
+    int Nx, Ny, Nz;
+    double org[3];
+    geom_extents(*cfg, dim, &Nx, &Ny, &Nz, org);
+    const int Na = dim == 2 ? Ny : Nz;
+    const double oa = dim == 2 ? org[1] : org[2];
+    if (nranks < 1 || rank < 0 || rank >= nranks || Na < nranks) PD_FAIL("pdgpu_partition_balanced: bad arguments");
+    const double w = pin_surcharge();
+    if (nranks == 1 || !(w > 0.0)) return pdgpu_partition(Na, nranks, rank, a0, a1);
+    const double lo = -cfg->m_ratio * cfg->dx, hi = cfg->L_wire + cfg->m_ratio * cfg->dx;
+    std::vector<double> cum(Na + 1, 0.0);
+    for (int k = 0; k < Na; ++k) {
+        const double z = geom_coord(oa, k, cfg->dx);
+        cum[k + 1] = cum[k] + 1.0 + ((z >= lo && z <= hi) ? w : 0.0);
+    }
+    const int min_planes = 2 * cfg->m_ratio + 2;
+    std::vector<int> b(nranks + 1, 0);
+    b[nranks] = Na;
+    for (int r = 1; r < nranks; ++r) {
+        const double target = cum[Na] * r / nranks;
+        int k = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+        if (k > 0 && target - cum[k - 1] < cum[k] - target) --k;      // nearest boundary
+        b[r] = std::max(k, b[r - 1] + min_planes);
+    }
+    for (int r = nranks - 1; r >= 1; --r) b[r] = std::min(b[r], b[r + 1] - min_planes);
+    for (int r = 0; r < nranks; ++r)
+        if (b[r + 1] - b[r] < 1) return pdgpu_partition(Na, nranks, rank, a0, a1);   // too short: equal counts
+    *a0 = b[rank]; *a1 = b[rank + 1];
+    return 0;
+}
+
 // Local layout of a z-slab: everything the halo exchange needs, as plain integers.
 // out[0..9] = a0, a1, local planes, NL, own_lo, own_hi, send_lo, recv_lo, send_hi, recv_hi
 // (node offsets into a local array; a halo block is reach*plane nodes).
@@ -65,6 +112,11 @@ extern "C" int pdgpu_slab_layout(int n_axial, long long plane, int reach, int nr
     if (!out || plane <= 0 || reach < 0) PD_FAIL("pdgpu_slab_layout: bad arguments");
     int a0 = 0, a1 = 0;
     PD_TRY(pdgpu_partition(n_axial, nranks, rank, &a0, &a1));
+    return pdgpu_slab_layout_range(a0, a1, plane, reach, out);
+}
+// the same for an arbitrary owned range [a0, a1) (cost-balanced slabs)
+extern "C" int pdgpu_slab_layout_range(int a0, int a1, long long plane, int reach, long long* out) {
+    if (!out || plane <= 0 || reach < 0 || a1 <= a0) PD_FAIL("pdgpu_slab_layout_range: bad arguments");
     long long nlp = (long long)(a1 - a0) + 2 * reach;
     long long hp = (long long)reach * plane;
     out[0] = a0; out[1] = a1; out[2] = nlp; out[3] = nlp * plane;

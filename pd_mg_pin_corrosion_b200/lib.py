@@ -80,6 +80,8 @@ def load() -> C.CDLL:
         "pdgpu_device_count": [ip],
         "pdgpu_grid_extents": [cfgp, C.c_int, ip, ip, ip, dp],
         "pdgpu_partition": [C.c_int, C.c_int, C.c_int, ip, ip],
+        "pdgpu_partition_balanced": [cfgp, C.c_int, C.c_int, C.c_int, ip, ip],
+        "pdgpu_slab_layout_range": [C.c_int, C.c_int, C.c_longlong, C.c_int, C.POINTER(C.c_longlong)],
         "pdgpu_slab_layout": [C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong)],
         "pdgpu_stencil": [cfgp, C.c_int, ip, vp, vp, vp, vp],
         "pdgpu_create": [cfgp, C.c_int, C.c_int, C.POINTER(vp)],

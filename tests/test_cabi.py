@@ -86,3 +86,46 @@ def test_no_gpu_means_loud_failure_not_fallback():
         S.Grid(2).build(cfg)
     # null-context calls are errors too, never silent no-ops
     assert L.pdgpu_ns_step(None, 1e-8) != 0
+
+
+def test_balanced_slab_partition():
+    """pdgpu_partition_balanced (what pdgpu_create_slab uses): contiguous cover of the axial planes, equal COST per
+    rank with the wire planes surcharged, deterministic, slabs thick enough for the halo; surcharge 0 = equal counts."""
+    import os
+    import subprocess
+    import sys
+    from pd_mg_pin_corrosion_b200.config import Config
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    L = L_.load()
+    for base, ov in (("params_fine.cfg", {}), ("params_fine.cfg", {"L_wire": 3200e-6, "L_upstream": 4000e-6, "L_downstream": 4000e-6}),
+                     ("params.cfg", {})):
+        cfg = Config.load(os.path.join(H.CONFIG_DIR, base), dict(ov, use_implicit=0), quiet=True)
+        s = cfg.to_struct()
+        Nx, Ny, Nz = C.c_int(), C.c_int(), C.c_int()
+        org = (C.c_double * 3)()
+        L_.check(L.pdgpu_grid_extents(C.byref(s), 3, C.byref(Nx), C.byref(Ny), C.byref(Nz), org))
+        z = org[2] + np.arange(Nz.value) * cfg.dx
+        cost = 1.0 + 0.048 * ((z >= -cfg.m_ratio * cfg.dx) & (z <= cfg.L_wire + cfg.m_ratio * cfg.dx))
+        for nranks in (2, 4, 8):
+            a0, a1 = C.c_int(), C.c_int()
+            prev, loads, counts = 0, [], []
+            for r in range(nranks):
+                L_.check(L.pdgpu_partition_balanced(C.byref(s), 3, nranks, r, C.byref(a0), C.byref(a1)))
+                assert a0.value == prev and a1.value - a0.value >= 2 * cfg.m_ratio + 2
+                prev = a1.value
+                loads.append(cost[a0.value:a1.value].sum()); counts.append(a1.value - a0.value)
+            assert prev == Nz.value
+            assert max(loads) - min(loads) <= 2.1, (base, nranks, loads)           # within two planes of equal cost
+            if nranks >= 4:
+                assert max(counts) > min(counts) + 1, counts                        # wire slabs are thinner
+    code = ("import ctypes as C, os, sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "from pd_mg_pin_corrosion_b200 import lib as L_; from pd_mg_pin_corrosion_b200.config import Config\n"
+            "L = L_.load(); cfg = Config.load(%r, {'use_implicit': 0}, quiet=True); s = cfg.to_struct()\n"
+            "a0, a1, b0, b1 = C.c_int(), C.c_int(), C.c_int(), C.c_int()\n"
+            "for r in range(8):\n"
+            "    L_.check(L.pdgpu_partition_balanced(C.byref(s), 3, 8, r, C.byref(a0), C.byref(a1)))\n"
+            "    L_.check(L.pdgpu_partition(707, 8, r, C.byref(b0), C.byref(b1)))\n"
+            "    assert (a0.value, a1.value) == (b0.value, b1.value)\n"
+            % (ROOT, os.path.join(ROOT, "tests"), os.path.join(H.CONFIG_DIR, "params_fine.cfg")))
+    env = dict(os.environ, PDGPU_SLAB_PIN_COST="0")
+    assert subprocess.run([sys.executable, "-c", code], env=env).returncode == 0
