@@ -1,0 +1,178 @@
+// host/amr_run.cpp -- the reference's main() + CoupledSolver::run with use_amr = 1 (src/main.cpp:151-174,
+// src/coupling.cpp:82-302, explicit ARD branch) over the pdamr_* entry points of libpdgpu.so: two-level grid and
+// cell-list neighbours (host code inside the library, bit-identical to the reference), grains on the cloud,
+// initialize_fields, then flow solve + IDW refresh / corrosion cycles / phase change on the device.
+// Writes diagnostics.csv and mass_loss.csv; snapshots of the cloud are VTU files in the reference and are not written.
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <string>
+#include <vector>
+
+#include "config.h"
+#include "grains.h"
+
+#define PDA(call)                                                                         \
+    do {                                                                                  \
+        if ((call) != 0) {                                                                \
+            std::fprintf(stderr, "libpdgpu: %s failed: %s\n", #call, pdgpu_last_error()); \
+            return 2;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+int run_amr(const HostConfig& cfg, int device) {
+    if (cfg.use_implicit) {
+        std::fprintf(stderr, "use_amr = 1: only the explicit ARD branch runs on the AMR cloud (set use_implicit = 0)\n");
+        return 1;
+    }
+    auto t0 = std::chrono::steady_clock::now();
+    PdConfig pod = cfg.to_pod();
+    pdamr_ctx* a = nullptr;
+    PDA(pdamr_create(&pod, cfg.amr_ratio, cfg.amr_buffer, &a));
+    std::printf("Building grid...\n");
+    PDA(pdamr_build(a));
+    PDA(pdamr_build_neighbors(a));
+    PdAmrInfo in;
+    PDA(pdamr_info(a, &in));
+    const int N = (int)in.N_total;
+    std::printf("AMR Node types: FLUID=%lld SOLID_MG=%lld WALL=%lld INLET=%lld OUTLET=%lld OUTSIDE=%lld FICT=%lld\n",
+                in.counts[0], in.counts[1], in.counts[2], in.counts[3], in.counts[4], in.counts[5], in.counts[6]);
+    std::printf("AMR total: %d nodes (fine=%lld, coarse=%lld, fict=%lld)\nCell-list neighbors: %lld total entries\n", N,
+                in.n_fine, in.n_coarse, in.n_fict, in.nnz);
+    std::vector<double> pos(2 * (size_t)N), dist((size_t)in.nnz);
+    std::vector<uint8_t> type(N);
+    std::vector<int> off(N + 1), idx((size_t)in.nnz);
+    PDA(pdamr_get(a, "pos", pos.data())); PDA(pdamr_get(a, "node_type", type.data()));
+    PDA(pdamr_get(a, "nbr_offset", off.data())); PDA(pdamr_get(a, "nbr_index", idx.data()));
+    PDA(pdamr_get(a, "nbr_dist", dist.data()));
+    std::printf("Generating grain structure...\n");
+    std::vector<int> grain_id(N);
+    std::vector<uint8_t> is_gb(N), is_precip(N);
+    int n_grains = 0;
+    if (pdhost_generate_grains_cloud(&pod, cfg.grain_size_mean, cfg.precip_fraction, cfg.gb_width_cells,
+                                     cfg.precip_cluster_cells, N, pos.data(), type.data(), off.data(), idx.data(),
+                                     dist.data(), 42, grain_id.data(), is_gb.data(), is_precip.data(), &n_grains) != 0) {
+        std::fprintf(stderr, "grain generation failed\n");
+        return 2;
+    }
+    std::printf("Grain generation: %d grains, %d boundary nodes\n", n_grains, (int)std::count(is_gb.begin(), is_gb.end(), 1));
+    // initialize_fields (src/main.cpp:9-126)
+    std::printf("Initializing fields...\n");
+    std::vector<double> rho(N), vel(2 * (size_t)N, 0.0), C(N, 0.0);
+    std::vector<uint8_t> phase(N, 1);
+    const double R2 = cfg.R_tube * cfg.R_tube;
+    for (int i = 0; i < N; ++i) {
+        const double px = pos[2 * i];
+        double rr = (px * px) / R2;
+        if (rr > 1.0) rr = 1.0;
+        const double v_ax = 1.5 * cfg.U_in * (1.0 - rr);
+        rho[i] = type[i] == PDGPU_OUTSIDE ? 0.0 : cfg.rho_f;
+        switch (type[i]) {
+            case PDGPU_FLUID: case PDGPU_INLET: vel[2 * i + 1] = v_ax; C[i] = cfg.C_liquid_init; break;
+            case PDGPU_OUTLET: C[i] = cfg.C_liquid_init; break;
+            case PDGPU_SOLID_MG: C[i] = cfg.C_solid_init; phase[i] = 0; break;
+            default: break;
+        }
+    }
+    PDA(pdamr_device_init(a, device));
+    for (const char* n : {"rho", "rho_new"}) PDA(pdamr_field_set(a, n, rho.data()));
+    for (const char* n : {"vel", "vel_new"}) PDA(pdamr_field_set(a, n, vel.data()));
+    for (const char* n : {"C", "C_new"}) PDA(pdamr_field_set(a, n, C.data()));
+    PDA(pdamr_field_set(a, "phase", phase.data()));
+    PDA(pdamr_field_set(a, "is_gb", is_gb.data()));
+    PDA(pdamr_field_set(a, "is_precip", is_precip.data()));
+
+    // CoupledSolver::run, explicit branch
+    mkdir(cfg.output_dir.c_str(), 0755);
+    { std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::trunc);
+      csv << "time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n"; }
+    { std::ofstream ml(cfg.output_dir + "/mass_loss.csv", std::ios::trunc); ml << "time_h,pin_mass_loss_pct\n"; }
+    std::vector<int> solid0;
+    for (int i = 0; i < N; ++i)
+        if (type[i] == PDGPU_SOLID_MG) solid0.push_back(i);
+    std::printf("Initial solid nodes: %d\nUsing EXPLICIT ARD solver\n", (int)solid0.size());
+    auto solid_sum = [&](const std::vector<double>& Cc) {
+        double s = 0.0;
+        for (int i : solid0) s += Cc[i];            // ordered sum (src/coupling.cpp:32-38)
+        return s;
+    };
+    auto diagnostics = [&](double t) -> int {
+        PDA(pdamr_field_get(a, "C", C.data())); PDA(pdamr_field_get(a, "vel", vel.data()));
+        PDA(pdamr_field_get(a, "node_type", type.data()));
+        double loss = (1.0 - solid_sum(C) / (solid0.size() + 1e-30)) * 100.0;
+        if (loss < 0.0) loss = 0.0;
+        long long solid = 0;
+        double vmax = 0.0, cmax = 0.0;
+        for (int i = 0; i < N; ++i) {
+            if (type[i] == PDGPU_SOLID_MG) ++solid;
+            if (type[i] != PDGPU_FLUID) continue;
+            vmax = std::max(vmax, std::sqrt(vel[2 * i] * vel[2 * i] + vel[2 * i + 1] * vel[2 * i + 1]));
+            cmax = std::max(cmax, C[i]);
+        }
+        std::printf("  t=%.1f s (%.2f h)  pin_mass_loss=%.2f%%  solid=%lld  v_max=%.3e  C_max_fluid=%.4f\n", t, t / 3600.0, loss,
+                    solid, vmax, cmax);
+        std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::app);
+        csv << std::scientific << std::setprecision(6) << t << "," << t / 3600.0 << "," << loss << "," << solid << "," << vmax
+            << "," << cmax << "\n";
+        std::ofstream ml(cfg.output_dir + "/mass_loss.csv", std::ios::app);
+        ml << std::fixed << std::setprecision(6) << t / 3600.0 << "," << loss << "\n";
+        return 0;
+    };
+    double t_corr = 0.0;
+    int cycle = 0, total_dissolved = 0;
+    bool need_flow = true;
+    while (t_corr < cfg.T_final) {
+        ++cycle;
+        std::printf("\n=== Coupling cycle %d, t=%.1f s (%.2f h) ===\n", cycle, t_corr, t_corr / 3600.0);
+        if (need_flow) {
+            PdSteadyResult r;
+            PDA(pdamr_ns_solve_steady(a, &r, 1));
+            PDA(pdamr_update_fictitious(a));        // src/coupling.cpp:139
+            need_flow = false;
+        }
+        PDA(pdamr_field_get(a, "C", C.data()));
+        double vl = 1.0 - solid_sum(C) / (solid0.size() + 1e-30);
+        PDA(pdamr_ard_set_volume_loss(a, vl < 0.0 ? 0.0 : vl));
+        double dtc = 0.0;
+        PDA(pdamr_ard_compute_dt(a, &dtc));
+        std::printf("  Corrosion dt = %.4e s\n", dtc);
+        int step = 0;
+        const int n_steps = cfg.corrosion_steps_per_check, every = cfg.output_every_corr;
+        while (step < n_steps) {
+            const int chunk = std::min(n_steps - step, every - step % every);
+            int done = 0;
+            while (done < chunk) {                  // t_corr advances per step and ends the cycle (:237, :248)
+                t_corr += dtc;
+                ++done;
+                if (t_corr >= cfg.T_final) break;
+            }
+            PDA(pdamr_ard_iterate(a, done, dtc));
+            step += done;
+            if (done == chunk && step % every == 0 && diagnostics(t_corr) != 0) return 2;
+            if (t_corr >= cfg.T_final) break;
+        }
+        int n = 0;
+        PDA(pdamr_phase_change(a, &n));
+        total_dissolved += n;
+        if (n > 0) {
+            std::printf("  Phase change: %d nodes dissolved (total: %d)\n", n, total_dissolved);
+            need_flow = true;
+        } else {
+            std::printf("  No phase changes this cycle\n");
+        }
+        PDA(pdamr_field_get(a, "node_type", type.data()));
+        if (std::count(type.begin(), type.end(), (uint8_t)PDGPU_SOLID_MG) == 0) {
+            std::printf("\n=== All solid nodes dissolved at t=%.1f s (%.2f h) ===\n", t_corr, t_corr / 3600.0);
+            break;
+        }
+    }
+    std::printf("\n=== Simulation complete ===\n  Final time: %.1f s (%.2f h)\n  [Timer] total_simulation: %.3f s\n", t_corr,
+                t_corr / 3600.0, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    pdamr_destroy(a);
+    return 0;
+}

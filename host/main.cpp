@@ -25,6 +25,8 @@
 #include "coupling.h"
 #include "grains.h"
 
+int run_amr(const HostConfig& cfg, int device);   // amr_run.cpp
+
 #define PD(call)                                                                  \
     do {                                                                          \
         if ((call) != 0) {                                                        \
@@ -88,9 +90,12 @@ int main(int argc, char** argv) {
     HostConfig cfg;
     cfg.load(cfg_path);
     cfg.print(dim);
-    if (cfg.use_amr) {
-        std::fprintf(stderr, "use_amr = 1 is out of scope of the GPU path\n");
-        return 1;
+    if (cfg.use_amr) {      // two-level AMR cloud (2D, one GPU): its own grid / solver entry points (amr_run.cpp)
+        if (dim != 2 || nranks > 1) {
+            std::fprintf(stderr, "use_amr = 1 runs in 2D on one GPU (like the reference's AMR grid)\n");
+            return 1;
+        }
+        return run_amr(cfg, device);
     }
     if (cfg.use_implicit && nranks > 1) {
         std::fprintf(stderr, "the implicit branch runs on one GPU only (set use_implicit = 0 for z-slab runs)\n");

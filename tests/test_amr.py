@@ -199,3 +199,34 @@ def test_amr_whole_coupled_run_matches_reference_main(tmp_path):
     got = np.loadtxt(tmp_path / "gpu" / "diagnostics.csv", delimiter=",", skiprows=1, ndmin=2)
     assert got.shape == gold.shape
     g.close()
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_amr_host_driver_matches_reference_main(tmp_path):
+    """host/pd_corrosion_gpu with use_amr = 1 (C++ driver over pdamr_*, host/amr_run.cpp) against the reference's own
+    main(): same number of diagnostics rows, identical solid counts, values within 1e-6."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "pd_corrosion_gpu")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "host")])
+    base, ov = AMR_CASES["amr_ratio2"]
+    outs = {}
+    for who in ("ref", "gpu"):
+        o = dict(ov, use_implicit=0, D_grain=5e-11, D_gb=5e-9, C_thresh=0.999, corrosion_steps_per_check=40,
+                 flow_max_iters=250, T_final=5e-4, output_every_corr=10, output_dir=str(tmp_path / who))
+        cfg_path = refapi.write_cfg(base, o, str(tmp_path / f"{who}.cfg"))
+        if who == "ref":
+            refapi._lib(2).ref_set_threads(1)
+            assert refapi.run_reference_main(2, cfg_path) == 0
+        else:
+            r = subprocess.run([exe, cfg_path, "--dim", "2"], capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[who] = np.loadtxt(tmp_path / who / "diagnostics.csv", delimiter=",", skiprows=1, ndmin=2)
+    gold, got = outs["ref"], outs["gpu"]
+    assert gold.shape == got.shape and gold.shape[0] >= 4
+    assert np.array_equal(gold[:, 3], got[:, 3]) and gold[-1, 3] < gold[0, 3]
+    for col in (0, 1, 2, 4, 5):
+        rel = np.abs(got[:, col] - gold[:, col]) / np.maximum(np.abs(gold[:, col]), 1e-300)
+        assert rel.max() <= 1e-6, (col, float(rel.max()))
