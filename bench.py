@@ -406,7 +406,11 @@ def main() -> None:
     L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms2)))
     barrier()
     t2 = torch.tensor([ms2.value], dtype=torch.float64, device="cuda")
+    e2e_per_rank = [ms2.value / max(e2e_steps, 1)]
     if dist is not None:
+        parts = [torch.zeros_like(t2) for _ in range(world)]
+        dist.all_gather(parts, t2)             # per-rank view: host-memory contention between the ranks shows here
+        e2e_per_rank = [float(p.item()) / max(e2e_steps, 1) for p in parts]
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = bonds_total * e2e_steps / (float(t2.item()) * 1e-3) if e2e_steps else None
 
@@ -508,6 +512,7 @@ def main() -> None:
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                         "chunks": int(used_chunks.value),
+                        "ms_per_step_per_rank": [round(x, 3) for x in e2e_per_rank] if e2e_steps else None,
                         "what": "pinned host rho/vel/C -> pdgpu_step_host (H2D, NS body + ARD body, D2H "
                                 "pipelined over axial chunks), every step"},
                 "roofline": roofline}
