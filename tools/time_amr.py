@@ -1,5 +1,5 @@
-"""AMR cloud (shipped params_amr.cfg): device time per NS loop body / ARD loop body and, when oracle/_ref is present,
-the reference's own loops on the host cores beside it.  usage: python tools/time_amr.py [--threads N]"""
+"""AMR cloud (shipped params_amr.cfg): device time per NS loop body / ARD loop body.
+usage: python tools/time_amr.py   (CPU side: tests/time_amr_reference.py)"""
 import os
 import sys
 import time
@@ -11,7 +11,6 @@ sys.path.insert(0, ROOT)
 from pd_mg_pin_corrosion_b200 import amr as A            # noqa: E402
 from pd_mg_pin_corrosion_b200.config import Config       # noqa: E402
 
-threads = int(sys.argv[sys.argv.index("--threads") + 1]) if "--threads" in sys.argv else os.cpu_count()
 cfg = Config.load(os.path.join(ROOT, "configs", "params_amr.cfg"), {"use_implicit": 0}, quiet=True)
 t0 = time.perf_counter()
 g = A.AmrGrid(cfg)
@@ -32,17 +31,4 @@ dtc = g.ard_compute_dt()
 g.ard_iterate(100, dtc)
 t0 = time.perf_counter(); g.ard_iterate(1000, dtc); t_ard = (time.perf_counter() - t0) / 1000
 print(f"device: NS loop body {1e6 * t_ns:.1f} us, ARD loop body {1e6 * t_ard:.1f} us per iteration")
-try:
-    from oracle import refapi
-    if refapi.have_ref(2):
-        for th in sorted({1, threads}):
-            r = refapi.RefSim(2, "params_amr.cfg", {"use_implicit": 0}, threads=th, build=True, fields=True)
-            dt_r = r.ns_compute_dt()
-            r.ns_iterate(5, dt_r)
-            t0 = time.perf_counter(); r.ns_iterate(40, dt_r); c_ns = (time.perf_counter() - t0) / 40
-            dtc_r = r.ard_compute_dt()
-            t0 = time.perf_counter(); r.ard_iterate(40, dtc_r); c_ard = (time.perf_counter() - t0) / 40
-            print(f"reference on {th} host thread(s): NS loop body {1e6 * c_ns:.0f} us, ARD loop body {1e6 * c_ard:.0f} us "
-                  f"-> {c_ns / t_ns:.0f}x / {c_ard / t_ard:.0f}x")
-except ImportError:
-    pass
+print("(the reference's own loops on the host cores: python tests/time_amr_reference.py)")
