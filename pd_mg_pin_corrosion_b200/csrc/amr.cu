@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -901,7 +902,8 @@ static int enqueue_bc(pdamr_ctx* c, int which, int buf) {   // 0 inlet, 1 outlet
             if (!n_out) break;
             const int n_e = (int)c->out_eidx.size();
             const size_t smem = sizeof(double) * 2 * n_out + sizeof(int) * n_e;
-            if (n_out <= 1024 && smem <= 48 * 1024) {
+            static const bool force_list = getenv("PDGPU_AMR_OUTLET_LIST") != nullptr;   // tests: the general kernel
+            if (n_out <= 1024 && smem <= 48 * 1024 && !force_list) {
                 k_amr_outlet_prepass<<<nb(n_out, 128), 128, 0, c->stream>>>(g, c->d_out_list, n_out, c->rho[buf], c->vel[buf],
                                                                             c->C[c->curC], k.rho_f, c->d_out_bv, c->d_out_bc,
                                                                             c->d_out_cnt);

@@ -142,6 +142,24 @@ def test_amr_loop_bodies_match_reference(case):
 
 @pytest.mark.gpu
 @needs_ref
+def test_amr_outlet_level_list_kernel():
+    """the general outlet kernel (levels over global memory; taken when the OUTLET nodes do not fit one CTA), forced
+    through the environment in a child process: same loop-body results"""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import test_amr as T\n"
+            "ref, cfg, g = T.gpu_pair('amr_default')\n"
+            "dt = ref.ns_compute_dt(); ref.ns_iterate(12, dt); g.ns_iterate(12, dt)\n"
+            "T.assert_close(g, ref, ('rho', 'vel', 'C'))\n"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PDGPU_AMR_OUTLET_LIST="1"), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+
+
+@pytest.mark.gpu
+@needs_ref
 def test_amr_solve_steady_and_phase_change():
     extra = {"flow_max_iters": 300, "D_grain": 5e-11, "D_gb": 5e-9, "C_thresh": 0.999}
     ref, cfg, g = gpu_pair("amr_default", extra)
