@@ -336,6 +336,19 @@ extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
     // every WALL node from FLUID values only), unless nobody evaluates it again: keep it pending
     PD_TRY(pd_set_dt(c, 1, dt));
     PD_TRY(pd_ensure_vmag(c, c->cur));
+    if (pd_ns2d_ok(c) && c->opt_lazy_wallc) {   // 2D: batches of loop bodies as one persistent kernel (ns2d.cu)
+        for (int done = 0; done < steps;) {
+            const int n = std::min(steps - done, 500);
+            PD_TRY(pd_enqueue_ard2d(c, c->cur, c->curC, n));
+            if (n & 1) c->curC = 1 - c->curC;
+            c->wallC_pending = true; c->wallC_src = 1 - c->curC;   // the buffer the last step read
+            done += n;
+        }
+        if (c->n_outlet) PD_TRY(pd_enqueue_ard_vmag_range(c, c->cur, c->out_l0_any, c->NL));   // |v| table: outlet velocities moved
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
     // opt_graph >= 2 also captures the bodies of slab contexts (NCCL send/recv inside the graph)
     bool use_graph = c->opt_graph && (c->opt_graph >= 2 || !(c->nranks > 1 && c->comm));
     for (int it = 0; it < steps; ++it) {

@@ -338,6 +338,8 @@ int pd_enqueue_halo(pdgpu_ctx* c, int which, int buf, int bufC);
 int pd_ns2d_prepare(pdgpu_ctx* c);                   // ns2d.cu
 bool pd_ns2d_ok(const pdgpu_ctx* c);
 int pd_enqueue_ns2d(pdgpu_ctx* c, int src, int iters);
+int pd_enqueue_ard2d(pdgpu_ctx* c, int buf, int srcC, int steps);
+int pd_enqueue_ard_vmag_range(pdgpu_ctx* c, int buf, long long lo, long long hi);
 int pd_max_fluid_speed(pdgpu_ctx* c, double* vmax);
 void pd_invalidate_graphs(pdgpu_ctx* c);
 int pd_refresh_eos(pdgpu_ctx* c, int buf);           // p[buf] = EOS(rho[buf]) on all local nodes

@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -74,6 +75,16 @@ struct Ns2dParams {
     const int* mirror;
     int n_wall;
     unsigned* bar;
+    // ARD loop (k_ard2d_loop)
+    double* Cb[2];            // concentration buffers; step `it` reads Cb[cs0 ^ (it & 1)]
+    int cs0, fb;              // first source C buffer, flow buffer (frozen)
+    const int* l_ssolid;      // SOLID_MG nodes with a fluid-like neighbour
+    int n_ssolid;
+    const uint8_t *is_gb, *is_precip;
+    uint8_t* salt;
+    double *dsol, *wpack;
+    const double* dt_ard;
+    double D_liquid, D_grain, D_gb, D_precip, decay, alpha_dx, beta, div_coeff, C_sat;
     unsigned long long* prof; // optional: globaltimer stamps of the last iteration, 8 per CTA
 };
 
@@ -86,8 +97,8 @@ struct Ns2dState {
     unsigned* bar = nullptr;
     unsigned long long* prof = nullptr;
     size_t smem = 0;
-    bool attr_set = false;
-    size_t attr_smem = 0;
+    bool attr_set = false, attr_set_ard = false;
+    size_t attr_smem = 0, attr_smem_ard = 0;
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned target) {
@@ -284,14 +295,14 @@ __device__ void outlet_setup(const Ns2dParams& q, const OutSmem& s, const Off2* 
     }
 }
 
-__device__ void outlet_phase(const Ns2dParams& q, const OutSmem& s, const Off2* s_off, int S, bool last) {
+__device__ void outlet_phase(const Ns2dParams& q, const OutSmem& s, const Off2* s_off, int S, bool last, double* Cb) {
     const int tid = threadIdx.x, Nx = q.Nx, R = q.R, PW = Nx + 2 * R;
     const long long g0 = (long long)(q.out_row0 - R) * Nx;   // global index of the first staged node
     const int ns = q.out_rows_staged * Nx, nk = q.KP * Nx, MW = mask_words(q);
     const double* vy = q.vy[S];
     for (int k = tid; k < ns; k += NT2D) {
         s.v[k] = __ldcg(vy + g0 + k);
-        s.c[k] = __ldcg(q.C + g0 + k);
+        s.c[k] = __ldcg(Cb + g0 + k);
     }
     __syncthreads();
     stamp(q, last, 5);
@@ -396,7 +407,7 @@ __device__ void outlet_phase(const Ns2dParams& q, const OutSmem& s, const Off2* 
         pr[l] = 0.0;            // EOS(rho_f) = 0 exactly
         vx[l] = 0.0;
         vyw[l] = n > 0 ? s.new_v[pd] : q.U_in;   // n = 0: an OUTLET node nobody is a neighbour of
-        q.C[l] = n > 0 ? s.new_c[pd] : 0.0;
+        Cb[l] = n > 0 ? s.new_c[pd] : 0.0;
     }
 }
 
@@ -429,7 +440,7 @@ __device__ __forceinline__ double eos2d(const Ns2dParams& q, double rho) {
     return eos_pressure(rho, q.rho_f, q.gamma, q.B);
 }
 
-__device__ void bc_phase(const Ns2dParams& q, const Off2* s_off, int S) {
+__device__ void bc_phase(const Ns2dParams& q, const Off2* s_off, int S, double* Cb, bool solid_bc) {
     // apply_inlet_bc (src/boundary.cpp:31-75): warp per node, neighbour loads in parallel, sum in CSR order
     const int lane = threadIdx.x & 31, wpc = NT2D / 32;
     const int gw = blockIdx.x * wpc + (threadIdx.x >> 5), nw = q.n_step * wpc;
@@ -461,10 +472,11 @@ __device__ void bc_phase(const Ns2dParams& q, const Off2* s_off, int S) {
             q.p[S][l] = eos2d(q, r);
             q.vx[S][l] = 0.0;
             q.vy[S][l] = q.inlet_vax[t];
-            q.C[l] = q.C_in;
+            Cb[l] = q.C_in;
         }
     }
     // apply_solid_surface_bc (src/boundary.cpp:381-390)
+    if (solid_bc)
     for (int t = blockIdx.x * NT2D + threadIdx.x; t < q.n_solid; t += q.n_step * NT2D) {
         const int l = q.l_solid[t];
         q.vx[S][l] = 0.0;
@@ -642,8 +654,8 @@ __global__ void __launch_bounds__(NT2D, 1) k_ns2d_loop(const __grid_constant__ N
         const int S = q.src0 ^ (it & 1);
         const bool last = it == q.iters - 1;
         stamp(q, last, 0);
-        if (is_out) outlet_phase(q, so, s_off, S, last);
-        else bc_phase(q, s_off, S);
+        if (is_out) outlet_phase(q, so, s_off, S, last, q.C);
+        else bc_phase(q, s_off, S, q.C, true);
         stamp(q, last, 1);
         target += nctas;
         grid_barrier(q.bar, target);
@@ -678,6 +690,189 @@ __global__ void __launch_bounds__(NT2D, 1) k_ns2d_loop(const __grid_constant__ N
                 if (!is_out) channel_write(q, ss, S, r0, r1);
             }
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The explicit corrosion loop body (src/coupling.cpp:232-240: inlet, outlet, wall-concentration BCs, ARD step,
+// swap C) with the same structure: `steps` bodies per launch, two grid barriers per step.
+//   phase 1: inlet BC; salt-layer flag and interface diffusivity of the surface solids (src/pd_ard.cpp:61-73,
+//            140-162) from the FLUID concentrations; the outlet CTA sweeps axial velocity and concentration.
+//   phase 2: the band + halo of C is staged through L2 together with what changes per step in the second staged
+//            value -- |v| of the OUTLET nodes (their velocity was just swept) and the interface diffusivity of the
+//            SOLID_MG nodes -- while |v| of the other fluid-like nodes, the node types and the own velocities of the
+//            band stay in shared memory for the whole launch (velocities are frozen during the corrosion phase);
+//            PD_ARD_Solver::step (src/pd_ard.cpp:81-190) per FLUID / SOLID_MG node in CSR order, copy-through else.
+// The wall-concentration BC stays lazy (no bond reads WALL C, :120): the caller keeps it owed as in the
+// per-operator loop.
+struct ArdSmem {
+    double *C, *a;      // staged concentration; |v| (fluid-like) or interface diffusivity (SOLID_MG), -1 otherwise
+    double *vx, *vy;    // own velocities of the band (static)
+    uint8_t* t;
+};
+__device__ __forceinline__ ArdSmem ard_smem(int ns_max, int n_own_max, unsigned char* raw) {
+    ArdSmem s;
+    double* d = (double*)raw;
+    s.C = d; d += ns_max;
+    s.a = d; d += ns_max;
+    s.vx = d; d += n_own_max;
+    s.vy = d; d += n_own_max;
+    s.t = (uint8_t*)d;
+    return s;
+}
+
+__device__ void ard_bc_phase(const Ns2dParams& q, const Off2* s_off, int S, double* Cb) {
+    bc_phase(q, s_off, S, Cb, false);                     // apply_inlet_bc
+    // salt flags / interface diffusivities of the surface solids: one thread per node, order-free
+    for (int t = blockIdx.x * NT2D + threadIdx.x; t < q.n_ssolid; t += q.n_step * NT2D) {
+        const int l = q.l_ssolid[t];
+        const int i = l % q.Nx;
+        bool blocked = false;
+        for (int o = 0; o < q.n_off && !blocked; ++o) {
+            const Off2 e = s_off[o];
+            if ((unsigned)(i + e.di) >= (unsigned)q.Nx) continue;
+            if (q.type[l + e.ds] == PDGPU_FLUID && __ldcg(Cb + l + e.ds) >= q.C_sat) blocked = true;
+        }
+        double ds = 0.0;
+        if (!blocked) {
+            double D_s = q.is_gb[l] ? q.D_gb : (q.is_precip[l] ? q.D_precip : q.D_grain);
+            D_s *= q.decay;
+            ds = 2.0 * q.D_liquid * D_s / (q.D_liquid + D_s + 1e-30);
+        }
+        q.salt[l] = blocked ? 1 : 0;
+        q.dsol[l] = ds;
+        q.wpack[l] = -ds;
+    }
+}
+
+template <int SPLIT>
+__device__ void ard_step_phase(const Ns2dParams& q, const ArdSmem& s, const Off2* s_off, const double* Cs, double* Cd,
+                               int r0, int r1) {
+    const int tid = threadIdx.x, Nx = q.Nx, R = q.R;
+    const int ns = (r1 - r0 + 2 * R) * Nx;
+    const long long g0 = (long long)(r0 - R) * Nx;
+    const int own0 = R * Nx, n_own = (r1 - r0) * Nx;
+    const double* vxg = q.vx[q.fb];
+    const double* vyg = q.vy[q.fb];
+    for (int k = tid; k < ns; k += NT2D) {
+        s.C[k] = __ldcg(Cs + g0 + k);
+        const uint8_t t = s.t[k];
+        if (t == PDGPU_SOLID_MG) s.a[k] = __ldcg(q.dsol + g0 + k);
+        else if (t == PDGPU_OUTLET || t == PDGPU_INLET) {    // velocities (re)written by the BCs of phase 1
+            const double a = __ldcg(vxg + g0 + k), b = __ldcg(vyg + g0 + k);
+            s.a[k] = sqrt(a * a + b * b);
+        }
+    }
+    __syncthreads();
+    const double dt = *q.dt_ard;
+    const int total = n_own * SPLIT;
+    const int per = (q.n_off + SPLIT - 1) / SPLIT;
+    for (int w0 = 0; w0 < total; w0 += NT2D) {
+        const int w = w0 + tid;
+        const bool in = w < total;
+        const int node = in ? w / SPLIT : 0, part = w & (SPLIT - 1);
+        const int k = own0 + node;
+        const uint8_t ti = s.t[k];
+        const bool i_fl = in && ti == PDGPU_FLUID, i_so = in && ti == PDGPU_SOLID_MG;
+        const double C_i = s.C[k];
+        double diff = 0.0, adv = 0.0;
+        if (i_fl || i_so) {
+            const int i = node % Nx;
+            const double vi0 = i_fl ? s.vx[node] : 0.0, vi1 = i_fl ? s.vy[node] : 0.0;
+            const double vi_mag = i_fl ? s.a[k] : 0.0, ds_i = i_so ? s.a[k] : 0.0;
+            const int o_end = min(q.n_off, (part + 1) * per);
+            for (int o = part * per; o < o_end; ++o) {
+                const Off2 e = s_off[o];
+                const int k2 = k + e.ds;
+                if ((unsigned)(i + e.di) >= (unsigned)Nx) continue;
+                const uint8_t tj = s.t[k2];
+                if (tj == PDGPU_OUTSIDE || tj == PDGPU_WALL) continue;                       // :120
+                const bool j_fl = tj == PDGPU_FLUID || tj == PDGPU_INLET || tj == PDGPU_OUTLET;
+                if (!i_fl && !j_fl) continue;                                                // solid-solid :134
+                const double dC = s.C[k2] - C_i;
+                double D;
+                if (i_fl && j_fl) {                                                          // :137-139, :166-181
+                    D = q.D_liquid + q.alpha_dx * fmax(vi_mag, s.a[k2]);
+                    const double vde = vi0 * e.ex + vi1 * e.ey;
+                    adv += dC * vde * e.w1;
+                } else {
+                    D = i_fl ? s.a[k2] : ds_i;                                               // interface :140-162
+                }
+                diff += q.beta * D * dC * e.w2;                                              // :173
+            }
+        }
+#pragma unroll
+        for (int x = 1; x < SPLIT; x <<= 1) {
+            diff += __shfl_xor_sync(0xffffffffu, diff, x);
+            adv += __shfl_xor_sync(0xffffffffu, adv, x);
+        }
+        if (in && part == 0) {
+            double cn = C_i;
+            if (i_fl || i_so) {
+                cn = C_i + dt * (diff - adv * q.div_coeff);
+                if (cn < 0.0) cn = 0.0;
+            }
+            Cd[g0 + k] = cn;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT2D, 1) k_ard2d_loop(const __grid_constant__ Ns2dParams q) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const int tid = threadIdx.x, b = blockIdx.x, Nx = q.Nx, R = q.R;
+    Off2* s_off = (Off2*)raw;
+    unsigned char* rest = raw + sizeof(Off2) * q.n_off;
+    for (int o = tid; o < q.n_off; o += NT2D) {
+        const OffEntry e = q.off[o];
+        Off2 f;
+        f.di = e.di; f.dj = e.dj; f.ds = e.dj * Nx + e.di; f.pad = 0;
+        f.ex = e.ex; f.ey = e.ey; f.w1 = e.w1; f.w2 = e.w2;
+        s_off[o] = f;
+    }
+    const bool is_out = q.KP > 0 && b == q.n_step;
+    const unsigned nctas = gridDim.x;
+    unsigned target = 0;
+    OutSmem so;
+    ArdSmem sa;
+    int r0 = 0, r1 = 0;
+    const int S = q.fb;
+    if (is_out) {
+        so = out_smem(q, rest);
+        __syncthreads();
+        outlet_setup(q, so, s_off);
+    } else {
+        r0 = row_lo(q, b); r1 = row_lo(q, b + 1);
+        const int rows_own_max = (q.Na + q.n_step - 1) / q.n_step;
+        sa = ard_smem((rows_own_max + 2 * R) * Nx, rows_own_max * Nx, rest);
+        const long long g0 = (long long)(r0 - R) * Nx;
+        const int ns = (r1 - r0 + 2 * R) * Nx, own0 = R * Nx, n_own = (r1 - r0) * Nx;
+        for (int k = tid; k < ns; k += NT2D) {
+            const uint8_t t = q.type[g0 + k];
+            sa.t[k] = t;
+            double a = -1.0;                                  // k_ard_vmag (ard.cu): |v| of the fluid-like nodes
+            if (t == PDGPU_FLUID || t == PDGPU_INLET || t == PDGPU_OUTLET) {
+                const double u = q.vx[S][g0 + k], v = q.vy[S][g0 + k];
+                a = sqrt(u * u + v * v);
+            }
+            sa.a[k] = a;
+        }
+        for (int n = tid; n < n_own; n += NT2D) { sa.vx[n] = q.vx[S][g0 + own0 + n]; sa.vy[n] = q.vy[S][g0 + own0 + n]; }
+    }
+    __syncthreads();
+    for (int it = 0; it < q.iters; ++it) {
+        double* Cs = q.Cb[q.cs0 ^ (it & 1)];
+        double* Cd = q.Cb[q.cs0 ^ (it & 1) ^ 1];
+        if (is_out) outlet_phase(q, so, s_off, S, false, Cs);
+        else ard_bc_phase(q, s_off, S, Cs);
+        target += nctas;
+        grid_barrier(q.bar, target);
+        if (!is_out) {
+            if (q.split == 4) ard_step_phase<4>(q, sa, s_off, Cs, Cd, r0, r1);
+            else if (q.split == 2) ard_step_phase<2>(q, sa, s_off, Cs, Cd, r0, r1);
+            else ard_step_phase<1>(q, sa, s_off, Cs, Cd, r0, r1);
+        }
+        target += nctas;
+        grid_barrier(q.bar, target);
     }
 }
 
@@ -843,5 +1038,49 @@ int pd_enqueue_ns2d(pdgpu_ctx* c, int src, int iters) {
                     (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3);
         }
     }
+    return 0;
+}
+
+// `steps` corrosion loop bodies (src/coupling.cpp:232-240) from concentration buffer `srcC`, flow buffer `buf`
+// frozen; the caller flips curC per step and keeps the lazy wall-concentration BC owed.
+int pd_enqueue_ard2d(pdgpu_ctx* c, int buf, int srcC, int steps) {
+    Ns2dState* st = (Ns2dState*)c->ns2d_state;
+    const PdConsts k = pd_consts(c->cfg, c->dim);
+    Ns2dParams q;
+    memset(&q, 0, sizeof(q));
+    q.Nx = c->Nx; q.R = c->R; q.Na = c->a1 - c->a0;
+    q.n_step = st->n_step; q.n_off = c->n_off; q.n_early = c->n_off / 2; q.split = st->split;
+    q.out_row0 = st->out_row0; q.KP = st->KP; q.out_rows_staged = st->out_rows_staged;
+    q.sweep_parts = st->KP <= 8 ? 4 : 2;
+    q.iters = steps; q.src0 = buf;
+    q.rho_f = c->cfg.rho_f; q.gamma = c->cfg.gamma_eos; q.B = k.B_eos;
+    q.C_in = c->cfg.C_liquid_init; q.U_in = c->cfg.U_in;
+    for (int bfr = 0; bfr < 2; ++bfr) {
+        q.rho[bfr] = c->rho[bfr]; q.p[bfr] = c->p[bfr]; q.vx[bfr] = c->v[bfr][0]; q.vy[bfr] = c->v[bfr][1];
+        q.Cb[bfr] = c->C[bfr];
+    }
+    q.C = nullptr;
+    q.type = c->type; q.wsrc = st->wsrc; q.off = c->d_off;
+    q.l_inlet = c->l_inlet; q.inlet_vax = c->inlet_vax; q.n_inlet = (int)c->n_inlet;
+    q.l_solid = c->l_solid; q.n_solid = (int)c->n_solid;
+    q.bar = st->bar;
+    q.prof = nullptr;
+    q.cs0 = srcC; q.fb = buf;
+    q.l_ssolid = c->l_ssolid; q.n_ssolid = (int)c->n_ssolid;
+    q.is_gb = c->is_gb; q.is_precip = c->is_precip; q.salt = c->salt; q.dsol = c->dsol; q.wpack = c->wpack;
+    q.dt_ard = c->d_dt + 1;
+    q.D_liquid = c->cfg.D_liquid; q.D_grain = c->cfg.D_grain; q.D_gb = c->cfg.D_gb; q.D_precip = c->cfg.D_precip;
+    q.decay = c->cfg.corrosion_decay_l > 0.0 ? std::pow(10.0, -c->volume_loss / c->cfg.corrosion_decay_l) : 1.0;
+    q.alpha_dx = c->cfg.alpha_art_diff * c->cfg.dx;
+    q.beta = k.beta_lap; q.div_coeff = k.alpha / k.V_H; q.C_sat = c->cfg.C_sat;
+    if (!st->attr_set_ard || st->attr_smem_ard < st->smem) {
+        CUDA_OK(cudaFuncSetAttribute(k_ard2d_loop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st->smem));
+        st->attr_set_ard = true; st->attr_smem_ard = st->smem;
+    }
+    CUDA_OK(cudaMemsetAsync(st->bar, 0, sizeof(unsigned), c->stream));
+    void* args[] = {(void*)&q};
+    const unsigned grid = (unsigned)(st->n_step + (st->KP > 0 ? 1 : 0));
+    CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_ard2d_loop, dim3(grid), dim3(NT2D), args, st->smem, c->stream));
+    c->launches++;
     return 0;
 }

@@ -353,6 +353,25 @@ def test_2d_persistent_flow_loop(case, extra):
         if not (extra and "channel_flow_corrections" in extra):   # (the oracle applies those in solve_steady only)
             for n in ("rho", "vel", "C"):
                 assert H.rel_err(out[0][0][n], ref.get(n)) <= TOL, (case, done, n, "vs oracle")
+    # the corrosion loop body (src/coupling.cpp:232-240) through k_ard2d_loop: 1, 2 and 31 steps
+    dtc = ref.ard_compute_dt()
+    ards = []
+    for S, cfg, grid, fields, ns in sides:
+        ard = S.PD_ARD_Solver(); ard.init(grid, cfg)
+        ards.append(ard)
+    for steps in (1, 2, 31):
+        out = []
+        for (S, cfg, grid, fields, ns), ard in zip(sides, ards):
+            n0 = grid.launch_count()
+            ard.iterate(fields, grid, cfg, steps, dtc)
+            out.append(({n: fields.get(n) for n in ("rho", "vel", "C", "C_new")}, grid.launch_count() - n0))
+        ref.ard_iterate(steps, dtc)
+        assert out[0][1] <= 6 and out[1][1] >= 4 * steps, (out[0][1], out[1][1])   # dt, |v| table, one kernel per batch
+        for n in ("rho", "vel", "C", "C_new"):
+            assert H.rel_err(out[0][0][n], out[1][0][n]) <= 1e-13, (case, steps, n, "persistent vs per-operator")
+        if not (extra and "channel_flow_corrections" in extra):
+            for n in ("rho", "vel", "C"):
+                assert H.rel_err(out[0][0][n], ref.get(n)) <= TOL, (case, steps, n, "vs oracle")
     for _, _, grid, _, _ in sides:
         grid.close()
 

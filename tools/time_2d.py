@@ -36,6 +36,14 @@ for st in sets:
     L_.check(L.pdgpu_ns_iterate(grid.ctx, iters, dt))
     L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
     print(f"{st:30s} {1e3 * ms.value / iters:8.2f} us per NS iteration", flush=True)
+    # ARD loop body (src/coupling.cpp:232-240) on the same lattice
+    ard = S.PD_ARD_Solver(); ard.init(grid, cfg)
+    dtc = ard.compute_dt(fields, grid, cfg)
+    L_.check(L.pdgpu_ard_iterate(grid.ctx, 500, dtc))
+    L_.check(L.pdgpu_timer_start(grid.ctx))
+    L_.check(L.pdgpu_ard_iterate(grid.ctx, iters, dtc))
+    L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
+    print(f"{st:30s} {1e3 * ms.value / iters:8.2f} us per ARD loop body", flush=True)
     if "--solve" in sys.argv:
         L_.check(L.pdgpu_fields_init(grid.ctx, None, None))
         t0 = time.perf_counter()
