@@ -332,12 +332,11 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def one_step():
-        L_.check(L.pdgpu_ns_iterate(grid.ctx, 1, dt))
-        L_.check(L.pdgpu_ard_iterate(grid.ctx, 1, dtc))
+    def steps_resident(n):
+        # n x { NS loop body ; ARD loop body } on the device, one host synchronisation at the end
+        L_.check(L.pdgpu_step_iterate(grid.ctx, n, dt, dtc))
 
-    for _ in range(args.warmup):
-        one_step()
+    steps_resident(args.warmup)
     # ---- device-resident throughput (`value`) ----
     sampler = ClockSampler(local)
     sampler.start()
@@ -346,8 +345,7 @@ def main() -> None:
     barrier()
     t0 = time.time()
     L_.check(L.pdgpu_timer_start(grid.ctx))
-    for _ in range(args.steps):
-        one_step()
+    steps_resident(args.steps)
     ms = C.c_float()
     L_.check(L.pdgpu_timer_stop(grid.ctx, C.byref(ms)))
     barrier()

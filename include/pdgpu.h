@@ -184,6 +184,9 @@ int pdgpu_ard_compute_dt(pdgpu_ctx* ctx, double* dt);
 int pdgpu_ard_step(pdgpu_ctx* ctx, double dt);       /* salt pre-pass + bond sums -> C_new */
 /* `steps` x { inlet, outlet, wall_conc, step, swap C } (src/coupling.cpp:232-240). */
 int pdgpu_ard_iterate(pdgpu_ctx* ctx, int steps, double dt);
+/* `steps` x { NS loop body ; ARD loop body }, device resident, one host synchronisation at the end: the unit of the
+ * throughput metric. Same state as pdgpu_ns_iterate(1) + pdgpu_ard_iterate(1) repeated. */
+int pdgpu_step_iterate(pdgpu_ctx* ctx, int steps, double dt_ns, double dt_ard);
 
 /* ---- One coupling-loop pass on HOST-resident Fields -------------------------------------
  * What a caller that keeps the reference's Fields vectors (src/fields.h:28-58) in host memory

@@ -329,29 +329,11 @@ static int enqueue_ard_body(pdgpu_ctx* c, int buf, int srcC) {
     return 0;
 }
 
-extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
-    NEED_FIELDS(c);
-    if (steps <= 0) return 0;
-    // an owed wall-C evaluation is superseded by the one of the first step of this call (both write
-    // every WALL node from FLUID values only), unless nobody evaluates it again: keep it pending
-    PD_TRY(pd_set_dt(c, 1, dt));
-    PD_TRY(pd_ensure_vmag(c, c->cur));
-    if (pd_ns2d_ok(c) && c->opt_lazy_wallc) {   // 2D: batches of loop bodies as one persistent kernel (ns2d.cu)
-        for (int done = 0; done < steps;) {
-            const int n = std::min(steps - done, 500);
-            PD_TRY(pd_enqueue_ard2d(c, c->cur, c->curC, n));
-            if (n & 1) c->curC = 1 - c->curC;
-            c->wallC_pending = true; c->wallC_src = 1 - c->curC;   // the buffer the last step read
-            done += n;
-        }
-        if (c->n_outlet) PD_TRY(pd_enqueue_ard_vmag_range(c, c->cur, c->out_l0_any, c->NL));   // |v| table: outlet velocities moved
-        CUDA_OK(cudaStreamSynchronize(c->stream));
-        CUDA_OK(cudaGetLastError());
-        return 0;
-    }
+// one corrosion loop body + swap of C, no host synchronisation (graph per (flow buffer, C buffer) where allowed)
+static int ard_body_step(pdgpu_ctx* c) {
     // opt_graph >= 2 also captures the bodies of slab contexts (NCCL send/recv inside the graph)
     bool use_graph = c->opt_graph && (c->opt_graph >= 2 || !(c->nranks > 1 && c->comm));
-    for (int it = 0; it < steps; ++it) {
+    {
         int buf = c->cur, srcC = c->curC;
         if (!use_graph) {
             PD_TRY(enqueue_ard_body(c, buf, srcC));
@@ -376,6 +358,57 @@ extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
         }
         c->curC = 1 - c->curC;   // std::swap(fields.C, fields.C_new)
         if (c->opt_lazy_wallc) { c->wallC_pending = true; c->wallC_src = 1 - c->curC; }
+    }
+    return 0;
+}
+
+extern "C" int pdgpu_ard_iterate(pdgpu_ctx* c, int steps, double dt) {
+    NEED_FIELDS(c);
+    if (steps <= 0) return 0;
+    // an owed wall-C evaluation is superseded by the one of the first step of this call (both write
+    // every WALL node from FLUID values only), unless nobody evaluates it again: keep it pending
+    PD_TRY(pd_set_dt(c, 1, dt));
+    PD_TRY(pd_ensure_vmag(c, c->cur));
+    if (pd_ns2d_ok(c) && c->opt_lazy_wallc) {   // 2D: batches of loop bodies as one persistent kernel (ns2d.cu)
+        for (int done = 0; done < steps;) {
+            const int n = std::min(steps - done, 500);
+            PD_TRY(pd_enqueue_ard2d(c, c->cur, c->curC, n));
+            if (n & 1) c->curC = 1 - c->curC;
+            c->wallC_pending = true; c->wallC_src = 1 - c->curC;   // the buffer the last step read
+            done += n;
+        }
+        if (c->n_outlet) PD_TRY(pd_enqueue_ard_vmag_range(c, c->cur, c->out_l0_any, c->NL));   // |v| table: outlet velocities moved
+        CUDA_OK(cudaStreamSynchronize(c->stream));
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    for (int it = 0; it < steps; ++it) PD_TRY(ard_body_step(c));
+    CUDA_OK(cudaStreamSynchronize(c->stream));
+    CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// `steps` x { NS loop body ; ARD loop body } without a host synchronisation in between: what a device-resident
+// driver that alternates the two solvers per step issues (the unit of the throughput metric). Same state as
+// pdgpu_ns_iterate(1) + pdgpu_ard_iterate(1) repeated.
+int pd_ns_body_step(pdgpu_ctx* c);   // ns.cu
+extern "C" int pdgpu_step_iterate(pdgpu_ctx* c, int steps, double dt_ns, double dt_ard) {
+    NEED_FIELDS(c);
+    if (steps <= 0) return 0;
+    PD_TRY(pd_set_dt(c, 0, dt_ns));
+    PD_TRY(pd_set_dt(c, 1, dt_ard));
+    const bool fused2d = pd_ns2d_ok(c) && c->opt_lazy_wallc;
+    for (int it = 0; it < steps; ++it) {
+        PD_TRY(pd_ns_body_step(c));
+        PD_TRY(pd_ensure_vmag(c, c->cur));               // |v| table of the new flow state
+        if (fused2d) {
+            PD_TRY(pd_enqueue_ard2d(c, c->cur, c->curC, 1));
+            c->curC = 1 - c->curC;
+            c->wallC_pending = true; c->wallC_src = 1 - c->curC;
+            if (c->n_outlet) PD_TRY(pd_enqueue_ard_vmag_range(c, c->cur, c->out_l0_any, c->NL));
+        } else {
+            PD_TRY(ard_body_step(c));
+        }
     }
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaGetLastError());

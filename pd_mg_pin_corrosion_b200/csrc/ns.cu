@@ -430,6 +430,19 @@ static int run_ns_body(pdgpu_ctx* c) {
     return 0;
 }
 
+// one loop body + swap, no host synchronisation (pdgpu_step_iterate, ard.cu)
+int pd_ns_body_step(pdgpu_ctx* c) {
+    if (pd_ns2d_ok(c)) {
+        pd_touch_flow(c);
+        PD_TRY(pd_enqueue_ns2d(c, c->cur, 1));
+    } else {
+        PD_TRY(run_ns_body(c));
+    }
+    c->p_input = c->cur; pd_pressure_recomputed(c);
+    c->cur = 1 - c->cur;
+    return 0;
+}
+
 extern "C" int pdgpu_ns_iterate(pdgpu_ctx* c, int iters, double dt) {
     NEED_FIELDS(c);
     PD_TRY(pd_set_dt(c, 0, dt));

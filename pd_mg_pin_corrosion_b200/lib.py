@@ -102,6 +102,7 @@ def load() -> C.CDLL:
         "pdgpu_ns_solve_steady": [vp, C.POINTER(PdSteadyResult), C.c_int],
         "pdgpu_ard_set_volume_loss": [vp, C.c_double], "pdgpu_ard_compute_dt": [vp, dp],
         "pdgpu_ard_step": [vp, C.c_double], "pdgpu_ard_iterate": [vp, C.c_int, C.c_double],
+        "pdgpu_step_iterate": [vp, C.c_int, C.c_double, C.c_double],
         "pdgpu_phase_change": [vp, ip, vp, C.c_int], "pdgpu_diag": [vp, C.POINTER(PdDiag)],
         "pdgpu_comm_get_uid": [vp], "pdgpu_comm_init": [vp, vp, C.c_int, C.c_int],
         "pdgpu_halo_exchange": [vp, C.c_int],

@@ -395,6 +395,29 @@ def test_2d_solve_steady_persistent(case):
         assert H.rel_err(a, res[1][3][n]) <= 1e-12, n
 
 
+@pytest.mark.parametrize("case", ["3d_small", "2d_default"])
+def test_step_iterate_equals_alternating_calls(case):
+    """pdgpu_step_iterate(n) (no host synchronisation between the bodies) leaves exactly the state of
+    n x { pdgpu_ns_iterate(1) ; pdgpu_ard_iterate(1) }."""
+    from pd_mg_pin_corrosion_b200 import lib as L_
+    import ctypes as C
+    ref = H.make_ref(case)
+    dt, dtc = ref.ns_compute_dt(), ref.ard_compute_dt()
+    out = []
+    for fused in (True, False):
+        S, cfg, grid, fields = gpu_side(case, ref=ref, upload=False)
+        if fused:
+            L_.check(L_.load().pdgpu_step_iterate(grid.ctx, 7, dt, dtc))
+        else:
+            for _ in range(7):
+                L_.check(L_.load().pdgpu_ns_iterate(grid.ctx, 1, dt))
+                L_.check(L_.load().pdgpu_ard_iterate(grid.ctx, 1, dtc))
+        out.append({n: fields.get(n) for n in ("rho", "vel", "C", "rho_new", "vel_new", "C_new")})
+        grid.close()
+    for n, a in out[0].items():
+        assert np.array_equal(a, out[1][n]), (case, n)
+
+
 @pytest.mark.parametrize("case,extra,n_chunks,expect", [
     ("3d_small", None, 3, 2), ("3d_default", None, 8, 8), ("3d_default", None, 16, 12),
     ("2d_default", None, 6, 4), ("2d_dissolve", None, 4, 3),
