@@ -591,6 +591,7 @@ class CoupledSolver:
                          f"({t_corr / 3600.0:.4f} h); last solve {imp.last.iters} iterations, "
                          f"|res| = {imp.last.rel_res:.2e}")
                 n_dissolved = imp.apply_phase_change(fields, grid, cfg)
+                n_dissolved = int(grid.allreduce([n_dissolved], "sum")[0])            # all ranks take the same branch
                 self.total_dissolved += n_dissolved
                 self.dissolved_since_flow += n_dissolved
                 if n_dissolved > 0:
