@@ -1,14 +1,16 @@
 """TEST INFRASTRUCTURE -- CPU restatement of the reference's implicit ARD branch
 (PD_ARD_ImplicitSolver, src/pd_ard_implicit.cpp) in numpy / scipy.  Never imported by the product.
 
-PARITY STATUS: the linear SOLVE is "unpinned".  The reference solves (I - dt M) C = b with Eigen 3.4.0
-(GMRES<SparseMatrix, IncompleteLUT>, tolerance 1e-10, restart 50, <= 200 iterations,
-src/pd_ard_implicit.cpp:384-409); Eigen is fetched at configure time (CMakeLists.txt:27-38) and is absent
-from the reference tree and from this image, so the reference's implicit branch cannot be run here and its
-tests (tests/test_implicit.cpp) cannot be built.  What this file restates is the reference's own code
-around that call -- operator assembly, boundary right-hand side, adaptive time step, write-back clamp --
-line by line, and it replaces the iterative solve by scipy's sparse direct solve, i.e. the exact solution
-that Eigen's GMRES approximates to its 1e-10 relative residual.
+PARITY STATUS: pinned on the reference's compiled code except for Eigen's internal arithmetic.  The reference
+solves (I - dt M) C = b with Eigen 3.4.0 (GMRES<SparseMatrix, IncompleteLUT>, tolerance 1e-10, restart 50, <= 200
+iterations, src/pd_ard_implicit.cpp:384-409); Eigen is fetched at configure time (CMakeLists.txt:27-38) and is absent
+from the reference tree and from this image.  This file restates the reference's own code around that call --
+operator assembly, boundary right-hand side, adaptive time step, write-back clamp -- line by line, and replaces the
+iterative solve by scipy's sparse direct solve, i.e. the exact solution Eigen's GMRES approximates to its 1e-10
+relative residual.  tests/test_reference_implicit.py checks it against the UNMODIFIED src/pd_ard_implicit.cpp compiled
+against the Eigen work-alike oracle/eigen_min/ (oracle/_ref/libpdrefimp{2,3}d.so): system matrix and right-hand side
+to 1e-14, adaptive step 1e-12, step results to the solve tolerance, and the whole implicit run of the reference's
+main() row for row.  Unpinned: Eigen's floating-point order inside GMRES / ILUT (acts below 1e-10).
 
     assemble()            src/pd_ard_implicit.cpp:104-346 (M over the FLUID + SOLID_MG unknowns, BC weights)
     bc_rhs()              :352-362

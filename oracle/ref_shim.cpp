@@ -18,14 +18,22 @@
 //   main()                                    src/main.cpp:129  (whole-run diagnostics.csv)
 //
 // The implicit solver (src/pd_ard_implicit.cpp) needs Eigen 3.4.0, which the
-// reference fetches from the network; it is out of scope (use_implicit = 0 on the
-// north-star path) and its five public methods are defined here as aborting stubs.
+// reference fetches from the network.  Two builds of this file (oracle/Makefile):
+//   libpdref{2,3}d.so     explicit path only: -Ieigen_stub (empty declarations), the solver's five public
+//                         methods are aborting stubs defined below.
+//   libpdrefimp{2,3}d.so  -DPD_REF_IMPLICIT -Ieigen_min: the UNMODIFIED src/pd_ard_implicit.cpp compiled against
+//                         an independently written work-alike of the few Eigen types it uses (oracle/eigen_min/).
+//                         Assembly, right-hand side, clamp, adaptive step and the implicit coupling loop are then
+//                         the reference's own code; the linear solve meets the reference's tolerance (1e-10) with
+//                         a different Krylov implementation.  ref_imp_* below wrap
+//   PD_ARD_ImplicitSolver::{init,assemble,step,compute_adaptive_dt,apply_phase_change}  src/pd_ard_implicit.cpp:9,104,371,438,538
 #include <omp.h>
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 // Pull in the reference driver TU so that its file-static initialize_fields()
 // is reachable; its main() is renamed, not modified.
@@ -35,7 +43,8 @@
 
 #include "boundary.h"
 
-// ---- aborting stubs for the out-of-scope implicit solver -------------------
+#ifndef PD_REF_IMPLICIT
+// ---- aborting stubs for the implicit solver (explicit-only build) -----------
 static void implicit_abort(const char* what) {
     std::fprintf(stderr,
                  "oracle/_ref: PD_ARD_ImplicitSolver::%s called, but the implicit "
@@ -53,6 +62,7 @@ int PD_ARD_ImplicitSolver::apply_phase_change(Fields&, Grid&, const Config&) {
     implicit_abort("apply_phase_change");
     return 0;
 }
+#endif
 
 namespace {
 struct RefSim {
@@ -62,6 +72,7 @@ struct RefSim {
     Fields fields;
     PD_NS_Solver ns;
     PD_ARD_Solver ard;
+    PD_ARD_ImplicitSolver imp;
     bool have_grains = false;
 };
 inline RefSim* S(void* h) { return static_cast<RefSim*>(h); }
@@ -256,6 +267,63 @@ double ref_write_vti(void* h, const char* path) {
     double t0 = omp_get_wtime();
     w.write(path, s->grid, s->fields, s->cfg);
     return omp_get_wtime() - t0;
+}
+
+#ifdef PD_REF_IMPLICIT
+// ---- PD-ARD (implicit) ---------------------------------------------------------
+// The system of the last PD_ARD_ImplicitSolver::step, observed through the work-alike's solve hook:
+// A = I - dt M (row-wise), b = C_old + dt bc_rhs, the solution before the clamp, iterations, relative residual.
+namespace {
+struct LastSolve {
+    std::vector<long long> ptr;
+    std::vector<int> col;
+    std::vector<double> val, b, x;
+    int iters = 0;
+    double err = 0.0;
+} g_last;
+void record_solve(const Eigen::SparseMatrix<double>& A, const Eigen::VectorXd& b, const Eigen::VectorXd& x, int iters,
+                  double err) {
+    const long long n = (long long)A.rows();
+    g_last.ptr.assign(1, 0);
+    g_last.col.clear(); g_last.val.clear();
+    for (long long i = 0; i < n; ++i) {
+        for (const auto& e : A.row(i)) { g_last.col.push_back(e.first); g_last.val.push_back(e.second); }
+        g_last.ptr.push_back((long long)g_last.col.size());
+    }
+    g_last.b.assign(b.data(), b.data() + n);
+    g_last.x.assign(x.data(), x.data() + n);
+    g_last.iters = iters;
+    g_last.err = err;
+}
+}  // namespace
+int ref_has_implicit() { return 1; }
+void ref_imp_init(void* h) { Eigen::pd_solve_hook = record_solve; S(h)->imp.init(S(h)->grid, S(h)->cfg); }
+void ref_imp_set_volume_loss(void* h, double vl) { S(h)->imp.set_volume_loss(vl); }
+void ref_imp_assemble(void* h) { S(h)->imp.assemble(S(h)->fields, S(h)->grid, S(h)->cfg); }
+double ref_imp_compute_adaptive_dt(void* h) { return S(h)->imp.compute_adaptive_dt(S(h)->fields, S(h)->grid, S(h)->cfg); }
+int ref_imp_step(void* h, double dt) { return S(h)->imp.step(S(h)->fields, S(h)->grid, S(h)->cfg, dt); }
+int ref_imp_phase_change(void* h) { return S(h)->imp.apply_phase_change(S(h)->fields, S(h)->grid, S(h)->cfg); }
+// out: n, nnz, iterations; err: relative preconditioned residual
+void ref_imp_last_info(long long* out, double* err) {
+    out[0] = (long long)g_last.b.size(); out[1] = (long long)g_last.col.size(); out[2] = g_last.iters;
+    *err = g_last.err;
+}
+void ref_imp_last_system(long long* ptr, int* col, double* val, double* b, double* x) {
+    std::memcpy(ptr, g_last.ptr.data(), sizeof(long long) * g_last.ptr.size());
+    std::memcpy(col, g_last.col.data(), sizeof(int) * g_last.col.size());
+    std::memcpy(val, g_last.val.data(), sizeof(double) * g_last.val.size());
+    std::memcpy(b, g_last.b.data(), sizeof(double) * g_last.b.size());
+    std::memcpy(x, g_last.x.data(), sizeof(double) * g_last.x.size());
+}
+#else
+int ref_has_implicit() { return 0; }
+#endif
+
+// The reference's own VTKWriter::write_vtu (src/vtk_writer.cpp:199-346; AMR clouds, 2D) on the current state.
+void ref_write_vtu(void* h, const char* path) {
+    RefSim* s = S(h);
+    VTKWriter w;
+    w.write_vtu(path, s->grid, s->fields, s->cfg);
 }
 
 // The reference's own main(): whole-run diagnostics.csv for the 1e-6 parity check.

@@ -28,22 +28,39 @@ CONFIG_FIELDS = [
 ]
 
 
-def ref_lib_path(dim: int) -> str:
-    return os.path.join(HERE, "_ref", f"libpdref{dim}d.so")
+def ref_lib_path(dim: int, implicit: bool = False) -> str:
+    """implicit=True: the build that also holds the reference's src/pd_ard_implicit.cpp, compiled against the
+    Eigen work-alike oracle/eigen_min/ (see oracle/ref_shim.cpp)."""
+    return os.path.join(HERE, "_ref", f"libpdref{'imp' if implicit else ''}{dim}d.so")
 
 
-def have_ref(dim: int) -> bool:
-    return os.path.exists(ref_lib_path(dim))
+def have_ref(dim: int, implicit: bool = False) -> bool:
+    return os.path.exists(ref_lib_path(dim, implicit))
 
 
-_LIBS: dict[int, C.CDLL] = {}
+_LIBS: dict[tuple, C.CDLL] = {}
 
 
-def _lib(dim: int) -> C.CDLL:
-    if dim in _LIBS:
-        return _LIBS[dim]
-    lib = C.CDLL(ref_lib_path(dim))
+def _lib(dim: int, implicit: bool = False) -> C.CDLL:
+    if (dim, implicit) in _LIBS:
+        return _LIBS[(dim, implicit)]
+    lib = C.CDLL(ref_lib_path(dim, implicit))
     vp = C.c_void_p
+    if implicit:
+        assert lib.ref_has_implicit() == 1
+        for name in ("ref_imp_init", "ref_imp_assemble"):
+            getattr(lib, name).restype = None
+            getattr(lib, name).argtypes = [vp]
+        lib.ref_imp_set_volume_loss.restype = None
+        lib.ref_imp_set_volume_loss.argtypes = [vp, C.c_double]
+        lib.ref_imp_compute_adaptive_dt.restype = C.c_double
+        lib.ref_imp_compute_adaptive_dt.argtypes = [vp]
+        lib.ref_imp_step.restype = C.c_int
+        lib.ref_imp_step.argtypes = [vp, C.c_double]
+        lib.ref_imp_phase_change.restype = C.c_int
+        lib.ref_imp_phase_change.argtypes = [vp]
+        lib.ref_imp_last_info.argtypes = [C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+        lib.ref_imp_last_system.argtypes = [vp] * 5
     lib.ref_create.restype = vp
     lib.ref_create.argtypes = [C.c_char_p]
     lib.ref_ptr.restype = vp
@@ -81,8 +98,10 @@ def _lib(dim: int) -> C.CDLL:
     lib.ref_write_vti.restype = C.c_double
     lib.ref_main.argtypes = [C.c_char_p]
     lib.ref_main.restype = C.c_int
+    lib.ref_write_vtu.argtypes = [vp, C.c_char_p]
+    lib.ref_write_vtu.restype = None
     lib.ref_set_threads.argtypes = [C.c_int]
-    _LIBS[dim] = lib
+    _LIBS[(dim, implicit)] = lib
     return lib
 
 
@@ -111,9 +130,9 @@ class RefSim:
     """One reference simulation state (Config + Grid + Fields + solvers)."""
 
     def __init__(self, dim: int, base: str | None = "params.cfg", overrides: dict | None = None,
-                 threads: int = 4, build: bool = True, fields: bool = True):
+                 threads: int = 4, build: bool = True, fields: bool = True, implicit: bool = False):
         self.dim = dim
-        self.lib = _lib(dim)
+        self.lib = _lib(dim, implicit)
         self.lib.ref_set_threads(threads)
         ov = {"use_implicit": 0}
         ov.update(overrides or {})
@@ -229,9 +248,34 @@ class RefSim:
         """VTKWriter::write of the current state; returns the seconds it took"""
         return self.lib.ref_write_vti(self.h, path.encode())
 
+    def write_vtu(self, path: str) -> None:
+        """VTKWriter::write_vtu of the current state (AMR clouds)"""
+        self.lib.ref_write_vtu(self.h, path.encode())
+
+    # -- implicit branch (implicit=True builds only) ------------------------------
+    def imp_init(self): self.lib.ref_imp_init(self.h)
+    def imp_set_volume_loss(self, v): self.lib.ref_imp_set_volume_loss(self.h, v)
+    def imp_assemble(self): self.lib.ref_imp_assemble(self.h)
+    def imp_compute_adaptive_dt(self) -> float: return self.lib.ref_imp_compute_adaptive_dt(self.h)
+    def imp_step(self, dt) -> int: return self.lib.ref_imp_step(self.h, dt)
+    def imp_phase_change(self) -> int: return self.lib.ref_imp_phase_change(self.h)
+
+    def imp_last_system(self):
+        """(A as scipy CSR, b, x before the clamp, iterations, relative residual) of the last imp_step:
+        the system the reference's own PD_ARD_ImplicitSolver::step built (src/pd_ard_implicit.cpp:380-409)."""
+        import scipy.sparse as sp
+        info = (C.c_longlong * 3)()
+        err = C.c_double()
+        self.lib.ref_imp_last_info(info, C.byref(err))
+        n, nnz, iters = int(info[0]), int(info[1]), int(info[2])
+        ptr, col = np.zeros(n + 1, np.int64), np.zeros(nnz, np.int32)
+        val, b, x = np.zeros(nnz), np.zeros(n), np.zeros(n)
+        self.lib.ref_imp_last_system(*[a.ctypes.data_as(C.c_void_p) for a in (ptr, col, val, b, x)])
+        return sp.csr_matrix((val, col, ptr), shape=(n, n)), b, x, iters, err.value
+
     def time_ns(self, n, dt) -> float: return self.lib.ref_time_ns_iterate(self.h, n, dt)
     def time_ard(self, n, dt) -> float: return self.lib.ref_time_ard_iterate(self.h, n, dt)
 
 
-def run_reference_main(dim: int, cfg_path: str) -> int:
-    return _lib(dim).ref_main(cfg_path.encode())
+def run_reference_main(dim: int, cfg_path: str, implicit: bool = False) -> int:
+    return _lib(dim, implicit).ref_main(cfg_path.encode())

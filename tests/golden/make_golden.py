@@ -111,7 +111,29 @@ def diagnostics_fixture(case: str = "2d_dissolve") -> None:
     os.unlink(cfg_path)
 
 
+IMPLICIT_RUN = {"use_implicit": 1, "D_grain": 5e-11, "D_gb": 5e-9, "C_thresh": 0.999, "corrosion_steps_per_check": 6,
+                "flow_max_iters": 300, "T_final": 1.2e-3, "implicit_dt_max": 0.004, "implicit_dt_fraction": 0.5,
+                "diagnostic_every": 1, "implicit_output_every": 1000000}
+
+
+def implicit_diagnostics_fixture() -> None:
+    """Whole run of the reference's own main() with use_implicit = 1 (src/coupling.cpp:154-216) on 2D params.cfg with
+    the overrides above (those of tests/test_gpu_implicit.py::test_whole_implicit_coupled_run).  The library is
+    oracle/_ref/libpdrefimp2d.so: the unmodified src/pd_ard_implicit.cpp compiled against the Eigen work-alike
+    oracle/eigen_min/ (the solve meets the reference's 1e-10 tolerance; the rows are printed with 7 digits)."""
+    dim, base, ov = H.CASES["2d_default"]
+    tmp = tempfile.mkdtemp(prefix="pdgold_")
+    cfg_path = refapi.write_cfg(base, dict(ov, **IMPLICIT_RUN, output_dir=os.path.join(tmp, "out")))
+    assert refapi.run_reference_main(dim, cfg_path, implicit=True) == 0
+    shutil.copy(os.path.join(tmp, "out", "diagnostics.csv"), os.path.join(HERE, "diagnostics_2d_implicit.csv"))
+    shutil.rmtree(tmp)
+    os.unlink(cfg_path)
+
+
 if __name__ == "__main__":
+    if "--implicit" in sys.argv:
+        implicit_diagnostics_fixture()
+        sys.exit(0)
     for c in ("2d_default", "2d_poiseuille", "2d_offgrid", "3d_small", "3d_offgrid"):
         step_fixture(c)
     diagnostics_fixture()
