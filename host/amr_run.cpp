@@ -2,7 +2,9 @@
 // src/coupling.cpp:82-302, explicit ARD branch) over the pdamr_* entry points of libpdgpu.so: two-level grid and
 // cell-list neighbours (host code inside the library, bit-identical to the reference), grains on the cloud,
 // initialize_fields, then flow solve + IDW refresh / corrosion cycles / phase change on the device.
-// Writes diagnostics.csv and mass_loss.csv; snapshots of the cloud are VTU files in the reference and are not written.
+// Writes diagnostics.csv, mass_loss.csv and -- like the reference (src/coupling.cpp:117-121,142-147,242-246,292-296) --
+// the state_/flow_/corr_/final_ VTU snapshots of the cloud with simulation.pvd / flow.pvd (host/vtu.cpp: the text of
+// VTKWriter::write_vtu, src/vtk_writer.cpp:199-346); --no-vti switches the snapshots off.
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -11,11 +13,14 @@
 #include <cstdio>
 #include <fstream>
 #include <iomanip>
+#include <sstream>
 #include <string>
 #include <vector>
 
 #include "config.h"
+#include "coupling.h"
 #include "grains.h"
+#include "vtu.h"
 
 #define PDA(call)                                                                         \
     do {                                                                                  \
@@ -25,7 +30,7 @@
         }                                                                                 \
     } while (0)
 
-int run_amr(const HostConfig& cfg, int device) {
+int run_amr(const HostConfig& cfg, int device, bool write_vtu) {
     if (cfg.use_implicit) {
         std::fprintf(stderr, "use_amr = 1: only the explicit ARD branch runs on the AMR cloud (set use_implicit = 0)\n");
         return 1;
@@ -89,6 +94,35 @@ int run_amr(const HostConfig& cfg, int device) {
 
     // CoupledSolver::run, explicit branch
     mkdir(cfg.output_dir.c_str(), 0755);
+    // snapshots: what the VTU writer reads besides the device fields lives on the host (D_map and
+    // grain_id are never read by the solvers); D_map is patched from the node types after every phase change
+    std::vector<double> D_map(N), dx_local(N), pressure(N);
+    std::vector<int> grid_level(N);
+    pdhost_init_dmap(N, type.data(), is_gb.data(), is_precip.data(), cfg.D_liquid, cfg.D_grain, cfg.D_gb, cfg.D_precip,
+                     D_map.data());
+    PDA(pdamr_get(a, "dx_local", dx_local.data())); PDA(pdamr_get(a, "grid_level", grid_level.data()));
+    PvdSeries writer, flow_writer;
+    writer.set_path(cfg.output_dir + "/simulation.pvd");
+    flow_writer.set_path(cfg.output_dir + "/flow.pvd");
+    int frame = 0;
+    auto snapshot = [&](const char* prefix, double t, PvdSeries& series, bool count_frame) -> int {
+        if (!write_vtu) return 0;
+        std::ostringstream ss;                  // make_filename (src/coupling.cpp:10-18) with use_amr = 1
+        ss << cfg.output_dir << "/" << prefix << "_" << std::setw(6) << std::setfill('0') << frame << "_t" << std::fixed
+           << std::setprecision(1) << t << "s.vtu";
+        const std::string fname = ss.str();
+        PDA(pdamr_field_get(a, "vel", vel.data())); PDA(pdamr_field_get(a, "pressure", pressure.data()));
+        PDA(pdamr_field_get(a, "C", C.data())); PDA(pdamr_field_get(a, "phase", phase.data()));
+        PDA(pdamr_field_get(a, "node_type", type.data()));
+        if (pdhost_write_vtu(fname.c_str(), N, pos.data(), type.data(), vel.data(), pressure.data(), C.data(), phase.data(),
+                             grid_level.data(), dx_local.data(), grain_id.data(), D_map.data(), is_gb.data(),
+                             is_precip.data()) != 0)
+            return 2;
+        series.add_timestep(t, fname);
+        if (count_frame) ++frame;
+        return 0;
+    };
+    if (snapshot("state", 0.0, writer, true) != 0) return 2;
     { std::ofstream csv(cfg.output_dir + "/diagnostics.csv", std::ios::trunc);
       csv << "time_s,time_h,pin_mass_loss_pct,solid_nodes,v_max,C_max_fluid\n"; }
     { std::ofstream ml(cfg.output_dir + "/mass_loss.csv", std::ios::trunc); ml << "time_h,pin_mass_loss_pct\n"; }
@@ -134,6 +168,7 @@ int run_amr(const HostConfig& cfg, int device) {
             PDA(pdamr_ns_solve_steady(a, &r, 1));
             PDA(pdamr_update_fictitious(a));        // src/coupling.cpp:139
             need_flow = false;
+            if (snapshot("flow", t_corr, flow_writer, true) != 0) return 2;
         }
         PDA(pdamr_field_get(a, "C", C.data()));
         double vl = 1.0 - solid_sum(C) / (solid0.size() + 1e-30);
@@ -153,7 +188,9 @@ int run_amr(const HostConfig& cfg, int device) {
             }
             PDA(pdamr_ard_iterate(a, done, dtc));
             step += done;
-            if (done == chunk && step % every == 0 && diagnostics(t_corr) != 0) return 2;
+            if (done == chunk && step % every == 0) {       // snapshot, then the diagnostics row (:242-248)
+                if (snapshot("corr", t_corr, writer, true) != 0 || diagnostics(t_corr) != 0) return 2;
+            }
             if (t_corr >= cfg.T_final) break;
         }
         int n = 0;
@@ -165,12 +202,19 @@ int run_amr(const HostConfig& cfg, int device) {
         } else {
             std::printf("  No phase changes this cycle\n");
         }
+        if (n > 0) {                                // apply_phase_change sets D_map = D_liquid (src/pd_ard.cpp:202)
+            std::vector<uint8_t> before = type;
+            PDA(pdamr_field_get(a, "node_type", type.data()));
+            for (int i = 0; i < N; ++i)
+                if (before[i] == PDGPU_SOLID_MG && type[i] == PDGPU_FLUID) D_map[i] = cfg.D_liquid;
+        }
         PDA(pdamr_field_get(a, "node_type", type.data()));
         if (std::count(type.begin(), type.end(), (uint8_t)PDGPU_SOLID_MG) == 0) {
             std::printf("\n=== All solid nodes dissolved at t=%.1f s (%.2f h) ===\n", t_corr, t_corr / 3600.0);
             break;
         }
     }
+    if (snapshot("final", t_corr, writer, false) != 0) return 2;
     std::printf("\n=== Simulation complete ===\n  Final time: %.1f s (%.2f h)\n  [Timer] total_simulation: %.3f s\n", t_corr,
                 t_corr / 3600.0, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     pdamr_destroy(a);

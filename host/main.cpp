@@ -25,7 +25,7 @@
 #include "coupling.h"
 #include "grains.h"
 
-int run_amr(const HostConfig& cfg, int device);   // amr_run.cpp
+int run_amr(const HostConfig& cfg, int device, bool write_vtu);   // amr_run.cpp
 
 #define PD(call)                                                                  \
     do {                                                                          \
@@ -95,7 +95,7 @@ int main(int argc, char** argv) {
             std::fprintf(stderr, "use_amr = 1 runs in 2D on one GPU (like the reference's AMR grid)\n");
             return 1;
         }
-        return run_amr(cfg, device);
+        return run_amr(cfg, device, !no_vti);
     }
     if (cfg.use_implicit && nranks > 1) {
         std::fprintf(stderr, "the implicit branch runs on one GPU only (set use_implicit = 0 for z-slab runs)\n");

@@ -163,6 +163,51 @@ def generate_grains(grid: AmrGrid, seed: int = 42):
     return gid, gb, pr, n.value
 
 
+def _host_lib():
+    from . import grains as _g
+    L = _g._load()
+    if not getattr(L, "_vtu_ready", False):
+        L.pdhost_write_vtu.restype = C.c_int
+        L.pdhost_write_vtu.argtypes = [C.c_char_p, C.c_int] + [C.c_void_p] * 12
+        L.pdhost_init_dmap.restype = None
+        L.pdhost_init_dmap.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                       C.c_double, C.c_void_p]
+        L._vtu_ready = True
+    return L
+
+
+def init_dmap(cfg: Config, node_type, is_gb, is_precip) -> np.ndarray:
+    """Fields::D_map as initialize_fields sets it (src/main.cpp:19-112); host-side, only the writer reads it"""
+    nt, gb, pr = (np.ascontiguousarray(a, np.uint8) for a in (node_type, is_gb, is_precip))
+    out = np.zeros(nt.size)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    _host_lib().pdhost_init_dmap(nt.size, p(nt), p(gb), p(pr), cfg.D_liquid, cfg.D_grain, cfg.D_gb, cfg.D_precip, p(out))
+    return out
+
+
+def write_vtu_arrays(path: str, pos, node_type, vel, pressure, Cc, phase, grid_level, dx_local, grain_id, D_map, is_gb,
+                     is_precip) -> None:
+    """VTKWriter::write_vtu (src/vtk_writer.cpp:199-346) from host arrays: byte-identical text (host/vtu.cpp)"""
+    arrs = [np.ascontiguousarray(pos, np.float64), np.ascontiguousarray(node_type, np.uint8),
+            np.ascontiguousarray(vel, np.float64), np.ascontiguousarray(pressure, np.float64),
+            np.ascontiguousarray(Cc, np.float64), np.ascontiguousarray(phase, np.uint8),
+            None if grid_level is None else np.ascontiguousarray(grid_level, np.int32),
+            None if dx_local is None else np.ascontiguousarray(dx_local, np.float64),
+            np.ascontiguousarray(grain_id, np.int32), np.ascontiguousarray(D_map, np.float64),
+            np.ascontiguousarray(is_gb, np.uint8), None if is_precip is None else np.ascontiguousarray(is_precip, np.uint8)]
+    N = arrs[1].size
+    ptrs = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in arrs]
+    if _host_lib().pdhost_write_vtu(path.encode(), N, *ptrs) != 0:
+        raise OSError(f"cannot write {path}")
+
+
+def write_vtu(path: str, grid: "AmrGrid", grain_id, D_map) -> None:
+    """snapshot of the cloud's current device state"""
+    write_vtu_arrays(path, grid.get("pos"), grid.get_field("node_type"), grid.get_field("vel"), grid.get_field("pressure"),
+                     grid.get_field("C"), grid.get_field("phase"), grid.get("grid_level"), grid.get("dx_local"), grain_id,
+                     D_map, grid.get_field("is_gb"), grid.get_field("is_precip"))
+
+
 def initialize_fields(grid: AmrGrid, is_gb, is_precip) -> None:
     """initialize_fields (src/main.cpp:9-126) on the AMR cloud: Poiseuille profile on FLUID / INLET nodes,
     C = C_solid_init on the wire, FICTITIOUS nodes at rest; new buffers = current buffers."""
@@ -194,12 +239,21 @@ class AmrCoupledSolver:
     """CoupledSolver::run with use_amr = 1, explicit ARD branch (src/coupling.cpp:82-302): flow solve when the
     geometry changed + IDW refresh of the FICTITIOUS nodes (:138-139), corrosion sub-steps with the frozen flow,
     phase change, diagnostics rows (:20-68) every output_every_corr steps.  Returns the rows; writes
-    <output_dir>/diagnostics.csv when `out_dir` is given.  (Snapshots of the cloud are VTU files in the
-    reference -- not written here.)"""
+    <output_dir>/diagnostics.csv when `out_dir` is given, and with `grain_id` (snapshots need the host-side
+    grain ids) the state_/flow_/corr_/final_ VTU series + simulation.pvd / flow.pvd the reference writes
+    (:117-121,142-147,242-246,292-296)."""
 
     def __init__(self, log=None):
         self.log = log or (lambda *a, **k: None)
         self.rows: list[list[float]] = []
+        self.frame_count = 0
+
+    def _snapshot(self, grid, out_dir, prefix, t, series, count=True):
+        fname = f"{out_dir}/{prefix}_{self.frame_count:06d}_t{t:.1f}s.vtu"      # make_filename (:10-18)
+        write_vtu(fname, grid, self._grain_id, self._D_map)
+        series.add_timestep(t, fname)
+        if count:
+            self.frame_count += 1
 
     def _diag(self, grid: AmrGrid, t: float, solid0: np.ndarray) -> None:
         nt = grid.get_field("node_type")
@@ -214,11 +268,22 @@ class AmrCoupledSolver:
         cmax = float(max(Cc[fl].max(), 0.0)) if fl.any() else 0.0
         self.rows.append([t, t / 3600.0, loss, float((nt == 1).sum()), vmax, cmax])
 
-    def run(self, grid: AmrGrid, out_dir: str | None = None) -> list[list[float]]:
+    def run(self, grid: AmrGrid, out_dir: str | None = None, grain_id=None) -> list[list[float]]:
         cfg = grid.cfg
         solid0 = np.nonzero(grid.get_field("node_type") == 1)[0]
         n0 = len(solid0)
         t_corr, need_flow, cycle = 0.0, True, 0
+        snap = out_dir is not None and grain_id is not None
+        if snap:
+            import os
+            from .solver import VTKWriter
+            os.makedirs(out_dir, exist_ok=True)
+            self._grain_id = grain_id
+            self._D_map = init_dmap(cfg, grid.get_field("node_type"), grid.get_field("is_gb"), grid.get_field("is_precip"))
+            writer, flow_writer = VTKWriter(), VTKWriter()
+            writer.set_pvd_path(out_dir + "/simulation.pvd")
+            flow_writer.set_pvd_path(out_dir + "/flow.pvd")
+            self._snapshot(grid, out_dir, "state", 0.0, writer)
         while t_corr < cfg.T_final:
             cycle += 1
             if need_flow:
@@ -226,6 +291,8 @@ class AmrCoupledSolver:
                 grid.update_fictitious()
                 self.log(f"cycle {cycle}: flow solve {r.iters} iterations, eps {r.eps:.3e}")
                 need_flow = False
+                if snap:
+                    self._snapshot(grid, out_dir, "flow", t_corr, flow_writer)
             s = 0.0
             for v in grid.get_field("C")[solid0].tolist():
                 s += v
@@ -245,15 +312,22 @@ class AmrCoupledSolver:
                 grid.ard_iterate(done, dtc)
                 step += done
                 if done == n and step % every == 0:
+                    if snap:
+                        self._snapshot(grid, out_dir, "corr", t_corr, writer)
                     self._diag(grid, t_corr, solid0)
                 if t_corr >= cfg.T_final:
                     break
+            before = grid.get_field("node_type") if snap else None
             n_diss = grid.phase_change()
             if n_diss > 0:
                 need_flow = True
+                if snap:                         # apply_phase_change: D_map = D_liquid (src/pd_ard.cpp:202)
+                    self._D_map[(before == 1) & (grid.get_field("node_type") == 0)] = cfg.D_liquid
             self.log(f"cycle {cycle}: t = {t_corr:.4e} s, {n_diss} nodes dissolved")
             if (grid.get_field("node_type") == 1).sum() == 0:
                 break
+        if snap:
+            self._snapshot(grid, out_dir, "final", t_corr, writer, count=False)
         if out_dir is not None:
             import os
             os.makedirs(out_dir, exist_ok=True)

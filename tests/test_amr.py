@@ -26,6 +26,39 @@ GEOM = ["pos", "node_type", "dx_local", "delta_local", "grid_level", "fict_offse
         "nbr_offset", "nbr_index", "nbr_dist", "nbr_evec", "nbr_vol"]
 
 
+def _vtu_arrays(path):
+    import re
+    out = {}
+    for m in re.finditer(r'<DataArray type="\w+"(?: Name="(\w+)")?[^>]*>\n(.*?)</DataArray>', open(path).read(), re.S):
+        out[m.group(1) or "points"] = np.array(m.group(2).split(), float)
+    return out
+
+
+def assert_same_snapshots(ref_dir, got_dir):
+    """the VTU series + PVD collections of a whole run against the reference's own files: same file names, the
+    initial state byte for byte, integer arrays and geometry exactly, fields to the 6 printed digits"""
+    import glob
+    names = sorted(os.path.basename(f) for f in glob.glob(os.path.join(str(ref_dir), "*.vtu")))
+    assert len(names) >= 4 and names == sorted(os.path.basename(f) for f in glob.glob(os.path.join(str(got_dir), "*.vtu")))
+    first = [n for n in names if n.startswith("state_000000")][0]
+    assert open(os.path.join(str(ref_dir), first), "rb").read() == open(os.path.join(str(got_dir), first), "rb").read()
+    for n in names:
+        a, b = _vtu_arrays(os.path.join(str(ref_dir), n)), _vtu_arrays(os.path.join(str(got_dir), n))
+        assert list(a) == list(b), n
+        for k in a:
+            assert a[k].shape == b[k].shape, (n, k)
+            if k in ("velocity", "pressure", "concentration", "D_map"):
+                assert np.abs(a[k] - b[k]).max() <= 2e-5 * max(np.abs(a[k]).max(), 1e-300), (n, k)
+            else:
+                assert np.array_equal(a[k], b[k]), (n, k)
+    for pvd in ("simulation.pvd", "flow.pvd"):
+        ra, rb = open(os.path.join(str(ref_dir), pvd)).read().split(), open(os.path.join(str(got_dir), pvd)).read().split()
+        assert [t for t in ra if t.startswith("file=")] == [t for t in rb if t.startswith("file=")], pvd
+        ta = np.array([float(t.split('"')[1]) for t in ra if t.startswith("timestep=")])
+        tb = np.array([float(t.split('"')[1]) for t in rb if t.startswith("timestep=")])
+        assert ta.shape == tb.shape and np.allclose(ta, tb, rtol=1e-6, atol=0.0), pvd
+
+
 def both(case, fields=False, extra=None):
     from pd_mg_pin_corrosion_b200.amr import AmrGrid
     base, ov = AMR_CASES[case]
@@ -51,6 +84,104 @@ def test_amr_grid_build_bit_exact(case):
         assert a.shape == b.shape, name
         assert np.array_equal(a, b), (case, name, int((a != b).sum()))
     assert (ref.origin[0], ref.origin[1]) == (i.origin[0], i.origin[1])
+
+
+@needs_ref
+@pytest.mark.parametrize("case", ["amr_default", "amr_offgrid"])
+def test_vtu_writer_bytes_match_reference(case, tmp_path):
+    """host/vtu.cpp (pdhost_write_vtu; the snapshot writer of both AMR drivers) against the reference's own
+    VTKWriter::write_vtu (src/vtk_writer.cpp:199-346) on the same arrays: byte-identical files, including the values
+    safe_val() flushes (NaN, inf, |v| < 1e-300), WALL velocities written as 0, negative zero and OUTSIDE filtering.
+    Also D_map of initialize_fields (pdhost_init_dmap vs src/main.cpp:19-112)."""
+    from pd_mg_pin_corrosion_b200 import amr as A
+    ref, cfg, g = both(case, fields=True)
+    nt = ref.get("node_type")
+    assert np.array_equal(A.init_dmap(cfg, nt, ref.get("is_gb"), ref.get("is_precip")), ref.get("D_map"))
+    rng = np.random.default_rng(11)
+    N = ref.N
+    for name, comps in (("vel", 2), ("pressure", 1), ("C", 1), ("D_map", 1)):
+        a = rng.standard_normal((N, comps) if comps > 1 else N) * 10.0 ** rng.integers(-12, 9, (N, comps) if comps > 1 else N)
+        flat = a.reshape(-1)
+        flat[::17] = 0.0
+        flat[3::101] = -0.0
+        flat[5::103] = np.nan
+        flat[7::107] = np.inf
+        flat[11::109] = -np.inf
+        flat[13::113] = 4.9e-324
+        flat[19::127] = -9.9e-301
+        flat[23::131] = 1e-300
+        flat[29::137] = 123456.5
+        flat[31::139] = 0.0001234565
+        flat[37::149] = 1e22
+        ref.set(name, a)
+    ref.set("phase", rng.integers(0, 2, N).astype(np.uint8))
+    ref.set("grain_id", rng.integers(-1, 500, N).astype(np.int32))
+    want, got = str(tmp_path / "ref.vtu"), str(tmp_path / "got.vtu")
+    ref.write_vtu(want)
+    A.write_vtu_arrays(got, ref.get("pos"), nt, ref.get("vel"), ref.get("pressure"), ref.get("C"), ref.get("phase"),
+                       ref.get("grid_level"), ref.get("dx_local"), ref.get("grain_id"), ref.get("D_map"), ref.get("is_gb"),
+                       ref.get("is_precip"))
+    a, b = open(want, "rb").read(), open(got, "rb").read()
+    assert len(a) > 100000 and a == b
+    ref.close()
+
+
+class _ReferenceBackedCloud:
+    """The AmrGrid surface amr.AmrCoupledSolver drives, served by the compiled reference instead of the device: lets
+    the HOST logic of the coupled loop (cycle structure, batching between diagnostics rows, snapshot schedule, frame
+    numbering, PVD files, D_map patching, CSV formatting) be checked on CPU against the reference's own main()."""
+
+    def __init__(self, ref, cfg):
+        self.ref, self.cfg = ref, cfg
+
+    def get(self, name): return self.ref.get(name)
+    def get_field(self, name): return self.ref.get(name)
+
+    def ns_solve_steady(self):
+        from types import SimpleNamespace
+        return SimpleNamespace(iters=self.ref.ns_solve_steady(), eps=0.0)
+
+    def update_fictitious(self): self.ref.update_fictitious()
+    def ard_set_volume_loss(self, v): self.ref.ard_set_volume_loss(v)
+    def ard_compute_dt(self): return self.ref.ard_compute_dt()
+    def ard_iterate(self, n, dt): self.ref.ard_iterate(n, dt)
+
+    def phase_change(self):
+        n = self.ref.phase_change()
+        if n > 0:                                   # src/coupling.cpp:262-268
+            self.ref.lib.ref_update_node_types(self.ref.h)
+            self.ref.lib.ref_build_neighbors_celllist(self.ref.h)
+        return n
+
+
+@needs_ref
+def test_amr_coupled_loop_host_logic_matches_reference_main(tmp_path):
+    """amr.AmrCoupledSolver.run (the Python driver of the AMR coupled loop) over reference-served operators against
+    the reference's own main() with use_amr = 1: every output file byte for byte -- 20+ VTU snapshots with their frame
+    numbers and times, simulation.pvd, flow.pvd, diagnostics.csv."""
+    import glob
+    from pd_mg_pin_corrosion_b200 import amr as A
+    base, ov = AMR_CASES["amr_ratio2"]
+    ov = dict(ov, use_implicit=0, D_grain=5e-11, D_gb=5e-9, C_thresh=0.999, corrosion_steps_per_check=40,
+              flow_max_iters=120, T_final=3.2e-4, output_every_corr=10)
+    cfg_path = refapi.write_cfg(base, dict(ov, output_dir=str(tmp_path / "ref")), str(tmp_path / "amr.cfg"))
+    refapi._lib(2).ref_set_threads(1)
+    assert refapi.run_reference_main(2, cfg_path) == 0
+    ref = refapi.RefSim(2, base, ov, threads=1, build=True, fields=True)
+    cfg = Config.load(os.path.join(H.CONFIG_DIR, base), ov, quiet=True)
+    cs = A.AmrCoupledSolver()
+    cs.run(_ReferenceBackedCloud(ref, cfg), str(tmp_path / "got"), grain_id=ref.get("grain_id"))
+    names = sorted(os.path.basename(f) for f in glob.glob(str(tmp_path / "ref" / "*")))
+    assert sorted(os.path.basename(f) for f in glob.glob(str(tmp_path / "got" / "*"))) == [n for n in names if n != "mass_loss.csv"]
+    assert sum(n.endswith(".vtu") for n in names) >= 12 and cs.rows[-1][3] < cs.rows[0][3]
+    for n in names:
+        if n == "mass_loss.csv":
+            continue
+        a, b = open(tmp_path / "ref" / n, "rb").read(), open(tmp_path / "got" / n, "rb").read()
+        if n.endswith(".pvd"):                       # the reference stores the path it was given; same relative names
+            a, b = a.replace(str(tmp_path / "ref").encode(), b""), b.replace(str(tmp_path / "got").encode(), b"")
+        assert a == b, n
+    ref.close()
 
 
 @needs_ref
@@ -204,11 +335,11 @@ def test_amr_whole_coupled_run_matches_reference_main(tmp_path):
     cfg = Config.load(os.path.join(H.CONFIG_DIR, base), ov, quiet=True)
     g = A.AmrGrid(cfg)
     g.build_amr(); g.build_neighbors_celllist(); g.device_init(0)
-    _, gb, pr, _ = A.generate_grains(g)                 # standalone: own grains (bit-exact, tested above)
+    gid, gb, pr, _ = A.generate_grains(g)               # standalone: own grains (bit-exact, tested above)
     A.initialize_fields(g, gb, pr)
     for n in ("rho", "vel", "C", "phase", "is_gb", "is_precip"):
         assert np.array_equal(g.get_field(n), ref.get(n)), n        # initialize_fields itself
-    rows = np.array(A.AmrCoupledSolver().run(g, str(tmp_path / "gpu")))
+    rows = np.array(A.AmrCoupledSolver().run(g, str(tmp_path / "gpu"), grain_id=gid))
     assert rows.shape == gold.shape
     assert np.array_equal(rows[:, 3], gold[:, 3])
     for col in (0, 1, 2, 4, 5):
@@ -216,6 +347,7 @@ def test_amr_whole_coupled_run_matches_reference_main(tmp_path):
         assert rel.max() <= 1e-6, (col, float(rel.max()))
     got = np.loadtxt(tmp_path / "gpu" / "diagnostics.csv", delimiter=",", skiprows=1, ndmin=2)
     assert got.shape == gold.shape
+    assert_same_snapshots(tmp_path / "ref", tmp_path / "gpu")          # VTU series + PVD files (src/coupling.cpp:117-296)
     g.close()
 
 
@@ -243,6 +375,7 @@ def test_amr_host_driver_matches_reference_main(tmp_path):
             assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         outs[who] = np.loadtxt(tmp_path / who / "diagnostics.csv", delimiter=",", skiprows=1, ndmin=2)
     gold, got = outs["ref"], outs["gpu"]
+    assert_same_snapshots(tmp_path / "ref", tmp_path / "gpu")
     assert gold.shape == got.shape and gold.shape[0] >= 4
     assert np.array_equal(gold[:, 3], got[:, 3]) and gold[-1, 3] < gold[0, 3]
     for col in (0, 1, 2, 4, 5):

@@ -1,6 +1,7 @@
 """Whole coupled run on the two-level AMR grid (explicit ARD branch), standalone: config -> Grid::build_amr ->
-cell-list neighbours -> grains -> initialize_fields -> CoupledSolver::run; writes <output_dir>/diagnostics.csv.
-usage: python tools/amr_run.py configs/params_amr.cfg [key=value ...]"""
+cell-list neighbours -> grains -> initialize_fields -> CoupledSolver::run; writes <output_dir>/diagnostics.csv and the
+state_/flow_/corr_/final_ VTU series with simulation.pvd / flow.pvd (as the reference does; --no-vti: none).
+usage: python tools/amr_run.py configs/params_amr.cfg [key=value ...] [--no-vti]"""
 import os
 import sys
 import time
@@ -12,7 +13,7 @@ from pd_mg_pin_corrosion_b200.config import Config       # noqa: E402
 
 path = sys.argv[1]
 ov = {"use_implicit": 0}
-for kv in sys.argv[2:]:
+for kv in [a for a in sys.argv[2:] if a != "--no-vti"]:
     k, v = kv.split("=", 1)
     ov[k] = type(getattr(Config(), k))(float(v)) if not isinstance(getattr(Config(), k), str) else v
 cfg = Config.load(path, ov, quiet=False)
@@ -26,5 +27,5 @@ gid, gb, pr, n = A.generate_grains(g)
 print(f"Grain generation: {n} grains, {int(gb.sum())} boundary nodes, {int(pr.sum())} precipitate nodes")
 g.device_init(0)
 A.initialize_fields(g, gb, pr)
-rows = A.AmrCoupledSolver(log=print).run(g, cfg.output_dir)
+rows = A.AmrCoupledSolver(log=print).run(g, cfg.output_dir, grain_id=None if "--no-vti" in sys.argv else gid)   # VTU series + PVD
 print(f"{len(rows)} diagnostics rows -> {os.path.join(cfg.output_dir, 'diagnostics.csv')}; total {time.perf_counter() - t0:.2f} s")
