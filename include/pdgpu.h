@@ -292,7 +292,8 @@ int pdamr_device_init(pdamr_ctx* ctx, int device);   /* uploads the tables, allo
 int pdamr_field_set(pdamr_ctx* ctx, const char* name, const void* src);
 int pdamr_field_get(pdamr_ctx* ctx, const char* name, void* dst);
 int pdamr_update_fictitious(pdamr_ctx* ctx);     /* Grid::update_fictitious: IDW of C, rho, pressure, vel */
-int pdamr_bc(pdamr_ctx* ctx, int which);         /* 0 inlet, 1 outlet, 2 wall, 3 solid, 4 wall conc., 5 wall (new buffers) */
+int pdamr_bc(pdamr_ctx* ctx, int which);         /* 0 inlet, 1 outlet, 2 wall, 3 solid, 4 wall conc., 5 wall (new buffers),
+                                                    6 smooth_boundary_concentration (src/boundary.cpp:332-376) */
 int pdamr_ns_compute_dt(pdamr_ctx* ctx, double* dt);
 int pdamr_ns_step(pdamr_ctx* ctx, double dt);    /* compute_pressure + step -> new buffers (no swap) */
 int pdamr_ns_iterate(pdamr_ctx* ctx, int iters, double dt);   /* loop bodies of solve_steady incl. the IDW update */
@@ -302,6 +303,16 @@ int pdamr_ard_compute_dt(pdamr_ctx* ctx, double* dt);
 int pdamr_ard_step(pdamr_ctx* ctx, double dt);
 int pdamr_ard_iterate(pdamr_ctx* ctx, int steps, double dt);
 int pdamr_phase_change(pdamr_ctx* ctx, int* n_dissolved);
+/* implicit ARD branch on the cloud: PD_ARD_ImplicitSolver with use_amr (src/pd_ard_implicit.cpp:22-38 per-node
+ * constants, :104-346 assemble, :371-429 step, :438-487 compute_adaptive_dt, :500-531 apply_fictitious_coupling).
+ * Vectors of matvec / rhs have one entry per node of the cloud (0 on nodes that are not FLUID / SOLID_MG /
+ * FICTITIOUS).  precond: 0 none, 1 axial sweep.  set the volume loss with pdamr_ard_set_volume_loss. */
+int pdamr_implicit_assemble(pdamr_ctx* ctx);
+int pdamr_implicit_matvec(pdamr_ctx* ctx, double dt, const double* x, double* y);
+int pdamr_implicit_rhs(pdamr_ctx* ctx, double dt, double* b);
+int pdamr_implicit_compute_dt(pdamr_ctx* ctx, double dt_fraction, double dt_max, double* dt);
+int pdamr_implicit_step(pdamr_ctx* ctx, double dt, double tol, int restart, int max_iters, int precond,
+                        PdLinSolveInfo* info);
 int pdamr_destroy(pdamr_ctx* ctx);
 
 /* ---- instrumentation --------------------------------------------------------------------- */

@@ -121,6 +121,38 @@ class AmrGrid:
         _l.check(_l.load().pdamr_phase_change(self.ctx, C.byref(n)))
         return n.value
 
+    # ---- implicit branch (PD_ARD_ImplicitSolver with use_amr, src/pd_ard_implicit.cpp) ----------
+    def smooth_conc(self): _l.check(_l.load().pdamr_bc(self.ctx, 6))
+
+    def implicit_assemble(self) -> None:
+        _l.check(_l.load().pdamr_implicit_assemble(self.ctx))
+
+    def implicit_matvec(self, dt: float, x) -> np.ndarray:
+        """y = (I - dt M) x with the fictitious-node coupling rows; one entry per node"""
+        x = np.ascontiguousarray(x, np.float64)
+        assert x.size == self.N_total
+        y = np.zeros(self.N_total)
+        _l.check(_l.load().pdamr_implicit_matvec(self.ctx, dt, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p)))
+        return y
+
+    def implicit_rhs(self, dt: float) -> np.ndarray:
+        b = np.zeros(self.N_total)
+        _l.check(_l.load().pdamr_implicit_rhs(self.ctx, dt, b.ctypes.data_as(C.c_void_p)))
+        return b
+
+    def implicit_compute_dt(self, dt_fraction: float | None = None, dt_max: float | None = None) -> float:
+        dt = C.c_double()
+        _l.check(_l.load().pdamr_implicit_compute_dt(
+            self.ctx, self.cfg.implicit_dt_fraction if dt_fraction is None else dt_fraction,
+            self.cfg.implicit_dt_max if dt_max is None else dt_max, C.byref(dt)))
+        return dt.value
+
+    def implicit_step(self, dt: float, tol: float = 1e-10, restart: int = 50, max_iters: int = 200, precond: int = 1):
+        """one backward-Euler step on the current C buffer; returns PdLinSolveInfo (iters, converged, rel_res)"""
+        info = _l.PdLinSolveInfo()
+        _l.check(_l.load().pdamr_implicit_step(self.ctx, dt, tol, restart, max_iters, precond, C.byref(info)))
+        return info
+
     def close(self) -> None:
         if self.ctx:
             _l.load().pdamr_destroy(self.ctx)
@@ -236,7 +268,7 @@ def initialize_fields(grid: AmrGrid, is_gb, is_precip) -> None:
 
 
 class AmrCoupledSolver:
-    """CoupledSolver::run with use_amr = 1, explicit ARD branch (src/coupling.cpp:82-302): flow solve when the
+    """CoupledSolver::run with use_amr = 1, explicit or implicit ARD branch (src/coupling.cpp:82-302): flow solve when the
     geometry changed + IDW refresh of the FICTITIOUS nodes (:138-139), corrosion sub-steps with the frozen flow,
     phase change, diagnostics rows (:20-68) every output_every_corr steps.  Returns the rows; writes
     <output_dir>/diagnostics.csv when `out_dir` is given, and with `grain_id` (snapshots need the host-side
@@ -247,6 +279,9 @@ class AmrCoupledSolver:
         self.log = log or (lambda *a, **k: None)
         self.rows: list[list[float]] = []
         self.frame_count = 0
+        self.total_implicit_steps = 0
+        self.tol, self.restart, self.max_iters = 1e-10, 50, 200      # src/pd_ard_implicit.cpp:400-402
+        self.last = None
 
     def _snapshot(self, grid, out_dir, prefix, t, series, count=True):
         fname = f"{out_dir}/{prefix}_{self.frame_count:06d}_t{t:.1f}s.vtu"      # make_filename (:10-18)
@@ -297,10 +332,29 @@ class AmrCoupledSolver:
             for v in grid.get_field("C")[solid0].tolist():
                 s += v
             grid.ard_set_volume_loss(max(1.0 - s / (n0 + 1e-30), 0.0))
-            dtc = grid.ard_compute_dt()
+            if cfg.use_implicit:                 # src/coupling.cpp:154-216
+                grid.implicit_assemble()
+                step, dissolved = 0, False
+                while step < cfg.corrosion_steps_per_check and t_corr < cfg.T_final and not dissolved:
+                    dt_impl = grid.implicit_compute_dt()
+                    grid.inlet_bc(); grid.outlet_bc(); grid.wall_conc_bc()
+                    self.last = grid.implicit_step(dt_impl, tol=self.tol, restart=self.restart, max_iters=self.max_iters)
+                    grid.smooth_conc()
+                    grid.update_fictitious()
+                    t_corr += dt_impl
+                    step += 1
+                    self.total_implicit_steps += 1
+                    if self.total_implicit_steps % int(cfg.diagnostic_every) == 0:
+                        self._diag(grid, t_corr, solid0)
+                    if snap and self.total_implicit_steps % int(cfg.implicit_output_every) == 0:
+                        self._snapshot(grid, out_dir, "corr", t_corr, writer)
+                    dissolved = bool(((grid.get_field("node_type") == 1) & (grid.get_field("C") < cfg.C_thresh)).any())
+                self.log(f"cycle {cycle}: {step} implicit steps to t = {t_corr:.4e} s; last solve {self.last.iters} "
+                         f"iterations, |res| = {self.last.rel_res:.2e}")
+            dtc = 0.0 if cfg.use_implicit else grid.ard_compute_dt()
             step = 0
             every = int(cfg.output_every_corr)
-            while step < cfg.corrosion_steps_per_check:
+            while not cfg.use_implicit and step < cfg.corrosion_steps_per_check:
                 # device-resident batches between two diagnostics rows
                 n = min(every - step % every, cfg.corrosion_steps_per_check - step)
                 done = 0

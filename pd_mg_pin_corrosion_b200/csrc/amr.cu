@@ -34,7 +34,9 @@ constexpr uint8_t T_FLUID = 0, T_SOLID = 1, T_WALL = 2, T_INLET = 3, T_OUTLET = 
 constexpr double kPi = 3.14159265358979323846;
 }   // namespace
 
+struct AmrImplicit;                     // implicit branch on the cloud: amr_implicit.cuh, included at the end of this file
 struct pdamr_ctx {
+    AmrImplicit* imp = nullptr;
     PdConfig cfg;
     int ratio = 3;
     double buffer = 0.0, dx_c = 0.0, delta_c = 0.0;
@@ -823,10 +825,15 @@ extern "C" int pdamr_device_init(pdamr_ctx* c, int device) {
     return 0;
 }
 
+static void amr_implicit_free(pdamr_ctx* c);
+static void amr_implicit_invalidate(pdamr_ctx* c);
+static int amr_smooth_conc(pdamr_ctx* c);
+
 extern "C" int pdamr_destroy(pdamr_ctx* c) {
     if (!c) return 0;
     if (c->dev) {
         cudaSetDevice(c->device);
+        amr_implicit_free(c);
         for (void* q : {(void*)c->d_type, (void*)c->d_phase, (void*)c->d_gb, (void*)c->d_precip, (void*)c->d_salt,
                         (void*)c->d_off, (void*)c->d_idx, (void*)c->d_foff, (void*)c->d_fsrc, (void*)c->d_mirror,
                         (void*)c->d_out_nodes, (void*)c->d_out_level_off, (void*)c->d_int, (void*)c->d_out_list,
@@ -922,11 +929,13 @@ static int enqueue_bc(pdamr_ctx* c, int which, int buf) {   // 0 inlet, 1 outlet
     }
     return 0;
 }
-// which: 0 inlet, 1 outlet, 2 wall (current buffers), 3 solid surface, 4 wall concentration, 5 wall (new buffers)
+// which: 0 inlet, 1 outlet, 2 wall (current buffers), 3 solid surface, 4 wall concentration, 5 wall (new buffers),
+// 6 smooth_boundary_concentration (implicit branch)
 extern "C" int pdamr_bc(pdamr_ctx* c, int which) {
     AMR_DEV(c);
-    if (which < 0 || which > 5) PD_FAIL("pdamr_bc: which must be 0..5");
-    PD_TRY(enqueue_bc(c, which == 5 ? 2 : which, which == 5 ? 1 - c->cur : c->cur));
+    if (which < 0 || which > 6) PD_FAIL("pdamr_bc: which must be 0..6");
+    if (which == 6) PD_TRY(amr_smooth_conc(c));
+    else PD_TRY(enqueue_bc(c, which == 5 ? 2 : which, which == 5 ? 1 - c->cur : c->cur));
     CUDA_OK(cudaStreamSynchronize(c->stream));
     CUDA_OK(cudaGetLastError());
     return 0;
@@ -1110,7 +1119,10 @@ extern "C" int pdamr_phase_change(pdamr_ctx* c, int* n_dissolved) {
         CUDA_OK(cudaMemcpy(c->type.data(), c->d_type, c->type.size(), cudaMemcpyDeviceToHost));
         amr_tables(c);
         PD_TRY(upload_tables(c));
+        amr_implicit_invalidate(c);
     }
     if (n_dissolved) *n_dissolved = n;
     return 0;
 }
+
+#include "amr_implicit.cuh"

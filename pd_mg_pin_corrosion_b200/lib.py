@@ -135,6 +135,9 @@ def load() -> C.CDLL:
         "pdamr_ard_set_volume_loss": [vp, C.c_double], "pdamr_ard_compute_dt": [vp, dp],
         "pdamr_ard_step": [vp, C.c_double], "pdamr_ard_iterate": [vp, C.c_int, C.c_double],
         "pdamr_phase_change": [vp, ip], "pdamr_destroy": [vp],
+        "pdamr_implicit_assemble": [vp], "pdamr_implicit_matvec": [vp, C.c_double, vp, vp],
+        "pdamr_implicit_rhs": [vp, C.c_double, vp], "pdamr_implicit_compute_dt": [vp, C.c_double, C.c_double, dp],
+        "pdamr_implicit_step": [vp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(PdLinSolveInfo)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
