@@ -1,7 +1,8 @@
 // host/amr_run.cpp -- the reference's main() + CoupledSolver::run with use_amr = 1 (src/main.cpp:151-174,
 // src/coupling.cpp:82-302, explicit ARD branch) over the pdamr_* entry points of libpdgpu.so: two-level grid and
 // cell-list neighbours (host code inside the library, bit-identical to the reference), grains on the cloud,
-// initialize_fields, then flow solve + IDW refresh / corrosion cycles / phase change on the device.
+// initialize_fields, then flow solve + IDW refresh / corrosion cycles (explicit, or implicit with use_implicit = 1:
+// src/coupling.cpp:154-216 over pdamr_implicit_*) / phase change on the device.
 // Writes diagnostics.csv, mass_loss.csv and -- like the reference (src/coupling.cpp:117-121,142-147,242-246,292-296) --
 // the state_/flow_/corr_/final_ VTU snapshots of the cloud with simulation.pvd / flow.pvd (host/vtu.cpp: the text of
 // VTKWriter::write_vtu, src/vtk_writer.cpp:199-346); --no-vti switches the snapshots off.
@@ -31,10 +32,6 @@
     } while (0)
 
 int run_amr(const HostConfig& cfg, int device, bool write_vtu) {
-    if (cfg.use_implicit) {
-        std::fprintf(stderr, "use_amr = 1: only the explicit ARD branch runs on the AMR cloud (set use_implicit = 0)\n");
-        return 1;
-    }
     auto t0 = std::chrono::steady_clock::now();
     PdConfig pod = cfg.to_pod();
     pdamr_ctx* a = nullptr;
@@ -129,7 +126,7 @@ int run_amr(const HostConfig& cfg, int device, bool write_vtu) {
     std::vector<int> solid0;
     for (int i = 0; i < N; ++i)
         if (type[i] == PDGPU_SOLID_MG) solid0.push_back(i);
-    std::printf("Initial solid nodes: %d\nUsing EXPLICIT ARD solver\n", (int)solid0.size());
+    std::printf("Initial solid nodes: %d\nUsing %s ARD solver\n", (int)solid0.size(), cfg.use_implicit ? "IMPLICIT" : "EXPLICIT");
     auto solid_sum = [&](const std::vector<double>& Cc) {
         double s = 0.0;
         for (int i : solid0) s += Cc[i];            // ordered sum (src/coupling.cpp:32-38)
@@ -158,7 +155,7 @@ int run_amr(const HostConfig& cfg, int device, bool write_vtu) {
         return 0;
     };
     double t_corr = 0.0;
-    int cycle = 0, total_dissolved = 0;
+    int cycle = 0, total_dissolved = 0, total_implicit_steps = 0;
     bool need_flow = true;
     while (t_corr < cfg.T_final) {
         ++cycle;
@@ -173,11 +170,38 @@ int run_amr(const HostConfig& cfg, int device, bool write_vtu) {
         PDA(pdamr_field_get(a, "C", C.data()));
         double vl = 1.0 - solid_sum(C) / (solid0.size() + 1e-30);
         PDA(pdamr_ard_set_volume_loss(a, vl < 0.0 ? 0.0 : vl));
+        if (cfg.use_implicit) {                         // src/coupling.cpp:154-216 on the cloud (pdamr_implicit_*)
+            PDA(pdamr_implicit_assemble(a));
+            int implicit_step = 0;
+            bool dissolved = false;
+            const double t_start = t_corr;
+            while (implicit_step < cfg.corrosion_steps_per_check && t_corr < cfg.T_final && !dissolved) {
+                double dt_impl = 0.0;
+                PDA(pdamr_implicit_compute_dt(a, cfg.implicit_dt_fraction, cfg.implicit_dt_max, &dt_impl));
+                PDA(pdamr_bc(a, 0)); PDA(pdamr_bc(a, 1)); PDA(pdamr_bc(a, 4));
+                PdLinSolveInfo info;
+                // true relative residual 1e-12 (the reference: 1e-10 on its preconditioned residual), axial-sweep GMRES(50)
+                PDA(pdamr_implicit_step(a, dt_impl, 1e-12, 50, 2000, 1, &info));
+                std::printf("    Linear solve: GMRES %d iters, |res|=%.2e\n", info.iters, info.rel_res);
+                PDA(pdamr_bc(a, 6));                    // smooth_boundary_concentration
+                PDA(pdamr_update_fictitious(a));
+                t_corr += dt_impl;
+                ++implicit_step;
+                ++total_implicit_steps;
+                if (total_implicit_steps % cfg.diagnostic_every == 0 && diagnostics(t_corr) != 0) return 2;
+                if (total_implicit_steps % cfg.implicit_output_every == 0 && snapshot("corr", t_corr, writer, true) != 0) return 2;
+                PDA(pdamr_field_get(a, "C", C.data())); PDA(pdamr_field_get(a, "node_type", type.data()));
+                for (int i = 0; i < N && !dissolved; ++i) dissolved = type[i] == PDGPU_SOLID_MG && C[i] < cfg.C_thresh;
+            }
+            std::printf("  Implicit cycle: %d steps, t=%.2f to %.2f s (%.4f h)\n", implicit_step, t_start, t_corr, t_corr / 3600.0);
+        }
         double dtc = 0.0;
-        PDA(pdamr_ard_compute_dt(a, &dtc));
-        std::printf("  Corrosion dt = %.4e s\n", dtc);
+        if (!cfg.use_implicit) {
+            PDA(pdamr_ard_compute_dt(a, &dtc));
+            std::printf("  Corrosion dt = %.4e s\n", dtc);
+        }
         int step = 0;
-        const int n_steps = cfg.corrosion_steps_per_check, every = cfg.output_every_corr;
+        const int n_steps = cfg.use_implicit ? 0 : cfg.corrosion_steps_per_check, every = cfg.output_every_corr;
         while (step < n_steps) {
             const int chunk = std::min(n_steps - step, every - step % every);
             int done = 0;

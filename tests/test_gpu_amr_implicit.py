@@ -132,3 +132,32 @@ def test_amr_implicit_whole_run_matches_reference_main(tmp_path):
         assert rel.max() <= 1e-6, (col, float(rel.max()))
     assert_same_snapshots(tmp_path / "ref", tmp_path / "gpu")
     g.close()
+
+
+def test_amr_implicit_host_driver_matches_reference_main(tmp_path):
+    """host/pd_corrosion_gpu with use_amr = 1 and use_implicit = 1 (host/amr_run.cpp over pdamr_implicit_*) against the
+    reference's own main(): diagnostics rows within 1e-6, identical solid counts, same VTU series."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "host", "pd_corrosion_gpu")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "host")])
+    base, ov = AMR_CASES["amr_default"]
+    outs = {}
+    for who in ("ref", "gpu"):
+        o = dict(ov, **dict(IMPLICIT_AMR_RUN, T_final=6e-4), output_dir=str(tmp_path / who))
+        cfg_path = refapi.write_cfg(base, o, str(tmp_path / f"{who}.cfg"))
+        if who == "ref":
+            refapi._lib(2, True).ref_set_threads(1)
+            assert refapi.run_reference_main(2, cfg_path, implicit=True) == 0
+        else:
+            r = subprocess.run([exe, cfg_path, "--dim", "2"], capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs[who] = np.loadtxt(tmp_path / who / "diagnostics.csv", delimiter=",", skiprows=1, ndmin=2)
+    gold, got = outs["ref"], outs["gpu"]
+    assert gold.shape == got.shape and gold.shape[0] >= 4
+    assert np.array_equal(gold[:, 3], got[:, 3]) and gold[-1, 3] < gold[0, 3]
+    for col in (0, 1, 2, 4, 5):
+        rel = np.abs(got[:, col] - gold[:, col]) / np.maximum(np.abs(gold[:, col]), 1e-300)
+        assert rel.max() <= 1e-6, (col, float(rel.max()))
+    assert_same_snapshots(tmp_path / "ref", tmp_path / "gpu")
