@@ -160,7 +160,7 @@ class Config:
 
     def check_supported(self) -> None:
         if self.use_amr:
-            raise ValueError("use_amr = 1: the two-level AMR cloud is built by amr.AmrGrid (2D, explicit branch), "
+            raise ValueError("use_amr = 1: the two-level AMR cloud is built by amr.AmrGrid (2D; explicit and implicit branch), "
                              "not by the uniform-lattice Grid")
 
     def describe(self, dim: int) -> str:
