@@ -59,7 +59,7 @@ class PdGpuError(RuntimeError):
 def declared_symbols(header: str = HEADER_PATH) -> list[str]:
     """Every function include/pdgpu.h declares (used by the CPU-side export test)."""
     text = open(header).read()
-    return sorted(set(re.findall(r"\b(pdgpu_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(pd(?:gpu|amr)_[a-z0-9_]+)\s*\(", text)))
 
 
 _lib = None

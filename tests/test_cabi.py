@@ -18,6 +18,21 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert L.pdgpu_version() == 100
+    assert sum(n.startswith("pdamr_") for n in names) >= 24          # the AMR context incl. pdamr_implicit_*
+
+
+def test_host_library_exports_declared_symbols():
+    """libpdhost.so (host/): every extern "C" function host/grains.h and host/vtu.h declare"""
+    import os
+    import re
+    from pd_mg_pin_corrosion_b200 import grains as G
+    H_ = G._load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set(re.findall(r'extern "C" \w+ (pdhost_[a-z0-9_]+)\s*\(', open(os.path.join(root, "host", "grains.h")).read()))
+    names |= set(re.findall(r"\b(pdhost_[a-z0-9_]+)\s*\(", open(os.path.join(root, "host", "vtu.h")).read()))
+    assert {"pdhost_generate_grains", "pdhost_generate_grains_cloud", "pdhost_write_vtu", "pdhost_init_dmap"} <= names
+    missing = [n for n in sorted(names) if not hasattr(H_, n)]
+    assert not missing, missing
 
 
 def test_struct_layout_matches_header():
