@@ -214,9 +214,9 @@ def test_amr_implicit_coupled_loop_host_logic_matches_reference_main(tmp_path):
     import glob
     from pd_mg_pin_corrosion_b200 import amr as A
     base, ov = AMR_CASES["amr_ratio2"]
-    ov = dict(ov, **IMPLICIT_AMR_RUN)
+    ov = dict(ov, **dict(IMPLICIT_AMR_RUN, T_final=4.5e-4))
     cfg_path = refapi.write_cfg(base, dict(ov, output_dir=str(tmp_path / "ref")), str(tmp_path / "amr.cfg"))
-    refapi._lib(2, True).ref_set_threads(1)
+    refapi._lib(2, True).ref_set_threads(1)          # one thread: the reference's in-place smoother is order dependent
     assert refapi.run_reference_main(2, cfg_path, implicit=True) == 0
     ref = refapi.RefSim(2, base, ov, threads=1, build=True, fields=True, implicit=True)
     cfg = Config.load(os.path.join(H.CONFIG_DIR, base), ov, quiet=True)
