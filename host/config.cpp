@@ -107,3 +107,18 @@ PdConfig HostConfig::to_pod() const {
     p.channel_flow_corrections = channel_flow_corrections; p.use_implicit = use_implicit;
     return p;
 }
+
+extern "C" int pdhost_load_config(const char* path, PdConfig* pod, double* host_members, char* output_dir, int output_dir_len) {
+    if (!path || !pod || !host_members) return 1;
+    HostConfig c;
+    c.load(path);
+    *pod = c.to_pod();
+    const double v[14] = {c.implicit_dt_fraction, c.implicit_dt_max, (double)c.implicit_output_every, (double)c.diagnostic_every,
+                          c.newton_tol, (double)c.newton_max_iter, (double)c.use_amr, (double)c.amr_ratio, c.amr_buffer,
+                          c.precip_fraction, c.grain_size_mean, (double)c.gb_width_cells, (double)c.precip_cluster_cells, c.C_sat};
+    for (int i = 0; i < 14; ++i) host_members[i] = v[i];
+    if (output_dir && output_dir_len > 0) {
+        std::snprintf(output_dir, (size_t)output_dir_len, "%s", c.output_dir.c_str());
+    }
+    return 0;
+}

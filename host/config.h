@@ -25,7 +25,7 @@ struct HostConfig {
     int flow_max_iters = 50000; double flow_conv_tol = 5.0e-6, T_final = 32400.0;
     int corrosion_steps_per_check = 200, output_every_flow = 2000, output_every_corr = 100;
     std::string output_dir = "output";
-    // parsed for file compatibility; the implicit and AMR branches are out of scope
+    // implicit branch (lattice: pdgpu_implicit_*, cloud: pdamr_implicit_*) and two-level AMR grid (pdamr_*)
     int use_implicit = 1; double implicit_dt_fraction = 0.5, implicit_dt_max = 60.0;
     int implicit_output_every = 10, diagnostic_every = 1; double newton_tol = 1.0e-8; int newton_max_iter = 20;
     int channel_flow_corrections = 0, use_amr = 0, amr_ratio = 3; double amr_buffer = 50.0e-6;
@@ -38,3 +38,9 @@ struct HostConfig {
     void print(int dim) const;
     PdConfig to_pod() const;
 };
+
+// C view for the parity tests: load `path` like the driver does and return the PdConfig that crosses the C ABI plus
+// the members that stay on the host, in the order implicit_dt_fraction, implicit_dt_max, implicit_output_every,
+// diagnostic_every, newton_tol, newton_max_iter, use_amr, amr_ratio, amr_buffer, precip_fraction, grain_size_mean,
+// gb_width_cells, precip_cluster_cells, C_sat (14 doubles).
+extern "C" int pdhost_load_config(const char* path, PdConfig* pod, double* host_members, char* output_dir, int output_dir_len);

@@ -107,6 +107,15 @@ void ref_get_config(void* h, double* out) {
     std::memcpy(out, v, sizeof(v));
 }
 int ref_config_len() { return 39; }
+// the remaining numeric members (implicit branch, AMR, their derived values) + rho_m
+void ref_get_config_extra(void* h, double* out) {
+    const Config& c = S(h)->cfg;
+    double v[] = {c.implicit_dt_fraction, c.implicit_dt_max, (double)c.implicit_output_every, (double)c.diagnostic_every,
+                  c.newton_tol, (double)c.newton_max_iter, (double)c.use_amr, (double)c.amr_ratio, c.amr_buffer,
+                  c.dx_coarse, c.delta_coarse, c.rho_m};
+    std::memcpy(out, v, sizeof(v));
+}
+const char* ref_config_output_dir(void* h) { return S(h)->cfg.output_dir.c_str(); }
 
 void ref_grid_build(void* h) { S(h)->grid.build(S(h)->cfg); }
 // two-level AMR grid (src/grid.cpp:352-842): what main() calls with use_amr = 1 (src/main.cpp:151-154)

@@ -28,6 +28,29 @@ CONFIG_FIELDS = [
 ]
 
 
+CONFIG_EXTRA_FIELDS = ["implicit_dt_fraction", "implicit_dt_max", "implicit_output_every", "diagnostic_every", "newton_tol",
+                       "newton_max_iter", "use_amr", "amr_ratio", "amr_buffer", "dx_coarse", "delta_coarse", "rho_m"]
+
+
+def parse_config_with_reference(dim: int, path: str) -> dict:
+    """Config::load + compute_derived of the reference on the file as it stands (no overrides appended): every
+    numeric member and output_dir."""
+    lib = _lib(dim)
+    lib.ref_get_config_extra.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.ref_config_output_dir.argtypes = [C.c_void_p]
+    lib.ref_config_output_dir.restype = C.c_char_p
+    h = C.c_void_p(lib.ref_create(path.encode()))
+    a = (C.c_double * len(CONFIG_FIELDS))()
+    b = (C.c_double * len(CONFIG_EXTRA_FIELDS))()
+    lib.ref_get_config(h, a)
+    lib.ref_get_config_extra(h, b)
+    out = dict(zip(CONFIG_FIELDS, list(a)))
+    out.update(zip(CONFIG_EXTRA_FIELDS, list(b)))
+    out["output_dir"] = lib.ref_config_output_dir(h).decode()
+    lib.ref_destroy(h)
+    return out
+
+
 def ref_lib_path(dim: int, implicit: bool = False) -> str:
     """implicit=True: the build that also holds the reference's src/pd_ard_implicit.cpp, compiled against the
     Eigen work-alike oracle/eigen_min/ (see oracle/ref_shim.cpp)."""

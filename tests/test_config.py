@@ -59,3 +59,50 @@ def test_matches_reference_parser(case):
     r = refapi.RefSim(dim, base, ov, build=False)
     for k, v in r.cfg.items():
         assert getattr(cfg, k) == v, k
+
+
+SHIPPED = ["params.cfg", "params_amr.cfg", "params_amr_r2.cfg", "params_calibration.cfg", "params_calibration_v2.cfg",
+           "params_diagnostic.cfg", "params_fine.cfg", "params_fine_calibration.cfg", "params_implicit_test.cfg",
+           "params_poiseuille.cfg", "params_transport_viz.cfg"]
+
+
+@pytest.mark.skipif(not refapi.have_ref(2), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", SHIPPED)
+def test_every_shipped_config_parses_like_the_reference(name):
+    """configs/<name> (the parameter values of every configuration file the reference ships) through the Python
+    mirror against the reference's own Config::load + compute_derived on the same file: every numeric member incl. the
+    implicit / AMR keys and the derived values; and, where the reference tree is present, configs/<name> against the
+    reference's own config/<name>."""
+    path = os.path.join(H.CONFIG_DIR, name)
+    want = refapi.parse_config_with_reference(2, path)
+    cfg = Config.load(path, quiet=True)
+    for k, v in want.items():
+        assert getattr(cfg, k) == v, (name, k, getattr(cfg, k), v)
+    theirs = os.path.join("/root/reference/config", name)
+    if os.path.exists(theirs):
+        assert refapi.parse_config_with_reference(2, theirs) == want, name
+
+
+@pytest.mark.skipif(not refapi.have_ref(2), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", SHIPPED)
+def test_cpp_driver_parser_matches_the_reference(name):
+    """host/config.cpp (what host/pd_corrosion_gpu reads its configuration with) against the reference's Config::load
+    on every shipped configuration: the PdConfig that crosses the C ABI and the members that stay on the host."""
+    import ctypes as C
+    from pd_mg_pin_corrosion_b200 import grains as G
+    L = G._load()
+    L.pdhost_load_config.restype = C.c_int
+    L.pdhost_load_config.argtypes = [C.c_char_p, C.POINTER(PdConfig), C.POINTER(C.c_double), C.c_char_p, C.c_int]
+    path = os.path.join(H.CONFIG_DIR, name)
+    pod, extra, out = PdConfig(), (C.c_double * 14)(), C.create_string_buffer(512)
+    assert L.pdhost_load_config(path.encode(), C.byref(pod), extra, out, 512) == 0
+    want = refapi.parse_config_with_reference(2, path)
+    for k, _ in PdConfig._fields_:
+        if k != "reserved":
+            assert getattr(pod, k) == want[k], (name, k)
+    host_members = ["implicit_dt_fraction", "implicit_dt_max", "implicit_output_every", "diagnostic_every", "newton_tol",
+                    "newton_max_iter", "use_amr", "amr_ratio", "amr_buffer", "precip_fraction", "grain_size_mean",
+                    "gb_width_cells", "precip_cluster_cells", "C_sat"]
+    for k, v in zip(host_members, list(extra)):
+        assert v == want[k], (name, k)
+    assert out.value.decode() == want["output_dir"]
