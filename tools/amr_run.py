@@ -1,4 +1,4 @@
-"""Whole coupled run on the two-level AMR grid (explicit ARD branch), standalone: config -> Grid::build_amr ->
+"""Whole coupled run on the two-level AMR grid (explicit or implicit ARD branch, as the config says), standalone: config -> Grid::build_amr ->
 cell-list neighbours -> grains -> initialize_fields -> CoupledSolver::run; writes <output_dir>/diagnostics.csv and the
 state_/flow_/corr_/final_ VTU series with simulation.pvd / flow.pvd (as the reference does; --no-vti: none).
 usage: python tools/amr_run.py configs/params_amr.cfg [key=value ...] [--no-vti]"""
@@ -12,7 +12,7 @@ from pd_mg_pin_corrosion_b200 import amr as A            # noqa: E402
 from pd_mg_pin_corrosion_b200.config import Config       # noqa: E402
 
 path = sys.argv[1]
-ov = {"use_implicit": 0}
+ov = {}                                                   # use_implicit as the file says (explicit: use_implicit=0 on the command line)
 for kv in [a for a in sys.argv[2:] if a != "--no-vti"]:
     k, v = kv.split("=", 1)
     ov[k] = type(getattr(Config(), k))(float(v)) if not isinstance(getattr(Config(), k), str) else v
