@@ -1,6 +1,7 @@
 """Re-type the parameter VALUES of the reference's shipped configuration files into configs/ (run in the build
-container only; /root/reference is not on the GPU box).  Only `key = value` pairs are taken, in file order, with the
-value text as written (so both parsers read the same digits); the reference's comments are not copied.
+container only; /root/reference is not on the GPU box).  Only `key = value` pairs are taken (the last occurrence of a key, as in the parser), written in this repository's key
+order and in shortest round-trip notation; the reference's comments are not copied.  tests/test_config.py checks that
+the reference's own parser reads the same values from both files.
 usage: python tools/gen_configs.py [--all]    (default: only the files configs/ does not hold yet)"""
 import os
 import sys
@@ -17,21 +18,42 @@ NOTE = {
     "params_transport_viz.cfg": "Transport visualisation run",
 }
 
+sys.path.insert(0, ROOT)
+from dataclasses import fields as dc_fields  # noqa: E402
+
+from pd_mg_pin_corrosion_b200.config import Config  # noqa: E402
+
+ORDER = [f.name for f in dc_fields(Config)]       # this repository's own grouping of the keys
+TYPES = {f.name: f.type for f in dc_fields(Config)}
+
+
+def norm(key: str, text: str) -> str:
+    """shortest text that parses to the same value"""
+    t = TYPES[key]
+    if t in ("int", int):
+        return str(int(text))
+    if t in ("float", float):
+        return repr(float(text))
+    return text
+
+
 for name in sorted(os.listdir(REF)):
     dst = os.path.join(ROOT, "configs", name)
     if os.path.exists(dst) and "--all" not in sys.argv:
         continue
-    rows = []
+    vals = {}
     for line in open(os.path.join(REF, name)):
         line = line.split("#", 1)[0].strip()
         if "=" not in line:
             continue
         k, v = (s.strip() for s in line.split("=", 1))
-        if k and v:
-            rows.append((k, v))
+        if k and v and k in TYPES:
+            vals[k] = v                              # later keys win, as in the parser
     with open(dst, "w") as f:
         f.write(f"# {NOTE.get(name, name)} (parameter values as in the reference's config/{name}).\n")
-        f.write("# key = value, read by pd_mg_pin_corrosion_b200/config.py and host/config.cpp like the reference's Config::load.\n")
-        for k, v in rows:
-            f.write(f"{k} = {v}\n")
-    print("wrote", dst, len(rows), "keys")
+        f.write("# key = value, read by pd_mg_pin_corrosion_b200/config.py and host/config.cpp like the reference's Config::load;\n")
+        f.write("# keys in the order of pd_mg_pin_corrosion_b200/config.py, values in shortest round-trip notation.\n")
+        for k in ORDER:
+            if k in vals:
+                f.write(f"{k} = {norm(k, vals[k])}\n")
+    print("wrote", dst, len(vals), "keys")
