@@ -303,12 +303,60 @@ class AmrCoupledSolver:
         cmax = float(max(Cc[fl].max(), 0.0)) if fl.any() else 0.0
         self.rows.append([t, t / 3600.0, loss, float((nt == 1).sum()), vmax, cmax])
 
+    def _implicit_cycle(self, grid, cycle: int, t_corr: float, solid0, snaps) -> float:
+        """phase 2, implicit (src/coupling.cpp:154-216): assemble once, then adaptive backward-Euler steps until
+        corrosion_steps_per_check, T_final or the first solid node below C_thresh"""
+        cfg = grid.cfg
+        grid.implicit_assemble()
+        step, dissolved = 0, False
+        while step < cfg.corrosion_steps_per_check and t_corr < cfg.T_final and not dissolved:
+            dt_impl = grid.implicit_compute_dt()
+            grid.inlet_bc(); grid.outlet_bc(); grid.wall_conc_bc()
+            self.last = grid.implicit_step(dt_impl, tol=self.tol, restart=self.restart, max_iters=self.max_iters)
+            grid.smooth_conc()
+            grid.update_fictitious()
+            t_corr += dt_impl
+            step += 1
+            self.total_implicit_steps += 1
+            if self.total_implicit_steps % int(cfg.diagnostic_every) == 0:
+                self._diag(grid, t_corr, solid0)
+            if snaps and self.total_implicit_steps % int(cfg.implicit_output_every) == 0:
+                self._snapshot(grid, snaps[0], "corr", t_corr, snaps[1])
+            dissolved = bool(((grid.get_field("node_type") == 1) & (grid.get_field("C") < cfg.C_thresh)).any())
+        self.log(f"cycle {cycle}: {step} implicit steps to t = {t_corr:.4e} s; last solve {self.last.iters} "
+                 f"iterations, |res| = {self.last.rel_res:.2e}")
+        return t_corr
+
+    def _explicit_cycle(self, grid, cycle: int, t_corr: float, solid0, snaps) -> float:
+        """phase 2, explicit (src/coupling.cpp:217-253): device-resident batches of sub-steps between output points"""
+        cfg = grid.cfg
+        dtc = grid.ard_compute_dt()
+        step, every = 0, int(cfg.output_every_corr)
+        while step < cfg.corrosion_steps_per_check:
+            n = min(every - step % every, cfg.corrosion_steps_per_check - step)
+            done = 0
+            while done < n:                      # t_corr advances per step (:237) and ends the cycle (:248)
+                t_corr += dtc
+                done += 1
+                if t_corr >= cfg.T_final:
+                    break
+            grid.ard_iterate(done, dtc)
+            step += done
+            if done == n and step % every == 0:
+                if snaps:
+                    self._snapshot(grid, snaps[0], "corr", t_corr, snaps[1])
+                self._diag(grid, t_corr, solid0)
+            if t_corr >= cfg.T_final:
+                break
+        return t_corr
+
     def run(self, grid: AmrGrid, out_dir: str | None = None, grain_id=None) -> list[list[float]]:
         cfg = grid.cfg
         solid0 = np.nonzero(grid.get_field("node_type") == 1)[0]
         n0 = len(solid0)
         t_corr, need_flow, cycle = 0.0, True, 0
         snap = out_dir is not None and grain_id is not None
+        writer = flow_writer = None
         if snap:
             import os
             from .solver import VTKWriter
@@ -332,45 +380,8 @@ class AmrCoupledSolver:
             for v in grid.get_field("C")[solid0].tolist():
                 s += v
             grid.ard_set_volume_loss(max(1.0 - s / (n0 + 1e-30), 0.0))
-            if cfg.use_implicit:                 # src/coupling.cpp:154-216
-                grid.implicit_assemble()
-                step, dissolved = 0, False
-                while step < cfg.corrosion_steps_per_check and t_corr < cfg.T_final and not dissolved:
-                    dt_impl = grid.implicit_compute_dt()
-                    grid.inlet_bc(); grid.outlet_bc(); grid.wall_conc_bc()
-                    self.last = grid.implicit_step(dt_impl, tol=self.tol, restart=self.restart, max_iters=self.max_iters)
-                    grid.smooth_conc()
-                    grid.update_fictitious()
-                    t_corr += dt_impl
-                    step += 1
-                    self.total_implicit_steps += 1
-                    if self.total_implicit_steps % int(cfg.diagnostic_every) == 0:
-                        self._diag(grid, t_corr, solid0)
-                    if snap and self.total_implicit_steps % int(cfg.implicit_output_every) == 0:
-                        self._snapshot(grid, out_dir, "corr", t_corr, writer)
-                    dissolved = bool(((grid.get_field("node_type") == 1) & (grid.get_field("C") < cfg.C_thresh)).any())
-                self.log(f"cycle {cycle}: {step} implicit steps to t = {t_corr:.4e} s; last solve {self.last.iters} "
-                         f"iterations, |res| = {self.last.rel_res:.2e}")
-            dtc = 0.0 if cfg.use_implicit else grid.ard_compute_dt()
-            step = 0
-            every = int(cfg.output_every_corr)
-            while not cfg.use_implicit and step < cfg.corrosion_steps_per_check:
-                # device-resident batches between two diagnostics rows
-                n = min(every - step % every, cfg.corrosion_steps_per_check - step)
-                done = 0
-                while done < n:                  # t_corr advances per step (:237) and ends the cycle (:248)
-                    t_corr += dtc
-                    done += 1
-                    if t_corr >= cfg.T_final:
-                        break
-                grid.ard_iterate(done, dtc)
-                step += done
-                if done == n and step % every == 0:
-                    if snap:
-                        self._snapshot(grid, out_dir, "corr", t_corr, writer)
-                    self._diag(grid, t_corr, solid0)
-                if t_corr >= cfg.T_final:
-                    break
+            snaps = (out_dir, writer) if snap else None
+            t_corr = (self._implicit_cycle if cfg.use_implicit else self._explicit_cycle)(grid, cycle, t_corr, solid0, snaps)
             before = grid.get_field("node_type") if snap else None
             n_diss = grid.phase_change()
             if n_diss > 0:
