@@ -116,6 +116,8 @@ void ref_get_config_extra(void* h, double* out) {
     std::memcpy(out, v, sizeof(v));
 }
 const char* ref_config_output_dir(void* h) { return S(h)->cfg.output_dir.c_str(); }
+// re-run Config::load on the existing object: keys present in `path` override, compute_derived runs again
+void ref_config_apply(void* h, const char* path) { S(h)->cfg.load(path); }
 
 void ref_grid_build(void* h) { S(h)->grid.build(S(h)->cfg); }
 // two-level AMR grid (src/grid.cpp:352-842): what main() calls with use_amr = 1 (src/main.cpp:151-154)
