@@ -5,10 +5,12 @@
 // with LD_LIBRARY_PATH, it lets the HOST logic of the C++ driver host/pd_corrosion_gpu (host/amr_run.cpp: cycle
 // structure, batching between output points, snapshot cadence, PVD / CSV / VTU writing, D_map bookkeeping) run on a
 // machine without a GPU; its output files must then equal those of the reference's own main() byte for byte.
-// The operators themselves are what the -m gpu tests check on the device.  The lattice entry points (pdgpu_*) are
-// present only so that the driver binary loads (it is linked BIND_NOW): fake_stubs.cpp, they fail when called.
+// The operators themselves are what the -m gpu tests check on the device.  The lattice entry points (pdgpu_*) the
+// drivers host/main.cpp + host/coupling.cpp call are served the same way for 2D single-rank runs; the remaining
+// ones exist only so that the binary loads (it is linked BIND_NOW): fake_stubs.cpp, they fail when called.
 #include <dlfcn.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -35,9 +37,10 @@ F sym(const char* name) {
 typedef void (*v_h)(void*);
 }  // namespace
 
-struct pdamr_ctx {
+struct pdamr_ctx {                // also stands in for pdgpu_ctx (the lattice context)
     void* h = nullptr;
     std::string cfg_path;
+    PdConfig cfg{};
 };
 
 static void apply(pdamr_ctx* c, const std::string& text) {
@@ -55,12 +58,10 @@ extern "C" {
 
 const char* pdgpu_last_error(void) { return g_err.c_str(); }
 
-int pdamr_create(const PdConfig* k, int amr_ratio, double amr_buffer, pdamr_ctx** out) {
-    pdamr_ctx* c = new pdamr_ctx();
+static std::string write_cfg(const PdConfig* k, const std::string& extra) {
     char tmpl[] = "/tmp/pdfake_XXXXXX";
     const int fd = mkstemp(tmpl);
-    if (fd < 0) return 1;
-    c->cfg_path = tmpl;
+    if (fd < 0) return "";
     FILE* f = fdopen(fd, "w");
 #define D(key) std::fprintf(f, #key " = %.17g\n", k->key)
 #define I(key) std::fprintf(f, #key " = %d\n", k->key)
@@ -71,9 +72,18 @@ int pdamr_create(const PdConfig* k, int amr_ratio, double amr_buffer, pdamr_ctx*
     I(output_every_corr); I(channel_flow_corrections); I(use_implicit);
 #undef D
 #undef I
-    std::fprintf(f, "use_amr = 1\namr_ratio = %d\namr_buffer = %.17g\n", amr_ratio, amr_buffer);
+    std::fputs(extra.c_str(), f);
     std::fclose(f);
     sym<void (*)(int)>("ref_set_threads")(1);                       // the reference's in-place loops are order dependent
+    return tmpl;
+}
+
+int pdamr_create(const PdConfig* k, int amr_ratio, double amr_buffer, pdamr_ctx** out) {
+    pdamr_ctx* c = new pdamr_ctx();
+    char extra[128];
+    std::snprintf(extra, sizeof extra, "use_amr = 1\namr_ratio = %d\namr_buffer = %.17g\n", amr_ratio, amr_buffer);
+    c->cfg_path = write_cfg(k, extra);
+    if (c->cfg_path.empty()) return 1;
     c->h = sym<void* (*)(const char*)>("ref_create")(c->cfg_path.c_str());
     *out = c;
     return 0;
@@ -190,5 +200,135 @@ int pdamr_destroy(pdamr_ctx* c) {
     delete c;
     return 0;
 }
+
+// ---- lattice context (2D, one rank): what host/main.cpp + host/coupling.cpp call ---------------------------------
+static const char* kFieldName[] = {"rho", "vel", "pressure", "C", "rho_new", "vel_new", "C_new", "phase", "is_gb", "is_precip",
+                                   "node_type"};
+static long long lat_N(pdgpu_ctx* c) { long long d[5]; dims((pdamr_ctx*)c, d); return d[3]; }
+
+int pdgpu_grid_extents(const PdConfig* k, int dim, int* Nx, int* Ny, int* Nz, double origin[3]) {
+    if (dim != 2) { g_err = "fake libpdgpu serves 2D only"; return 1; }
+    const std::string p = write_cfg(k, "use_amr = 0\n");
+    void* h = sym<void* (*)(const char*)>("ref_create")(p.c_str());
+    REF0(ref_grid_build)(h);
+    long long d[5];
+    sym<void (*)(void*, long long*)>("ref_get_dims")(h, d);
+    *Nx = (int)d[0]; *Ny = (int)d[1]; *Nz = (int)d[2];
+    sym<void (*)(void*, double*)>("ref_get_origin")(h, origin);
+    REF0(ref_destroy)(h);
+    std::remove(p.c_str());
+    return 0;
+}
+int pdgpu_create_slab(const PdConfig* k, int dim, int, int, int nranks, pdgpu_ctx** out) {
+    if (dim != 2 || nranks != 1) { g_err = "fake libpdgpu serves 2D single-rank runs only"; return 1; }
+    pdamr_ctx* c = new pdamr_ctx();
+    c->cfg_path = write_cfg(k, "use_amr = 0\n");
+    c->h = sym<void* (*)(const char*)>("ref_create")(c->cfg_path.c_str());
+    c->cfg = *k;
+    // members that do not cross the C ABI (grain parameters): from the run's own configuration file, so that the
+    // reference's grains can be compared with the driver's in pdgpu_fields_init
+    if (const char* p = std::getenv("PD_FAKE_CFG")) sym<void (*)(void*, const char*)>("ref_config_apply")(c->h, p);
+    *out = (pdgpu_ctx*)c;
+    return 0;
+}
+int pdgpu_destroy(pdgpu_ctx* c) { return pdamr_destroy((pdamr_ctx*)c); }
+int pdgpu_grid_build(pdgpu_ctx* c) { REF0(ref_grid_build)(((pdamr_ctx*)c)->h); REF0(ref_build_neighbors)(((pdamr_ctx*)c)->h); return 0; }
+int pdgpu_grid_info(pdgpu_ctx* c, PdGridInfo* o) {
+    std::memset(o, 0, sizeof(*o));
+    long long d[5];
+    dims((pdamr_ctx*)c, d);
+    o->dim = 2; o->Nx = (int)d[0]; o->Ny = (int)d[1]; o->Nz = (int)d[2]; o->N_total = d[3]; o->nnz = d[4];
+    o->m = ((pdamr_ctx*)c)->cfg.m_ratio; o->n_off = 36; o->reach = o->m + 1; o->a0 = 0; o->a1 = o->Ny; o->plane = o->Nx;
+    const uint8_t* t = (const uint8_t*)ptr((pdamr_ctx*)c, "node_type");
+    for (long long i = 0; i < d[3]; ++i) o->counts[t[i]]++;
+    sym<void (*)(void*, double*)>("ref_get_origin")(((pdamr_ctx*)c)->h, o->origin);
+    return 0;
+}
+int pdgpu_fields_download_all(pdgpu_ctx* c, int field, void* out) {
+    if (field < 0 || field > 10) return 1;
+    const size_t b = field_bytes((pdamr_ctx*)c, kFieldName[field]);
+    std::memcpy(out, ptr((pdamr_ctx*)c, kFieldName[field]), b);
+    return 0;
+}
+int pdgpu_fields_init(pdgpu_ctx* c, const uint8_t* gb, const uint8_t* pr) {
+    pdamr_ctx* a = (pdamr_ctx*)c;
+    REF0(ref_fields_init)(a->h);                 // the reference's own grains and initialize_fields ...
+    const size_t N = (size_t)lat_N(c);
+    if (std::memcmp(ptr(a, "is_gb"), gb, N) != 0 || std::memcmp(ptr(a, "is_precip"), pr, N) != 0) {
+        g_err = "fake pdgpu_fields_init: the driver's grain flags differ from the reference's";   // ... must agree with the driver's
+        return 1;
+    }
+    REF0(ref_ns_init)(a->h); REF0(ref_ard_init)(a->h); REF0(ref_imp_init)(a->h);
+    return 0;
+}
+int pdgpu_gather(pdgpu_ctx* c, int field, const int* idx, long long n, double* out) {
+    if (field != 3 && field != 0) return 1;
+    const double* a = (const double*)ptr((pdamr_ctx*)c, kFieldName[field]);
+    for (long long q = 0; q < n; ++q) out[q] = a[idx[q]];
+    return 0;
+}
+int pdgpu_diag(pdgpu_ctx* c, PdDiag* o) {        // reductions of write_diagnostics (src/coupling.cpp:20-49)
+    pdamr_ctx* a = (pdamr_ctx*)c;
+    const long long N = lat_N(c);
+    const uint8_t* t = (const uint8_t*)ptr(a, "node_type");
+    const double *v = (const double*)ptr(a, "vel"), *C = (const double*)ptr(a, "C");
+    o->solid_count = 0; o->v_max = 0.0; o->C_max_fluid = 0.0;
+    for (long long i = 0; i < N; ++i) {
+        if (t[i] == 1) o->solid_count++;
+        if (t[i] != 0) continue;
+        const double m = std::sqrt(v[2 * i] * v[2 * i] + v[2 * i + 1] * v[2 * i + 1]);
+        if (m > o->v_max) o->v_max = m;
+        if (C[i] > o->C_max_fluid) o->C_max_fluid = C[i];
+    }
+    return 0;
+}
+int pdgpu_vti_write(pdgpu_ctx* c, const char* path, const int* grain_id, const double* D_map, long long* bytes_out, float* ms) {
+    pdamr_ctx* a = (pdamr_ctx*)c;                // the reference's writer on its state with the DRIVER's host-side arrays
+    const size_t N = (size_t)lat_N(c);
+    if (grain_id) std::memcpy(ptr(a, "grain_id"), grain_id, 4 * N);
+    if (D_map) std::memcpy(ptr(a, "D_map"), D_map, 8 * N);
+    sym<double (*)(void*, const char*)>("ref_write_vti")(a->h, path);
+    if (bytes_out) *bytes_out = 0;
+    if (ms) *ms = 0.0f;
+    return 0;
+}
+int pdgpu_ns_solve_steady(pdgpu_ctx* c, PdSteadyResult* out, int v) { return pdamr_ns_solve_steady((pdamr_ctx*)c, out, v); }
+int pdgpu_ard_set_volume_loss(pdgpu_ctx* c, double v) { return pdamr_ard_set_volume_loss((pdamr_ctx*)c, v); }
+int pdgpu_ard_compute_dt(pdgpu_ctx* c, double* dt) { return pdamr_ard_compute_dt((pdamr_ctx*)c, dt); }
+int pdgpu_ard_iterate(pdgpu_ctx* c, int n, double dt) { return pdamr_ard_iterate((pdamr_ctx*)c, n, dt); }
+int pdgpu_implicit_assemble(pdgpu_ctx* c) { return pdamr_implicit_assemble((pdamr_ctx*)c); }
+int pdgpu_implicit_compute_dt(pdgpu_ctx* c, double f, double m, double* dt) { return pdamr_implicit_compute_dt((pdamr_ctx*)c, f, m, dt); }
+int pdgpu_implicit_step(pdgpu_ctx* c, double dt, double tol, int r, int mi, int, PdLinSolveInfo* info) {
+    return pdamr_implicit_step((pdamr_ctx*)c, dt, tol, r, mi, 1, info);
+}
+int pdgpu_bc_inlet(pdgpu_ctx* c) { return pdamr_bc((pdamr_ctx*)c, 0); }
+int pdgpu_bc_outlet(pdgpu_ctx* c) { return pdamr_bc((pdamr_ctx*)c, 1); }
+int pdgpu_bc_wall_conc(pdgpu_ctx* c) { return pdamr_bc((pdamr_ctx*)c, 4); }
+int pdgpu_bc_smooth_conc(pdgpu_ctx* c) { return pdamr_bc((pdamr_ctx*)c, 6); }
+int pdgpu_solid_below_thresh(pdgpu_ctx* c, int* count) {
+    pdamr_ctx* a = (pdamr_ctx*)c;
+    const long long N = lat_N(c);
+    const uint8_t* t = (const uint8_t*)ptr(a, "node_type");
+    const double* C = (const double*)ptr(a, "C");
+    int n = 0;
+    for (long long i = 0; i < N; ++i) n += (t[i] == 1 && C[i] < a->cfg.C_thresh);
+    *count = n;
+    return 0;
+}
+int pdgpu_phase_change(pdgpu_ctx* c, int* n_dissolved, int* dissolved, int cap) {
+    pdamr_ctx* a = (pdamr_ctx*)c;
+    const long long N = lat_N(c);
+    const uint8_t* t = (const uint8_t*)ptr(a, "node_type");
+    std::vector<uint8_t> before(t, t + N);
+    const int n = sym<int (*)(void*)>("ref_ard_phase_change")(a->h);
+    if (n > 0) { REF0(ref_update_node_types)(a->h); REF0(ref_build_neighbors)(a->h); }            // src/coupling.cpp:262-270
+    t = (const uint8_t*)ptr(a, "node_type");
+    int k = 0;
+    for (long long i = 0; i < N && dissolved && k < cap; ++i)
+        if (before[i] == 1 && t[i] == 0) dissolved[k++] = (int)i;
+    if (n_dissolved) *n_dissolved = n;
+    return 0;
+}
+int pdgpu_comm_allreduce(pdgpu_ctx*, double*, int, int) { return 0; }      // one rank
 
 }  // extern "C"
