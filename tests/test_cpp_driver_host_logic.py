@@ -64,7 +64,7 @@ def test_cpp_lattice_driver_reproduces_reference_main(branch, fake_lib_dir, tmp_
     dim, base, cov = H.CASES["2d_default"]
     ov = dict(cov, D_grain=5e-11, D_gb=5e-9, C_thresh=0.999, flow_max_iters=200)
     if branch == "implicit":
-        ov.update(use_implicit=1, corrosion_steps_per_check=6, T_final=3.2e-4, implicit_dt_max=0.004, implicit_dt_fraction=0.5,
+        ov.update(use_implicit=1, corrosion_steps_per_check=6, T_final=5e-4, implicit_dt_max=0.004, implicit_dt_fraction=0.5,
                   diagnostic_every=2, implicit_output_every=3)
     else:
         ov.update(use_implicit=0, corrosion_steps_per_check=50, T_final=2.6e-4, output_every_corr=10)
