@@ -9,6 +9,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/config"
 NOTE = {
+    "params.cfg": "80 um Mg-4Ag wire in an SBF flow cell, dx = 5 um, m = 3 (BASELINE configs 1 and 3); as shipped it runs the\n# implicit branch -- the north-star path is the EXPLICIT branch: use_implicit = 0 (the tests / bench override it)",
+    "params_fine.cfg": "dx = 2 um resolution of the params.cfg geometry (BASELINE config 4; bench.py's workload with use_implicit = 0)",
+    "params_poiseuille.cfg": "Flow-only 2D Poiseuille validation, no wire (BASELINE config 2)",
+    "params_amr.cfg": "Two-level AMR production set-up: dx = 2.5 um around the wire, 7.5 um in the far field, R_tube = 425 um; built by\n# pdamr_* (csrc/amr.cu), 2D, implicit branch",
     "params_amr_r2.cfg": "Two-level AMR set-up with refinement ratio 2",
     "params_calibration.cfg": "Calibration run of the corrosion parameters (2D)",
     "params_calibration_v2.cfg": "Calibration run of the corrosion parameters, second parameter set (2D)",
